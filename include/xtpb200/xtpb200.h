@@ -1,0 +1,216 @@
+/* libxtpb200 -- C ABI of the B200-native GW-BSE tensor-contraction path of VOTCA-XTP.
+ *
+ * Drop-in boundary.  The reference has no C ABI for this path:
+ * its boundary is a set of C++/Eigen classes called from GWBSE::Evaluate
+ * (upstream xtp/src/libxtp/gwbse/gwbse.cc).  Each entry point below names the
+ * reference member function it replaces; upstream paths are relative to
+ * votca/votca and carry NO line numbers because the mounted reference
+ * (/root/reference/README.md:1) is a one-line redirect stub -- see SURVEY.md section 0.
+ * The header-only C++ facade in xtp_facade.hpp re-creates the reference's class
+ * names on top of these functions; INTEGRATION.md shows the binding a
+ * maintainer would add on the XTP side.
+ *
+ * Conventions
+ *   - every function returns 0 on success; otherwise xtpb_last_error() holds a
+ *     thread-local message (the reference throws std::runtime_error instead).
+ *   - all matrices are FP64 column-major (Eigen::MatrixXd default) with an
+ *     explicit leading dimension where one is taken; indices are 64-bit signed
+ *     (Eigen::Index) in the option structs, absolute DFT level indices.
+ *   - pointers named *_host are caller-owned host memory; the library owns all
+ *     device memory.  Handles are not thread-safe; one host thread per context.
+ *   - no CPU fallback: without a CUDA device xtpb_ctx_create fails.
+ */
+#ifndef XTPB200_H
+#define XTPB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef long long xtpb_index;
+typedef struct xtpb_ctx xtpb_ctx;
+typedef struct xtpb_tc xtpb_tc;
+typedef struct xtpb_gw xtpb_gw;
+typedef struct xtpb_bse xtpb_bse;
+typedef struct xtpb_op xtpb_op;
+
+const char* xtpb_last_error(void);
+int xtpb_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+long long xtpb_launch_count(void);
+
+/* ---- context: one CUDA device + stream + scratch.  Replaces OpenMP_CUDA / CudaPipeline
+ *      (upstream xtp/src/libxtp/openmp_cuda.cc, cudapipeline.cc). ---- */
+int xtpb_ctx_create(int device, xtpb_ctx** out);
+int xtpb_ctx_destroy(xtpb_ctx* ctx);
+int xtpb_ctx_sync(xtpb_ctx* ctx);
+/* seconds spent inside cuSOLVER eigh/inverse since the last reset (reported apart from contractions) */
+int xtpb_ctx_solver_seconds(xtpb_ctx* ctx, double* seconds, int reset);
+
+/* ---- TCMatrix_gwbse (upstream xtp/include/votca/xtp/threecenter.h, xtp/src/libxtp/threecenter_gwbse.cc) ---- */
+/* TCMatrix_gwbse::Initialize(basissize, mmin, mmax, nmin, nmax) */
+int xtpb_tc_create(xtpb_ctx* ctx, xtpb_index auxsize, xtpb_index mmin, xtpb_index mmax, xtpb_index nmin,
+                   xtpb_index nmax, xtpb_tc** out);
+int xtpb_tc_destroy(xtpb_tc* tc);
+/* accessors auxsize()/msize()/nsize() */
+int xtpb_tc_sizes(const xtpb_tc* tc, xtpb_index* auxsize, xtpb_index* msize, xtpb_index* nsize);
+/* whole tensor in the reference's host layout: mtotal slabs, each ntotal x auxsize column-major */
+int xtpb_tc_set_raw(xtpb_tc* tc, const double* M_host);
+/* TCMatrix_gwbse::operator[](m): slab m (ntotal x auxsize, column-major, ld = ntotal) */
+int xtpb_tc_get_slab(xtpb_tc* tc, xtpb_index m, double* slab_host);
+/* TCMatrix_gwbse::Fill3cMO, split so the caller's integral loop can stream aux shells:
+ *   fill_begin : dft_orbitals (n_basis x >= max(mmax,nmax)+1, column-major, ld = ldc)
+ *   fill_block : nP consecutive aux functions starting at P0; ao3c holds nP symmetric
+ *                n_basis x n_basis slices (column-major, ld = ld_ao, slice stride = ld_ao*n_basis).
+ *                Replaces OpenMP_CUDA::setOperators + MultiplyLeftRight.
+ *   the _dev variant takes a device pointer (inputs already resident in HBM). */
+int xtpb_tc_fill_begin(xtpb_tc* tc, xtpb_index n_basis, const double* C_host, xtpb_index ldc);
+int xtpb_tc_fill_block(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_host, xtpb_index ld_ao);
+int xtpb_tc_fill_block_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_dev, xtpb_index ld_ao);
+/* TCMatrix_gwbse::MultiplyRightWithAuxMatrix(matrix): matrix is auxsize x auxsize */
+int xtpb_tc_multiply_right_with_aux_matrix(xtpb_tc* tc, const double* A_host, xtpb_index lda);
+/* second half of TCMatrix_gwbse::Fill: AOCoulomb::Pseudo_InvSqrt_GWBSE(auxoverlap, etol) followed by
+ * MultiplyRightWithAuxMatrix.  S_host may be NULL (orthonormal aux basis). */
+int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
+                                 xtpb_index lds, double etol, xtpb_index* removed_functions);
+
+/* ---- RPA (upstream xtp/src/libxtp/gwbse/rpa.cc) ---- */
+/* RPA::calculate_epsilon_i / calculate_epsilon_r for n_omega frequencies in one call.
+ * energies_host: RPA input energies, length rpamax-rpamin+1.  eps_host: n_omega matrices auxsize x auxsize. */
+int xtpb_rpa_epsilon(xtpb_tc* tc, const double* energies_host, xtpb_index homo, xtpb_index rpamin, xtpb_index rpamax,
+                     double eta, const double* omegas_host, int n_omega, int imaginary_axis, double* eps_host);
+
+/* ---- Sigma_base / Sigma_PPM / Sigma_Exact / Sigma_CDA / GW
+ *      (upstream xtp/src/libxtp/gwbse/sigma_base.cc, sigma_ppm.cc, sigma_exact.cc, sigma_cda.cc, ppm.cc, gw.cc) ---- */
+enum { XTPB_SIGMA_PPM = 0, XTPB_SIGMA_EXACT = 1, XTPB_SIGMA_CDA = 2 };
+enum { XTPB_QP_GRID = 0, XTPB_QP_FIXEDPOINT = 1 };
+enum { XTPB_QUAD_LEGENDRE = 0, XTPB_QUAD_LAGUERRE = 1, XTPB_QUAD_HERMITE = 2 };
+
+typedef struct xtpb_gw_options {   /* GW::options + Sigma_base::options, upstream gw.h / sigma_base.h */
+  xtpb_index homo, qpmin, qpmax, rpamin, rpamax;
+  double eta;                 /* 1e-3 */
+  double g_sc_limit;          /* 1e-5  QP equation convergence [Ha] */
+  xtpb_index g_sc_max_iterations; /* 100 */
+  double gw_sc_limit;         /* 1e-5  evGW convergence */
+  xtpb_index gw_sc_max_iterations; /* 1 = G0W0 */
+  double shift;               /* scissor shift */
+  double ScaHFX;
+  int sigma_integration;      /* XTPB_SIGMA_* */
+  xtpb_index reset_3c;        /* 5 */
+  int qp_solver;              /* XTPB_QP_* */
+  xtpb_index qp_grid_steps;   /* 1001 */
+  double qp_grid_spacing;     /* 0.01 Ha */
+  xtpb_index gw_mixing_order; /* 0 = plain */
+  double gw_mixing_alpha;     /* 0.7 */
+  int quadrature_scheme;      /* XTPB_QUAD_* (CDA) */
+  xtpb_index order;           /* 12 (CDA) */
+  double alpha;               /* 1e-3 (CDA tail) */
+} xtpb_gw_options;
+void xtpb_gw_options_default(xtpb_gw_options* opt);
+
+/* GW::GW(log, Mmn, vxc, dft_energies) + GW::configure(opt).  vxc is qptotal x qptotal. */
+int xtpb_gw_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_gw_options* opt, const double* vxc_host, xtpb_index ldv,
+                   const double* dft_energies_host, xtpb_index n_energies, xtpb_gw** out);
+int xtpb_gw_destroy(xtpb_gw* gw);
+/* Sigma_base::CalcExchangeMatrix (qptotal x qptotal, unscaled by ScaHFX) */
+int xtpb_gw_sigma_exchange(xtpb_gw* gw, double* sigma_x_host);
+/* RPA::setRPAInputEnergies / getRPAInputEnergies (length rpatotal) */
+int xtpb_gw_set_rpa_input_energies(xtpb_gw* gw, const double* e_host);
+int xtpb_gw_get_rpa_input_energies(xtpb_gw* gw, double* e_host);
+/* Sigma_*::PrepareScreening() */
+int xtpb_gw_prepare_screening(xtpb_gw* gw);
+/* PPM::getPpm_weight / getPpm_freq (length auxsize) after PrepareScreening with XTPB_SIGMA_PPM */
+int xtpb_gw_get_ppm(xtpb_gw* gw, double* weight_host, double* freq_host);
+/* Sigma_*::CalcCorrelationDiagElement and ...DiagElementDerivative for n (level, frequency) pairs in one
+ * call; levels are gw-level indices (0 = qpmin).  derivs_host may be NULL. */
+int xtpb_gw_sigma_c_diag_elements(xtpb_gw* gw, xtpb_index n, const xtpb_index* levels_host,
+                                  const double* frequencies_host, double* values_host, double* derivs_host);
+/* Sigma_base::CalcCorrelationDiag(frequencies): one frequency per gw level */
+int xtpb_gw_sigma_c_diag(xtpb_gw* gw, const double* frequencies_host, double* values_host);
+/* Sigma_base::CalcCorrelationOffDiag(frequencies): qptotal x qptotal, zero diagonal */
+int xtpb_gw_sigma_c_offdiag(xtpb_gw* gw, const double* frequencies_host, double* sigma_c_host);
+/* GW::CalculateGWPerturbation / CalculateHQP / getGWAResults / getHQP / DiagonalizeQPHamiltonian */
+int xtpb_gw_calculate_gw_perturbation(xtpb_gw* gw);
+int xtpb_gw_calculate_hqp(xtpb_gw* gw);
+int xtpb_gw_get_gwa_results(xtpb_gw* gw, double* qp_energies_host);
+int xtpb_gw_get_hqp(xtpb_gw* gw, double* hqp_host);
+int xtpb_gw_diagonalize_qp_hamiltonian(xtpb_gw* gw, double* eigenvalues_host, double* eigenvectors_host);
+/* number of gw levels whose QP equation did not converge in the last SolveQP */
+int xtpb_gw_unconverged_levels(xtpb_gw* gw, xtpb_index* count);
+
+/* ---- BSE / BSE_OPERATOR (upstream xtp/src/libxtp/gwbse/bse.cc, bse_operator.{h,cc}) ---- */
+typedef struct xtpb_bse_options {  /* BSE::options, upstream bse.h */
+  xtpb_index homo, rpamin, rpamax, qpmin, qpmax, vmin, cmax;
+  xtpb_index nmax;
+  int use_Hqp_offdiag;        /* 1 */
+} xtpb_bse_options;
+
+/* BSE::configure(opt, RPAInputEnergies, Hqp_in): AdjustHqpSize + SetupDirectInteractionOperator
+ * (epsilon(0) at the given energies, eigen-decomposition, aux rotation of the BSE windows).
+ * The rotated windows are kept in BSE-owned device buffers; unlike the reference the
+ * TCMatrix itself is left untouched unless rotate_full_tc != 0. */
+int xtpb_bse_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_bse_options* opt, const double* rpa_input_energies_host,
+                    const double* hqp_host, xtpb_index ldh, int rotate_full_tc, xtpb_bse** out);
+int xtpb_bse_destroy(xtpb_bse* bse);
+int xtpb_bse_get_epsilon_0_inv(xtpb_bse* bse, double* eps_inv_host);
+/* BSE_OPERATOR<cqp,cx,cd,cd2>(epsilon_0_inv, Mmn, Hqp) + configure(BSEOperator_Options).
+ * Typedefs upstream: SingletOperator_TDA <1,2,1,0>, TripletOperator_TDA <1,0,1,0>, SingletOperator_BTDA_B <0,2,0,1>,
+ * TripletOperator_BTDA_B <0,0,0,1>, HxOperator <0,1,0,0>, HdOperator <0,0,1,0>, Hd2Operator <0,0,0,1>, HqpOperator <1,0,0,0>. */
+int xtpb_bse_operator_create(xtpb_bse* bse, int cqp, int cx, int cd, int cd2, xtpb_op** out);
+/* same operator built from explicit pieces, without an epsilon(0) rotation: eps_inv (auxsize),
+ * Hqp ((vtotal+ctotal)^2).  Used by operator-level tests, mirrors the reference constructor. */
+int xtpb_bse_operator_create_raw(xtpb_ctx* ctx, xtpb_tc* tc, xtpb_index homo, xtpb_index rpamin, xtpb_index vmin,
+                                 xtpb_index cmax, const double* eps_inv_host, const double* hqp_host, xtpb_index ldh,
+                                 int cqp, int cx, int cd, int cd2, xtpb_op** out);
+/* a dense symmetric matrix as a MatrixFreeOperator (tests of the Davidson solver) */
+int xtpb_dense_operator_create(xtpb_ctx* ctx, const double* A_host, xtpb_index n, xtpb_index lda, xtpb_op** out);
+int xtpb_op_destroy(xtpb_op* op);
+/* MatrixFreeOperator::rows() */
+int xtpb_op_size(xtpb_op* op, xtpb_index* size);
+/* MatrixFreeOperator::matmul(X): X, Y are size x k */
+int xtpb_op_matmul(xtpb_op* op, const double* X_host, xtpb_index ldx, xtpb_index k, double* Y_host, xtpb_index ldy);
+/* MatrixFreeOperator::diagonal() */
+int xtpb_op_diagonal(xtpb_op* op, double* diag_host);
+/* MatrixFreeOperator::get_full_matrix() (size x size; small problems only) */
+int xtpb_op_get_full_matrix(xtpb_op* op, double* H_host, xtpb_index ldh);
+
+/* ---- DavidsonSolver (upstream xtp/src/libxtp/davidsonsolver.cc) ---- */
+enum { XTPB_DAVIDSON_DPR = 0, XTPB_DAVIDSON_OLSEN = 1 };
+enum { XTPB_UPDATE_MIN = 0, XTPB_UPDATE_SAFE = 1, XTPB_UPDATE_MAX = 2 };
+typedef struct xtpb_davidson_options {
+  double tolerance;           /* loose 1e-3, normal 1e-4, strict 1e-5, lapack 1e-9 */
+  int correction;             /* XTPB_DAVIDSON_* */
+  int size_update;            /* XTPB_UPDATE_* */
+  xtpb_index iter_max;        /* 50 */
+  xtpb_index max_search_space;/* 0 -> 5*neigen; BSE uses 10*nmax */
+  xtpb_index size_initial_guess; /* 0 -> 2*neigen */
+} xtpb_davidson_options;
+void xtpb_davidson_options_default(xtpb_davidson_options* opt);
+/* DavidsonSolver::solve(A, neigen, size_initial_guess) for symmetric operators.
+ * eigenvalues_host: neigen; eigenvectors_host: size x neigen (ld = ldv).
+ * info: 0 = Eigen::Success, 1 = Eigen::NoConvergence.  iterations: num_iterations(). */
+int xtpb_davidson_solve(xtpb_op* op, xtpb_index neigen, const xtpb_davidson_options* opt, double* eigenvalues_host,
+                        double* eigenvectors_host, xtpb_index ldv, int* info, xtpb_index* iterations);
+
+/* ---- engine-level hook used by the parity tests of the contraction kernel ----
+ * C = alpha * sum_{outer,k} A(row,outer,k) d(outer,k) B(col,outer,k) + beta*C with every stride explicit
+ * (element units, host buffers of the given lengths are copied to the device and back). */
+typedef struct xtpb_contract_desc {
+  xtpb_index M, N, K, n_outer, n_batch;
+  xtpb_index a_row, a_k, a_outer, a_batch, a_len;
+  xtpb_index b_row, b_k, b_outer, b_batch, b_len;
+  xtpb_index c_row, c_col, c_batch, c_len, c_col_inner, c_col_outer;
+  xtpb_index d_outer, d_batch, d_len;   /* d_len = 0: no weights */
+  double alpha, beta;
+  int lower, force_cfg, force_splits;
+} xtpb_contract_desc;
+int xtpb_contract_host(xtpb_ctx* ctx, const xtpb_contract_desc* desc, const double* A_host, const double* B_host,
+                       const double* d_host, double* C_host);
+/* times `reps` launches of the same contraction on device buffers filled with pseudo-random data; returns
+ * the mean milliseconds per launch (CUDA events on the library stream). */
+int xtpb_contract_bench(xtpb_ctx* ctx, const xtpb_contract_desc* desc, int reps, double* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XTPB200_H */

@@ -1,0 +1,284 @@
+"""-m gpu parity tests: every stage of the GW-BSE path through the C ABI (ctypes) against the CPU oracle on
+identical seeded inputs.  Tolerances are those of BASELINE.json's north_star: M_mn^P 1e-10 relative,
+energies 1e-6 Hartree (tests use tighter bounds where FP64 allows)."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import gwbse_oracle as orc
+from xtp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from xtp_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module", params=["tiny", "ch4-svp-shape", "odd"])
+def prob(request):
+    if request.param == "odd":      # odd level counts everywhere: exercises the 8-byte (unaligned) load paths
+        sz = synth.Sizes(n_basis=45, n_aux=91, homo=6, qpmax=15, cmax=15)
+        p = synth.make_problem(sz, seed=77)
+    else:
+        p = synth.make_problem(request.param)
+    sz = p["sizes"]
+    tc = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.Fill(p["ao3c"], p["C"], p["aux_coulomb"])
+    p["tc_o"] = tc
+    return p
+
+
+def gpu_tc(ctx, prob, raw=None):
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.set_raw(prob["tc_o"].M if raw is None else raw)
+    return tc
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+def test_set_raw_roundtrip(ctx, prob):
+    tc = gpu_tc(ctx, prob)
+    np.testing.assert_array_equal(tc.get_raw(), prob["tc_o"].M)
+    np.testing.assert_array_equal(tc[1], prob["tc_o"][1])
+
+
+def test_fill_matches_oracle(ctx, prob):
+    """TCMatrix_gwbse::Fill: K1 (MO transform) + Coulomb metric + K2 (aux rotation)."""
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.Fill3cMO(prob["ao3c"], prob["C"], block=7)
+    ref = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    ref.Fill3cMO(prob["ao3c"], prob["C"])
+    assert rel(tc.get_raw(), ref.M) < 1e-12
+    removed = tc.apply_coulomb_metric(prob["aux_coulomb"])
+    assert removed == 0
+    assert rel(tc.get_raw(), prob["tc_o"].M) < 1e-10
+
+
+def test_coulomb_metric_with_overlap_and_removed_functions(ctx, prob):
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((sz.n_aux, sz.n_aux))
+    S = B @ B.T / sz.n_aux + 0.5 * np.eye(sz.n_aux)
+    # rank-deficient Coulomb matrix: three functions must be removed
+    w, U = np.linalg.eigh(prob["aux_coulomb"])
+    w[:3] = 1e-9
+    V = (U * w) @ U.T
+    tc = gpu_tc(ctx, prob)
+    removed = tc.apply_coulomb_metric(V, S)
+    ref = copy.deepcopy(prob["tc_o"])
+    R, removed_ref = orc.Pseudo_InvSqrt_GWBSE(V, S)
+    ref.MultiplyRightWithAuxMatrix(R)
+    assert removed == removed_ref
+    assert rel(tc.get_raw(), ref.M) < 1e-8
+
+
+def test_multiply_right_with_aux_matrix(ctx, prob):
+    sz = prob["sizes"]
+    R = np.random.default_rng(2).standard_normal((sz.n_aux, sz.n_aux))
+    tc = gpu_tc(ctx, prob)
+    tc.MultiplyRightWithAuxMatrix(R)
+    ref = copy.deepcopy(prob["tc_o"])
+    ref.MultiplyRightWithAuxMatrix(R)
+    assert rel(tc.get_raw(), ref.M) < 1e-12
+
+
+def _rpa_pair(ctx, prob):
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    e = prob["energies"][sz.rpamin:sz.rpamax + 1]
+    tc = gpu_tc(ctx, prob)
+    g = api.RPA(tc); g.configure(sz.homo, sz.rpamin, sz.rpamax); g.setRPAInputEnergies(e)
+    o = orc.RPA(prob["tc_o"]); o.configure(sz.homo, sz.rpamin, sz.rpamax); o.setRPAInputEnergies(e)
+    return g, o
+
+
+def test_epsilon_imag_and_real(ctx, prob):
+    g, o = _rpa_pair(ctx, prob)
+    for w in [0.0, 0.5, 3.0]:
+        assert rel(g.calculate_epsilon_i(w), o.calculate_epsilon_i(w)) < 1e-12
+    for w in [0.0, 0.2]:
+        assert rel(g.calculate_epsilon_r(w), o.calculate_epsilon_r(w)) < 1e-12
+    batch = g.calculate_epsilon_batch([0.1, 0.7, 2.0], imag=True)
+    for i, w in enumerate([0.1, 0.7, 2.0]):
+        assert rel(batch[i], o.calculate_epsilon_i(w)) < 1e-12
+
+
+def _gw_pair(ctx, prob, **kw):
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    tc = gpu_tc(ctx, prob)
+    gw = api.GW(ctx, tc, prob["vxc"], prob["energies"])
+    gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax, **kw))
+    tco = copy.deepcopy(prob["tc_o"])
+    okw = dict(kw)
+    if "sigma_integration" in okw:
+        okw["sigma_integration"] = okw["sigma_integration"]
+    gwo = orc.GW(tco, prob["vxc"], prob["energies"])
+    gwo.configure(orc.GWOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax, **okw))
+    return gw, gwo, tc, tco
+
+
+def test_sigma_exchange(ctx, prob):
+    gw, gwo, _, _ = _gw_pair(ctx, prob)
+    assert rel(gw.CalcExchangeMatrix(), gwo.sigma.CalcExchangeMatrix()) < 1e-12
+
+
+def test_ppm_parameters_and_sigma_c(ctx, prob):
+    sz = prob["sizes"]
+    gw, gwo, tc, tco = _gw_pair(ctx, prob)
+    gwo.rpa.setRPAInputEnergies(prob["energies"][sz.rpamin:sz.rpamax + 1])
+    gw.PrepareScreening()
+    gwo.sigma.PrepareScreening()
+    w, f = gw.getPpm()
+    np.testing.assert_allclose(w, gwo.sigma.ppm.ppm_weight, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(f, gwo.sigma.ppm.ppm_freq, rtol=1e-8, atol=1e-12)
+    q = sz.qptotal
+    rng = np.random.default_rng(4)
+    levels = rng.integers(0, q, 40)
+    freqs = rng.uniform(-1.5, 1.5, 40)
+    val, der = gw.CalcCorrelationDiagElements(levels, freqs, derivative=True)
+    ref = np.array([gwo.sigma.CalcCorrelationDiagElement(int(l), float(x)) for l, x in zip(levels, freqs)])
+    refd = np.array([gwo.sigma.CalcCorrelationDiagElementDerivative(int(l), float(x)) for l, x in zip(levels, freqs)])
+    np.testing.assert_allclose(val, ref, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(der, refd, rtol=1e-9, atol=1e-10)
+    fr = prob["energies"][sz.qpmin:sz.qpmax + 1]
+    np.testing.assert_allclose(gw.CalcCorrelationDiag(fr), gwo.sigma.CalcCorrelationDiag(fr), rtol=1e-9, atol=1e-11)
+    off = gw.CalcCorrelationOffDiag(fr)
+    np.testing.assert_allclose(off, gwo.sigma.CalcCorrelationOffDiag(fr), rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("solver", ["grid", "fixedpoint"])
+def test_g0w0_qp_energies(ctx, prob, solver):
+    gw, gwo, _, _ = _gw_pair(ctx, prob, qp_solver=solver, qp_grid_steps=401)
+    gw.CalculateGWPerturbation()
+    gwo.CalculateGWPerturbation()
+    np.testing.assert_allclose(gw.getGWAResults(), gwo.getGWAResults(), rtol=0, atol=1e-6)
+    gw.CalculateHQP()
+    gwo.CalculateHQP()
+    np.testing.assert_allclose(gw.getHQP(), gwo.getHQP(), rtol=0, atol=1e-6)
+    wq, _ = gw.DiagonalizeQPHamiltonian()
+    np.testing.assert_allclose(wq, gwo.DiagonalizeQPHamiltonian()[0], rtol=0, atol=1e-6)
+
+
+def test_evgw(ctx, prob):
+    gw, gwo, _, _ = _gw_pair(ctx, prob, gw_sc_max_iterations=4, qp_grid_steps=201)
+    gw.CalculateGWPerturbation()
+    gwo.Mmn._fill_args = (prob["ao3c"], prob["C"], prob["aux_coulomb"], None, 5e-7)
+    gwo.CalculateGWPerturbation()
+    np.testing.assert_allclose(gw.getGWAResults(), gwo.getGWAResults(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(gw.RPAInputEnergies(), gwo.RPAInputEnergies(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(orc.OPERATOR_TYPES))
+def test_bse_operator_matmul_diagonal(ctx, prob, name):
+    """BSE_OPERATOR<...>::matmul / diagonal / get_full_matrix vs the dense element-wise Hamiltonian."""
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    rng = np.random.default_rng(3)
+    hq = rng.standard_normal((sz.vtotal + sz.ctotal,) * 2)
+    hq = 0.5 * (hq + hq.T)
+    eps_inv = rng.uniform(0.2, 1.0, sz.n_aux)
+    cqp, cx, cd, cd2 = orc.OPERATOR_TYPES[name]
+    tc = gpu_tc(ctx, prob)
+    op = api.BSE_OPERATOR(ctx, cqp, cx, cd, cd2, eps_inv, tc, hq, sz.homo, sz.rpamin, sz.vmin, sz.cmax)
+    ref = orc.BSE_OPERATOR(cqp, cx, cd, cd2, eps_inv, prob["tc_o"], hq)
+    ref.configure(orc.BSEOperator_Options(sz.homo, sz.rpamin, sz.qpmin, sz.vmin, sz.cmax))
+    H = ref.get_full_matrix()
+    scale = np.abs(H).max()
+    for k in (1, 5, 37):
+        X = rng.standard_normal((op.rows(), k))
+        assert np.abs(op.matmul(X) - H @ X).max() < 1e-11 * scale * np.sqrt(op.rows())
+    assert np.abs(op.diagonal() - np.diag(H)).max() < 1e-12 * scale
+    assert np.abs(op.get_full_matrix() - H).max() < 1e-12 * scale
+
+
+@pytest.mark.parametrize("corr", ["DPR", "OLSEN"])
+def test_davidson_dense_vs_eigh(ctx, corr):
+    """test_davidson pattern of the reference: random diagonally dominant matrix vs a dense eigensolver."""
+    from xtp_b200 import api
+    rng = np.random.default_rng(7)
+    n = 501
+    A = rng.standard_normal((n, n)) * 0.01
+    A = 0.5 * (A + A.T) + np.diag(np.sort(rng.uniform(0, 10, n)))
+    op = api.DenseOperator(ctx, A)
+    ds = api.DavidsonSolver()
+    ds.set_tolerance("lapack"); ds.set_correction(corr); ds.set_max_search_space(80)
+    ds.solve(op, 7)
+    assert ds.info() == "Success"
+    w, Z = np.linalg.eigh(A)
+    np.testing.assert_allclose(ds.eigenvalues(), w[:7], atol=1e-9)
+    ov = np.abs(np.einsum('ij,ij->j', ds.eigenvectors(), Z[:, :7]))
+    np.testing.assert_allclose(ov, 1.0, atol=1e-7)
+    # the oracle's Davidson on the same problem converges to the same values
+    dso = orc.DavidsonSolver(); dso.set_tolerance("lapack"); dso.set_correction(corr); dso.set_max_search_space(80)
+
+    class D:
+        def rows(self): return n
+        def diagonal(self): return np.diag(A).copy()
+        def matmul(self, X): return A @ X
+    dso.solve(D(), 7)
+    np.testing.assert_allclose(ds.eigenvalues(), dso.eigenvalues(), atol=1e-9)
+
+
+def test_davidson_restart_and_nonconvergence(ctx):
+    from xtp_b200 import api
+    rng = np.random.default_rng(8)
+    n = 300
+    A = rng.standard_normal((n, n)) * 0.05
+    A = 0.5 * (A + A.T) + np.diag(np.sort(rng.uniform(0, 5, n)))
+    op = api.DenseOperator(ctx, A)
+    ds = api.DavidsonSolver()
+    ds.set_tolerance("strict"); ds.set_max_search_space(24)      # forces restarts
+    ds.solve(op, 4)
+    assert ds.info() == "Success"
+    np.testing.assert_allclose(ds.eigenvalues(), np.linalg.eigvalsh(A)[:4], atol=1e-6)
+    ds2 = api.DavidsonSolver(); ds2.set_tolerance("lapack"); ds2.set_iter_max(2)
+    ds2.solve(op, 4)
+    assert ds2.info() == "NoConvergence" and ds2.num_iterations() == 2
+
+
+def test_full_gwbse_step(ctx, prob):
+    """Whole hot path on the GPU vs the oracle: Fill -> G0W0 (PPM) -> Hqp -> BSE singlets + triplets."""
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    nmax = 4
+    gwopt = orc.GWOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax, qp_grid_steps=401)
+    bseopt = orc.BSEOptions(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, nmax=nmax,
+                            davidson_tolerance="lapack")
+    ref = orc.run_gwbse(prob["ao3c"], prob["C"], prob["energies"], prob["vxc"], prob["aux_coulomb"], gwopt, bseopt,
+                        triplets=True)
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.Fill(prob["ao3c"], prob["C"], prob["aux_coulomb"])
+    gw = api.GW(ctx, tc, prob["vxc"], prob["energies"])
+    gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax,
+                                qp_grid_steps=401))
+    gw.CalculateGWPerturbation()
+    np.testing.assert_allclose(gw.getGWAResults(), ref["qp_pert"], rtol=0, atol=1e-6)
+    gw.CalculateHQP()
+    bse = api.BSE(ctx, tc)
+    bse.configure(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, nmax, gw.RPAInputEnergies(),
+                  gw.getHQP(), davidson_tolerance="lapack")
+    np.testing.assert_allclose(np.sort(bse.epsilon_0_inv()), np.sort(ref["eps0_inv"]), rtol=1e-8)
+    es, vs = bse.Solve_singlets_TDA()
+    assert bse.last_davidson.info() == "Success"
+    np.testing.assert_allclose(es, ref["singlet_energies"], rtol=0, atol=1e-6)
+    et, _ = bse.Solve_triplets_TDA()
+    np.testing.assert_allclose(et, ref["triplet_energies"], rtol=0, atol=1e-6)
+    # eigenvectors: same subspace (sign/phase free)
+    ov = np.abs(np.einsum('ij,ij->j', vs, ref["singlet_vectors"]))
+    gaps = np.diff(ref["singlet_energies"])
+    if gaps.min() > 1e-4:
+        np.testing.assert_allclose(ov, 1.0, atol=1e-5)

@@ -1,0 +1,499 @@
+"""Host-side mirror of the reference's GW-BSE interface over libxtpb200's C ABI.
+
+Class and method names follow upstream votca/xtp (TCMatrix_gwbse, RPA, GW,
+Sigma via GW, BSE, BSE_OPERATOR, DavidsonSolver) so parity tests read like the
+reference's own tests.  All arrays are numpy float64; matrices are passed to the
+library column-major (Eigen's default).  Every call goes to CUDA; a missing or
+unloadable library raises (see ``_lib.lib``)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, dptr, idx, iptr, vp
+
+
+def _d(a):
+    return a.ctypes.data_as(dptr)
+
+
+def _f(a):
+    """Column-major float64 copy/view."""
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+class Context:
+    """One CUDA device + stream (replaces OpenMP_CUDA / CudaPipeline)."""
+
+    def __init__(self, device=0):
+        self._h = vp()
+        check(_lib.lib().xtpb_ctx_create(int(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().xtpb_ctx_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(_lib.lib().xtpb_ctx_sync(self._h))
+
+    def solver_seconds(self, reset=False):
+        s = C.c_double()
+        check(_lib.lib().xtpb_ctx_solver_seconds(self._h, C.byref(s), int(reset)))
+        return s.value
+
+
+def launch_count():
+    return int(_lib.lib().xtpb_launch_count())
+
+
+class TCMatrix_gwbse:
+    """upstream xtp/src/libxtp/threecenter_gwbse.cc"""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._h = vp()
+
+    def Initialize(self, auxsize, mmin, mmax, nmin, nmax):
+        self.close()
+        check(_lib.lib().xtpb_tc_create(self.ctx._h, auxsize, mmin, mmax, nmin, nmax, C.byref(self._h)))
+        self._aux, self.mmin, self.mmax, self.nmin, self.nmax = int(auxsize), int(mmin), int(mmax), int(nmin), int(nmax)
+        return self
+
+    def close(self):
+        if self._h:
+            _lib.lib().xtpb_tc_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def auxsize(self): return self._aux
+    def msize(self): return self.mmax - self.mmin + 1
+    def nsize(self): return self.nmax - self.nmin + 1
+    def get_mmin(self): return self.mmin
+    def get_mmax(self): return self.mmax
+    def get_nmin(self): return self.nmin
+    def get_nmax(self): return self.nmax
+
+    def set_raw(self, M):
+        """M[m, P, n] C-contiguous == the reference's vector of column-major (n x aux) slabs."""
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        assert M.shape == (self.msize(), self._aux, self.nsize())
+        check(_lib.lib().xtpb_tc_set_raw(self._h, _d(M)))
+
+    def __getitem__(self, m):
+        """operator[]: slab m as an (nsize x auxsize) matrix."""
+        out = np.empty((self._aux, self.nsize()))
+        check(_lib.lib().xtpb_tc_get_slab(self._h, int(m), _d(out)))
+        return out.T
+
+    def get_raw(self):
+        return np.stack([self[m].T for m in range(self.msize())])
+
+    def Fill3cMO(self, ao3c, C_mo, block=64):
+        """ao3c[P, mu, nu] symmetric slices (host), C_mo (n_basis x n_levels)."""
+        Cf = _f(C_mo)
+        nb = Cf.shape[0]
+        check(_lib.lib().xtpb_tc_fill_begin(self._h, nb, _d(Cf), Cf.shape[0]))
+        ao3c = np.ascontiguousarray(ao3c, dtype=np.float64)
+        for p0 in range(0, self._aux, block):
+            cnt = min(block, self._aux - p0)
+            blk = ao3c[p0:p0 + cnt]
+            check(_lib.lib().xtpb_tc_fill_block(self._h, p0, cnt, _d(blk), nb))
+
+    def fill_begin(self, C_mo):
+        Cf = _f(C_mo)
+        check(_lib.lib().xtpb_tc_fill_begin(self._h, Cf.shape[0], _d(Cf), Cf.shape[0]))
+
+    def fill_block_dev(self, P0, nP, dev_ptr, ld):
+        check(_lib.lib().xtpb_tc_fill_block_dev(self._h, int(P0), int(nP), vp(int(dev_ptr)), int(ld)))
+
+    def fill_block(self, P0, blk, ld=None):
+        blk = np.ascontiguousarray(blk, dtype=np.float64)
+        check(_lib.lib().xtpb_tc_fill_block(self._h, int(P0), blk.shape[0], _d(blk), int(ld or blk.shape[-1])))
+
+    def MultiplyRightWithAuxMatrix(self, A):
+        Af = _f(A)
+        check(_lib.lib().xtpb_tc_multiply_right_with_aux_matrix(self._h, _d(Af), Af.shape[0]))
+
+    def Fill(self, ao3c, C_mo, aux_coulomb, aux_overlap=None, etol=5e-7):
+        self.Fill3cMO(ao3c, C_mo)
+        self.removedfunctions = self.apply_coulomb_metric(aux_coulomb, aux_overlap, etol)
+
+    def apply_coulomb_metric(self, V, S=None, etol=5e-7):
+        Vf = _f(V)
+        Sf = _f(S) if S is not None else None
+        removed = idx(0)
+        check(_lib.lib().xtpb_tc_apply_coulomb_metric(
+            self._h, _d(Vf), Vf.shape[0], _d(Sf) if Sf is not None else None,
+            Sf.shape[0] if Sf is not None else 0, float(etol), C.byref(removed)))
+        return int(removed.value)
+
+
+class RPA:
+    """upstream xtp/src/libxtp/gwbse/rpa.cc"""
+
+    def __init__(self, Mmn: TCMatrix_gwbse):
+        self.Mmn = Mmn
+        self.eta = 1e-3
+
+    def configure(self, homo, rpamin, rpamax):
+        self.homo, self.rpamin, self.rpamax = int(homo), int(rpamin), int(rpamax)
+
+    def setRPAInputEnergies(self, e):
+        self.energies = np.ascontiguousarray(e, dtype=np.float64)
+
+    def getRPAInputEnergies(self):
+        return self.energies
+
+    def _eps(self, omegas, imag):
+        om = np.ascontiguousarray(np.atleast_1d(omegas), dtype=np.float64)
+        na = self.Mmn.auxsize()
+        out = np.empty((len(om), na, na))
+        check(_lib.lib().xtpb_rpa_epsilon(self.Mmn._h, _d(self.energies), self.homo, self.rpamin, self.rpamax,
+                                          float(self.eta), _d(om), len(om), int(imag), _d(out)))
+        return out
+
+    def calculate_epsilon_i(self, omega):
+        return self._eps(omega, True)[0]
+
+    def calculate_epsilon_r(self, omega):
+        return self._eps(omega, False)[0]
+
+    def calculate_epsilon_batch(self, omegas, imag=True):
+        return self._eps(omegas, imag)
+
+
+SIGMA = {"ppm": 0, "exact": 1, "cda": 2}
+QPSOLVER = {"grid": 0, "fixedpoint": 1}
+QUAD = {"legendre": 0, "laguerre": 1, "hermite": 2}
+
+
+def gw_options(**kw):
+    o = _lib.GwOptions()
+    _lib.lib().xtpb_gw_options_default(C.byref(o))
+    for k, v in kw.items():
+        if k == "sigma_integration" and isinstance(v, str):
+            v = SIGMA[v]
+        if k == "qp_solver" and isinstance(v, str):
+            v = QPSOLVER[v]
+        if k == "quadrature_scheme" and isinstance(v, str):
+            v = QUAD[v]
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+class GW:
+    """upstream xtp/src/libxtp/gwbse/gw.cc (+ sigma_base / sigma_ppm / ppm)"""
+
+    def __init__(self, ctx: Context, Mmn: TCMatrix_gwbse, vxc, dft_energies):
+        self.ctx, self.Mmn = ctx, Mmn
+        self.vxc = _f(vxc)
+        self.dft_energies = np.ascontiguousarray(dft_energies, dtype=np.float64)
+        self._h = vp()
+
+    def configure(self, opt):
+        self.close()
+        self.opt = opt
+        self.qptotal = int(opt.qpmax - opt.qpmin + 1)
+        self.rpatotal = int(opt.rpamax - opt.rpamin + 1)
+        check(_lib.lib().xtpb_gw_create(self.ctx._h, self.Mmn._h, C.byref(opt), _d(self.vxc), self.vxc.shape[0],
+                                        _d(self.dft_energies), len(self.dft_energies), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().xtpb_gw_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def CalcExchangeMatrix(self):
+        out = np.empty((self.qptotal, self.qptotal), order="F")
+        check(_lib.lib().xtpb_gw_sigma_exchange(self._h, _d(out)))
+        return out
+
+    def setRPAInputEnergies(self, e):
+        e = np.ascontiguousarray(e, dtype=np.float64)
+        assert len(e) == self.rpatotal
+        check(_lib.lib().xtpb_gw_set_rpa_input_energies(self._h, _d(e)))
+
+    def RPAInputEnergies(self):
+        out = np.empty(self.rpatotal)
+        check(_lib.lib().xtpb_gw_get_rpa_input_energies(self._h, _d(out)))
+        return out
+
+    def PrepareScreening(self):
+        check(_lib.lib().xtpb_gw_prepare_screening(self._h))
+
+    def getPpm(self):
+        na = self.Mmn.auxsize()
+        w, f = np.empty(na), np.empty(na)
+        check(_lib.lib().xtpb_gw_get_ppm(self._h, _d(w), _d(f)))
+        return w, f
+
+    def CalcCorrelationDiagElements(self, levels, frequencies, derivative=False):
+        lv = np.ascontiguousarray(levels, dtype=np.int64)
+        fr = np.ascontiguousarray(frequencies, dtype=np.float64)
+        val = np.empty(len(lv))
+        der = np.empty(len(lv)) if derivative else None
+        check(_lib.lib().xtpb_gw_sigma_c_diag_elements(self._h, len(lv), lv.ctypes.data_as(iptr), _d(fr), _d(val),
+                                                       _d(der) if derivative else None))
+        return (val, der) if derivative else val
+
+    def CalcCorrelationDiagElement(self, level, frequency):
+        return float(self.CalcCorrelationDiagElements([level], [frequency])[0])
+
+    def CalcCorrelationDiagElementDerivative(self, level, frequency):
+        return float(self.CalcCorrelationDiagElements([level], [frequency], True)[1][0])
+
+    def CalcCorrelationDiag(self, frequencies):
+        fr = np.ascontiguousarray(frequencies, dtype=np.float64)
+        out = np.empty(self.qptotal)
+        check(_lib.lib().xtpb_gw_sigma_c_diag(self._h, _d(fr), _d(out)))
+        return out
+
+    def CalcCorrelationOffDiag(self, frequencies):
+        fr = np.ascontiguousarray(frequencies, dtype=np.float64)
+        out = np.empty((self.qptotal, self.qptotal), order="F")
+        check(_lib.lib().xtpb_gw_sigma_c_offdiag(self._h, _d(fr), _d(out)))
+        return out
+
+    def CalculateGWPerturbation(self):
+        check(_lib.lib().xtpb_gw_calculate_gw_perturbation(self._h))
+
+    def CalculateHQP(self):
+        check(_lib.lib().xtpb_gw_calculate_hqp(self._h))
+
+    def getGWAResults(self):
+        out = np.empty(self.qptotal)
+        check(_lib.lib().xtpb_gw_get_gwa_results(self._h, _d(out)))
+        return out
+
+    def getHQP(self):
+        out = np.empty((self.qptotal, self.qptotal), order="F")
+        check(_lib.lib().xtpb_gw_get_hqp(self._h, _d(out)))
+        return out
+
+    def DiagonalizeQPHamiltonian(self):
+        w = np.empty(self.qptotal)
+        v = np.empty((self.qptotal, self.qptotal), order="F")
+        check(_lib.lib().xtpb_gw_diagonalize_qp_hamiltonian(self._h, _d(w), _d(v)))
+        return w, v
+
+    def unconverged_levels(self):
+        n = idx(0)
+        check(_lib.lib().xtpb_gw_unconverged_levels(self._h, C.byref(n)))
+        return int(n.value)
+
+
+class _Operator:
+    def __init__(self, handle, ctx):
+        self._h, self.ctx = handle, ctx
+        n = idx(0)
+        check(_lib.lib().xtpb_op_size(self._h, C.byref(n)))
+        self._n = int(n.value)
+
+    def close(self):
+        if self._h:
+            _lib.lib().xtpb_op_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rows(self): return self._n
+    def cols(self): return self._n
+    def size(self): return self._n
+
+    def matmul(self, X):
+        Xf = _f(X)
+        if Xf.ndim == 1:
+            Xf = Xf.reshape(-1, 1, order="F")
+        k = Xf.shape[1]
+        Y = np.empty((self._n, k), order="F")
+        check(_lib.lib().xtpb_op_matmul(self._h, _d(Xf), Xf.shape[0], k, _d(Y), self._n))
+        return Y
+
+    def diagonal(self):
+        d = np.empty(self._n)
+        check(_lib.lib().xtpb_op_diagonal(self._h, _d(d)))
+        return d
+
+    def get_full_matrix(self):
+        H = np.empty((self._n, self._n), order="F")
+        check(_lib.lib().xtpb_op_get_full_matrix(self._h, _d(H), self._n))
+        return H
+
+
+OPERATOR_TYPES = {
+    "SingletOperator_TDA": (1, 2, 1, 0),
+    "TripletOperator_TDA": (1, 0, 1, 0),
+    "SingletOperator_BTDA_B": (0, 2, 0, 1),
+    "TripletOperator_BTDA_B": (0, 0, 0, 1),
+    "HxOperator": (0, 1, 0, 0),
+    "HdOperator": (0, 0, 1, 0),
+    "Hd2Operator": (0, 0, 0, 1),
+    "HqpOperator": (1, 0, 0, 0),
+}
+
+
+class BSE_OPERATOR(_Operator):
+    """BSE_OPERATOR<cqp,cx,cd,cd2>(epsilon_0_inv, Mmn, Hqp) + configure(opt); upstream bse_operator.{h,cc}"""
+
+    def __init__(self, ctx: Context, cqp, cx, cd, cd2, epsilon_0_inv, Mmn: TCMatrix_gwbse, Hqp, homo, rpamin, vmin, cmax):
+        e = np.ascontiguousarray(epsilon_0_inv, dtype=np.float64)
+        H = _f(Hqp)
+        h = vp()
+        check(_lib.lib().xtpb_bse_operator_create_raw(ctx._h, Mmn._h, homo, rpamin, vmin, cmax, _d(e), _d(H),
+                                                      H.shape[0], cqp, cx, cd, cd2, C.byref(h)))
+        super().__init__(h, ctx)
+
+
+class DenseOperator(_Operator):
+    def __init__(self, ctx: Context, A):
+        Af = _f(A)
+        h = vp()
+        check(_lib.lib().xtpb_dense_operator_create(ctx._h, _d(Af), Af.shape[0], Af.shape[0], C.byref(h)))
+        super().__init__(h, ctx)
+
+
+class DavidsonSolver:
+    """upstream xtp/src/libxtp/davidsonsolver.cc"""
+    TOL = {"loose": 1e-3, "normal": 1e-4, "strict": 1e-5, "lapack": 1e-9}
+
+    def __init__(self):
+        self.opt = _lib.DavidsonOptions()
+        _lib.lib().xtpb_davidson_options_default(C.byref(self.opt))
+        self._info, self._iters = 1, 0
+
+    def set_iter_max(self, n): self.opt.iter_max = int(n)
+    def set_max_search_space(self, n): self.opt.max_search_space = int(n)
+    def set_tolerance(self, name): self.opt.tolerance = self.TOL[name]
+    def set_correction(self, name): self.opt.correction = {"DPR": 0, "OLSEN": 1}[name.upper()]
+    def set_size_update(self, name): self.opt.size_update = {"min": 0, "safe": 1, "max": 2}[name.lower()]
+
+    def solve(self, A: _Operator, neigen, size_initial_guess=0):
+        self.opt.size_initial_guess = int(size_initial_guess)
+        n = A.rows()
+        self._evals = np.empty(neigen)
+        self._evecs = np.empty((n, neigen), order="F")
+        info, iters = C.c_int(1), idx(0)
+        check(_lib.lib().xtpb_davidson_solve(A._h, int(neigen), C.byref(self.opt), _d(self._evals), _d(self._evecs), n,
+                                             C.byref(info), C.byref(iters)))
+        self._info, self._iters = info.value, int(iters.value)
+        return self
+
+    def eigenvalues(self): return self._evals
+    def eigenvectors(self): return self._evecs
+    def info(self): return "Success" if self._info == 0 else "NoConvergence"
+    def num_iterations(self): return self._iters
+
+
+class BSE:
+    """upstream xtp/src/libxtp/gwbse/bse.cc"""
+
+    def __init__(self, ctx: Context, Mmn: TCMatrix_gwbse):
+        self.ctx, self.Mmn = ctx, Mmn
+        self._h = vp()
+
+    def configure(self, homo, rpamin, rpamax, qpmin, qpmax, vmin, cmax, nmax, RPAInputEnergies, Hqp,
+                  use_Hqp_offdiag=True, rotate_full_tc=False, davidson_correction="DPR", davidson_tolerance="normal",
+                  davidson_update="safe", davidson_maxiter=50):
+        self.close()
+        o = _lib.BseOptions(homo, rpamin, rpamax, qpmin, qpmax, vmin, cmax, nmax, int(use_Hqp_offdiag))
+        self.opt = o
+        self.davidson = (davidson_correction, davidson_tolerance, davidson_update, davidson_maxiter)
+        e = np.ascontiguousarray(RPAInputEnergies, dtype=np.float64)
+        H = _f(Hqp)
+        check(_lib.lib().xtpb_bse_create(self.ctx._h, self.Mmn._h, C.byref(o), _d(e), _d(H), H.shape[0],
+                                         int(rotate_full_tc), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().xtpb_bse_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def epsilon_0_inv(self):
+        out = np.empty(self.Mmn.auxsize())
+        check(_lib.lib().xtpb_bse_get_epsilon_0_inv(self._h, _d(out)))
+        return out
+
+    def make_operator(self, name):
+        cqp, cx, cd, cd2 = OPERATOR_TYPES[name]
+        h = vp()
+        check(_lib.lib().xtpb_bse_operator_create(self._h, cqp, cx, cd, cd2, C.byref(h)))
+        return _Operator(h, self.ctx)
+
+    def solve_hermitian(self, op):
+        ds = DavidsonSolver()
+        corr, tol, upd, maxiter = self.davidson
+        ds.set_correction(corr)
+        ds.set_tolerance(tol)
+        ds.set_size_update(upd)
+        ds.set_iter_max(maxiter)
+        ds.set_max_search_space(10 * int(self.opt.nmax))
+        ds.solve(op, int(self.opt.nmax))
+        self.last_davidson = ds
+        return ds.eigenvalues(), ds.eigenvectors()
+
+    def Solve_singlets_TDA(self):
+        op = self.make_operator("SingletOperator_TDA")
+        try:
+            return self.solve_hermitian(op)
+        finally:
+            op.close()
+
+    def Solve_triplets_TDA(self):
+        op = self.make_operator("TripletOperator_TDA")
+        try:
+            return self.solve_hermitian(op)
+        finally:
+            op.close()
+
+
+def contract_host(ctx: Context, desc: "_lib.ContractDesc", A, B, d, Cmat):
+    """Engine-level test hook: raw strided contraction on host buffers (flat float64 arrays)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    Cmat = np.ascontiguousarray(Cmat, dtype=np.float64)
+    desc.a_len, desc.b_len, desc.c_len = A.size, B.size, Cmat.size
+    if d is not None:
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        desc.d_len = d.size
+    else:
+        desc.d_len = 0
+    check(_lib.lib().xtpb_contract_host(ctx._h, C.byref(desc), _d(A), _d(B), _d(d) if d is not None else None, _d(Cmat)))
+    return Cmat
+
+
+def contract_bench(ctx: Context, desc: "_lib.ContractDesc", reps=10):
+    ms = C.c_double()
+    check(_lib.lib().xtpb_contract_bench(ctx._h, C.byref(desc), int(reps), C.byref(ms)))
+    return ms.value

@@ -1,0 +1,459 @@
+// extern "C" surface of libxtpb200 (include/xtpb200/xtpb200.h).
+#include <cstring>
+
+#include "internal.h"
+
+namespace xtpb {
+const char* last_error_cstr();
+std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e);
+}
+using namespace xtpb;
+
+extern "C" {
+
+const char* xtpb_last_error(void) { return last_error_cstr(); }
+int xtpb_version(void) { return 100; }
+long long xtpb_launch_count(void) { return g_launch_count; }
+
+int xtpb_ctx_create(int device, xtpb_ctx** out) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(out != nullptr, "null output pointer");
+  *out = new xtpb_ctx(device);
+  XTPB_API_END
+}
+int xtpb_ctx_destroy(xtpb_ctx* ctx) {
+  XTPB_API_BEGIN
+  delete ctx;
+  XTPB_API_END
+}
+int xtpb_ctx_sync(xtpb_ctx* ctx) {
+  XTPB_API_BEGIN
+  ctx->impl.sync();
+  XTPB_API_END
+}
+int xtpb_ctx_solver_seconds(xtpb_ctx* ctx, double* seconds, int reset) {
+  XTPB_API_BEGIN
+  if (seconds) *seconds = ctx->impl.solver_seconds;
+  if (reset) ctx->impl.solver_seconds = 0.0;
+  XTPB_API_END
+}
+
+// ---------------------------------------------------------------- TCMatrix_gwbse
+int xtpb_tc_create(xtpb_ctx* ctx, xtpb_index auxsize, xtpb_index mmin, xtpb_index mmax, xtpb_index nmin,
+                   xtpb_index nmax, xtpb_tc** out) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(ctx && out, "null pointer");
+  *out = new xtpb_tc{TCMatrix(&ctx->impl, auxsize, mmin, mmax, nmin, nmax)};
+  XTPB_API_END
+}
+int xtpb_tc_destroy(xtpb_tc* tc) {
+  XTPB_API_BEGIN
+  delete tc;
+  XTPB_API_END
+}
+int xtpb_tc_sizes(const xtpb_tc* tc, xtpb_index* auxsize, xtpb_index* msize, xtpb_index* nsize) {
+  XTPB_API_BEGIN
+  if (auxsize) *auxsize = tc->impl.naux;
+  if (msize) *msize = tc->impl.mtotal;
+  if (nsize) *nsize = tc->impl.ntotal;
+  XTPB_API_END
+}
+int xtpb_tc_set_raw(xtpb_tc* tc, const double* M_host) {
+  XTPB_API_BEGIN
+  tc->impl.set_raw(M_host);
+  XTPB_API_END
+}
+int xtpb_tc_get_slab(xtpb_tc* tc, xtpb_index m, double* slab_host) {
+  XTPB_API_BEGIN
+  tc->impl.get_slab(m, slab_host);
+  XTPB_API_END
+}
+int xtpb_tc_fill_begin(xtpb_tc* tc, xtpb_index n_basis, const double* C_host, xtpb_index ldc) {
+  XTPB_API_BEGIN
+  tc->impl.fill_begin(n_basis, C_host, ldc);
+  XTPB_API_END
+}
+int xtpb_tc_fill_block(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_host, xtpb_index ld_ao) {
+  XTPB_API_BEGIN
+  tc->impl.fill_block_host(P0, nP, ao3c_host, ld_ao);
+  XTPB_API_END
+}
+int xtpb_tc_fill_block_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_dev, xtpb_index ld_ao) {
+  XTPB_API_BEGIN
+  tc->impl.fill_block_dev(P0, nP, ao3c_dev, ld_ao);
+  XTPB_API_END
+}
+int xtpb_tc_multiply_right_with_aux_matrix(xtpb_tc* tc, const double* A_host, xtpb_index lda) {
+  XTPB_API_BEGIN
+  TCMatrix& t = tc->impl;
+  DBuf R((size_t)(t.naux * t.naux));
+  t.ctx->h2d_2d(R.p, t.naux, A_host, lda, t.naux, t.naux);
+  t.rotate(R.p, t.naux);
+  t.ctx->sync();
+  XTPB_API_END
+}
+// AOCoulomb::Pseudo_InvSqrt_GWBSE (upstream xtp/src/libxtp/aomatrices/aocoulomb.cc) + MultiplyRightWithAuxMatrix
+int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
+                                 xtpb_index lds, double etol, xtpb_index* removed_functions) {
+  XTPB_API_BEGIN
+  TCMatrix& t = tc->impl;
+  Context* ctx = t.ctx;
+  const long long na = t.naux;
+  long long removed = 0;
+  DBuf A((size_t)(na * na)), B((size_t)(na * na)), Cc((size_t)(na * na)), w((size_t)na), Ssqrt;
+  std::vector<double> lam((size_t)na), sc((size_t)na);
+  auto mm = [&](const double* X, bool, const double* Yp, double* Z) {
+    // Z = X * Y for symmetric X (read through its K-contiguous view), Y column-major
+    GemmParams g{};
+    g.A = op_k_contig(X, na);
+    g.B = op_k_contig(Yp, na);
+    g.C = Z; g.c_sm = 1; g.c_sn = na;
+    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+  };
+  // f(X) = U diag(1/sqrt(lambda) | 0) U^T for symmetric X (eigenvalues < etol dropped)
+  auto inv_sqrt = [&](double* X, double* out) {
+    ctx->eigh((int)na, X, na, w.p);              // X <- U
+    ctx->d2h(lam.data(), w.p, (size_t)na);
+    for (long long i = 0; i < na; ++i) {
+      if (lam[i] < etol) { ++removed; sc[i] = 0.0; } else sc[i] = 1.0 / std::sqrt(lam[i]);
+    }
+    ctx->h2d(w.p, sc.data(), (size_t)na);
+    XTPB_CUDA(cudaMemcpyAsync(B.p, X, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_scale_columns(B.p, (int)na, (int)na, na, w.p, ctx->stream);   // B = U diag(s)
+    // out = B U^T : out(i,j) = sum_k B(i,k) U(j,k)  -> A rows-contig (B), B-operand rows-contig (U)
+    GemmParams g{};
+    g.A = op_rows_contig(B.p, na);
+    g.B = op_rows_contig(X, na);
+    g.C = out; g.c_sm = 1; g.c_sn = na;
+    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+  };
+  ctx->h2d_2d(A.p, na, V_host, ldv, na, na);
+  if (S_host) {
+    Ssqrt.alloc((size_t)(na * na));
+    DBuf S((size_t)(na * na));
+    ctx->h2d_2d(S.p, na, S_host, lds, na, na);
+    inv_sqrt(S.p, Ssqrt.p);
+    // ortho = Ssqrt V Ssqrt  (all symmetric)
+    mm(Ssqrt.p, true, A.p, Cc.p);
+    // Cc is not symmetric: (Cc * Ssqrt)(i,j) = sum_k Cc(i,k) Ssqrt(k,j) -> rows-contiguous view of Cc
+    GemmParams g{};
+    g.A = op_rows_contig(Cc.p, na);
+    g.B = op_k_contig(Ssqrt.p, na);
+    g.C = A.p; g.c_sm = 1; g.c_sn = na;
+    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+  }
+  DBuf Vm1((size_t)(na * na));
+  inv_sqrt(A.p, Vm1.p);
+  double* R = Vm1.p;
+  if (S_host) {
+    mm(Ssqrt.p, true, Vm1.p, Cc.p);      // Cc = Ssqrt * Vm1
+    GemmParams g{};
+    g.A = op_rows_contig(Cc.p, na);
+    g.B = op_k_contig(Ssqrt.p, na);
+    g.C = A.p; g.c_sm = 1; g.c_sn = na;
+    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+    R = A.p;
+  }
+  t.rotate(R, na);
+  ctx->sync();
+  if (removed_functions) *removed_functions = removed;
+  XTPB_API_END
+}
+
+// ---------------------------------------------------------------- RPA
+int xtpb_rpa_epsilon(xtpb_tc* tc, const double* energies_host, xtpb_index homo, xtpb_index rpamin, xtpb_index rpamax,
+                     double eta, const double* omegas_host, int n_omega, int imaginary_axis, double* eps_host) {
+  XTPB_API_BEGIN
+  TCMatrix& t = tc->impl;
+  XTPB_REQUIRE(rpamin == t.nmin && rpamax == t.nmax && rpamin == t.mmin, "TCMatrix ranges do not match rpamin/rpamax");
+  XTPB_REQUIRE(n_omega >= 1, "need at least one frequency");
+  const long long na = t.naux, rpatotal = rpamax - rpamin + 1;
+  DBuf e((size_t)rpatotal), eps((size_t)(na * na * n_omega));
+  t.ctx->h2d(e.p, energies_host, (size_t)rpatotal);
+  rpa_epsilon_dev(t, e.p, homo - rpamin + 1, eta, omegas_host, n_omega, imaginary_axis != 0, 0.0, eps.p);
+  t.ctx->d2h(eps_host, eps.p, (size_t)(na * na * n_omega));
+  XTPB_API_END
+}
+
+// ---------------------------------------------------------------- GW
+void xtpb_gw_options_default(xtpb_gw_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->eta = 1e-3; o->g_sc_limit = 1e-5; o->g_sc_max_iterations = 100; o->gw_sc_limit = 1e-5;
+  o->gw_sc_max_iterations = 1; o->shift = 0.0; o->ScaHFX = 0.0; o->sigma_integration = XTPB_SIGMA_PPM;
+  o->reset_3c = 5; o->qp_solver = XTPB_QP_GRID; o->qp_grid_steps = 1001; o->qp_grid_spacing = 0.01;
+  o->gw_mixing_order = 0; o->gw_mixing_alpha = 0.7; o->quadrature_scheme = XTPB_QUAD_LEGENDRE; o->order = 12;
+  o->alpha = 1e-3;
+}
+int xtpb_gw_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_gw_options* opt, const double* vxc_host, xtpb_index ldv,
+                   const double* dft_energies_host, xtpb_index n_energies, xtpb_gw** out) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(ctx && tc && opt && out, "null pointer");
+  *out = new xtpb_gw{GW(&ctx->impl, &tc->impl, *opt, vxc_host, ldv, dft_energies_host, n_energies)};
+  XTPB_API_END
+}
+int xtpb_gw_destroy(xtpb_gw* gw) {
+  XTPB_API_BEGIN
+  delete gw;
+  XTPB_API_END
+}
+int xtpb_gw_sigma_exchange(xtpb_gw* gw, double* sigma_x_host) {
+  XTPB_API_BEGIN
+  gw->impl.exchange(sigma_x_host);
+  XTPB_API_END
+}
+int xtpb_gw_set_rpa_input_energies(xtpb_gw* gw, const double* e_host) {
+  XTPB_API_BEGIN
+  gw->impl.set_rpa_energies(e_host);
+  XTPB_API_END
+}
+int xtpb_gw_get_rpa_input_energies(xtpb_gw* gw, double* e_host) {
+  XTPB_API_BEGIN
+  std::memcpy(e_host, gw->impl.rpa_energies.data(), gw->impl.rpa_energies.size() * 8);
+  XTPB_API_END
+}
+int xtpb_gw_prepare_screening(xtpb_gw* gw) {
+  XTPB_API_BEGIN
+  gw->impl.prepare_screening();
+  XTPB_API_END
+}
+int xtpb_gw_get_ppm(xtpb_gw* gw, double* weight_host, double* freq_host) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(!gw->impl.ppm_weight.empty(), "no plasmon-pole parameters (PrepareScreening with PPM first)");
+  if (weight_host) std::memcpy(weight_host, gw->impl.ppm_weight.data(), gw->impl.ppm_weight.size() * 8);
+  if (freq_host) std::memcpy(freq_host, gw->impl.ppm_freq.data(), gw->impl.ppm_freq.size() * 8);
+  XTPB_API_END
+}
+int xtpb_gw_sigma_c_diag_elements(xtpb_gw* gw, xtpb_index n, const xtpb_index* levels_host,
+                                  const double* frequencies_host, double* values_host, double* derivs_host) {
+  XTPB_API_BEGIN
+  gw->impl.sigma_c_diag_elements(n, levels_host, frequencies_host, values_host, derivs_host);
+  XTPB_API_END
+}
+int xtpb_gw_sigma_c_diag(xtpb_gw* gw, const double* frequencies_host, double* values_host) {
+  XTPB_API_BEGIN
+  std::vector<long long> lv((size_t)gw->impl.qptotal);
+  for (size_t i = 0; i < lv.size(); ++i) lv[i] = (long long)i;
+  gw->impl.sigma_c_diag_elements((long long)lv.size(), lv.data(), frequencies_host, values_host, nullptr);
+  XTPB_API_END
+}
+int xtpb_gw_sigma_c_offdiag(xtpb_gw* gw, const double* frequencies_host, double* sigma_c_host) {
+  XTPB_API_BEGIN
+  gw->impl.sigma_c_offdiag(frequencies_host, sigma_c_host);
+  XTPB_API_END
+}
+int xtpb_gw_calculate_gw_perturbation(xtpb_gw* gw) {
+  XTPB_API_BEGIN
+  gw->impl.calculate_gw_perturbation();
+  XTPB_API_END
+}
+int xtpb_gw_calculate_hqp(xtpb_gw* gw) {
+  XTPB_API_BEGIN
+  gw->impl.calculate_hqp();
+  XTPB_API_END
+}
+int xtpb_gw_get_gwa_results(xtpb_gw* gw, double* qp_energies_host) {
+  XTPB_API_BEGIN
+  const std::vector<double> r = gw->impl.gwa_results();
+  std::memcpy(qp_energies_host, r.data(), r.size() * 8);
+  XTPB_API_END
+}
+int xtpb_gw_get_hqp(xtpb_gw* gw, double* hqp_host) {
+  XTPB_API_BEGIN
+  const std::vector<double> h = gw->impl.hqp();
+  std::memcpy(hqp_host, h.data(), h.size() * 8);
+  XTPB_API_END
+}
+int xtpb_gw_diagonalize_qp_hamiltonian(xtpb_gw* gw, double* eigenvalues_host, double* eigenvectors_host) {
+  XTPB_API_BEGIN
+  GW& g = gw->impl;
+  const long long q = g.qptotal;
+  const std::vector<double> h = g.hqp();
+  DBuf H((size_t)(q * q)), w((size_t)q);
+  g.ctx->h2d(H.p, h.data(), (size_t)(q * q));
+  g.ctx->eigh((int)q, H.p, q, w.p);
+  g.ctx->d2h(eigenvalues_host, w.p, (size_t)q);
+  if (eigenvectors_host) g.ctx->d2h(eigenvectors_host, H.p, (size_t)(q * q));
+  XTPB_API_END
+}
+int xtpb_gw_unconverged_levels(xtpb_gw* gw, xtpb_index* count) {
+  XTPB_API_BEGIN
+  *count = gw->impl.unconverged;
+  XTPB_API_END
+}
+
+// ---------------------------------------------------------------- BSE
+int xtpb_bse_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_bse_options* opt, const double* rpa_input_energies_host,
+                    const double* hqp_host, xtpb_index ldh, int rotate_full_tc, xtpb_bse** out) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(ctx && tc && opt && out, "null pointer");
+  auto* b = new xtpb_bse{BSE(&ctx->impl, &tc->impl, *opt, rpa_input_energies_host, hqp_host, ldh, rotate_full_tc != 0),
+                         nullptr};
+  try {
+    b->R = bse_setup_screening(b->impl, rpa_input_energies_host);
+    if (rotate_full_tc) {
+      tc->impl.rotate(b->R->p, tc->impl.naux);
+      ctx->impl.sync();
+      b->R.reset();
+    }
+  } catch (...) {
+    delete b;
+    throw;
+  }
+  *out = b;
+  XTPB_API_END
+}
+int xtpb_bse_destroy(xtpb_bse* bse) {
+  XTPB_API_BEGIN
+  delete bse;
+  XTPB_API_END
+}
+int xtpb_bse_get_epsilon_0_inv(xtpb_bse* bse, double* eps_inv_host) {
+  XTPB_API_BEGIN
+  std::memcpy(eps_inv_host, bse->impl.eps_inv.data(), bse->impl.eps_inv.size() * 8);
+  XTPB_API_END
+}
+int xtpb_bse_operator_create(xtpb_bse* bse, int cqp, int cx, int cd, int cd2, xtpb_op** out) {
+  XTPB_API_BEGIN
+  BSE& b = bse->impl;
+  auto op = std::make_unique<BseOperator>(b.ctx, b.tc, b.opt.homo, b.opt.rpamin, b.opt.vmin, b.opt.cmax,
+                                          b.eps_inv.data(), b.hqp.data(), b.vt + b.ct, cqp, cx, cd, cd2,
+                                          bse->R ? bse->R->p : nullptr);
+  *out = new xtpb_op{std::move(op)};
+  XTPB_API_END
+}
+int xtpb_bse_operator_create_raw(xtpb_ctx* ctx, xtpb_tc* tc, xtpb_index homo, xtpb_index rpamin, xtpb_index vmin,
+                                 xtpb_index cmax, const double* eps_inv_host, const double* hqp_host, xtpb_index ldh,
+                                 int cqp, int cx, int cd, int cd2, xtpb_op** out) {
+  XTPB_API_BEGIN
+  auto op = std::make_unique<BseOperator>(&ctx->impl, &tc->impl, homo, rpamin, vmin, cmax, eps_inv_host, hqp_host, ldh,
+                                          cqp, cx, cd, cd2, nullptr);
+  *out = new xtpb_op{std::move(op)};
+  XTPB_API_END
+}
+int xtpb_dense_operator_create(xtpb_ctx* ctx, const double* A_host, xtpb_index n, xtpb_index lda, xtpb_op** out) {
+  XTPB_API_BEGIN
+  *out = new xtpb_op{std::make_unique<DenseOperator>(&ctx->impl, A_host, n, lda)};
+  XTPB_API_END
+}
+int xtpb_op_destroy(xtpb_op* op) {
+  XTPB_API_BEGIN
+  delete op;
+  XTPB_API_END
+}
+int xtpb_op_size(xtpb_op* op, xtpb_index* size) {
+  XTPB_API_BEGIN
+  *size = op->impl->size;
+  XTPB_API_END
+}
+int xtpb_op_matmul(xtpb_op* op, const double* X_host, xtpb_index ldx, xtpb_index k, double* Y_host, xtpb_index ldy) {
+  XTPB_API_BEGIN
+  Operator& A = *op->impl;
+  const long long n = A.size;
+  XTPB_REQUIRE(k >= 1 && ldx >= n && ldy >= n, "bad matmul shapes");
+  DBuf X((size_t)(n * k)), Y((size_t)(n * k));
+  A.ctx->h2d_2d(X.p, n, X_host, ldx, n, k);
+  A.matmul_dev(X.p, n, (int)k, Y.p, n);
+  A.ctx->d2h_2d(Y_host, ldy, Y.p, n, n, k);
+  XTPB_API_END
+}
+int xtpb_op_diagonal(xtpb_op* op, double* diag_host) {
+  XTPB_API_BEGIN
+  Operator& A = *op->impl;
+  DBuf d((size_t)A.size);
+  A.diagonal_dev(d.p);
+  A.ctx->d2h(diag_host, d.p, (size_t)A.size);
+  XTPB_API_END
+}
+int xtpb_op_get_full_matrix(xtpb_op* op, double* H_host, xtpb_index ldh) {
+  XTPB_API_BEGIN
+  Operator& A = *op->impl;
+  const long long n = A.size;
+  XTPB_REQUIRE(n <= 8192, "get_full_matrix is limited to operators of size <= 8192");
+  DBuf I((size_t)(n * n)), H((size_t)(n * n));
+  k_set_identity(I.p, (int)n, n, A.ctx->stream);
+  A.matmul_dev(I.p, n, (int)n, H.p, n);
+  A.ctx->d2h_2d(H_host, ldh, H.p, n, n, n);
+  XTPB_API_END
+}
+
+void xtpb_davidson_options_default(xtpb_davidson_options* o) {
+  o->tolerance = 1e-4; o->correction = XTPB_DAVIDSON_DPR; o->size_update = XTPB_UPDATE_SAFE; o->iter_max = 50;
+  o->max_search_space = 0; o->size_initial_guess = 0;
+}
+int xtpb_davidson_solve(xtpb_op* op, xtpb_index neigen, const xtpb_davidson_options* opt, double* eigenvalues_host,
+                        double* eigenvectors_host, xtpb_index ldv, int* info, xtpb_index* iterations) {
+  XTPB_API_BEGIN
+  Operator& A = *op->impl;
+  DavidsonResult res;
+  davidson_solve(A, neigen, *opt, res);
+  std::memcpy(eigenvalues_host, res.evals.data(), res.evals.size() * 8);
+  if (eigenvectors_host) A.ctx->d2h_2d(eigenvectors_host, ldv, res.evecs.p, A.size, A.size, neigen);
+  if (info) *info = res.info;
+  if (iterations) *iterations = res.iterations;
+  XTPB_API_END
+}
+
+// ---------------------------------------------------------------- contraction test / bench hooks
+static GemmParams params_from_desc(const xtpb_contract_desc* d, const double* A, const double* B, const double* dw,
+                                   double* C) {
+  GemmParams g{};
+  g.A = GemmOperand{A, d->a_row, d->a_k, d->a_outer, d->a_batch};
+  g.B = GemmOperand{B, d->b_row, d->b_k, d->b_outer, d->b_batch};
+  g.C = C; g.c_sm = d->c_row; g.c_sn = d->c_col; g.c_batch = d->c_batch;
+  g.c_n_inner = (int)d->c_col_inner; g.c_sn_outer = d->c_col_outer;
+  g.d = d->d_len > 0 ? dw : nullptr; g.d_outer = d->d_outer; g.d_batch = d->d_batch;
+  g.M = (int)d->M; g.N = (int)d->N; g.K = (int)d->K; g.n_outer = (int)d->n_outer; g.n_batch = (int)d->n_batch;
+  g.alpha = d->alpha; g.beta = d->beta; g.lower = d->lower;
+  return g;
+}
+int xtpb_contract_host(xtpb_ctx* ctx, const xtpb_contract_desc* desc, const double* A_host, const double* B_host,
+                       const double* d_host, double* C_host) {
+  XTPB_API_BEGIN
+  Context& c = ctx->impl;
+  // one element of slack in front of A and B lets tests exercise 8-byte-aligned (non-16-byte) operands
+  DBuf A((size_t)desc->a_len), B((size_t)desc->b_len), C((size_t)desc->c_len), D((size_t)std::max<long long>(1, desc->d_len));
+  c.h2d(A.p, A_host, (size_t)desc->a_len);
+  c.h2d(B.p, B_host, (size_t)desc->b_len);
+  c.h2d(C.p, C_host, (size_t)desc->c_len);
+  if (desc->d_len > 0) c.h2d(D.p, d_host, (size_t)desc->d_len);
+  GemmParams g = params_from_desc(desc, A.p, B.p, D.p, C.p);
+  contract(g, c.ws, c.stream, desc->force_cfg, desc->force_splits);
+  c.d2h(C_host, C.p, (size_t)desc->c_len);
+  XTPB_API_END
+}
+int xtpb_contract_bench(xtpb_ctx* ctx, const xtpb_contract_desc* desc, int reps, double* ms_per_launch) {
+  XTPB_API_BEGIN
+  Context& c = ctx->impl;
+  DBuf A((size_t)desc->a_len), B((size_t)desc->b_len), C((size_t)desc->c_len), D((size_t)std::max<long long>(1, desc->d_len));
+  // deterministic non-trivial contents: small values from an LCG-filled host strip, tiled
+  std::vector<double> strip(1 << 16);
+  unsigned long long s = 88172645463325252ULL;
+  for (auto& v : strip) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v = ((double)(s >> 11) / 9007199254740992.0 - 0.5) * 1e-2; }
+  auto fill = [&](DBuf& buf) {
+    for (size_t off = 0; off < buf.n; off += strip.size())
+      c.h2d(buf.p + off, strip.data(), std::min(strip.size(), buf.n - off));
+  };
+  fill(A); fill(B); fill(D);
+  C.zero(c.stream);
+  GemmParams g = params_from_desc(desc, A.p, B.p, D.p, C.p);
+  for (int i = 0; i < 3; ++i) contract(g, c.ws, c.stream, desc->force_cfg, desc->force_splits);
+  cudaEvent_t e0, e1;
+  XTPB_CUDA(cudaEventCreate(&e0));
+  XTPB_CUDA(cudaEventCreate(&e1));
+  XTPB_CUDA(cudaEventRecord(e0, c.stream));
+  for (int i = 0; i < reps; ++i) contract(g, c.ws, c.stream, desc->force_cfg, desc->force_splits);
+  XTPB_CUDA(cudaEventRecord(e1, c.stream));
+  XTPB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  XTPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / reps;
+  XTPB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// Launcher for the DMMA contraction engine: picks the tile configuration, split-K,
+// alignment path; reduces split-K partials.
+#include "contract.h"
+
+#include <algorithm>
+#include <cstdint>
+
+namespace xtpb {
+
+long long g_launch_count = 0;
+
+namespace {
+
+constexpr int kStages = 4;
+int g_num_sms = 0;
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    XTPB_CUDA(cudaGetDevice(&dev));
+    XTPB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return g_num_sms;
+}
+
+template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D>
+void launch_cfg(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BM, BN, WM, WN, A_KC, B_KC, kStages>;
+  auto kern = contract_kernel<Cfg, BM, BN, WM, WN, A_KC, B_KC, kStages, HAS_D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XTPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  dim3 grid(tiles_m * tiles_n, 1, p.n_batch * p.splits);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  XTPB_CUDA(cudaGetLastError());
+  ++g_launch_count;
+}
+
+template <bool A_KC, bool B_KC, bool HAS_D>
+void launch_tile(const GemmParams& p, int cfg, cudaStream_t stream) {
+  switch (cfg) {
+    case 0: launch_cfg<128, 128, 64, 32, A_KC, B_KC, HAS_D>(p, stream); break;
+    case 1: launch_cfg<128, 64, 64, 32, A_KC, B_KC, HAS_D>(p, stream); break;
+    default: launch_cfg<128, 32, 32, 32, A_KC, B_KC, HAS_D>(p, stream); break;
+  }
+}
+
+template <bool A_KC, bool B_KC>
+void launch_d(const GemmParams& p, int cfg, cudaStream_t stream) {
+  if (p.d) launch_tile<A_KC, B_KC, true>(p, cfg, stream);
+  else launch_tile<A_KC, B_KC, false>(p, cfg, stream);
+}
+
+__global__ void splitk_reduce_kernel(const double* __restrict__ ws, double* __restrict__ C, int M, int N, int splits,
+                                     long long c_sm, long long c_sn, long long c_batch, int c_n_inner,
+                                     long long c_sn_outer, int c_m_inner, long long c_sm_outer, double alpha,
+                                     double beta, int lower) {
+  const long long mn = (long long)M * N;
+  const int batch = blockIdx.y;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < mn;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % M), c = (int)(idx / M);
+    if (lower && c > r) continue;
+    const double* w = ws + (long long)batch * splits * mn + idx;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += w[(long long)k * mn];
+    const long long coff = c_n_inner > 0 ? (long long)(c / c_n_inner) * c_sn_outer + (long long)(c % c_n_inner) * c_sn
+                                         : (long long)c * c_sn;
+    const long long roff = c_m_inner > 0 ? (long long)(r / c_m_inner) * c_sm_outer + (long long)(r % c_m_inner) * c_sm
+                                         : (long long)r * c_sm;
+    double* dst = C + (long long)batch * c_batch + roff + coff;
+    double v = alpha * s;
+    if (beta != 0.0) v += beta * (*dst);
+    *dst = v;
+  }
+}
+
+__global__ void symmetrize_kernel(double* C, int n, long long ld, double diag_add) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y;   // tile (bi, bj) of the lower triangle, bi >= bj
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  // read lower tile: rows bi*32.., cols bj*32..
+  for (int cc = ty; cc < 32; cc += blockDim.y) {
+    const int r = bi * 32 + tx, c = bj * 32 + cc;
+    tile[cc][tx] = (r < n && c < n) ? C[r + c * ld] : 0.0;
+  }
+  __syncthreads();
+  // write transposed into the upper tile: rows bj*32.., cols bi*32..
+  for (int cc = ty; cc < 32; cc += blockDim.y) {
+    const int r = bj * 32 + tx, c = bi * 32 + cc;   // element (r, c) = lower(c, r) = tile[r - bj*32][c - bi*32]
+    if (r < n && c < n) {
+      if (c > r) C[r + c * ld] = tile[tx][cc];
+      else if (c == r && diag_add != 0.0) C[r + c * ld] = tile[tx][cc] + diag_add;
+    }
+  }
+}
+
+bool aligned16(const GemmOperand& o, bool kc, int n_outer, int n_batch) {
+  if (reinterpret_cast<uintptr_t>(o.p) % 16) return false;
+  const long long other = kc ? o.s_row : o.s_k;
+  if (other % 2) return false;
+  if (n_outer > 1 && o.s_outer % 2) return false;
+  if (n_batch > 1 && o.s_batch % 2) return false;
+  return true;
+}
+
+}  // namespace
+
+int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, int force_splits) {
+  XTPB_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0 && p.n_outer >= 1 && p.n_batch >= 1, "bad contraction sizes");
+  XTPB_REQUIRE((p.A.s_row == 1) != (p.A.s_k == 1) || (p.A.s_row == 1 && p.A.s_k == 1 && (p.M == 1 || p.K == 1)) ||
+                   (p.A.s_row == 1 && p.A.s_k == 1),
+               "operand A needs a unit stride");
+  const bool a_kc = p.A.s_k == 1;
+  const bool b_kc = p.B.s_k == 1;
+  XTPB_REQUIRE(a_kc || p.A.s_row == 1, "operand A needs a unit stride");
+  XTPB_REQUIRE(b_kc || p.B.s_row == 1, "operand B needs a unit stride");
+  p.a_vec = aligned16(p.A, a_kc, p.n_outer, p.n_batch) ? 1 : 0;
+  p.b_vec = aligned16(p.B, b_kc, p.n_outer, p.n_batch) ? 1 : 0;
+
+  int cfg = force_cfg;
+  if (cfg < 0) {
+    if (p.N <= 32) cfg = 2;
+    else if (p.N <= 64) cfg = 1;
+    else {
+      const long long pad128 = round_up(p.N, 128), pad64 = round_up(p.N, 64);
+      cfg = (pad64 < pad128) ? 1 : 0;
+    }
+    if (p.lower) cfg = 0;
+  }
+  const int bn = cfg == 0 ? 128 : (cfg == 1 ? 64 : 32);
+  const long long tiles = (long long)((p.M + 127) / 128) * ((p.N + bn - 1) / bn) * p.n_batch;
+  const long long nkt = (long long)((p.K + BK - 1) / BK) * p.n_outer;
+  int splits = force_splits;
+  if (splits <= 0) {
+    splits = 1;
+    const int sms = num_sms();
+    if (tiles < sms && nkt >= 16) {
+      splits = (int)std::min<long long>({(2LL * sms + tiles - 1) / tiles, nkt / 8, 64LL});
+      if (splits < 1) splits = 1;
+    }
+  }
+  XTPB_REQUIRE((long long)p.n_batch * splits <= 65535, "batch*splits exceeds gridDim.z");
+  p.splits = splits;
+  p.ws = nullptr;
+  if (splits > 1) p.ws = ws.get((size_t)p.n_batch * splits * p.M * p.N);
+
+  if (a_kc && b_kc) launch_d<true, true>(p, cfg, stream);
+  else if (a_kc && !b_kc) launch_d<true, false>(p, cfg, stream);
+  else if (!a_kc && b_kc) launch_d<false, true>(p, cfg, stream);
+  else launch_d<false, false>(p, cfg, stream);
+
+  int launches = 1;
+  if (splits > 1) {
+    const long long mn = (long long)p.M * p.N;
+    dim3 grid((unsigned)std::min<long long>((mn + 255) / 256, 4096), p.n_batch);
+    splitk_reduce_kernel<<<grid, 256, 0, stream>>>(p.ws, p.C, p.M, p.N, splits, p.c_sm, p.c_sn, p.c_batch, p.c_n_inner,
+                                                   p.c_sn_outer, p.c_m_inner, p.c_sm_outer, p.alpha, p.beta, p.lower);
+    XTPB_CUDA(cudaGetLastError());
+    ++g_launch_count;
+    ++launches;
+  }
+  return launches;
+}
+
+void symmetrize_from_lower(double* C, int n, long long ld, double diag_add, cudaStream_t stream) {
+  const int t = (n + 31) / 32;
+  symmetrize_kernel<<<dim3(t, t), dim3(32, 8), 0, stream>>>(C, n, ld, diag_add);
+  XTPB_CUDA(cudaGetLastError());
+  ++g_launch_count;
+}
+
+}  // namespace xtpb

@@ -1,0 +1,307 @@
+// FP64 tensor-contraction engine for sm_100a: C = alpha * A * diag(d) * B^T-ish + beta * C
+// on DMMA.8x8x4 (mma.sync.m8n8k4.f64), operands staged global->shared with a
+// multi-stage cp.async pipeline into 128B-swizzled tiles (the same swizzle TMA's
+// SWIZZLE_128B mode produces, so the consumer side is shared with the TMA path).
+//
+// Every GW-BSE contraction of SURVEY.md section 8a is an instance of this one kernel:
+//   K1  M build           (T_P * C_m, C_n^T * W_P)        A K-contig, B K-contig
+//   K2  aux rotation      (M[m] * R)                      A M-contig, B K-contig
+//   K3  epsilon(w)        (A^T diag(d) A, two-level K)    A K-contig, B K-contig, d, lower-only
+//   Sigma_x, BSE exchange / direct terms, Davidson projections.
+//
+// Index model.  A is addressed as  A.p + batch*A.s_batch + outer*A.s_outer + row*A.s_row + k*A.s_k
+// with exactly one of (s_row, s_k) equal to 1; the contraction index is two-level:
+// K_total = n_outer x K (each outer block is zero-padded to a multiple of 16).
+// B likewise with row = output column.  C is written with arbitrary (c_sm, c_sn).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace xtpb {
+
+struct GemmOperand {
+  const double* p;
+  long long s_row, s_k, s_outer, s_batch;
+};
+
+struct GemmParams {
+  GemmOperand A, B;
+  double* C;
+  long long c_sm, c_sn, c_batch;
+  int c_n_inner;            // >0: two-level output column, col = co*c_n_inner + ci -> co*c_sn_outer + ci*c_sn
+  long long c_sn_outer;
+  int c_m_inner;            // >0: two-level output row,    row = ro*c_m_inner + ri -> ro*c_sm_outer + ri*c_sm
+  long long c_sm_outer;
+  const double* d;          // optional weights on the contraction index (nullptr = none)
+  long long d_outer, d_batch;
+  int M, N, K, n_outer, n_batch, splits;
+  double alpha, beta;
+  int lower;                // 1: skip tiles strictly above the diagonal (SYRK-style output)
+  int a_vec, b_vec;         // 1: 16-byte cp.async legal for that operand
+  double* ws;               // split-K workspace: [batch][split][N][M] (M fastest)
+};
+
+constexpr int BK = 16;                 // doubles per k-tile: one 128-byte swizzle row
+constexpr int ROW_BYTES = BK * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void lds128(uint32_t addr, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- shared-memory tile layouts (host+device so tests can check them on the CPU) ----
+// K-contiguous operand: tile[row][16 k]; 16-byte chunk c of row r lives at chunk (c ^ (r & 7)).
+__host__ __device__ constexpr inline uint32_t kc_offset(int row, int k) {
+  return static_cast<uint32_t>(row * ROW_BYTES + ((((k >> 1) ^ (row & 7)) & 7) << 4) + ((k & 1) << 3));
+}
+// row-contiguous ("M-contiguous") operand: tile[row/16][k][16 rows]; chunk (r/2)%8 of k-row k at (chunk ^ (k & 7)).
+__host__ __device__ constexpr inline uint32_t mc_offset(int row, int k) {
+  return static_cast<uint32_t>((row >> 4) * (BK * ROW_BYTES) + k * ROW_BYTES +
+                               (((((row >> 1) & 7) ^ (k & 7)) & 7) << 4) + ((row & 1) << 3));
+}
+// fragment slot -> tile row.  Slot i = lane >> 2.
+//   K-contig : frag f covers rows 8f..8f+7,  slot i -> 8f + (i>>1) + 4(i&1)
+//   M-contig : frags come in pairs covering 16 rows, slot i of frag f -> 16(f>>1) + 2i + (f&1)
+__host__ __device__ constexpr inline int kc_slot_row(int f, int i) { return 8 * f + (i >> 1) + 4 * (i & 1); }
+__host__ __device__ constexpr inline int mc_slot_row(int f, int i) { return 16 * (f >> 1) + 2 * i + (f & 1); }
+// k consumed by k-slot t (= lane & 3) at half h (0/1), sub-step j (0/1) of a 16-wide k-tile
+__host__ __device__ constexpr inline int slot_k(int h, int t, int j) { return 8 * h + 2 * t + j; }
+
+template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES>
+struct GemmCfg {
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int MF = WM / 8, NF = WN / 8;
+  static constexpr int A_BYTES = BM * ROW_BYTES, B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + ROW_BYTES;   // + d tile
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES;
+  static_assert((BM * 8) % THREADS == 0 && (BN * 8) % THREADS == 0, "loader mapping");
+  static_assert(MF % 2 == 0 && NF % 2 == 0, "fragment pairs");
+};
+
+// ---- tile loader: one operand tile (R rows x 16 k) for k-tile starting at k0 of `outer` ----
+template <int R, int THREADS, bool KC>
+__device__ __forceinline__ void load_operand_tile(uint32_t sbase, const double* __restrict__ base,
+                                                  long long s_row, long long s_k, int rows_left, int k_left,
+                                                  bool vec, int tid) {
+  constexpr int CHUNKS = R * 8;
+#pragma unroll
+  for (int it = 0; it < CHUNKS / THREADS; ++it) {
+    const int ci = tid + it * THREADS;
+    if (KC) {
+      const int c = ci & 7, row = ci >> 3;
+      const int k = 2 * c;
+      const uint32_t dst = sbase + row * ROW_BYTES + (((c ^ (row & 7)) & 7) << 4);
+      const bool rv = row < rows_left;
+      if (vec) {
+        int nb = rv ? (k_left - k) * 8 : 0;
+        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+        const double* src = nb > 0 ? base + (long long)row * s_row + k : base;
+        cp_async16(dst, src, nb);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool v = rv && (k + e) < k_left;
+          const double* src = v ? base + (long long)row * s_row + (k + e) : base;
+          cp_async8(dst + 8 * e, src, v ? 8 : 0);
+        }
+      }
+    } else {
+      const int rg = ci % (R / 2), k = ci / (R / 2);
+      const int row = 2 * rg;
+      const uint32_t dst = sbase + (row >> 4) * (BK * ROW_BYTES) + k * ROW_BYTES + ((((rg & 7) ^ (k & 7)) & 7) << 4);
+      const bool kv = k < k_left;
+      if (vec) {
+        int nb = kv ? (rows_left - row) * 8 : 0;
+        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+        const double* src = nb > 0 ? base + (long long)k * s_k + row : base;
+        cp_async16(dst, src, nb);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool v = kv && (row + e) < rows_left;
+          const double* src = v ? base + (long long)k * s_k + (row + e) : base;
+          cp_async8(dst + 8 * e, src, v ? 8 : 0);
+        }
+      }
+    }
+  }
+}
+
+template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D>
+__global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp % Cfg::WARPS_M) * WM, wn0 = (warp / Cfg::WARPS_M) * WN;
+  const int li = lane >> 2, lt = lane & 3;
+
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  if (p.lower && tn * BN > tm * BM + BM - 1) return;
+  const int split = blockIdx.z % p.splits, batch = blockIdx.z / p.splits;
+
+  const int tpo = (p.K + BK - 1) / BK;                 // k-tiles per outer block
+  const int nkt_total = tpo * p.n_outer;
+  const int per = (nkt_total + p.splits - 1) / p.splits;
+  const int kt_begin = split * per;
+  const int kt_end = min(nkt_total, kt_begin + per);
+  const int nkt = max(0, kt_end - kt_begin);
+
+  const int m0 = tm * BM, n0 = tn * BN;
+  const double* Ab = p.A.p + (long long)batch * p.A.s_batch + (long long)m0 * p.A.s_row;
+  const double* Bb = p.B.p + (long long)batch * p.B.s_batch + (long long)n0 * p.B.s_row;
+  const double* Db = HAS_D ? p.d + (long long)batch * p.d_batch : nullptr;
+  const int m_left = p.M - m0, n_left = p.N - n0;
+
+  auto load_tile = [&](int stage, int kt) {
+    const int outer = kt / tpo, k0 = (kt - outer * tpo) * BK;
+    const uint32_t sA = smem + stage * Cfg::STAGE_BYTES, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
+    const int k_left = p.K - k0;
+    load_operand_tile<BM, Cfg::THREADS, A_KC>(sA, Ab + (long long)outer * p.A.s_outer + (long long)k0 * p.A.s_k,
+                                              p.A.s_row, p.A.s_k, m_left, k_left, p.a_vec != 0, tid);
+    load_operand_tile<BN, Cfg::THREADS, B_KC>(sB, Bb + (long long)outer * p.B.s_outer + (long long)k0 * p.B.s_k,
+                                              p.B.s_row, p.B.s_k, n_left, k_left, p.b_vec != 0, tid);
+    if (HAS_D && tid < BK) {
+      const bool v = tid < k_left;
+      const double* src = v ? Db + (long long)outer * p.d_outer + k0 + tid : Db;
+      cp_async8(sD + tid * 8, src, v ? 8 : 0);
+    }
+  };
+
+  double acc[Cfg::MF][Cfg::NF][2];
+#pragma unroll
+  for (int i = 0; i < Cfg::MF; ++i)
+#pragma unroll
+    for (int j = 0; j < Cfg::NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nkt) load_tile(s, kt_begin + s);
+    cp_async_commit();
+  }
+
+#pragma unroll 1
+  for (int it = 0; it < nkt; ++it) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = it + STAGES - 1;
+      if (nxt < nkt) load_tile(nxt % STAGES, kt_begin + nxt);
+      cp_async_commit();
+    }
+    const int stage = it % STAGES;
+    const uint32_t sA = smem + stage * Cfg::STAGE_BYTES, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double bf[Cfg::NF][2];
+      if (B_KC) {
+#pragma unroll
+        for (int nf = 0; nf < Cfg::NF; ++nf) {
+          const int row = wn0 + kc_slot_row(nf, li);
+          lds128(sB + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), bf[nf][0], bf[nf][1]);
+        }
+      } else {
+#pragma unroll
+        for (int np = 0; np < Cfg::NF / 2; ++np)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int k = slot_k(h, lt, j);
+            const int rb = (wn0 >> 4) + np;
+            lds128(sB + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), bf[2 * np][j],
+                   bf[2 * np + 1][j]);
+          }
+      }
+      if (HAS_D) {
+        double d0, d1;
+        lds128(sD + (8 * h + 2 * lt) * 8, d0, d1);
+#pragma unroll
+        for (int nf = 0; nf < Cfg::NF; ++nf) {
+          bf[nf][0] *= d0;
+          bf[nf][1] *= d1;
+        }
+      }
+      if (A_KC) {
+#pragma unroll
+        for (int mf = 0; mf < Cfg::MF; ++mf) {
+          double a0, a1;
+          const int row = wm0 + kc_slot_row(mf, li);
+          lds128(sA + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), a0, a1);
+#pragma unroll
+          for (int nf = 0; nf < Cfg::NF; ++nf) {
+            dmma884(acc[mf][nf][0], acc[mf][nf][1], a0, bf[nf][0]);
+            dmma884(acc[mf][nf][0], acc[mf][nf][1], a1, bf[nf][1]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int mp = 0; mp < Cfg::MF / 2; ++mp)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            double a0, a1;
+            const int k = slot_k(h, lt, j);
+            const int rb = (wm0 >> 4) + mp;
+            lds128(sA + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), a0, a1);
+#pragma unroll
+            for (int nf = 0; nf < Cfg::NF; ++nf) {
+              dmma884(acc[2 * mp][nf][0], acc[2 * mp][nf][1], a0, bf[nf][j]);
+              dmma884(acc[2 * mp + 1][nf][0], acc[2 * mp + 1][nf][1], a1, bf[nf][j]);
+            }
+          }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue ----
+  const bool to_ws = p.splits > 1;
+  double* Cb = to_ws ? p.ws + ((long long)batch * p.splits + split) * (long long)p.M * p.N
+                     : p.C + (long long)batch * p.c_batch;
+  const long long csm = to_ws ? 1 : p.c_sm, csn = to_ws ? (long long)p.M : p.c_sn;
+  const double alpha = to_ws ? 1.0 : p.alpha, beta = to_ws ? 0.0 : p.beta;
+#pragma unroll
+  for (int mf = 0; mf < Cfg::MF; ++mf) {
+    const int r = m0 + wm0 + (A_KC ? kc_slot_row(mf, li) : mc_slot_row(mf, li));
+    if (r >= p.M) continue;
+    const long long roff = (!to_ws && p.c_m_inner > 0)
+                               ? (long long)(r / p.c_m_inner) * p.c_sm_outer + (long long)(r % p.c_m_inner) * csm
+                               : (long long)r * csm;
+#pragma unroll
+    for (int nf = 0; nf < Cfg::NF; ++nf)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int s = 2 * lt + e;
+        const int c = n0 + wn0 + (B_KC ? kc_slot_row(nf, s) : mc_slot_row(nf, s));
+        if (c >= p.N) continue;
+        if (p.lower && c > r) continue;
+        const long long coff = (!to_ws && p.c_n_inner > 0)
+                                   ? (long long)(c / p.c_n_inner) * p.c_sn_outer + (long long)(c % p.c_n_inner) * csn
+                                   : (long long)c * csn;
+        double* dst = Cb + roff + coff;
+        double v = alpha * acc[mf][nf][e];
+        if (beta != 0.0) v += beta * (*dst);
+        *dst = v;
+      }
+  }
+}
+
+}  // namespace xtpb

@@ -1,0 +1,422 @@
+// RPA screening, plasmon-pole model, Sigma_x / Sigma_c and the GW driver (host control, device math).
+// Upstream: xtp/src/libxtp/gwbse/{rpa,ppm,sigma_base,sigma_ppm,gw}.cc.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "internal.h"
+
+namespace xtpb {
+
+int sigma_ppm_pair_partial_doubles(int n_pairs);
+
+GW::GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host, long long ldv, const double* e,
+       long long ne)
+    : ctx(c), tc(t), opt(o) {
+  XTPB_REQUIRE(o.rpamin == t->nmin && o.rpamax == t->nmax && o.rpamin == t->mmin, "TCMatrix ranges do not match rpamin/rpamax");
+  XTPB_REQUIRE(o.qpmin >= o.rpamin && o.qpmax <= t->mmax && o.qpmax >= o.qpmin, "QP range outside the TCMatrix m-range");
+  XTPB_REQUIRE(o.homo >= o.qpmin && o.homo + 1 <= o.qpmax, "QP range must contain HOMO and LUMO");
+  XTPB_REQUIRE(ne > o.rpamax, "dft_energies shorter than rpamax");
+  qptotal = o.qpmax - o.qpmin + 1;
+  rpatotal = o.rpamax - o.rpamin + 1;
+  n_occ = o.homo - o.rpamin + 1;
+  q0 = o.qpmin - o.rpamin;
+  dft_energies.assign(e, e + ne);
+  vxc.resize((size_t)(qptotal * qptotal));
+  for (long long j = 0; j < qptotal; ++j)
+    for (long long i = 0; i < qptotal; ++i) vxc[i + j * qptotal] = vxc_host[i + j * ldv];
+  sigma_x.assign((size_t)(qptotal * qptotal), 0.0);
+  sigma_c.assign((size_t)(qptotal * qptotal), 0.0);
+  energies_dev.alloc((size_t)rpatotal);
+  std::vector<double> init(dft_energies.begin() + o.rpamin, dft_energies.begin() + o.rpamax + 1);
+  set_rpa_energies(init.data());
+}
+
+void GW::set_rpa_energies(const double* e) {
+  rpa_energies.assign(e, e + rpatotal);
+  ctx->h2d(energies_dev.p, rpa_energies.data(), (size_t)rpatotal);
+  ctx->sync();
+}
+
+// Sigma_x(n,n') = - sum_{m occ} sum_P M[n](m,P) M[n'](m,P)   (upstream Sigma_base::CalcExchangeMatrix)
+void GW::exchange(double* out_host) {
+  DBuf S((size_t)(qptotal * qptotal));
+  GemmParams g{};
+  g.A = GemmOperand{tc->slab_ptr(q0), tc->slab, 1, tc->ldn, 0};
+  g.B = g.A;
+  g.C = S.p; g.c_sm = 1; g.c_sn = qptotal;
+  g.M = (int)qptotal; g.N = (int)qptotal; g.K = (int)n_occ; g.n_outer = (int)tc->naux; g.n_batch = 1;
+  g.alpha = -1.0; g.beta = 0.0; g.lower = 1;
+  contract(g, ctx->ws, ctx->stream);
+  symmetrize_from_lower(S.p, (int)qptotal, qptotal, 0.0, ctx->stream);
+  ctx->d2h(out_host, S.p, (size_t)(qptotal * qptotal));
+}
+
+// PPM::PPM_construct_parameters (ppm.cc) followed by the aux rotation of Sigma_PPM::PrepareScreening.
+void GW::prepare_ppm() {
+  const long long na = tc->naux;
+  DBuf eps((size_t)(2 * na * na)), T1((size_t)(na * na)), lam((size_t)na);
+  const double w_r = 0.0, w_i = 0.5;    // screening_r, screening_i [Ha]
+  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_r, 1, false, 0.0, eps.p);
+  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
+  double* phi = eps.p;                  // eigh overwrites eps(0) with its eigenvectors
+  ctx->eigh((int)na, phi, na, lam.p);
+  std::vector<double> lambda((size_t)na);
+  ctx->d2h(lambda.data(), lam.p, (size_t)na);
+  // ortho = phi^T eps(i 0.5) phi
+  GemmParams g{};
+  g.A = op_k_contig(eps.p + na * na, na);          // eps symmetric
+  g.B = op_k_contig(phi, na);
+  g.C = T1.p; g.c_sm = 1; g.c_sn = na;
+  g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+  contract(g, ctx->ws, ctx->stream);
+  double* ortho = eps.p + na * na;
+  GemmParams h{};
+  h.A = op_k_contig(phi, na);
+  h.B = op_k_contig(T1.p, na);
+  h.C = ortho; h.c_sm = 1; h.c_sn = na;
+  h.M = h.N = h.K = (int)na; h.n_outer = 1; h.n_batch = 1; h.alpha = 1.0; h.lower = 1;
+  contract(h, ctx->ws, ctx->stream);
+  ctx->spd_inverse((int)na, ortho, na);
+  k_extract_diagonal(ortho, (int)na, na, lam.p, ctx->stream);
+  std::vector<double> inv_diag((size_t)na);
+  ctx->d2h(inv_diag.data(), lam.p, (size_t)na);
+
+  ppm_weight.resize((size_t)na);
+  ppm_freq.resize((size_t)na);
+  std::vector<double> fac((size_t)na);
+  for (long long i = 0; i < na; ++i) {
+    double w = 1.0 - 1.0 / lambda[i];
+    double f;
+    if (w < 1e-5) {
+      w = 0.0;
+      f = 0.5;
+    } else {
+      const double nom = inv_diag[i] - 1.0;
+      const double frac = -nom / (nom + w) * w_i * w_i;
+      f = std::sqrt(std::fabs(frac));
+    }
+    ppm_weight[i] = w;
+    ppm_freq[i] = f;
+    fac[i] = w < 1e-9 ? 0.0 : 0.5 * w * f;
+  }
+  ppm_freq_dev.ensure((size_t)na);
+  ppm_fac_dev.ensure((size_t)na);
+  ctx->h2d(ppm_freq_dev.p, ppm_freq.data(), (size_t)na);
+  ctx->h2d(ppm_fac_dev.p, fac.data(), (size_t)na);
+  tc->rotate(phi, na);
+  ctx->sync();
+}
+
+void GW::prepare_screening() {
+  switch (opt.sigma_integration) {
+    case XTPB_SIGMA_PPM: prepare_ppm(); break;
+    case XTPB_SIGMA_EXACT: prepare_exact(); break;
+    case XTPB_SIGMA_CDA: prepare_cda(); break;
+    default: throw Error("xtpb: unknown sigma_integration");
+  }
+  screening_ready = true;
+}
+
+void GW::sigma_c_diag_elements(long long n, const long long* levels, const double* freqs, double* values,
+                               double* derivs) {
+  XTPB_REQUIRE(screening_ready, "PrepareScreening has not been called");
+  if (n == 0) return;
+  if (opt.sigma_integration == XTPB_SIGMA_PPM) {
+    std::vector<int> slabs((size_t)n);
+    for (long long i = 0; i < n; ++i) {
+      XTPB_REQUIRE(levels[i] >= 0 && levels[i] < qptotal, "gw level out of range");
+      slabs[i] = (int)(q0 + levels[i]);
+    }
+    DBuf buf((size_t)(3 * n + (n + 1) / 2 + 1 + sigma_ppm_pair_partial_doubles((int)n)));
+    double* om = buf.p;
+    double* val = om + n;
+    double* der = val + n;
+    int* sl = reinterpret_cast<int*>(der + n);
+    double* partial = der + n + (n + 1) / 2 + 1;
+    ctx->h2d(om, freqs, (size_t)n);
+    XTPB_CUDA(cudaMemcpyAsync(sl, slabs.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    k_sigma_ppm_pairs(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ, energies_dev.p,
+                      ppm_freq_dev.p, ppm_fac_dev.p, sl, om, (int)n, val, der, partial, ctx->stream);
+    ctx->d2h(values, val, (size_t)n);
+    if (derivs) ctx->d2h(derivs, der, (size_t)n);
+    return;
+  }
+  sigma_c_diag_elements_other(n, levels, freqs, values, derivs);
+}
+
+// values[level*steps + j] = Sigma_c(level, f0[level] - range + j*spacing)
+void GW::grid_scan(const std::vector<double>& f0, std::vector<double>& values) {
+  const long long steps = opt.qp_grid_steps;
+  const double range = opt.qp_grid_spacing * double(steps - 1) / 2.0;
+  values.resize((size_t)(qptotal * steps));
+  if (opt.sigma_integration == XTPB_SIGMA_PPM) {
+    std::vector<int> slabs((size_t)qptotal);
+    std::vector<double> om0((size_t)qptotal);
+    for (long long l = 0; l < qptotal; ++l) {
+      slabs[l] = (int)(q0 + l);
+      om0[l] = f0[l] - range;
+    }
+    DBuf buf((size_t)(qptotal * steps + qptotal + (qptotal + 1) / 2 + 1));
+    double* val = buf.p;
+    double* om = val + qptotal * steps;
+    int* sl = reinterpret_cast<int*>(om + qptotal);
+    ctx->h2d(om, om0.data(), (size_t)qptotal);
+    XTPB_CUDA(cudaMemcpyAsync(sl, slabs.data(), (size_t)qptotal * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    k_sigma_ppm_grid(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ, energies_dev.p,
+                     ppm_freq_dev.p, ppm_fac_dev.p, sl, om, opt.qp_grid_spacing, (int)steps, (int)qptotal, val,
+                     ctx->stream);
+    ctx->d2h(values.data(), val, (size_t)(qptotal * steps));
+    return;
+  }
+  std::vector<long long> lv((size_t)(qptotal * steps));
+  std::vector<double> fr((size_t)(qptotal * steps));
+  for (long long l = 0; l < qptotal; ++l)
+    for (long long j = 0; j < steps; ++j) {
+      lv[l * steps + j] = l;
+      fr[l * steps + j] = f0[l] - range + opt.qp_grid_spacing * double(j);
+    }
+  sigma_c_diag_elements((long long)lv.size(), lv.data(), fr.data(), values.data(), nullptr);
+}
+
+// GW::SolveQP (gw.cc): fixed-point (optional) -> grid + bisection -> linearisation, batched over levels so that
+// every Sigma_c evaluation round is one kernel launch.
+std::vector<double> GW::solve_qp(const std::vector<double>& frequencies) {
+  const long long q = qptotal;
+  std::vector<double> intercept((size_t)q), result = frequencies;
+  for (long long l = 0; l < q; ++l)
+    intercept[l] = dft_energies[opt.qpmin + l] + sigma_x[l + l * q] - vxc[l + l * q];
+  std::vector<char> solved((size_t)q, 0);
+
+  if (opt.qp_solver == XTPB_QP_FIXEDPOINT) {   // Newton-Raphson on f(w) = Sigma_c(w) + intercept - w
+    std::vector<double> x = frequencies;
+    std::vector<char> active((size_t)q, 1);
+    for (long long it = 0; it < opt.g_sc_max_iterations; ++it) {
+      std::vector<long long> lv;
+      std::vector<double> fr;
+      for (long long l = 0; l < q; ++l)
+        if (active[l]) { lv.push_back(l); fr.push_back(x[l]); }
+      if (lv.empty()) break;
+      std::vector<double> val(lv.size()), der(lv.size());
+      sigma_c_diag_elements((long long)lv.size(), lv.data(), fr.data(), val.data(), der.data());
+      for (size_t i = 0; i < lv.size(); ++i) {
+        const long long l = lv[i];
+        const double fx = val[i] + intercept[l] - x[l];
+        const double dx = der[i] - 1.0;
+        const double xn = x[l] - fx / dx;
+        if (std::fabs(xn - x[l]) < opt.g_sc_limit) {
+          active[l] = 0;
+          solved[l] = 1;
+          result[l] = xn;
+        }
+        x[l] = xn;
+      }
+    }
+  }
+
+  bool need_grid = false;
+  for (long long l = 0; l < q; ++l) need_grid |= !solved[l];
+  if (need_grid) {
+    const long long steps = opt.qp_grid_steps;
+    const double range = opt.qp_grid_spacing * double(steps - 1) / 2.0;
+    std::vector<double> sig;
+    grid_scan(frequencies, sig);
+    struct Bracket { long long level; double lo, flo, hi, fhi, root; bool done; };
+    std::vector<Bracket> br;
+    for (long long l = 0; l < q; ++l) {
+      if (solved[l]) continue;
+      double fprev = frequencies[l] - range;
+      double tprev = sig[l * steps] + intercept[l] - fprev;
+      for (long long j = 1; j < steps; ++j) {
+        const double f = frequencies[l] - range + opt.qp_grid_spacing * double(j);
+        const double tv = sig[l * steps + j] + intercept[l] - f;
+        if (tprev * tv < 0.0) br.push_back(Bracket{l, fprev, tprev, f, tv, 0.0, false});
+        fprev = f;
+        tprev = tv;
+      }
+    }
+    // GW::SolveQP_Bisection, all brackets advanced together
+    while (true) {
+      std::vector<long long> lv;
+      std::vector<double> fr;
+      std::vector<size_t> who;
+      for (size_t b = 0; b < br.size(); ++b) {
+        if (br[b].done) continue;
+        const double cmid = 0.5 * (br[b].lo + br[b].hi);
+        if (std::fabs(br[b].hi - br[b].lo) < opt.g_sc_limit) {
+          br[b].root = cmid;
+          br[b].done = true;
+          continue;
+        }
+        lv.push_back(br[b].level);
+        fr.push_back(cmid);
+        who.push_back(b);
+      }
+      if (who.empty()) break;
+      std::vector<double> val(who.size());
+      sigma_c_diag_elements((long long)who.size(), lv.data(), fr.data(), val.data(), nullptr);
+      for (size_t i = 0; i < who.size(); ++i) {
+        Bracket& B = br[who[i]];
+        const double cmid = fr[i];
+        const double yc = val[i] + intercept[B.level] - cmid;
+        if (std::fabs(yc) < opt.g_sc_limit) {
+          B.root = cmid;
+          B.done = true;
+        } else if (yc * B.flo > 0) {
+          B.lo = cmid;
+          B.flo = yc;
+        } else {
+          B.hi = cmid;
+          B.fhi = yc;
+        }
+      }
+    }
+    if (!br.empty()) {   // choose the root with the smallest |dSigma/dw - 1| (largest pole weight)
+      std::vector<long long> lv(br.size());
+      std::vector<double> fr(br.size()), val(br.size()), der(br.size());
+      for (size_t b = 0; b < br.size(); ++b) { lv[b] = br[b].level; fr[b] = br[b].root; }
+      sigma_c_diag_elements((long long)br.size(), lv.data(), fr.data(), val.data(), der.data());
+      std::vector<double> best((size_t)q, std::numeric_limits<double>::max());
+      for (size_t b = 0; b < br.size(); ++b) {
+        const double grad = std::fabs(der[b] - 1.0);
+        if (grad < best[br[b].level]) {
+          best[br[b].level] = grad;
+          result[br[b].level] = br[b].root;
+          solved[br[b].level] = 1;
+        }
+      }
+    }
+  }
+
+  // GW::SolveQP_Linearisation for what is left
+  std::vector<long long> lv;
+  std::vector<double> fr;
+  for (long long l = 0; l < q; ++l)
+    if (!solved[l]) { lv.push_back(l); fr.push_back(frequencies[l]); }
+  unconverged = (long long)lv.size();
+  if (!lv.empty()) {
+    std::vector<double> val(lv.size()), der(lv.size());
+    sigma_c_diag_elements((long long)lv.size(), lv.data(), fr.data(), val.data(), der.data());
+    for (size_t i = 0; i < lv.size(); ++i) {
+      const double Z = 1.0 - der[i];
+      if (std::fabs(Z) > 1e-9) result[lv[i]] = fr[i] + (intercept[lv[i]] - fr[i] + val[i]) / Z;
+    }
+  }
+  return result;
+}
+
+// RPA::UpdateRPAInputEnergies (rpa.cc)
+static std::vector<double> update_rpa_energies(const std::vector<double>& dft, const std::vector<double>& gwa,
+                                               const xtpb_gw_options& o) {
+  const long long rpatotal = o.rpamax - o.rpamin + 1, gwsize = (long long)gwa.size();
+  std::vector<double> e(dft.begin() + o.rpamin, dft.begin() + o.rpamin + rpatotal);
+  const long long lumo = o.homo + 1, qpmax = o.qpmin + gwsize - 1;
+  for (long long i = 0; i < gwsize; ++i) e[o.qpmin - o.rpamin + i] = gwa[i];
+  const double dftgap = dft[lumo] - dft[o.homo];
+  const double qpgap = gwa[lumo - o.qpmin] - gwa[o.homo - o.qpmin];
+  const double shift = qpgap - dftgap;
+  for (long long i = qpmax + 1 - o.rpamin; i < rpatotal; ++i) e[i] += shift;
+  for (long long i = 0; i < o.qpmin - o.rpamin; ++i) e[i] -= shift;
+  return e;
+}
+
+// GW::CalculateGWPerturbation (gw.cc)
+void GW::calculate_gw_perturbation() {
+  const long long q = qptotal;
+  exchange(sigma_x.data());
+  for (auto& v : sigma_x) v *= (1.0 - opt.ScaHFX);
+  std::vector<double> shifted = dft_energies;          // ScissorShift_DFTlevel
+  for (size_t i = (size_t)opt.homo + 1; i < shifted.size(); ++i) shifted[i] += opt.shift;
+  std::vector<double> init(shifted.begin() + opt.rpamin, shifted.begin() + opt.rpamax + 1);
+  set_rpa_energies(init.data());
+  std::vector<double> freqs(shifted.begin() + opt.qpmin, shifted.begin() + opt.qpmin + q);
+  const bool evgw = opt.gw_sc_max_iterations > 1;
+  if (evgw && backup.n == 0) {     // stands in for TCMatrix_gwbse::Rebuild: restore the un-rotated tensor
+    backup.alloc(tc->M.n);
+    XTPB_CUDA(cudaMemcpyAsync(backup.p, tc->M.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  for (long long i_gw = 0; i_gw < opt.gw_sc_max_iterations; ++i_gw) {
+    if (i_gw % opt.reset_3c == 0 && i_gw != 0)
+      XTPB_CUDA(cudaMemcpyAsync(tc->M.p, backup.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    prepare_screening();
+    freqs = solve_qp(freqs);
+    if (evgw) {
+      const std::vector<double> old = rpa_energies;
+      std::vector<double> upd = update_rpa_energies(dft_energies, freqs, opt);
+      if (opt.gw_mixing_order > 0 && i_gw > 0) {
+        for (size_t i = 0; i < upd.size(); ++i)
+          upd[i] = opt.gw_mixing_alpha * upd[i] + (1.0 - opt.gw_mixing_alpha) * old[i];
+        for (long long l = 0; l < q; ++l) freqs[l] = upd[opt.qpmin - opt.rpamin + l];
+      }
+      set_rpa_energies(upd.data());
+      double diff = 0.0;
+      for (long long l = 0; l < q; ++l)
+        diff = std::max(diff, std::fabs(old[opt.qpmin - opt.rpamin + l] - upd[opt.qpmin - opt.rpamin + l]));
+      if (diff < opt.gw_sc_limit) break;
+    }
+  }
+  std::vector<long long> lv((size_t)q);
+  for (long long l = 0; l < q; ++l) lv[l] = l;
+  std::vector<double> diag((size_t)q);
+  sigma_c_diag_elements(q, lv.data(), freqs.data(), diag.data(), nullptr);
+  for (long long l = 0; l < q; ++l) sigma_c[l + l * q] = diag[l];
+}
+
+std::vector<double> GW::gwa_results() const {
+  const long long q = qptotal;
+  std::vector<double> r((size_t)q);
+  for (long long l = 0; l < q; ++l)
+    r[l] = sigma_x[l + l * q] + sigma_c[l + l * q] - vxc[l + l * q] + dft_energies[opt.qpmin + l];
+  return r;
+}
+
+std::vector<double> GW::hqp() const {
+  const long long q = qptotal;
+  std::vector<double> h((size_t)(q * q));
+  for (long long i = 0; i < q * q; ++i) h[i] = sigma_x[i] + sigma_c[i] - vxc[i];
+  for (long long l = 0; l < q; ++l) h[l + l * q] += dft_energies[opt.qpmin + l];
+  return h;
+}
+
+// Sigma_base::CalcCorrelationOffDiag; for the PPM as one weighted contraction per aux chunk (see kernels.cu (3)).
+void GW::sigma_c_offdiag(const double* freqs, double* out_host) {
+  XTPB_REQUIRE(screening_ready, "PrepareScreening has not been called");
+  const long long q = qptotal;
+  if (opt.sigma_integration != XTPB_SIGMA_PPM) {
+    sigma_c_offdiag_other(freqs, out_host);
+    return;
+  }
+  const long long na = tc->naux, ldn = tc->ldn;
+  const long long budget = 1LL << 28;                               // doubles (2 GiB) for the weighted slab chunk
+  const long long pchunk = std::max<long long>(1, std::min<long long>(na, budget / (q * ldn)));
+  DBuf W((size_t)(q * pchunk * ldn)), S((size_t)(q * q)), om((size_t)q);
+  ctx->h2d(om.p, freqs, (size_t)q);
+  for (long long p0 = 0; p0 < na; p0 += pchunk) {
+    const long long pc = std::min(pchunk, na - p0);
+    k_sigma_ppm_weighted_slab(W.p, tc->M.p, ldn, tc->slab, (int)tc->ntotal, (int)p0, (int)pc, (int)n_occ,
+                              energies_dev.p, ppm_freq_dev.p, ppm_fac_dev.p, (int)q0, (int)q, om.p, ctx->stream);
+    GemmParams g{};
+    g.A = GemmOperand{W.p, pc * ldn, 1, ldn, 0};
+    g.B = GemmOperand{tc->slab_ptr(q0) + p0 * ldn, tc->slab, 1, ldn, 0};
+    g.C = S.p; g.c_sm = 1; g.c_sn = q;
+    g.M = (int)q; g.N = (int)q; g.K = (int)tc->ntotal; g.n_outer = (int)pc; g.n_batch = 1;
+    g.alpha = 1.0; g.beta = p0 == 0 ? 0.0 : 1.0;
+    contract(g, ctx->ws, ctx->stream);
+  }
+  std::vector<double> s((size_t)(q * q));
+  ctx->d2h(s.data(), S.p, (size_t)(q * q));
+  for (long long j = 0; j < q; ++j)
+    for (long long i = 0; i < q; ++i) out_host[i + j * q] = i == j ? 0.0 : 0.5 * (s[i + j * q] + s[j + i * q]);
+}
+
+// GW::CalculateHQP (gw.cc)
+void GW::calculate_hqp() {
+  const long long q = qptotal;
+  std::vector<double> diag((size_t)q);
+  for (long long l = 0; l < q; ++l) diag[l] = sigma_c[l + l * q];
+  const std::vector<double> f = gwa_results();
+  sigma_c_offdiag(f.data(), sigma_c.data());
+  for (long long l = 0; l < q; ++l) sigma_c[l + l * q] = diag[l];
+}
+
+}  // namespace xtpb

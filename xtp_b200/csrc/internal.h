@@ -1,0 +1,219 @@
+// Internal C++ objects behind the C ABI handles of include/xtpb200/xtpb200.h.
+#pragma once
+#include <cusolverDn.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/xtpb200/xtpb200.h"
+#include "common.h"
+#include "contract.h"
+
+namespace xtpb {
+
+// ---------------------------------------------------------------- context
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Workspace ws;                 // split-K partials
+  cusolverDnHandle_t solver = nullptr;
+  DBuf solver_work;
+  DBuf scratch_a, scratch_b;    // transient operands (fill blocks, rotation targets)
+  int* dev_info = nullptr;
+  double solver_seconds = 0.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  explicit Context(int dev);
+  ~Context();
+  void sync() { XTPB_CUDA(cudaStreamSynchronize(stream)); }
+  void h2d(double* dst, const double* src, size_t n) {
+    XTPB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  void d2h(double* dst, const double* src, size_t n) {
+    XTPB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    sync();
+  }
+  void h2d_2d(double* dst, long long ldd, const double* src, long long lds, long long rows, long long cols) {
+    XTPB_CUDA(cudaMemcpy2DAsync(dst, ldd * 8, src, lds * 8, rows * 8, cols, cudaMemcpyHostToDevice, stream));
+  }
+  void d2h_2d(double* dst, long long ldd, const double* src, long long lds, long long rows, long long cols) {
+    XTPB_CUDA(cudaMemcpy2DAsync(dst, ldd * 8, src, lds * 8, rows * 8, cols, cudaMemcpyDeviceToHost, stream));
+    sync();
+  }
+  // dense solver calls (cuSOLVER; timed separately from the contraction kernels)
+  void eigh(int n, double* A, long long lda, double* w);            // A <- eigenvectors (ascending w)
+  void spd_inverse(int n, double* A, long long lda);                // in place, full symmetric output
+  void general_inverse(int n, double* A, long long lda, double* Ainv, long long ldi);   // A destroyed
+  void solver_begin();
+  void solver_end();
+};
+
+// ---------------------------------------------------------------- small kernels (kernels.cu)
+void k_chi0_weights(double* d, const double* energies, int n_occ, int a0, int K, const double* omegas, int n_omega,
+                    bool imag, double eta, double gamma_extra, cudaStream_t s);
+void k_set_identity(double* A, int n, long long ld, cudaStream_t s);
+void k_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s);
+void k_scale_columns(double* A, int rows, int cols, long long ld, const double* scale, cudaStream_t s);  // A(:,j)*=scale[j]
+void k_extract_diagonal(const double* A, int n, long long ld, double* out, cudaStream_t s);
+void k_copy_2d(double* dst, long long ldd, const double* src, long long lds, int rows, long long cols, cudaStream_t s);
+void k_scale(double* x, long long n, double a, cudaStream_t s);
+void k_axpby(double* y, const double* x, long long n, double a, double b, cudaStream_t s);   // y = a*x + b*y
+// window extraction with optional per-P scaling: dst[i][P][j] = scale[P] * M[(m0+i)][P][n0+j]
+void k_extract_window(double* dst, long long dst_ld, long long dst_slab, const double* M, long long ldn, long long slab,
+                      int m0, int mcnt, int n0, int ncnt, int naux, const double* scale, cudaStream_t s);
+// Sigma_c (PPM): see kernels.cu
+void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                      const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
+                      const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s);
+void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                       const double* energies, const double* ppm_freq, const double* ppm_fac, const int* pair_slab,
+                       const double* pair_omega, int n_pairs, double* values, double* derivs, double* partial,
+                       cudaStream_t s);
+void k_sigma_ppm_weighted_slab(double* W, const double* M, long long ldn, long long slab, int ntotal, int p0, int pcnt,
+                               int n_occ, const double* energies, const double* ppm_freq, const double* ppm_fac,
+                               int slab0, int n_levels, const double* level_omega, cudaStream_t s);
+void k_bse_diagonal(double* diag, int vt, int ct, int naux, const double* Mvc, long long ldvc, long long slabvc,
+                    const double* Mvv, long long ldvv, long long slabvv, const double* Mcc, long long ldcc,
+                    long long slabcc, const double* Mcv, long long ldcv, long long slabcv, const double* eps_inv,
+                    const double* hqp_diag, int cqp, int cx, int cd, int cd2, cudaStream_t s);
+void k_col_norms(const double* A, long long ld, long long rows, int cols, double* out, cudaStream_t s);
+void k_residuals(double* res, long long ldr, const double* q, long long ldq, const double* lambda, long long rows,
+                 int cols, cudaStream_t s);                            // res(:,j) -= lambda[j]*q(:,j)
+void k_davidson_correction(double* out, const double* r, const double* x, const double* D, double lambda, long long n,
+                           int olsen, double* scratch2, cudaStream_t s);
+void k_unit_vectors(double* V, long long ld, long long n, const long long* idx, int cols, cudaStream_t s);
+
+// ---------------------------------------------------------------- TCMatrix_gwbse
+struct TCMatrix {
+  Context* ctx;
+  long long naux, mmin, mmax, nmin, nmax, mtotal, ntotal;
+  long long ldn, slab;          // device layout [m][P][ldn], ldn = ntotal rounded up to even
+  DBuf M;
+  // Fill state
+  long long n_basis = 0, ldc = 0;
+  DBuf Cm, Cn;                  // MO coefficient blocks (n_basis x mtotal / ntotal, ld = ldc)
+  DBuf stage;                   // host->device staging of AO slices
+
+  TCMatrix(Context* c, long long auxsize, long long mmin_, long long mmax_, long long nmin_, long long nmax_);
+  double* slab_ptr(long long m) { return M.p + m * slab; }
+  void set_raw(const double* host);
+  void get_slab(long long m, double* host);
+  void fill_begin(long long nb, const double* C_host, long long ldc_host);
+  void fill_block_dev(long long P0, long long nP, const double* ao_dev, long long ld_ao);
+  void fill_block_host(long long P0, long long nP, const double* ao_host, long long ld_ao);
+  // M[m] <- M[m] * R for all m (R on the device, naux x naux, ld = ldr)
+  void rotate(const double* R_dev, long long ldr);
+  // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]   (window rotation into a caller-owned buffer)
+  void rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
+                     const double* R_dev, long long ldr);
+};
+
+// eps(w) for n_omega frequencies on the device: out[w] (naux x naux, ld = naux).  energies_dev: rpatotal.
+void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
+                     int n_omega, bool imag, double gamma_extra, double* out_dev);
+
+// ---------------------------------------------------------------- GW
+struct GW {
+  Context* ctx;
+  TCMatrix* tc;
+  xtpb_gw_options opt;
+  long long qptotal, rpatotal, n_occ, q0;     // q0 = qpmin - rpamin (slab offset of gw level 0)
+  std::vector<double> vxc, dft_energies, rpa_energies, sigma_x, sigma_c;   // host copies (q x q col-major)
+  DBuf energies_dev;
+  bool screening_ready = false;
+  long long unconverged = 0;
+  // PPM
+  std::vector<double> ppm_weight, ppm_freq;
+  DBuf ppm_freq_dev, ppm_fac_dev;
+  // exact
+  std::vector<double> rpa_omegas;
+  DBuf residues;                // [level][s][m]  (m fastest, ld = rpatotal)
+  long long rpasize = 0;
+  // CDA
+  std::vector<double> quad_points, quad_weights;
+  DBuf cda_kernels;             // (order+1) matrices naux x naux: dielinv_j ..., kappa0 last
+  DBuf backup;                  // un-rotated tensor for evGW (stands in for TCMatrix_gwbse::Rebuild)
+
+  GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host, long long ldv, const double* e,
+     long long ne);
+  void set_rpa_energies(const double* e);
+  void exchange(double* out_host);                 // unscaled Sigma_x
+  void prepare_screening();
+  void sigma_c_diag_elements(long long n, const long long* levels, const double* freqs, double* values, double* derivs);
+  void sigma_c_offdiag(const double* freqs, double* out_host);
+  void calculate_gw_perturbation();
+  void calculate_hqp();
+  std::vector<double> gwa_results() const;
+  std::vector<double> hqp() const;
+  std::vector<double> solve_qp(const std::vector<double>& frequencies);
+
+ private:
+  void prepare_ppm();
+  void prepare_exact();
+  void prepare_cda();
+  void grid_scan(const std::vector<double>& f0, std::vector<double>& values);   // values[level*steps + j]
+  void sigma_c_diag_elements_other(long long n, const long long* levels, const double* freqs, double* values,
+                                   double* derivs);   // exact / CDA
+  void sigma_c_offdiag_other(const double* freqs, double* out_host);
+};
+
+// ---------------------------------------------------------------- operators + Davidson
+struct Operator {
+  Context* ctx;
+  long long size = 0;
+  virtual ~Operator() = default;
+  virtual void matmul_dev(const double* X, long long ldx, int k, double* Y, long long ldy) = 0;
+  virtual void diagonal_dev(double* d) = 0;
+};
+
+struct BSE {
+  Context* ctx;
+  TCMatrix* tc;
+  xtpb_bse_options opt;
+  long long vt, ct, size, naux;
+  std::vector<double> hqp;          // (vt+ct)^2 host, col-major
+  std::vector<double> eps_inv;      // host
+  BSE(Context* c, TCMatrix* t, const xtpb_bse_options& o, const double* rpa_e, const double* hqp_in, long long ldh,
+      bool rotate_full);
+};
+
+struct BseOperator : Operator {
+  long long vt, ct, naux;
+  int cqp, cx, cd, cd2;
+  long long ldvc, slabvc, ldvv, slabvv, ldcc, slabcc, ldcv, slabcv;
+  DBuf Mvc, Mvv, Mcc, Mcv;          // rotated windows; Mvv/Mcv carry eps_inv (scaled per P)
+  DBuf Mvv_raw_diag, Mcc_diag;      // not used (diagonal kernel reads windows directly)
+  DBuf eps_inv_dev, hqp_dev, hqp_diag_dev;   // hqp_dev: (vt+ct)^2 col-major
+  DBuf T, U;
+  // windows are built from tc (optionally rotated by R_dev)
+  BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpamin, long long vmin, long long cmax,
+              const double* eps_inv_host, const double* hqp_host, long long ldh, int cqp_, int cx_, int cd_, int cd2_,
+              const double* R_dev);
+  void matmul_dev(const double* X, long long ldx, int k, double* Y, long long ldy) override;
+  void diagonal_dev(double* d) override;
+};
+
+struct DenseOperator : Operator {
+  DBuf A;
+  long long lda;
+  DenseOperator(Context* c, const double* A_host, long long n, long long lda_host);
+  void matmul_dev(const double* X, long long ldx, int k, double* Y, long long ldy) override;
+  void diagonal_dev(double* d) override;
+};
+
+struct DavidsonResult {
+  std::vector<double> evals;
+  DBuf evecs;          // size x neigen
+  int info = 1;
+  long long iterations = 0;
+};
+void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& opt, DavidsonResult& out);
+
+}  // namespace xtpb
+
+struct xtpb_ctx { xtpb::Context impl; explicit xtpb_ctx(int d) : impl(d) {} };
+struct xtpb_tc { xtpb::TCMatrix impl; };
+struct xtpb_gw { xtpb::GW impl; };
+struct xtpb_bse { xtpb::BSE impl; std::unique_ptr<xtpb::DBuf> R; };
+struct xtpb_op { std::unique_ptr<xtpb::Operator> impl; };

@@ -1,0 +1,515 @@
+// Element-wise and reduction kernels of the GW-BSE path (everything that is not a contraction):
+// chi0 weights, Sigma_c plasmon-pole sums (FP64 ALU / HBM bound), BSE diagonal, Davidson vector ops.
+#include "internal.h"
+
+namespace xtpb {
+
+namespace {
+
+constexpr double kFourPi = 12.566370614359172953850573533118;
+
+inline int blocks_for(long long n, int threads, int cap = 65535 * 16) {
+  long long b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+#define LAUNCH_CHECK()                 \
+  do {                                 \
+    XTPB_CUDA(cudaGetLastError());     \
+    ++g_launch_count;                  \
+  } while (0)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum, result valid in thread 0 (deterministic order)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < THREADS / 32 ? sh[threadIdx.x] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// Rohlfing-stabilised inverse, upstream Sigma_PPM::Stabilize (sigma_ppm.cc): 1/x for |x| >= 0.25,
+// 0.5 (1 - cos 4 pi x) / x otherwise (-> 0 at x = 0).
+__device__ __forceinline__ double ppm_ginv(double x) {
+  const double ax = fabs(x);
+  if (ax >= 0.25) return 1.0 / x;
+  if (x == 0.0) return 0.0;
+  return 0.5 * (1.0 - cos(kFourPi * x)) / x;
+}
+
+// ------------------------------------------------------------------ chi0 weights
+// d[w][m][k], k <-> level a = a0 + k (relative to rpamin); zero for a < n_occ (alignment padding).
+// Upstream: the `denom` vector of RPA::calculate_epsilon<imag> (rpa.cc).
+__global__ void chi0_weights_kernel(double* __restrict__ d, const double* __restrict__ e, int n_occ, int a0, int K,
+                                    const double* __restrict__ omegas, int n_omega, int imag, double eta) {
+  const long long total = (long long)n_omega * n_occ * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % K);
+    const int m = (int)((idx / K) % n_occ);
+    const int w = (int)(idx / ((long long)K * n_occ));
+    const int a = a0 + k;
+    double v = 0.0;
+    if (a >= n_occ) {
+      const double dE = e[a] - e[m];
+      const double om = omegas[w];
+      if (imag) {
+        v = 4.0 * dE / (dE * dE + om * om);
+      } else {
+        const double dm = dE - om, dp = dE + om, eta2 = eta * eta;
+        v = 2.0 * (dm / (dm * dm + eta2) + dp / (dp * dp + eta2));
+      }
+    }
+    d[idx] = v;
+  }
+}
+
+__global__ void set_identity_kernel(double* A, int n, long long ld) {
+  const long long total = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % n), c = (int)(idx / n);
+    A[r + c * ld] = r == c ? 1.0 : 0.0;
+  }
+}
+__global__ void add_diagonal_kernel(double* A, int n, long long ld, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i + i * ld] += v;
+}
+__global__ void scale_columns_kernel(double* A, int rows, int cols, long long ld, const double* __restrict__ scale) {
+  const long long total = (long long)rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % rows), c = (int)(idx / rows);
+    A[r + c * ld] *= scale[c];
+  }
+}
+__global__ void extract_diagonal_kernel(const double* A, int n, long long ld, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = A[i + i * ld];
+}
+__global__ void copy_2d_kernel(double* dst, long long ldd, const double* __restrict__ src, long long lds, int rows,
+                               long long cols) {
+  const long long total = (long long)rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % rows);
+    const long long c = idx / rows;
+    dst[r + c * ldd] = src[r + c * lds];
+  }
+}
+__global__ void scale_kernel(double* x, long long n, double a) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] *= a;
+}
+__global__ void axpby_kernel(double* y, const double* __restrict__ x, long long n, double a, double b) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + (b == 0.0 ? 0.0 : b * y[i]);
+}
+__global__ void extract_window_kernel(double* __restrict__ dst, long long dst_ld, long long dst_slab,
+                                      const double* __restrict__ M, long long ldn, long long slab, int m0, int mcnt,
+                                      int n0, int ncnt, int naux, const double* __restrict__ scale) {
+  const long long total = (long long)mcnt * naux * ncnt;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % ncnt);
+    const int P = (int)((idx / ncnt) % naux);
+    const int i = (int)(idx / ((long long)ncnt * naux));
+    double v = M[(long long)(m0 + i) * slab + (long long)P * ldn + n0 + j];
+    if (scale) v *= scale[P];
+    dst[(long long)i * dst_slab + (long long)P * dst_ld + j] = v;
+  }
+}
+
+// ------------------------------------------------------------------ Sigma_c, plasmon-pole model
+// Upstream Sigma_PPM::CalcCorrelationDiagElement (sigma_ppm.cc):
+//   Sigma_c(level, w) = sum_P fac_P sum_m M~[level](m,P)^2 * ginv(w - e_m +/- Omega_P)   (+ occupied, - unoccupied)
+//
+// (1) grid kernel: the QP grid solver (GW::SolveQP_Grid, gw.cc) needs ~1001 frequencies per level.  Threads own
+//     frequencies (NW each, held in registers, consecutive lanes = consecutive grid points so the |x|<0.25 branch
+//     is warp-coherent), the (P,m) elements of the level's slab stream through shared memory and are broadcast.
+//     Bound: FP64 ALU (one reciprocal per element and frequency); the slab is read once per 2*T*NW frequencies.
+constexpr int kGridThreads = 128, kGridNW = 4, kGridTile = 512;
+
+__global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
+    const double* __restrict__ M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+    const double* __restrict__ energies, const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac,
+    const int* __restrict__ level_slab, const double* __restrict__ omega0, double domega, int n_omega,
+    double* __restrict__ values) {
+  __shared__ double2 tile[kGridTile];
+  const int level = blockIdx.y;
+  const double* S = M + (long long)level_slab[level] * slab;
+  const int jbase = blockIdx.x * (kGridThreads * kGridNW) + threadIdx.x;
+  double om[kGridNW], acc[kGridNW];
+#pragma unroll
+  for (int w = 0; w < kGridNW; ++w) {
+    om[w] = omega0[level] + domega * (double)(jbase + w * kGridThreads);
+    acc[w] = 0.0;
+  }
+  for (int P = 0; P < naux; ++P) {
+    const double fac = ppm_fac[P];
+    if (fac == 0.0) continue;     // uniform across the block
+    const double Om = ppm_freq[P];
+    const double* row = S + (long long)P * ldn;
+    for (int m0 = 0; m0 < ntotal; m0 += kGridTile) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < kGridTile; t += kGridThreads) {
+        const int m = m0 + t;
+        double2 el = make_double2(0.0, 1.0e300);
+        if (m < ntotal) {
+          const double v = row[m];
+          el.x = fac * v * v;
+          el.y = energies[m] + (m < n_occ ? -Om : Om);     // pole position z: x = w - z
+        }
+        tile[t] = el;
+      }
+      __syncthreads();
+      const int cnt = min(kGridTile, ntotal - m0);
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const double2 el = tile[t];
+#pragma unroll
+        for (int w = 0; w < kGridNW; ++w) acc[w] += el.x * ppm_ginv(om[w] - el.y);
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < kGridNW; ++w) {
+    const int j = jbase + w * kGridThreads;
+    if (j < n_omega) values[(long long)level * n_omega + j] = acc[w];
+  }
+}
+
+// (2) pair kernel: arbitrary (level, frequency) pairs (bisection steps, final Sigma_c, derivatives).
+//     One CTA column per pair, kPairChunks CTAs split the aux range; deterministic two-stage reduction.
+//     Bound: HBM/L2 (each pair streams its slab once).
+constexpr int kPairThreads = 256, kPairChunks = 32;
+
+__global__ void __launch_bounds__(kPairThreads) sigma_ppm_pairs_kernel(
+    const double* __restrict__ M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+    const double* __restrict__ energies, const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac,
+    const int* __restrict__ pair_slab, const double* __restrict__ pair_omega, double* __restrict__ partial) {
+  __shared__ double sh[kPairThreads / 32];
+  const int pair = blockIdx.y, chunk = blockIdx.x;
+  const double* S = M + (long long)pair_slab[pair] * slab;
+  const double om = pair_omega[pair];
+  const int per = (naux + kPairChunks - 1) / kPairChunks;
+  const int p_begin = chunk * per, p_end = min(naux, p_begin + per);
+  double val = 0.0, der = 0.0;
+  for (int P = p_begin; P < p_end; ++P) {
+    const double fac = ppm_fac[P];
+    if (fac == 0.0) continue;
+    const double Om = ppm_freq[P];
+    const double* row = S + (long long)P * ldn;
+    double v1 = 0.0, d1 = 0.0;
+    for (int m = threadIdx.x; m < ntotal; m += kPairThreads) {
+      const double v = row[m];
+      const double g = ppm_ginv(om - energies[m] + (m < n_occ ? Om : -Om));
+      const double a = v * v * g;
+      v1 += a;
+      d1 -= a * g;
+    }
+    val += fac * v1;
+    der += fac * d1;
+  }
+  val = block_sum<kPairThreads>(val, sh);
+  der = block_sum<kPairThreads>(der, sh);
+  if (threadIdx.x == 0) {
+    partial[((long long)pair * kPairChunks + chunk) * 2 + 0] = val;
+    partial[((long long)pair * kPairChunks + chunk) * 2 + 1] = der;
+  }
+}
+__global__ void sigma_ppm_pairs_finalize(const double* __restrict__ partial, int n_pairs, double* values,
+                                         double* derivs) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  double v = 0.0, d = 0.0;
+  for (int c = 0; c < kPairChunks; ++c) {
+    v += partial[((long long)pair * kPairChunks + c) * 2 + 0];
+    d += partial[((long long)pair * kPairChunks + c) * 2 + 1];
+  }
+  values[pair] = v;
+  if (derivs) derivs[pair] = d;
+}
+
+// (3) off-diagonal elements as a contraction (upstream Sigma_PPM::CalcCorrelationOffDiagElement does it pair by
+//     pair): W[l][p][m] = fac_P ginv(w_l - z_Pm) M~[l][P][m]; then S = W * M~^T and Sigma_c = (S + S^T)/2.
+__global__ void sigma_ppm_weighted_slab_kernel(double* __restrict__ W, const double* __restrict__ M, long long ldn,
+                                               long long slab, int ntotal, int p0, int pcnt, int n_occ,
+                                               const double* __restrict__ energies,
+                                               const double* __restrict__ ppm_freq,
+                                               const double* __restrict__ ppm_fac, int slab0, int n_levels,
+                                               const double* __restrict__ level_omega) {
+  const long long per_level = (long long)pcnt * ldn;
+  const long long total = per_level * n_levels;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx % ldn);
+    const int p = (int)((idx / ldn) % pcnt);
+    const int l = (int)(idx / per_level);
+    double out = 0.0;
+    if (m < ntotal) {
+      const int P = p0 + p;
+      const double fac = ppm_fac[P];
+      if (fac != 0.0) {
+        const double Om = ppm_freq[P];
+        const double g = ppm_ginv(level_omega[l] - energies[m] + (m < n_occ ? Om : -Om));
+        out = fac * g * M[(long long)(slab0 + l) * slab + (long long)P * ldn + m];
+      }
+    }
+    W[idx] = out;
+  }
+}
+
+// ------------------------------------------------------------------ BSE diagonal
+// Upstream BSE_OPERATOR::diagonal (bse_operator.cc).  Block = one valence index v, threads = conduction index c.
+__global__ void bse_diag_helpers_kernel(double* __restrict__ dvv, double* __restrict__ dcc, int vt, int ct, int naux,
+                                        const double* __restrict__ Mvv, long long ldvv, long long slabvv,
+                                        const double* __restrict__ Mcc, long long ldcc, long long slabcc) {
+  const long long nv = (long long)vt * naux, nc = (long long)ct * naux;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < nv + nc;
+       idx += (long long)gridDim.x * blockDim.x) {
+    if (idx < nv) {
+      const int P = (int)(idx % naux), v = (int)(idx / naux);
+      dvv[idx] = Mvv[(long long)v * slabvv + (long long)P * ldvv + v];          // carries eps_inv[P]
+    } else {
+      const long long j = idx - nv;
+      const int c = (int)(j % ct), P = (int)(j / ct);
+      dcc[j] = Mcc[(long long)c * slabcc + (long long)P * ldcc + c];            // dcc[P][c]
+    }
+  }
+}
+__global__ void bse_diagonal_kernel(double* __restrict__ diag, int vt, int ct, int naux, const double* __restrict__ Mvc,
+                                    long long ldvc, long long slabvc, const double* __restrict__ dvv,
+                                    const double* __restrict__ dcc, const double* __restrict__ Mcv, long long ldcv,
+                                    long long slabcv, const double* __restrict__ hqp_diag, int cqp, int cx, int cd,
+                                    int cd2) {
+  const int v = blockIdx.x;
+  for (int c = threadIdx.x; c < ct; c += blockDim.x) {
+    double acc = 0.0;
+    if (cqp) acc += cqp * (hqp_diag[vt + c] - hqp_diag[v]);
+    if (cx || cd || cd2) {
+      double sx = 0.0, sd = 0.0, sd2 = 0.0;
+      for (int P = 0; P < naux; ++P) {
+        const double mvc = (cx || cd2) ? Mvc[(long long)v * slabvc + (long long)P * ldvc + c] : 0.0;
+        if (cx) sx += mvc * mvc;
+        if (cd) sd += dvv[(long long)v * naux + P] * dcc[(long long)P * ct + c];
+        if (cd2) sd2 += Mcv[(long long)c * slabcv + (long long)P * ldcv + v] * mvc;   // Mcv carries eps_inv[P]
+      }
+      acc += cx * sx - cd * sd - cd2 * sd2;
+    }
+    diag[(long long)v * ct + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ Davidson vector kernels
+__global__ void __launch_bounds__(256) col_norms_kernel(const double* __restrict__ A, long long ld, long long rows,
+                                                        double* out) {
+  __shared__ double sh[8];
+  const double* col = A + (long long)blockIdx.x * ld;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < rows; i += 256) s += col[i] * col[i];
+  s = block_sum<256>(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = sqrt(s);
+}
+__global__ void residuals_kernel(double* res, long long ldr, const double* __restrict__ q, long long ldq,
+                                 const double* __restrict__ lambda, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx % rows;
+    const int c = (int)(idx / rows);
+    res[r + c * ldr] -= lambda[c] * q[r + c * ldq];
+  }
+}
+// t = r / (lambda - D); xd = x / (lambda - D); partial dots (x.t, x.xd) per block -> scratch
+__global__ void __launch_bounds__(256) correction_kernel(double* __restrict__ t, double* __restrict__ xd,
+                                                         const double* __restrict__ r, const double* __restrict__ x,
+                                                         const double* __restrict__ D, double lambda, long long n,
+                                                         int olsen, double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double d1 = 0.0, d2 = 0.0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    double den = lambda - D[i];
+    if (fabs(den) < 1e-12) den = 1e-12;
+    const double ti = r[i] / den;
+    t[i] = ti;
+    if (olsen) {
+      const double xi = x[i], xdi = xi / den;
+      xd[i] = xdi;
+      d1 += xi * ti;
+      d2 += xi * xdi;
+    }
+  }
+  if (olsen) {
+    d1 = block_sum<256>(d1, sh);
+    d2 = block_sum<256>(d2, sh);
+    if (threadIdx.x == 0) {
+      partial[2 * blockIdx.x] = d1;
+      partial[2 * blockIdx.x + 1] = d2;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) olsen_finish_kernel(double* __restrict__ t, const double* __restrict__ xd,
+                                                           const double* __restrict__ partial, int nblocks,
+                                                           long long n) {
+  __shared__ double eps_sh;
+  if (threadIdx.x == 0) {
+    double d1 = 0.0, d2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      d1 += partial[2 * b];
+      d2 += partial[2 * b + 1];
+    }
+    eps_sh = d1 / d2;
+  }
+  __syncthreads();
+  const double eps = eps_sh;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) t[i] -= eps * xd[i];
+}
+__global__ void unit_vectors_kernel(double* V, long long ld, const long long* __restrict__ idx, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < cols) V[idx[c] + (long long)c * ld] = 1.0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host wrappers
+void k_chi0_weights(double* d, const double* energies, int n_occ, int a0, int K, const double* omegas_dev, int n_omega,
+                    bool imag, double eta, double, cudaStream_t s) {
+  const long long total = (long long)n_omega * n_occ * K;
+  chi0_weights_kernel<<<blocks_for(total, 256, 4096), 256, 0, s>>>(d, energies, n_occ, a0, K, omegas_dev, n_omega,
+                                                                   imag ? 1 : 0, eta);
+  LAUNCH_CHECK();
+}
+void k_set_identity(double* A, int n, long long ld, cudaStream_t s) {
+  set_identity_kernel<<<blocks_for((long long)n * n, 256, 4096), 256, 0, s>>>(A, n, ld);
+  LAUNCH_CHECK();
+}
+void k_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s) {
+  add_diagonal_kernel<<<blocks_for(n, 256), 256, 0, s>>>(A, n, ld, v);
+  LAUNCH_CHECK();
+}
+void k_scale_columns(double* A, int rows, int cols, long long ld, const double* scale, cudaStream_t s) {
+  scale_columns_kernel<<<blocks_for((long long)rows * cols, 256, 4096), 256, 0, s>>>(A, rows, cols, ld, scale);
+  LAUNCH_CHECK();
+}
+void k_extract_diagonal(const double* A, int n, long long ld, double* out, cudaStream_t s) {
+  extract_diagonal_kernel<<<blocks_for(n, 256), 256, 0, s>>>(A, n, ld, out);
+  LAUNCH_CHECK();
+}
+void k_copy_2d(double* dst, long long ldd, const double* src, long long lds, int rows, long long cols, cudaStream_t s) {
+  copy_2d_kernel<<<blocks_for((long long)rows * cols, 256, 8192), 256, 0, s>>>(dst, ldd, src, lds, rows, cols);
+  LAUNCH_CHECK();
+}
+void k_scale(double* x, long long n, double a, cudaStream_t s) {
+  scale_kernel<<<blocks_for(n, 256, 4096), 256, 0, s>>>(x, n, a);
+  LAUNCH_CHECK();
+}
+void k_axpby(double* y, const double* x, long long n, double a, double b, cudaStream_t s) {
+  axpby_kernel<<<blocks_for(n, 256, 4096), 256, 0, s>>>(y, x, n, a, b);
+  LAUNCH_CHECK();
+}
+void k_extract_window(double* dst, long long dst_ld, long long dst_slab, const double* M, long long ldn, long long slab,
+                      int m0, int mcnt, int n0, int ncnt, int naux, const double* scale, cudaStream_t s) {
+  const long long total = (long long)mcnt * naux * ncnt;
+  extract_window_kernel<<<blocks_for(total, 256, 8192), 256, 0, s>>>(dst, dst_ld, dst_slab, M, ldn, slab, m0, mcnt, n0,
+                                                                    ncnt, naux, scale);
+  LAUNCH_CHECK();
+}
+
+void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                      const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
+                      const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s) {
+  const int per_block = kGridThreads * kGridNW;
+  dim3 grid((n_omega + per_block - 1) / per_block, n_levels);
+  sigma_ppm_grid_kernel<<<grid, kGridThreads, 0, s>>>(M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq, ppm_fac,
+                                                      level_slab, omega0, domega, n_omega, values);
+  LAUNCH_CHECK();
+}
+void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                       const double* energies, const double* ppm_freq, const double* ppm_fac, const int* pair_slab,
+                       const double* pair_omega, int n_pairs, double* values, double* derivs, double* partial,
+                       cudaStream_t s) {
+  if (n_pairs == 0) return;
+  for (int off = 0; off < n_pairs; off += 32768) {
+    const int cnt = std::min(32768, n_pairs - off);
+    sigma_ppm_pairs_kernel<<<dim3(kPairChunks, cnt), kPairThreads, 0, s>>>(
+        M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq, ppm_fac, pair_slab + off, pair_omega + off,
+        partial + (long long)off * kPairChunks * 2);
+    LAUNCH_CHECK();
+  }
+  sigma_ppm_pairs_finalize<<<blocks_for(n_pairs, 128), 128, 0, s>>>(partial, n_pairs, values, derivs);
+  LAUNCH_CHECK();
+}
+void k_sigma_ppm_weighted_slab(double* W, const double* M, long long ldn, long long slab, int ntotal, int p0, int pcnt,
+                               int n_occ, const double* energies, const double* ppm_freq, const double* ppm_fac,
+                               int slab0, int n_levels, const double* level_omega, cudaStream_t s) {
+  const long long total = (long long)pcnt * ldn * n_levels;
+  sigma_ppm_weighted_slab_kernel<<<blocks_for(total, 256, 16384), 256, 0, s>>>(
+      W, M, ldn, slab, ntotal, p0, pcnt, n_occ, energies, ppm_freq, ppm_fac, slab0, n_levels, level_omega);
+  LAUNCH_CHECK();
+}
+int sigma_ppm_pair_partial_doubles(int n_pairs) { return n_pairs * kPairChunks * 2; }
+
+void k_bse_diagonal(double* diag, int vt, int ct, int naux, const double* Mvc, long long ldvc, long long slabvc,
+                    const double* Mvv, long long ldvv, long long slabvv, const double* Mcc, long long ldcc,
+                    long long slabcc, const double* Mcv, long long ldcv, long long slabcv, const double*,
+                    const double* hqp_diag, int cqp, int cx, int cd, int cd2, cudaStream_t s) {
+  DBuf dvv, dcc;
+  if (cd) {
+    dvv.alloc((size_t)vt * naux);
+    dcc.alloc((size_t)ct * naux);
+    bse_diag_helpers_kernel<<<blocks_for((long long)(vt + ct) * naux, 256, 4096), 256, 0, s>>>(
+        dvv.p, dcc.p, vt, ct, naux, Mvv, ldvv, slabvv, Mcc, ldcc, slabcc);
+    LAUNCH_CHECK();
+  }
+  bse_diagonal_kernel<<<vt, 128, 0, s>>>(diag, vt, ct, naux, Mvc, ldvc, slabvc, dvv.p, dcc.p, Mcv, ldcv, slabcv,
+                                         hqp_diag, cqp, cx, cd, cd2);
+  LAUNCH_CHECK();
+  XTPB_CUDA(cudaStreamSynchronize(s));   // dvv/dcc are freed on return
+}
+
+void k_col_norms(const double* A, long long ld, long long rows, int cols, double* out, cudaStream_t s) {
+  if (cols == 0) return;
+  col_norms_kernel<<<cols, 256, 0, s>>>(A, ld, rows, out);
+  LAUNCH_CHECK();
+}
+void k_residuals(double* res, long long ldr, const double* q, long long ldq, const double* lambda, long long rows,
+                 int cols, cudaStream_t s) {
+  residuals_kernel<<<blocks_for(rows * cols, 256, 4096), 256, 0, s>>>(res, ldr, q, ldq, lambda, rows, cols);
+  LAUNCH_CHECK();
+}
+void k_davidson_correction(double* out, const double* r, const double* x, const double* D, double lambda, long long n,
+                           int olsen, double* scratch2, cudaStream_t s) {
+  // scratch2: n doubles (xd) followed by 2*nblocks partials
+  const int nblocks = blocks_for(n, 256, 256);
+  double* xd = scratch2;
+  double* partial = scratch2 + n;
+  correction_kernel<<<nblocks, 256, 0, s>>>(out, xd, r, x, D, lambda, n, olsen, partial);
+  LAUNCH_CHECK();
+  if (olsen) {
+    olsen_finish_kernel<<<nblocks, 256, 0, s>>>(out, xd, partial, nblocks, n);
+    LAUNCH_CHECK();
+  }
+}
+void k_unit_vectors(double* V, long long ld, long long, const long long* idx, int cols, cudaStream_t s) {
+  unit_vectors_kernel<<<blocks_for(cols, 128), 128, 0, s>>>(V, ld, idx, cols);
+  LAUNCH_CHECK();
+}
+
+}  // namespace xtpb

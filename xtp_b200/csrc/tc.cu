@@ -1,0 +1,150 @@
+// TCMatrix_gwbse on the device: the RI tensor M[m][P][n] stays resident in HBM for the whole GW-BSE step.
+// Upstream: xtp/src/libxtp/threecenter_gwbse.cc (Initialize, Fill3cMO, MultiplyRightWithAuxMatrix, operator[]).
+#include <algorithm>
+
+#include "internal.h"
+
+namespace xtpb {
+
+TCMatrix::TCMatrix(Context* c, long long auxsize, long long mmin_, long long mmax_, long long nmin_, long long nmax_)
+    : ctx(c), naux(auxsize), mmin(mmin_), mmax(mmax_), nmin(nmin_), nmax(nmax_) {
+  XTPB_REQUIRE(auxsize > 0 && mmax_ >= mmin_ && nmax_ >= nmin_ && mmin_ >= 0 && nmin_ >= 0, "bad TCMatrix ranges");
+  mtotal = mmax - mmin + 1;
+  ntotal = nmax - nmin + 1;
+  ldn = round_up(ntotal, 2);
+  slab = naux * ldn;
+  M.alloc((size_t)(mtotal * slab));
+  M.zero(ctx->stream);
+}
+
+void TCMatrix::set_raw(const double* host) {
+  ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
+  ctx->sync();
+}
+
+void TCMatrix::get_slab(long long m, double* host) {
+  XTPB_REQUIRE(m >= 0 && m < mtotal, "slab index out of range");
+  ctx->d2h_2d(host, ntotal, slab_ptr(m), ldn, ntotal, naux);
+}
+
+void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host) {
+  XTPB_REQUIRE(nb > 0 && ldc_host >= nb, "bad MO coefficient matrix");
+  n_basis = nb;
+  ldc = round_up(nb, 2);
+  Cm.alloc((size_t)(ldc * mtotal));
+  Cn.alloc((size_t)(ldc * ntotal));
+  Cm.zero(ctx->stream);
+  Cn.zero(ctx->stream);
+  ctx->h2d_2d(Cm.p, ldc, C_host + mmin * ldc_host, ldc_host, nb, mtotal);
+  ctx->h2d_2d(Cn.p, ldc, C_host + nmin * ldc_host, ldc_host, nb, ntotal);
+  ctx->sync();
+}
+
+// Fill3cMO for aux functions P0..P0+nP-1 (upstream: per aux function dftn^T * T_P * dftm; here batched over P):
+//   W_P  = T_P * C_m            (n_basis x mtotal)      2 n_basis^2 mtotal flops per P
+//   M[m][P][:] = C_n^T * W_P    (ntotal x mtotal)       2 ntotal n_basis mtotal flops per P
+void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long long ld_ao) {
+  XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill_block");
+  XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux && ld_ao >= n_basis, "bad aux block");
+  const long long ldw = round_up(n_basis, 2);
+  const long long wslice = ldw * mtotal;
+  const long long sub_max = std::max<long long>(1, std::min<long long>(64, (1LL << 27) / std::max<long long>(1, wslice)));
+  ctx->scratch_a.ensure((size_t)(sub_max * wslice));
+  double* W = ctx->scratch_a.p;
+  for (long long p = 0; p < nP; p += sub_max) {
+    const long long cnt = std::min(sub_max, nP - p);
+    GemmParams g{};
+    // W(mu, m) = sum_nu T(mu,nu) Cm(nu,m):   A(row mu, k nu) = T[nu + mu*ld]  (T symmetric)
+    g.A = GemmOperand{ao + p * ld_ao * n_basis, ld_ao, 1, 0, ld_ao * n_basis};
+    g.B = GemmOperand{Cm.p, ldc, 1, 0, 0};
+    g.C = W; g.c_sm = 1; g.c_sn = ldw; g.c_batch = wslice;
+    g.M = (int)n_basis; g.N = (int)mtotal; g.K = (int)n_basis; g.n_outer = 1; g.n_batch = (int)cnt;
+    g.alpha = 1.0; g.beta = 0.0;
+    contract(g, ctx->ws, ctx->stream);
+    GemmParams h{};
+    // out(n, m) = sum_mu Cn(mu,n) W(mu,m) -> M[m][P0+p+b][n]
+    h.A = GemmOperand{Cn.p, ldc, 1, 0, 0};
+    h.B = GemmOperand{W, ldw, 1, 0, wslice};
+    h.C = M.p + (P0 + p) * ldn; h.c_sm = 1; h.c_sn = slab; h.c_batch = ldn;
+    h.M = (int)ntotal; h.N = (int)mtotal; h.K = (int)n_basis; h.n_outer = 1; h.n_batch = (int)cnt;
+    h.alpha = 1.0; h.beta = 0.0;
+    contract(h, ctx->ws, ctx->stream);
+  }
+}
+
+void TCMatrix::fill_block_host(long long P0, long long nP, const double* ao_host, long long ld_ao) {
+  XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill_block");
+  const long long ldt = round_up(n_basis, 2);
+  const long long slice = ldt * n_basis;
+  const long long sub_max = std::max<long long>(1, std::min<long long>(nP, (1LL << 28) / slice));
+  stage.ensure((size_t)(sub_max * slice));
+  for (long long p = 0; p < nP; p += sub_max) {
+    const long long cnt = std::min(sub_max, nP - p);
+    // the previous sub-block's kernels read `stage`; the copy is stream-ordered behind them
+    if (ld_ao == ldt) {
+      ctx->h2d(stage.p, ao_host + p * ld_ao * n_basis, (size_t)(cnt * slice));
+    } else {
+      ctx->h2d_2d(stage.p, ldt, ao_host + p * ld_ao * n_basis, ld_ao, n_basis, n_basis * cnt);
+    }
+    fill_block_dev(P0 + p, cnt, stage.p, ldt);
+  }
+  ctx->sync();
+}
+
+// dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]; A rows-contiguous (j), B = R K-contiguous (column Q of R).
+void TCMatrix::rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
+                             const double* R_dev, long long ldr) {
+  GemmParams g{};
+  g.A = GemmOperand{M.p + (long long)m0 * slab + n0, 1, ldn, 0, slab};
+  g.B = GemmOperand{R_dev, ldr, 1, 0, 0};
+  g.C = dst; g.c_sm = 1; g.c_sn = dst_ld; g.c_batch = dst_slab;
+  g.M = ncnt; g.N = (int)naux; g.K = (int)naux; g.n_outer = 1;
+  g.alpha = 1.0; g.beta = 0.0;
+  for (int b = 0; b < mcnt; b += 16384) {      // gridDim.z limit
+    GemmParams gg = g;
+    gg.n_batch = std::min(16384, mcnt - b);
+    gg.A.p += (long long)b * slab;
+    gg.C += (long long)b * dst_slab;
+    contract(gg, ctx->ws, ctx->stream);
+  }
+}
+
+// MultiplyRightWithAuxMatrix: out of place through a bounded scratch of `chunk` slabs, copied back.
+void TCMatrix::rotate(const double* R_dev, long long ldr) {
+  const long long budget = 1LL << 29;   // doubles (4 GiB)
+  const long long chunk = std::max<long long>(1, std::min<long long>(mtotal, budget / slab));
+  ctx->scratch_b.ensure((size_t)(chunk * slab));
+  for (long long m = 0; m < mtotal; m += chunk) {
+    const long long cnt = std::min(chunk, mtotal - m);
+    rotate_window(ctx->scratch_b.p, ldn, slab, (int)m, (int)cnt, 0, (int)ntotal, R_dev, ldr);
+    // padding column (ldn > ntotal) of the scratch is never written; copy only the payload rows
+    k_copy_2d(slab_ptr(m), ldn, ctx->scratch_b.p, ldn, (int)ntotal, cnt * naux, ctx->stream);
+  }
+}
+
+// eps(w) = 1 + sum_{m occ} A_m^T diag(d_m(w)) A_m with A_m = M[m](unocc, :)   (upstream RPA::calculate_epsilon)
+// One lower-triangular SYRK-style launch per call; the frequency index is the batch dimension.
+void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
+                     int n_omega, bool imag, double, double* out_dev) {
+  Context* ctx = tc.ctx;
+  XTPB_REQUIRE(n_occ > 0 && n_occ < tc.ntotal && n_occ <= tc.mtotal, "RPA needs occupied and unoccupied levels");
+  const int a0 = (int)(n_occ & ~1LL);          // 16-byte aligned start of the contraction range
+  const int K = (int)(tc.ntotal - a0);
+  DBuf d((size_t)n_omega * n_occ * K + n_omega);
+  double* om_dev = d.p + (size_t)n_omega * n_occ * K;
+  ctx->h2d(om_dev, omegas_host, n_omega);
+  k_chi0_weights(d.p, energies_dev, (int)n_occ, a0, K, om_dev, n_omega, imag, eta, 0.0, ctx->stream);
+  GemmParams g{};
+  g.A = GemmOperand{tc.M.p + a0, tc.ldn, 1, tc.slab, 0};
+  g.B = g.A;
+  g.C = out_dev; g.c_sm = 1; g.c_sn = tc.naux; g.c_batch = tc.naux * tc.naux;
+  g.d = d.p; g.d_outer = K; g.d_batch = (long long)n_occ * K;
+  g.M = (int)tc.naux; g.N = (int)tc.naux; g.K = K; g.n_outer = (int)n_occ; g.n_batch = n_omega;
+  g.alpha = 1.0; g.beta = 0.0; g.lower = 1;
+  contract(g, ctx->ws, ctx->stream);
+  for (int w = 0; w < n_omega; ++w)
+    symmetrize_from_lower(out_dev + (long long)w * tc.naux * tc.naux, (int)tc.naux, tc.naux, 1.0, ctx->stream);
+  ctx->sync();   // d is freed on return
+}
+
+}  // namespace xtpb
