@@ -47,6 +47,21 @@ int xtpb_ctx_sync(xtpb_ctx* ctx);
 /* seconds spent inside cuSOLVER eigh/inverse since the last reset (reported apart from contractions) */
 int xtpb_ctx_solver_seconds(xtpb_ctx* ctx, double* seconds, int reset);
 
+/* pinned (page-locked) host memory for the caller's AO-integral and result buffers: H2D/D2H copies from it run
+ * asynchronously at PCIe rate and overlap the contractions (xtpb_tc_fill_block*). */
+int xtpb_host_alloc(unsigned long long bytes, void** out);
+int xtpb_host_free(void* p);
+
+/* ---- kernel timing for roofline reports: when enabled, every launch of the contraction engine and of the fused
+ *      Sigma_c kernels is bracketed by a CUDA-event pair on the launching stream.  Tags (xtpb_profile_get):
+ *      0 other, 1 Fill3cMO, 2 aux rotation, 3 epsilon, 4 Sigma_x, 5 Sigma_c off-diagonal, 6 BSE matmul,
+ *      7 Davidson projections, 8 small dense (PPM), 9 Sigma_c PPM grid kernel (work = pole evaluations),
+ *      10 Sigma_c PPM pair kernel (work = bytes), 11 cuSOLVER, 12 AO unpack (work = bytes), 13 CDA, 14 exact.
+ *      `work` is the summed algorithmic flop count (2MNK; MNK for lower-triangular outputs) unless noted. ---- */
+int xtpb_profile_enable(int on);
+int xtpb_profile_reset(void);
+int xtpb_profile_get(int tag, double* ms, double* work, long long* launches);
+
 /* ---- TCMatrix_gwbse (upstream xtp/include/votca/xtp/threecenter.h, xtp/src/libxtp/threecenter_gwbse.cc) ---- */
 /* TCMatrix_gwbse::Initialize(basissize, mmin, mmax, nmin, nmax) */
 int xtpb_tc_create(xtpb_ctx* ctx, xtpb_index auxsize, xtpb_index mmin, xtpb_index mmax, xtpb_index nmin,
@@ -67,6 +82,10 @@ int xtpb_tc_get_slab(xtpb_tc* tc, xtpb_index m, double* slab_host);
 int xtpb_tc_fill_begin(xtpb_tc* tc, xtpb_index n_basis, const double* C_host, xtpb_index ldc);
 int xtpb_tc_fill_block(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_host, xtpb_index ld_ao);
 int xtpb_tc_fill_block_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_dev, xtpb_index ld_ao);
+/* the same with packed lower triangles (row mu holds nu = 0..mu; slice stride n_basis(n_basis+1)/2): half the
+ * PCIe / HBM bytes of the full symmetric slices */
+int xtpb_tc_fill_block_packed(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_packed_host);
+int xtpb_tc_fill_block_packed_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_packed_dev);
 /* TCMatrix_gwbse::MultiplyRightWithAuxMatrix(matrix): matrix is auxsize x auxsize */
 int xtpb_tc_multiply_right_with_aux_matrix(xtpb_tc* tc, const double* A_host, xtpb_index lda);
 /* second half of TCMatrix_gwbse::Fill: AOCoulomb::Pseudo_InvSqrt_GWBSE(auxoverlap, etol) followed by

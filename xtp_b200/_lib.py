@@ -62,6 +62,11 @@ PROTOTYPES = {
     "xtpb_ctx_destroy": (C.c_int, [vp]),
     "xtpb_ctx_sync": (C.c_int, [vp]),
     "xtpb_ctx_solver_seconds": (C.c_int, [vp, dptr, C.c_int]),
+    "xtpb_host_alloc": (C.c_int, [C.c_ulonglong, C.POINTER(vp)]),
+    "xtpb_host_free": (C.c_int, [vp]),
+    "xtpb_profile_enable": (C.c_int, [C.c_int]),
+    "xtpb_profile_reset": (C.c_int, []),
+    "xtpb_profile_get": (C.c_int, [C.c_int, dptr, dptr, iptr]),
     "xtpb_tc_create": (C.c_int, [vp, idx, idx, idx, idx, idx, C.POINTER(vp)]),
     "xtpb_tc_destroy": (C.c_int, [vp]),
     "xtpb_tc_sizes": (C.c_int, [vp, iptr, iptr, iptr]),
@@ -70,6 +75,8 @@ PROTOTYPES = {
     "xtpb_tc_fill_begin": (C.c_int, [vp, idx, dptr, idx]),
     "xtpb_tc_fill_block": (C.c_int, [vp, idx, idx, dptr, idx]),
     "xtpb_tc_fill_block_dev": (C.c_int, [vp, idx, idx, vp, idx]),
+    "xtpb_tc_fill_block_packed": (C.c_int, [vp, idx, idx, vp]),
+    "xtpb_tc_fill_block_packed_dev": (C.c_int, [vp, idx, idx, vp]),
     "xtpb_tc_multiply_right_with_aux_matrix": (C.c_int, [vp, dptr, idx]),
     "xtpb_tc_apply_coulomb_metric": (C.c_int, [vp, dptr, idx, dptr, idx, C.c_double, iptr]),
     "xtpb_rpa_epsilon": (C.c_int, [vp, dptr, idx, idx, idx, C.c_double, dptr, C.c_int, C.c_int, dptr]),

@@ -55,6 +55,61 @@ def launch_count():
     return int(_lib.lib().xtpb_launch_count())
 
 
+class PinnedBuffer:
+    """float64 numpy view of page-locked host memory (xtpb_host_alloc); keeps the allocation alive."""
+
+    def __init__(self, count):
+        self._p = vp()
+        self.count = int(count)
+        check(_lib.lib().xtpb_host_alloc(C.c_ulonglong(max(8, self.count * 8)), C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, dptr), shape=(max(1, self.count),))[:self.count]
+
+    def close(self):
+        if self._p:
+            self.array = None
+            _lib.lib().xtpb_host_free(self._p)
+            self._p = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+PROFILE_TAGS = {"other": 0, "fill": 1, "rotate": 2, "epsilon": 3, "sigma_x": 4, "sigma_offdiag": 5, "bse_matmul": 6,
+                "davidson": 7, "dense_aux": 8, "sigma_ppm_grid": 9, "sigma_ppm_pairs": 10, "solver": 11,
+                "unpack": 12, "cda": 13, "exact": 14}
+CONTRACTION_TAGS = ("other", "fill", "rotate", "epsilon", "sigma_x", "sigma_offdiag", "bse_matmul", "davidson",
+                    "dense_aux", "cda", "exact")
+
+
+def profile_enable(on=True):
+    check(_lib.lib().xtpb_profile_enable(int(on)))
+
+
+def profile_reset():
+    check(_lib.lib().xtpb_profile_reset())
+
+
+def profile_summary():
+    """{tag: {"ms", "work", "launches"}} for every tag with at least one launch (synchronises the device)."""
+    out = {}
+    for name, tag in PROFILE_TAGS.items():
+        ms, work, n = C.c_double(), C.c_double(), idx(0)
+        check(_lib.lib().xtpb_profile_get(tag, C.byref(ms), C.byref(work), C.byref(n)))
+        if n.value:
+            out[name] = {"ms": ms.value, "work": work.value, "launches": int(n.value)}
+    return out
+
+
+def pack_lower(ao3c):
+    """ao3c[P, mu, nu] symmetric -> packed lower triangles [P, n(n+1)/2] (row mu holds nu = 0..mu)."""
+    n = ao3c.shape[-1]
+    il = np.tril_indices(n)
+    return np.ascontiguousarray(ao3c[:, il[0], il[1]])
+
+
 class TCMatrix_gwbse:
     """upstream xtp/src/libxtp/threecenter_gwbse.cc"""
 
@@ -119,6 +174,14 @@ class TCMatrix_gwbse:
 
     def fill_block_dev(self, P0, nP, dev_ptr, ld):
         check(_lib.lib().xtpb_tc_fill_block_dev(self._h, int(P0), int(nP), vp(int(dev_ptr)), int(ld)))
+
+    def fill_block_packed(self, P0, packed):
+        """packed[P, n(n+1)/2] host array (ideally a PinnedBuffer view)."""
+        assert packed.dtype == np.float64 and packed.flags.c_contiguous
+        check(_lib.lib().xtpb_tc_fill_block_packed(self._h, int(P0), packed.shape[0], vp(packed.ctypes.data)))
+
+    def fill_block_packed_dev(self, P0, nP, dev_ptr):
+        check(_lib.lib().xtpb_tc_fill_block_packed_dev(self._h, int(P0), int(nP), vp(int(dev_ptr))))
 
     def fill_block(self, P0, blk, ld=None):
         blk = np.ascontiguousarray(blk, dtype=np.float64)

@@ -144,6 +144,7 @@ void BseOperator::diagonal_dev(double* d) {
 
 void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, long long ldy) {
   XTPB_REQUIRE(k > 0, "matmul needs at least one column");
+  ProfScope prof(PROF_BSE_MATMUL);
   cudaStream_t st = ctx->stream;
   bool first = true;
   auto beta = [&]() { const double b = first ? 0.0 : 1.0; first = false; return b; };
@@ -325,6 +326,7 @@ int gram_schmidt(DavidsonWork& w, int nstart, int ncols) {
 
 void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& opt, DavidsonResult& out) {
   Context* ctx = A.ctx;
+  ProfScope prof(PROF_DAVIDSON);
   const long long n = A.size;
   XTPB_REQUIRE(neigen >= 1 && neigen <= n, "neigen out of range");
   long long max_space = opt.max_search_space;

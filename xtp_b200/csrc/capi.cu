@@ -31,6 +31,34 @@ int xtpb_ctx_sync(xtpb_ctx* ctx) {
   ctx->impl.sync();
   XTPB_API_END
 }
+int xtpb_host_alloc(unsigned long long bytes, void** out) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(out != nullptr, "null output pointer");
+  XTPB_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+  XTPB_API_END
+}
+int xtpb_host_free(void* p) {
+  XTPB_API_BEGIN
+  if (p) XTPB_CUDA(cudaFreeHost(p));
+  XTPB_API_END
+}
+int xtpb_profile_enable(int on) {
+  XTPB_API_BEGIN
+  prof_enable(on != 0);
+  XTPB_API_END
+}
+int xtpb_profile_reset(void) {
+  XTPB_API_BEGIN
+  prof_reset();
+  XTPB_API_END
+}
+int xtpb_profile_get(int tag, double* ms, double* work, long long* launches) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(tag >= 0 && tag < PROF_NTAGS, "profile tag out of range");
+  XTPB_CUDA(cudaDeviceSynchronize());
+  prof_get(tag, ms, work, launches);
+  XTPB_API_END
+}
 int xtpb_ctx_solver_seconds(xtpb_ctx* ctx, double* seconds, int reset) {
   XTPB_API_BEGIN
   if (seconds) *seconds = ctx->impl.solver_seconds;
@@ -75,7 +103,18 @@ int xtpb_tc_fill_begin(xtpb_tc* tc, xtpb_index n_basis, const double* C_host, xt
 }
 int xtpb_tc_fill_block(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_host, xtpb_index ld_ao) {
   XTPB_API_BEGIN
-  tc->impl.fill_block_host(P0, nP, ao3c_host, ld_ao);
+  XTPB_REQUIRE(ld_ao >= tc->impl.n_basis, "ld_ao smaller than n_basis");
+  tc->impl.fill_block_host(P0, nP, ao3c_host, ld_ao, false);
+  XTPB_API_END
+}
+int xtpb_tc_fill_block_packed(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_packed_host) {
+  XTPB_API_BEGIN
+  tc->impl.fill_block_host(P0, nP, ao3c_packed_host, 0, true);
+  XTPB_API_END
+}
+int xtpb_tc_fill_block_packed_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_packed_dev) {
+  XTPB_API_BEGIN
+  tc->impl.fill_block_packed_dev(P0, nP, ao3c_packed_dev);
   XTPB_API_END
 }
 int xtpb_tc_fill_block_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_dev, xtpb_index ld_ao) {

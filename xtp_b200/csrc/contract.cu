@@ -4,10 +4,61 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <vector>
 
 namespace xtpb {
 
 long long g_launch_count = 0;
+
+// ------------------------------------------------------------------ event-pair profiler
+namespace {
+struct ProfRec { cudaEvent_t e0, e1; int tag; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_pool;      // events are created once and reused after prof_reset()
+size_t g_prof_used = 0;
+constexpr size_t kProfCap = 1 << 17;
+thread_local int t_prof_tag = PROF_OTHER;
+}  // namespace
+
+void prof_enable(bool on) { g_prof_on = on; }
+bool prof_enabled() { return g_prof_on; }
+void prof_reset() { g_prof_used = 0; }
+int prof_begin(int tag, double work, cudaStream_t s) {
+  if (!g_prof_on || g_prof_used >= kProfCap) return -1;
+  if (g_prof_used == g_prof_pool.size()) {
+    ProfRec r{};
+    XTPB_CUDA(cudaEventCreate(&r.e0));
+    XTPB_CUDA(cudaEventCreate(&r.e1));
+    g_prof_pool.push_back(r);
+  }
+  ProfRec& r = g_prof_pool[g_prof_used];
+  r.tag = tag < 0 ? t_prof_tag : tag;
+  r.work = work;
+  XTPB_CUDA(cudaEventRecord(r.e0, s));
+  return (int)g_prof_used++;
+}
+void prof_end(int slot, cudaStream_t s) {
+  if (slot < 0) return;
+  XTPB_CUDA(cudaEventRecord(g_prof_pool[(size_t)slot].e1, s));
+}
+void prof_get(int tag, double* ms, double* work, long long* launches) {
+  double tms = 0.0, tw = 0.0;
+  long long n = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    const ProfRec& r = g_prof_pool[i];
+    if (r.tag != tag) continue;
+    float t = 0.f;
+    XTPB_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    tms += t;
+    tw += r.work;
+    ++n;
+  }
+  if (ms) *ms = tms;
+  if (work) *work = tw;
+  if (launches) *launches = n;
+}
+ProfScope::ProfScope(int tag) : prev(t_prof_tag) { t_prof_tag = tag; }
+ProfScope::~ProfScope() { t_prof_tag = prev; }
 
 namespace {
 
@@ -149,6 +200,9 @@ int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, in
   p.ws = nullptr;
   if (splits > 1) p.ws = ws.get((size_t)p.n_batch * splits * p.M * p.N);
 
+  // algorithmic flops: 2 M N K_total, halved for the lower-triangular (SYRK-style) outputs
+  const double flops = (p.lower ? 1.0 : 2.0) * (double)p.M * p.N * (double)p.K * p.n_outer * p.n_batch;
+  const int prof_slot = prof_begin(-1, flops, stream);
   if (a_kc && b_kc) launch_d<true, true>(p, cfg, stream);
   else if (a_kc && !b_kc) launch_d<true, false>(p, cfg, stream);
   else if (!a_kc && b_kc) launch_d<false, true>(p, cfg, stream);
@@ -164,6 +218,7 @@ int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, in
     ++g_launch_count;
     ++launches;
   }
+  prof_end(prof_slot, stream);
   return launches;
 }
 

@@ -23,4 +23,25 @@ inline GemmOperand op_k_contig(const double* p, long long ld) { return GemmOpera
 
 extern long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
 
+// ---- in-library kernel timing (bench.py's roofline object): CUDA-event pairs on the launching stream around
+// every launch of a tagged kernel family; summed per tag.  Off by default (no events recorded).
+enum ProfTag {
+  PROF_OTHER = 0, PROF_FILL = 1, PROF_ROTATE = 2, PROF_EPSILON = 3, PROF_SIGMA_X = 4, PROF_SIGMA_OFFDIAG = 5,
+  PROF_BSE_MATMUL = 6, PROF_DAVIDSON = 7, PROF_DENSE_AUX = 8, PROF_SIGMA_GRID = 9, PROF_SIGMA_PAIRS = 10,
+  PROF_SOLVER = 11, PROF_UNPACK = 12, PROF_CDA = 13, PROF_EXACT = 14, PROF_NTAGS = 16
+};
+void prof_enable(bool on);
+void prof_reset();
+bool prof_enabled();
+// returns a slot (or -1 when disabled / pool exhausted); `work` = algorithmic flops (or bytes) of the launch
+int prof_begin(int tag, double work, cudaStream_t s);
+void prof_end(int slot, cudaStream_t s);
+// device must be idle (caller synchronises); sums elapsed ms / work / launches for `tag`
+void prof_get(int tag, double* ms, double* work, long long* launches);
+struct ProfScope {     // tags every contract() call issued while it is alive (thread-local)
+  int prev;
+  explicit ProfScope(int tag);
+  ~ProfScope();
+};
+
 }  // namespace xtpb

@@ -43,8 +43,12 @@ Context::~Context() {
   if (stream) cudaStreamDestroy(stream);
 }
 
-void Context::solver_begin() { XTPB_CUDA(cudaEventRecord(ev0, stream)); }
+void Context::solver_begin() {
+  XTPB_CUDA(cudaEventRecord(ev0, stream));
+  solver_prof_slot = prof_begin(PROF_SOLVER, 0.0, stream);
+}
 void Context::solver_end() {
+  prof_end(solver_prof_slot, stream);
   XTPB_CUDA(cudaEventRecord(ev1, stream));
   XTPB_CUDA(cudaEventSynchronize(ev1));
   float ms = 0;

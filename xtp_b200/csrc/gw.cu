@@ -40,6 +40,7 @@ void GW::set_rpa_energies(const double* e) {
 
 // Sigma_x(n,n') = - sum_{m occ} sum_P M[n](m,P) M[n'](m,P)   (upstream Sigma_base::CalcExchangeMatrix)
 void GW::exchange(double* out_host) {
+  ProfScope prof(PROF_SIGMA_X);
   DBuf S((size_t)(qptotal * qptotal));
   GemmParams g{};
   g.A = GemmOperand{tc->slab_ptr(q0), tc->slab, 1, tc->ldn, 0};
@@ -54,6 +55,7 @@ void GW::exchange(double* out_host) {
 
 // PPM::PPM_construct_parameters (ppm.cc) followed by the aux rotation of Sigma_PPM::PrepareScreening.
 void GW::prepare_ppm() {
+  ProfScope prof(PROF_DENSE_AUX);
   const long long na = tc->naux;
   DBuf eps((size_t)(2 * na * na)), T1((size_t)(na * na)), lam((size_t)na);
   const double w_r = 0.0, w_i = 0.5;    // screening_r, screening_i [Ha]
@@ -381,6 +383,7 @@ std::vector<double> GW::hqp() const {
 // Sigma_base::CalcCorrelationOffDiag; for the PPM as one weighted contraction per aux chunk (see kernels.cu (3)).
 void GW::sigma_c_offdiag(const double* freqs, double* out_host) {
   XTPB_REQUIRE(screening_ready, "PrepareScreening has not been called");
+  ProfScope prof(PROF_SIGMA_OFFDIAG);
   const long long q = qptotal;
   if (opt.sigma_integration != XTPB_SIGMA_PPM) {
     sigma_c_offdiag_other(freqs, out_host);

@@ -22,6 +22,7 @@ struct Context {
   DBuf scratch_a, scratch_b;    // transient operands (fill blocks, rotation targets)
   int* dev_info = nullptr;
   double solver_seconds = 0.0;
+  int solver_prof_slot = -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   explicit Context(int dev);
@@ -83,6 +84,9 @@ void k_residuals(double* res, long long ldr, const double* q, long long ldq, con
 void k_davidson_correction(double* out, const double* r, const double* x, const double* D, double lambda, long long n,
                            int olsen, double* scratch2, cudaStream_t s);
 void k_unit_vectors(double* V, long long ld, long long n, const long long* idx, int cols, cudaStream_t s);
+// full[b](mu,nu) = full[b](nu,mu) = packed[b][mu(mu+1)/2 + nu] (nu <= mu), b < count
+void k_unpack_symmetric(double* full, long long ld, long long full_slice, const double* packed, long long pk_slice,
+                        int n, int count, cudaStream_t s);
 
 // ---------------------------------------------------------------- TCMatrix_gwbse
 struct TCMatrix {
@@ -93,7 +97,9 @@ struct TCMatrix {
   // Fill state
   long long n_basis = 0, ldc = 0;
   DBuf Cm, Cn;                  // MO coefficient blocks (n_basis x mtotal / ntotal, ld = ldc)
-  DBuf stage;                   // host->device staging of AO slices
+  DBuf stage2[2], unpacked;     // host->device staging of AO slices (double-buffered) / unpacked symmetric slices
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
 
   TCMatrix(Context* c, long long auxsize, long long mmin_, long long mmax_, long long nmin_, long long nmax_);
   double* slab_ptr(long long m) { return M.p + m * slab; }
@@ -101,7 +107,10 @@ struct TCMatrix {
   void get_slab(long long m, double* host);
   void fill_begin(long long nb, const double* C_host, long long ldc_host);
   void fill_block_dev(long long P0, long long nP, const double* ao_dev, long long ld_ao);
-  void fill_block_host(long long P0, long long nP, const double* ao_host, long long ld_ao);
+  void fill_block_host(long long P0, long long nP, const double* ao_host, long long ld_ao, bool packed);
+  void fill_block_packed_dev(long long P0, long long nP, const double* packed_dev);
+  ~TCMatrix();
+  TCMatrix(TCMatrix&&) = delete;
   // M[m] <- M[m] * R for all m (R on the device, naux x naux, ld = ldr)
   void rotate(const double* R_dev, long long ldr);
   // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]   (window rotation into a caller-owned buffer)

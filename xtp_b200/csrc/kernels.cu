@@ -136,6 +136,40 @@ __global__ void extract_window_kernel(double* __restrict__ dst, long long dst_ld
   }
 }
 
+// ------------------------------------------------------------------ packed symmetric AO slices -> full
+// One 32x32 tile (ti >= tj) of the lower triangle per block: rows of the packed triangle are read coalesced, written
+// to the lower tile directly and to the mirrored upper tile through a shared-memory transpose.  HBM-bound:
+// 4 n^2 bytes read + 8 n^2 written per slice.
+__global__ void __launch_bounds__(256) unpack_symmetric_kernel(double* __restrict__ full, long long ld,
+                                                               long long full_slice, const double* __restrict__ packed,
+                                                               long long pk_slice, int n) {
+  __shared__ double tile[32][33];
+  // linear block index -> (ti, tj) with ti >= tj
+  const int t = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((long long)(ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while ((long long)ti * (ti + 1) / 2 > t) --ti;
+  const int tj = t - ti * (ti + 1) / 2;
+  const double* src = packed + (long long)blockIdx.y * pk_slice;
+  double* dst = full + (long long)blockIdx.y * full_slice;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int mu = ti * 32 + r, nu = tj * 32 + tx;
+    double v = 0.0;
+    if (mu < n && nu <= mu) v = src[(long long)mu * (mu + 1) / 2 + nu];
+    tile[r][tx] = v;
+    // column-major full matrix: element (row mu, col nu) at mu + nu*ld; writing row-index-fastest needs the transpose,
+    // so the direct write below covers (row nu, col mu) = upper mirror, contiguous in nu
+    if (mu < n && nu <= mu) dst[nu + (long long)mu * ld] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    // transposed read: element (mu = ti*32 + tx, nu = tj*32 + r) -> (row mu, col nu), contiguous in mu
+    const int mu = ti * 32 + tx, nu = tj * 32 + r;
+    if (mu < n && nu < mu) dst[mu + (long long)nu * ld] = tile[tx][r];
+  }
+}
+
 // ------------------------------------------------------------------ Sigma_c, plasmon-pole model
 // Upstream Sigma_PPM::CalcCorrelationDiagElement (sigma_ppm.cc):
 //   Sigma_c(level, w) = sum_P fac_P sum_m M~[level](m,P)^2 * ginv(w - e_m +/- Omega_P)   (+ occupied, - unoccupied)
@@ -437,15 +471,19 @@ void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal
                       const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s) {
   const int per_block = kGridThreads * kGridNW;
   dim3 grid((n_omega + per_block - 1) / per_block, n_levels);
+  // work = pole evaluations (one reciprocal + ~6 flops each)
+  const int slot = prof_begin(PROF_SIGMA_GRID, (double)ntotal * naux * (double)n_omega * n_levels, s);
   sigma_ppm_grid_kernel<<<grid, kGridThreads, 0, s>>>(M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq, ppm_fac,
                                                       level_slab, omega0, domega, n_omega, values);
   LAUNCH_CHECK();
+  prof_end(slot, s);
 }
 void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                        const double* energies, const double* ppm_freq, const double* ppm_fac, const int* pair_slab,
                        const double* pair_omega, int n_pairs, double* values, double* derivs, double* partial,
                        cudaStream_t s) {
   if (n_pairs == 0) return;
+  const int slot = prof_begin(PROF_SIGMA_PAIRS, 8.0 * ntotal * (double)naux * n_pairs, s);   // work = slab bytes streamed
   for (int off = 0; off < n_pairs; off += 32768) {
     const int cnt = std::min(32768, n_pairs - off);
     sigma_ppm_pairs_kernel<<<dim3(kPairChunks, cnt), kPairThreads, 0, s>>>(
@@ -455,6 +493,7 @@ void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntota
   }
   sigma_ppm_pairs_finalize<<<blocks_for(n_pairs, 128), 128, 0, s>>>(partial, n_pairs, values, derivs);
   LAUNCH_CHECK();
+  prof_end(slot, s);
 }
 void k_sigma_ppm_weighted_slab(double* W, const double* M, long long ldn, long long slab, int ntotal, int p0, int pcnt,
                                int n_occ, const double* energies, const double* ppm_freq, const double* ppm_fac,
@@ -506,6 +545,19 @@ void k_davidson_correction(double* out, const double* r, const double* x, const 
     olsen_finish_kernel<<<nblocks, 256, 0, s>>>(out, xd, partial, nblocks, n);
     LAUNCH_CHECK();
   }
+}
+void k_unpack_symmetric(double* full, long long ld, long long full_slice, const double* packed, long long pk_slice,
+                        int n, int count, cudaStream_t s) {
+  if (count == 0) return;
+  const int t = (n + 31) / 32;
+  const int slot = prof_begin(PROF_UNPACK, 12.0 * n * (double)n * count, s);
+  for (int off = 0; off < count; off += 32768) {
+    const int cnt = std::min(32768, count - off);
+    unpack_symmetric_kernel<<<dim3(t * (t + 1) / 2, cnt), 256, 0, s>>>(full + (long long)off * full_slice, ld, full_slice,
+                                                                      packed + (long long)off * pk_slice, pk_slice, n);
+    LAUNCH_CHECK();
+  }
+  prof_end(slot, s);
 }
 void k_unit_vectors(double* V, long long ld, long long, const long long* idx, int cols, cudaStream_t s) {
   unit_vectors_kernel<<<blocks_for(cols, 128), 128, 0, s>>>(V, ld, idx, cols);

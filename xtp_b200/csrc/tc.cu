@@ -17,6 +17,14 @@ TCMatrix::TCMatrix(Context* c, long long auxsize, long long mmin_, long long mma
   M.zero(ctx->stream);
 }
 
+TCMatrix::~TCMatrix() {
+  for (int b = 0; b < 2; ++b) {
+    if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
+    if (ev_consumed[b]) cudaEventDestroy(ev_consumed[b]);
+  }
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+}
+
 void TCMatrix::set_raw(const double* host) {
   ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
   ctx->sync();
@@ -46,6 +54,7 @@ void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host
 void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long long ld_ao) {
   XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill_block");
   XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux && ld_ao >= n_basis, "bad aux block");
+  ProfScope prof(PROF_FILL);
   const long long ldw = round_up(n_basis, 2);
   const long long wslice = ldw * mtotal;
   const long long sub_max = std::max<long long>(1, std::min<long long>(64, (1LL << 27) / std::max<long long>(1, wslice)));
@@ -72,28 +81,75 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
   }
 }
 
-void TCMatrix::fill_block_host(long long P0, long long nP, const double* ao_host, long long ld_ao) {
+// Host-side Fill3cMO for a range of aux functions: the caller's AO slices (full symmetric n_basis x n_basis with
+// leading dimension ld_ao, or packed lower triangles, row mu holding nu = 0..mu) stream through two device staging
+// buffers on a dedicated copy stream, so the H2D copy of chunk i+1 overlaps the contractions of chunk i.  With
+// pinned host memory (xtpb_host_alloc) the copies run at PCIe rate; pageable memory works but serialises.
+void TCMatrix::fill_block_host(long long P0, long long nP, const double* ao_host, long long ld_ao, bool packed) {
   XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill_block");
+  XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux, "bad aux block");
+  if (nP == 0) return;
   const long long ldt = round_up(n_basis, 2);
-  const long long slice = ldt * n_basis;
-  const long long sub_max = std::max<long long>(1, std::min<long long>(nP, (1LL << 28) / slice));
-  stage.ensure((size_t)(sub_max * slice));
-  for (long long p = 0; p < nP; p += sub_max) {
-    const long long cnt = std::min(sub_max, nP - p);
-    // the previous sub-block's kernels read `stage`; the copy is stream-ordered behind them
-    if (ld_ao == ldt) {
-      ctx->h2d(stage.p, ao_host + p * ld_ao * n_basis, (size_t)(cnt * slice));
-    } else {
-      ctx->h2d_2d(stage.p, ldt, ao_host + p * ld_ao * n_basis, ld_ao, n_basis, n_basis * cnt);
+  const long long full_slice = ldt * n_basis;
+  const long long host_slice = packed ? n_basis * (n_basis + 1) / 2 : ld_ao * n_basis;
+  const long long dev_slice = packed ? host_slice : full_slice;
+  const long long sub_max = std::max<long long>(1, std::min<long long>(nP, (1LL << 26) / full_slice));   // <= 512 MiB full
+  for (int b = 0; b < 2; ++b) stage2[b].ensure((size_t)(sub_max * dev_slice));
+  if (packed) unpacked.ensure((size_t)(sub_max * full_slice));
+  if (!copy_stream) {
+    XTPB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      XTPB_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+      XTPB_CUDA(cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming));
     }
-    fill_block_dev(P0 + p, cnt, stage.p, ldt);
+  }
+  // staging buffers may have been (re)allocated on the compute stream's timeline: order the copy stream behind it
+  XTPB_CUDA(cudaEventRecord(ev_consumed[0], ctx->stream));
+  XTPB_CUDA(cudaEventRecord(ev_consumed[1], ctx->stream));
+  long long chunk = 0;
+  for (long long p = 0; p < nP; p += sub_max, ++chunk) {
+    const int b = (int)(chunk & 1);
+    const long long cnt = std::min(sub_max, nP - p);
+    XTPB_CUDA(cudaStreamWaitEvent(copy_stream, ev_consumed[b], 0));
+    const double* src = ao_host + p * host_slice;
+    if (packed || ld_ao == ldt) {
+      XTPB_CUDA(cudaMemcpyAsync(stage2[b].p, src, (size_t)(cnt * dev_slice) * 8, cudaMemcpyHostToDevice, copy_stream));
+    } else {
+      XTPB_CUDA(cudaMemcpy2DAsync(stage2[b].p, ldt * 8, src, ld_ao * 8, n_basis * 8, n_basis * cnt,
+                                  cudaMemcpyHostToDevice, copy_stream));
+    }
+    XTPB_CUDA(cudaEventRecord(ev_copied[b], copy_stream));
+    XTPB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
+    if (packed) {
+      fill_block_packed_dev(P0 + p, cnt, stage2[b].p);
+    } else {
+      fill_block_dev(P0 + p, cnt, stage2[b].p, ldt);
+    }
+    XTPB_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
   }
   ctx->sync();
+}
+
+// packed lower-triangular slices already on the device: unpack a bounded group into full symmetric matrices, contract.
+void TCMatrix::fill_block_packed_dev(long long P0, long long nP, const double* packed_dev) {
+  XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill_block");
+  XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux, "bad aux block");
+  const long long ldt = round_up(n_basis, 2);
+  const long long full_slice = ldt * n_basis, pk_slice = n_basis * (n_basis + 1) / 2;
+  const long long sub_max = std::max<long long>(1, std::min<long long>(nP, (1LL << 26) / full_slice));
+  unpacked.ensure((size_t)(sub_max * full_slice));
+  for (long long p = 0; p < nP; p += sub_max) {
+    const long long cnt = std::min(sub_max, nP - p);
+    k_unpack_symmetric(unpacked.p, ldt, full_slice, packed_dev + p * pk_slice, pk_slice, (int)n_basis, (int)cnt,
+                       ctx->stream);
+    fill_block_dev(P0 + p, cnt, unpacked.p, ldt);
+  }
 }
 
 // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]; A rows-contiguous (j), B = R K-contiguous (column Q of R).
 void TCMatrix::rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
                              const double* R_dev, long long ldr) {
+  ProfScope prof(PROF_ROTATE);
   GemmParams g{};
   g.A = GemmOperand{M.p + (long long)m0 * slab + n0, 1, ldn, 0, slab};
   g.B = GemmOperand{R_dev, ldr, 1, 0, 0};
@@ -127,6 +183,7 @@ void TCMatrix::rotate(const double* R_dev, long long ldr) {
 void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
                      int n_omega, bool imag, double, double* out_dev) {
   Context* ctx = tc.ctx;
+  ProfScope prof(PROF_EPSILON);
   XTPB_REQUIRE(n_occ > 0 && n_occ < tc.ntotal && n_occ <= tc.mtotal, "RPA needs occupied and unoccupied levels");
   const int a0 = (int)(n_occ & ~1LL);          // 16-byte aligned start of the contraction range
   const int K = (int)(tc.ntotal - a0);
