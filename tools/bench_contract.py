@@ -102,11 +102,15 @@ def main():
     ap.add_argument("--naux", type=int, default=5500)
     ap.add_argument("--homo", type=int, default=179)
     ap.add_argument("--out", default="gpurun_out/contract_sweep.jsonl")
+    ap.add_argument("--only", default="", help="comma-separated shape names")
     args = ap.parse_args()
     ctx = api.Context(0)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
+        only = set(x for x in args.only.split(",") if x)
         for name, d, flops in shapes(args.nb, args.naux, args.homo):
+            if only and name not in only:
+                continue
             try:
                 ms = api.contract_bench(ctx, d, args.reps)
                 rec = {"shape": name, "M": d.M, "N": d.N, "K": d.K, "n_outer": d.n_outer, "n_batch": d.n_batch,
