@@ -121,7 +121,7 @@ class GwbseJob:
     def __init__(self, workload, device, rank=0, world=1, comm=None, e2e=True, seed=None):
         import torch
 
-        from xtp_b200 import api, synth
+        from xtp_b200 import api, dist, synth
         self.api, self.torch = api, torch
         self.sz = sz = synth.WORKLOADS[workload]
         self.workload = workload
@@ -133,6 +133,7 @@ class GwbseJob:
         self.vxc = synth.make_vxc(sz, rng)
         self.V = self._metric(sz.n_aux)
         self.ctx = api.Context(device)
+        dist.join_library_communicator(self.ctx, rank, world)     # NCCL communicator of the library (world > 1)
         self.tc = api.TCMatrix_gwbse(self.ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
         # synthetic AO three-centre tensor, packed lower triangles, generated on the device slice block by block
         nb = sz.n_basis
@@ -150,10 +151,8 @@ class GwbseJob:
         self.last = {}
 
     def _aux_range(self):
-        na = self.sz.n_aux
-        lo = na * self.rank // self.world
-        hi = na * (self.rank + 1) // self.world
-        return lo, hi
+        lo, cnt = self.tc.local_aux_range()       # canonical contiguous split of the aux functions over ranks
+        return lo, lo + cnt
 
     def _metric(self, na):
         """aux Coulomb metric A A^T / N + 1 (synth.make_aux_metric) -- built with torch on the GPU for speed."""
@@ -196,7 +195,13 @@ class GwbseJob:
         tc = self.tc
         tc.fill_begin(self.C)
         n_loc = self.p_hi - self.p_lo
-        if resident:
+        if self.world > 1:
+            # collective Fill3cMO: every rank contributes the slices of its aux range (device-resident or pinned host)
+            if resident:
+                tc.fill_sharded_packed(dev_ptr=self.ao_dev.data_ptr())
+            else:
+                tc.fill_sharded_packed(packed_local=self.ao_host.numpy())
+        elif resident:
             base = self.ao_dev.data_ptr()
             for p in range(0, n_loc, self.block):
                 cnt = min(self.block, n_loc - p)
@@ -296,21 +301,28 @@ def main():
         return
 
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: xtp_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        raise SystemExit("multi-GPU sharding is not wired into bench.py yet")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    from xtp_b200 import api, dist
+    rank, world, local = dist.init_process_group_from_env("nccl")
+    import torch.distributed as tdist
 
-    from xtp_b200 import api
     job = GwbseJob(args.workload, local, rank, world, e2e=not args.no_e2e)
     sz = job.sz
 
     def barrier():
         torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
 
     # timing rule: at least 3 untimed steps (XTPB_BENCH_MIN_WARMUP=0 only for runs under ncu, never a bench value)
     warmup = max(int(os.environ.get("XTPB_BENCH_MIN_WARMUP", "3")), args.warmup)
@@ -336,8 +348,8 @@ def main():
     barrier()
     e1.record()
     torch.cuda.synchronize()
-    host_s = time.perf_counter() - t_host
-    dev_ms = e0.elapsed_time(e1)
+    host_s = max_over_ranks(time.perf_counter() - t_host)
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = api.launch_count() - launches0
     api.profile_enable(False)
     prof = api.profile_summary()
@@ -381,6 +393,10 @@ def main():
     if "solver" in prof:
         other["cusolver"] = {"ms_per_step": round(prof["solver"]["ms"] / args.steps, 3),
                              "calls_per_step": prof["solver"]["launches"] / args.steps}
+    if "comm" in prof:      # NCCL collectives issued by the library on rank 0 (not counted in gpu_launches)
+        g = prof["comm"]
+        other["nccl"] = {"ms_per_step": round(g["ms"] / args.steps, 3), "calls_per_step": g["launches"] / args.steps,
+                         "payload_gb_per_step": round(g["work"] / args.steps * 1e-9, 3)}
 
     # e2e: host buffers in, host results out, through the public API
     e2e = None
@@ -392,13 +408,13 @@ def main():
         for _ in range(n_e2e):
             job.run(resident=False)
         barrier()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e_s = max_over_ranks(time.perf_counter() - t0) / n_e2e
         e2e = {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(job.h2d_bytes(False)),
                "d2h_bytes_per_step": int(job.d2h_bytes()), "steps": n_e2e,
                "stage_seconds": {k: round(v, 4) for k, v in job.last["stage_seconds"].items()}}
 
     cpu = None
-    if not args.no_cpu_baseline and rank == 0:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
         from oracle import cpu_reference as cr
         iters = int(job.last["davidson_iterations"])
         s = cr.sampled_step(sz, davidson_matmul_calls=iters)
@@ -415,6 +431,9 @@ def main():
             "config": {"workload": args.workload, "n_basis": sz.n_basis, "n_aux": sz.n_aux, "homo": sz.homo,
                        "mtotal": sz.mtotal, "qptotal": sz.qptotal, "bse_size": sz.bse_size, "nmax": NMAX,
                        "sigma": "ppm", "qp_solver": "grid(1001)", "bse": "singlets TDA, Davidson DPR tol 1e-4",
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"{world} ranks: tensor split over its second index (cyclic), Fill3cMO and "
+                                       f"BSE operator split over the aux index, NCCL all-reduce/all-gather"),
                        "l2": "inputs larger than L2 (AO tensor %.1f GB, M %.1f GB)" % (
                            sz.n_aux * job.pk * 8e-9, sz.mtotal * sz.n_aux * sz.ntotal * 8e-9)},
             "roofline": roofline, "other_kernels": other, "cpu_baseline": cpu, "e2e": e2e,

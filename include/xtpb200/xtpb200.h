@@ -47,6 +47,16 @@ int xtpb_ctx_sync(xtpb_ctx* ctx);
 /* seconds spent inside cuSOLVER eigh/inverse since the last reset (reported apart from contractions) */
 int xtpb_ctx_solver_seconds(xtpb_ctx* ctx, double* seconds, int reset);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink.  The reference has no distributed layer on this path (one
+ *      process, an OpenMP thread per GPU, host reductions: upstream xtp/src/libxtp/openmp_cuda.cc); here rank 0 obtains
+ *      a 128-byte id, the host program distributes it (torch.distributed, MPI, a file), and every rank joins BEFORE
+ *      creating its TCMatrix.  From then on every rank makes the same sequence of calls with the same host inputs
+ *      (the calls are collective); the tensor is distributed over its second index, the BSE operator over the
+ *      auxiliary index, and all results returned to the host are complete and identical on every rank. ---- */
+int xtpb_comm_unique_id(char* id_128);
+int xtpb_ctx_comm_init(xtpb_ctx* ctx, const char* id_128, int rank, int world);
+int xtpb_ctx_comm_info(xtpb_ctx* ctx, int* rank, int* world);
+
 /* pinned (page-locked) host memory for the caller's AO-integral and result buffers: H2D/D2H copies from it run
  * asynchronously at PCIe rate and overlap the contractions (xtpb_tc_fill_block*). */
 int xtpb_host_alloc(unsigned long long bytes, void** out);
@@ -56,7 +66,8 @@ int xtpb_host_free(void* p);
  *      Sigma_c kernels is bracketed by a CUDA-event pair on the launching stream.  Tags (xtpb_profile_get):
  *      0 other, 1 Fill3cMO, 2 aux rotation, 3 epsilon, 4 Sigma_x, 5 Sigma_c off-diagonal, 6 BSE matmul,
  *      7 Davidson projections, 8 small dense (PPM), 9 Sigma_c PPM grid kernel (work = pole evaluations),
- *      10 Sigma_c PPM pair kernel (work = bytes), 11 cuSOLVER, 12 AO unpack (work = bytes), 13 CDA, 14 exact.
+ *      10 Sigma_c PPM pair kernel (work = bytes), 11 cuSOLVER, 12 AO unpack (work = bytes), 13 CDA, 14 exact,
+ *      15 NCCL collectives (work = payload bytes).
  *      `work` is the summed algorithmic flop count (2MNK; MNK for lower-triangular outputs) unless noted. ---- */
 int xtpb_profile_enable(int on);
 int xtpb_profile_reset(void);
@@ -86,6 +97,11 @@ int xtpb_tc_fill_block_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const doub
  * PCIe / HBM bytes of the full symmetric slices */
 int xtpb_tc_fill_block_packed(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_packed_host);
 int xtpb_tc_fill_block_packed_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_packed_dev);
+/* collective Fill3cMO for world > 1 (also valid for world == 1): this rank passes the packed slices of ITS aux range
+ * [P0, P0+nP) = xtpb_tc_local_aux_range (naux*rank/world .. naux*(rank+1)/world), host (pinned) or device pointer.
+ * Half-transformed blocks are all-gathered over NVLink while the next block is being contracted. */
+int xtpb_tc_local_aux_range(xtpb_tc* tc, xtpb_index* P0, xtpb_index* nP);
+int xtpb_tc_fill_sharded_packed(xtpb_tc* tc, const double* ao3c_packed_local, int on_device);
 /* TCMatrix_gwbse::MultiplyRightWithAuxMatrix(matrix): matrix is auxsize x auxsize */
 int xtpb_tc_multiply_right_with_aux_matrix(xtpb_tc* tc, const double* A_host, xtpb_index lda);
 /* second half of TCMatrix_gwbse::Fill: AOCoulomb::Pseudo_InvSqrt_GWBSE(auxoverlap, etol) followed by

@@ -1,0 +1,146 @@
+"""world_size-2 `gloo` tests (CPU) of the multi-GPU host logic (xtp_b200/dist.py).
+
+The CUDA library distributes the tensor over its second index (cyclic) and the BSE operator over the aux index and
+all-reduces partial results.  Here two CPU processes replay exactly that partition with the numpy oracle and a gloo
+all-reduce / all-gather, and every rank must recover the unsharded oracle result -- this pins the index arithmetic
+(local column maps, local occupied counts, canonical aux ranges, the Fill3cMO gather schedule)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as tdist
+import torch.multiprocessing as mp
+
+from oracle import gwbse_oracle as orc
+from xtp_b200 import dist, synth
+
+
+def _allreduce(a):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).copy())
+    tdist.all_reduce(t)
+    return t.numpy()
+
+
+def _worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = dist.init_process_group_from_env("gloo")
+    assert (r, w) == (rank, world)
+    try:
+        sz = synth.Sizes(n_basis=23, n_aux=37, homo=4, qpmax=11, cmax=11)      # odd everywhere, ragged splits
+        prob = synth.make_problem(sz, seed=5)
+        e = prob["energies"][sz.rpamin:sz.rpamax + 1]
+        tc = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+        tc.Fill3cMO(prob["ao3c"], prob["C"])
+        M = tc.M                                                    # [m, P, n]
+        cols = dist.local_columns(sz.ntotal, rank, world)
+        n_occ = sz.n_occ
+        n_occ_loc = dist.n_local_below(n_occ, rank, world)
+        assert n_occ_loc == int((cols < n_occ).sum())
+        Ml, el = M[:, :, cols], e[cols]
+
+        # ---- Fill3cMO schedule: first half split over the aux index, all-gather, second half over local columns
+        lo, hi = dist.aux_range(sz.n_aux, rank, world)
+        Cm = prob["C"][:, sz.rpamin:sz.mmax + 1]
+        Cn = prob["C"][:, sz.rpamin + cols]
+        W_loc = np.einsum('pab,bm->pam', prob["ao3c"][lo:hi], Cm)           # T_P C_m for the local aux range
+        maxcnt = max(dist.aux_range(sz.n_aux, s, world)[1] - dist.aux_range(sz.n_aux, s, world)[0] for s in range(world))
+        pad = np.zeros((maxcnt,) + W_loc.shape[1:])
+        pad[:hi - lo] = W_loc
+        gathered = [torch.zeros(pad.shape, dtype=torch.float64) for _ in range(world)]
+        tdist.all_gather(gathered, torch.from_numpy(pad))
+        M_fill = np.zeros((sz.mtotal, sz.n_aux, len(cols)))
+        for s in range(world):
+            a, b = dist.aux_range(sz.n_aux, s, world)
+            M_fill[:, a:b, :] = np.einsum('an,pam->mpn', Cn, gathered[s].numpy()[:b - a])
+        np.testing.assert_allclose(M_fill, Ml, rtol=0, atol=1e-13)
+
+        # ---- epsilon: all occupied m (first index), local unoccupied a (second index), all-reduce
+        rpa = orc.RPA(tc)
+        rpa.configure(sz.homo, sz.rpamin, sz.rpamax)
+        rpa.setRPAInputEnergies(e)
+        for omega, imag in ((0.5, True), (0.0, False)):
+            part = np.zeros((sz.n_aux, sz.n_aux))
+            dE = el[n_occ_loc:][None, :] - e[:n_occ][:, None]
+            if imag:
+                d = 4.0 * dE / (dE * dE + omega * omega)
+            else:
+                d = 2.0 * ((dE - omega) / ((dE - omega) ** 2 + rpa.eta ** 2) + (dE + omega) / ((dE + omega) ** 2 + rpa.eta ** 2))
+            for m in range(n_occ):
+                A = Ml[m][:, n_occ_loc:]
+                part += (A * d[m][None, :]) @ A.T
+            eps = _allreduce(part) + np.eye(sz.n_aux)
+            full = rpa.calculate_epsilon_i(omega) if imag else rpa.calculate_epsilon_r(omega)
+            np.testing.assert_allclose(eps, full, rtol=0, atol=1e-12)
+
+        # ---- Sigma_x: partial sums over the local occupied second-index levels
+        gwopt = orc.GWOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax, qp_grid_steps=51)
+        sig = orc.Sigma_PPM(tc, rpa)
+        sig.configure(gwopt)
+        sx_full = sig.CalcExchangeMatrix()
+        q0, q = sz.qpmin - sz.rpamin, sz.qptotal
+        occ = Ml[q0:q0 + q][:, :, :n_occ_loc]
+        sx = _allreduce(-np.einsum('npm,kpm->nk', occ, occ))
+        np.testing.assert_allclose(sx, sx_full, rtol=0, atol=1e-12)
+
+        # ---- Sigma_c (PPM) diagonal: partial pole sums over the local columns with the local occupied count
+        sig.PrepareScreening()                        # rotates tc.M in place (identically on both ranks)
+        Ml = tc.M[:, :, cols]
+        fac, Om = sig._fac(), sig.ppm.ppm_freq
+        for level, freq in ((0, -0.6), (q - 1, 0.31)):
+            x = freq - el[None, :] + np.zeros((sz.n_aux, 1))
+            x[:, :n_occ_loc] += Om[:, None]
+            x[:, n_occ_loc:] -= Om[:, None]
+            g = orc.ppm_stabilized_inverse(x)
+            slab = Ml[q0 + level]
+            val = _allreduce(np.array([(fac[:, None] * g * slab * slab).sum()]))[0]
+            assert abs(val - sig.CalcCorrelationDiagElement(level, freq)) < 1e-12
+
+        # ---- BSE operator distributed over the aux index: Y = sum over ranks of the partial products
+        v0, c0 = sz.vmin - sz.rpamin, sz.homo + 1 - sz.rpamin
+        vt, ct = sz.vtotal, sz.ctotal
+        rng = np.random.default_rng(11)
+        X = rng.standard_normal((vt * ct, 3))
+        eps_inv = rng.uniform(0.3, 1.0, sz.n_aux)
+        P = slice(*dist.aux_range(sz.n_aux, rank, world))
+        Mf = tc.M
+        Mvc = Mf[v0:v0 + vt, P, c0:c0 + ct]
+        Mvv = Mf[v0:v0 + vt, P, v0:v0 + vt]
+        Mcc = Mf[c0:c0 + ct, P, c0:c0 + ct]
+        Xr = X.reshape(vt, ct, -1)
+        T = np.einsum('vpc,vck->pk', Mvc, Xr)
+        Yx = np.einsum('vpc,pk->vck', Mvc, T)
+        Yd = np.einsum('vpw,p,cpd,wdk->vck', Mvv, eps_inv[P], Mcc, Xr)
+        Y = _allreduce((2.0 * Yx - Yd).reshape(vt * ct, -1))
+        Mvc_f, Mvv_f, Mcc_f = Mf[v0:v0 + vt, :, c0:c0 + ct], Mf[v0:v0 + vt, :, v0:v0 + vt], Mf[c0:c0 + ct, :, c0:c0 + ct]
+        Hx = np.einsum('vpc,wpd->vcwd', Mvc_f, Mvc_f).reshape(vt * ct, vt * ct)
+        Hd = np.einsum('vpw,p,cpd->vcwd', Mvv_f, eps_inv, Mcc_f).reshape(vt * ct, vt * ct)
+        np.testing.assert_allclose(Y, (2.0 * Hx - Hd) @ X, rtol=0, atol=1e-11)
+        results[rank] = "ok"
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        results[rank] = traceback.format_exc() + str(exc)
+    finally:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+def test_partition_helpers():
+    for n, world in ((23, 2), (7, 3), (1860, 8), (5, 5)):
+        seen = np.concatenate([dist.local_columns(n, r, world) for r in range(world)])
+        assert sorted(seen) == list(range(n))
+        for g in (0, 1, n // 2, n):
+            assert sum(dist.n_local_below(g, r, world) for r in range(world)) == g
+        edges = [dist.aux_range(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n and all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+
+
+@pytest.mark.timeout(300)
+def test_sharded_pipeline_world2_gloo():
+    world = 2
+    port = 29500 + os.getpid() % 400
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+        assert dict(results) == {0: "ok", 1: "ok"}, dict(results)

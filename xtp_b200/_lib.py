@@ -62,6 +62,9 @@ PROTOTYPES = {
     "xtpb_ctx_destroy": (C.c_int, [vp]),
     "xtpb_ctx_sync": (C.c_int, [vp]),
     "xtpb_ctx_solver_seconds": (C.c_int, [vp, dptr, C.c_int]),
+    "xtpb_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "xtpb_ctx_comm_init": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int]),
+    "xtpb_ctx_comm_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "xtpb_host_alloc": (C.c_int, [C.c_ulonglong, C.POINTER(vp)]),
     "xtpb_host_free": (C.c_int, [vp]),
     "xtpb_profile_enable": (C.c_int, [C.c_int]),
@@ -77,6 +80,8 @@ PROTOTYPES = {
     "xtpb_tc_fill_block_dev": (C.c_int, [vp, idx, idx, vp, idx]),
     "xtpb_tc_fill_block_packed": (C.c_int, [vp, idx, idx, vp]),
     "xtpb_tc_fill_block_packed_dev": (C.c_int, [vp, idx, idx, vp]),
+    "xtpb_tc_local_aux_range": (C.c_int, [vp, iptr, iptr]),
+    "xtpb_tc_fill_sharded_packed": (C.c_int, [vp, vp, C.c_int]),
     "xtpb_tc_multiply_right_with_aux_matrix": (C.c_int, [vp, dptr, idx]),
     "xtpb_tc_apply_coulomb_metric": (C.c_int, [vp, dptr, idx, dptr, idx, C.c_double, iptr]),
     "xtpb_rpa_epsilon": (C.c_int, [vp, dptr, idx, idx, idx, C.c_double, dptr, C.c_int, C.c_int, dptr]),

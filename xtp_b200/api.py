@@ -45,6 +45,16 @@ class Context:
     def sync(self):
         check(_lib.lib().xtpb_ctx_sync(self._h))
 
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Join the NCCL communicator (one process per GPU); must precede TCMatrix_gwbse.Initialize."""
+        assert len(unique_id) == 128
+        check(_lib.lib().xtpb_ctx_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(world)))
+
+    def comm_info(self):
+        r, w = C.c_int(0), C.c_int(1)
+        check(_lib.lib().xtpb_ctx_comm_info(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
     def solver_seconds(self, reset=False):
         s = C.c_double()
         check(_lib.lib().xtpb_ctx_solver_seconds(self._h, C.byref(s), int(reset)))
@@ -53,6 +63,13 @@ class Context:
 
 def launch_count():
     return int(_lib.lib().xtpb_launch_count())
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on rank 0, distribute to every rank, then Context.comm_init)."""
+    buf = C.create_string_buffer(128)
+    check(_lib.lib().xtpb_comm_unique_id(buf))
+    return buf.raw
 
 
 class PinnedBuffer:
@@ -79,7 +96,7 @@ class PinnedBuffer:
 
 PROFILE_TAGS = {"other": 0, "fill": 1, "rotate": 2, "epsilon": 3, "sigma_x": 4, "sigma_offdiag": 5, "bse_matmul": 6,
                 "davidson": 7, "dense_aux": 8, "sigma_ppm_grid": 9, "sigma_ppm_pairs": 10, "solver": 11,
-                "unpack": 12, "cda": 13, "exact": 14}
+                "unpack": 12, "cda": 13, "exact": 14, "comm": 15}
 CONTRACTION_TAGS = ("other", "fill", "rotate", "epsilon", "sigma_x", "sigma_offdiag", "bse_matmul", "davidson",
                     "dense_aux", "cda", "exact")
 
@@ -182,6 +199,20 @@ class TCMatrix_gwbse:
 
     def fill_block_packed_dev(self, P0, nP, dev_ptr):
         check(_lib.lib().xtpb_tc_fill_block_packed_dev(self._h, int(P0), int(nP), vp(int(dev_ptr))))
+
+    def local_aux_range(self):
+        """(P0, nP): the aux functions whose AO slices this rank contributes to the collective fill."""
+        p0, n = idx(0), idx(0)
+        check(_lib.lib().xtpb_tc_local_aux_range(self._h, C.byref(p0), C.byref(n)))
+        return int(p0.value), int(n.value)
+
+    def fill_sharded_packed(self, packed_local=None, dev_ptr=None):
+        """Collective Fill3cMO: packed lower-triangular slices of this rank's aux range (host array or device pointer)."""
+        if dev_ptr is not None:
+            check(_lib.lib().xtpb_tc_fill_sharded_packed(self._h, vp(int(dev_ptr)), 1))
+        else:
+            assert packed_local.dtype == np.float64 and packed_local.flags.c_contiguous
+            check(_lib.lib().xtpb_tc_fill_sharded_packed(self._h, vp(packed_local.ctypes.data), 0))
 
     def fill_block(self, P0, blk, ld=None):
         blk = np.ascontiguousarray(blk, dtype=np.float64)

@@ -73,7 +73,7 @@ BSE::BSE(Context* c, TCMatrix* t, const xtpb_bse_options& o, const double* rpa_e
 std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e) {
   TCMatrix* tc = b.tc;
   Context* ctx = b.ctx;
-  const long long na = tc->naux, rpatotal = tc->ntotal;
+  const long long na = tc->naux, rpatotal = tc->ntotal_glob;
   DBuf e_dev((size_t)rpatotal), lam((size_t)na);
   ctx->h2d(e_dev.p, rpa_e, (size_t)rpatotal);
   auto U = std::make_unique<DBuf>((size_t)(na * na));
@@ -99,10 +99,16 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
   vt = homo - vmin + 1;
   ct = cmax - homo;
   size = vt * ct;
-  naux = tc->naux;
+  // Multi-GPU: the operator is sharded over the auxiliary index (every term of H X is a sum over P); this rank
+  // keeps the windows for P in [P0, P0 + naux) and matmul/diagonal all-reduce their partial results.
+  const int world = ctx->world;
+  const long long naux_glob = tc->naux;
+  const long long P0 = naux_glob * ctx->rank / world;
+  naux = naux_glob * (ctx->rank + 1) / world - P0;
+  XTPB_REQUIRE(naux > 0, "fewer auxiliary functions than ranks");
   const int v0 = (int)(vmin - rpamin), c0 = (int)(homo + 1 - rpamin);
-  eps_inv_dev.alloc((size_t)naux);
-  ctx->h2d(eps_inv_dev.p, eps_inv_host, (size_t)naux);
+  eps_inv_dev.alloc((size_t)naux_glob);
+  ctx->h2d(eps_inv_dev.p, eps_inv_host, (size_t)naux_glob);
   const long long hs = vt + ct;
   hqp_dev.alloc((size_t)(hs * hs));
   ctx->h2d_2d(hqp_dev.p, hs, hqp_host, ldh, hs, hs);
@@ -112,20 +118,40 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
   // rotation matrix with eps_inv folded into its columns, for the windows that carry the screening
   DBuf Rs;
   if (R_dev && (cd || cd2)) {
-    Rs.alloc((size_t)(naux * naux));
-    XTPB_CUDA(cudaMemcpyAsync(Rs.p, R_dev, (size_t)(naux * naux) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_scale_columns(Rs.p, (int)naux, (int)naux, naux, eps_inv_dev.p, ctx->stream);
+    Rs.alloc((size_t)(naux_glob * naux_glob));
+    XTPB_CUDA(cudaMemcpyAsync(Rs.p, R_dev, (size_t)(naux_glob * naux_glob) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_scale_columns(Rs.p, (int)naux_glob, (int)naux_glob, naux_glob, eps_inv_dev.p, ctx->stream);
   }
   auto window = [&](DBuf& dst, long long& ld, long long& sl, int m0, int mcnt, int n0, int ncnt, bool screened) {
     ld = round_up(ncnt, 2);
     sl = naux * ld;
     dst.alloc((size_t)(sl * mcnt));
     dst.zero(ctx->stream);
-    if (R_dev)
-      tc->rotate_window(dst.p, ld, sl, m0, mcnt, n0, ncnt, screened ? Rs.p : R_dev, naux);
-    else
-      k_extract_window(dst.p, ld, sl, tc->M.p, tc->ldn, tc->slab, m0, mcnt, n0, ncnt, (int)naux,
-                       screened ? eps_inv_dev.p : nullptr, ctx->stream);
+    if (world == 1) {
+      if (R_dev)
+        tc->rotate_window(dst.p, ld, sl, m0, mcnt, n0, ncnt, screened ? Rs.p : R_dev, naux);
+      else
+        k_extract_window(dst.p, ld, sl, tc->M.p, tc->ldn, tc->slab, m0, mcnt, n0, ncnt, (int)naux,
+                         screened ? eps_inv_dev.p : nullptr, ctx->stream);
+      return;
+    }
+    // re-shard: the tensor is distributed over the second index, the operator over P.  Rotate / extract the local
+    // columns of the window for all P, all-gather the (small) window, keep this rank's P range.
+    const long long jl0 = tc->nloc_below(n0), cl = tc->nloc_below(n0 + ncnt) - jl0;
+    const long long ldl = round_up((ncnt + world - 1) / world + 1, 2), lslab = naux_glob * ldl;
+    DBuf loc((size_t)(lslab * mcnt)), G((size_t)(lslab * mcnt * world));
+    loc.zero(ctx->stream);
+    if (cl > 0) {
+      if (R_dev)
+        tc->rotate_window(loc.p, ldl, lslab, m0, mcnt, (int)jl0, (int)cl, screened ? Rs.p : R_dev, naux_glob);
+      else
+        k_extract_window(loc.p, ldl, lslab, tc->M.p, tc->ldn, tc->slab, m0, mcnt, (int)jl0, (int)cl, (int)naux_glob,
+                         screened ? eps_inv_dev.p : nullptr, ctx->stream);
+    }
+    ctx->allgather(loc.p, G.p, (size_t)(lslab * mcnt));
+    k_window_from_gathered(dst.p, ld, sl, G.p, ldl, mcnt, (int)naux_glob, (int)P0, (int)naux, n0, ncnt, world,
+                           ctx->stream);
+    ctx->sync();   // loc / G are freed on return
   };
   ldvc = slabvc = ldvv = slabvv = ldcc = slabcc = ldcv = slabcv = 0;
   if (cx || cd2) window(Mvc, ldvc, slabvc, v0, (int)vt, c0, (int)ct, false);
@@ -138,8 +164,10 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
 }
 
 void BseOperator::diagonal_dev(double* d) {
+  // partial sums over the local aux range; the P-independent Hqp part is contributed by rank 0 only
   k_bse_diagonal(d, (int)vt, (int)ct, (int)naux, Mvc.p, ldvc, slabvc, Mvv.p, ldvv, slabvv, Mcc.p, ldcc, slabcc, Mcv.p,
-                 ldcv, slabcv, eps_inv_dev.p, hqp_diag_dev.p, cqp, cx, cd, cd2, ctx->stream);
+                 ldcv, slabcv, eps_inv_dev.p, hqp_diag_dev.p, ctx->rank == 0 ? cqp : 0, cx, cd, cd2, ctx->stream);
+  ctx->allreduce_sum(d, (size_t)size);
 }
 
 void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, long long ldy) {
@@ -152,7 +180,7 @@ void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, l
 
   XTPB_REQUIRE(k <= 8192, "more than 8192 trial vectors per matmul are not supported");
 
-  if (cqp) {
+  if (cqp && ctx->rank == 0) {   // P-independent term: one rank contributes it, the all-reduce below spreads it
     // Y_k(c,v) = cqp * sum_c2 Hc(c,c2) X_k(c2,v)          (Hqp symmetric: K-contiguous view of the cc block)
     GemmParams g{};
     g.A = GemmOperand{hqp_dev.p + vt + vt * hs, hs, 1, 0, 0};
@@ -242,6 +270,8 @@ void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, l
     }
   }
   if (first) XTPB_CUDA(cudaMemset2DAsync(Y, ldy * 8, 0, size * 8, k, st));   // all coefficients zero
+  // one all-reduce of Y per matmul (C60, k = 15: 3.9 MB); Y columns are ldy apart, padding rows ride along
+  ctx->allreduce_sum(Y, (size_t)(ldy * (k - 1) + size));
 }
 
 // ------------------------------------------------------------------ dense operator (Davidson tests)

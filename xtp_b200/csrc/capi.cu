@@ -31,6 +31,24 @@ int xtpb_ctx_sync(xtpb_ctx* ctx) {
   ctx->impl.sync();
   XTPB_API_END
 }
+int xtpb_comm_unique_id(char* id_128) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(id_128 != nullptr, "null output pointer");
+  comm_unique_id(id_128);
+  XTPB_API_END
+}
+int xtpb_ctx_comm_init(xtpb_ctx* ctx, const char* id_128, int rank, int world) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(ctx && id_128, "null pointer");
+  ctx->impl.comm_init(id_128, rank, world);
+  XTPB_API_END
+}
+int xtpb_ctx_comm_info(xtpb_ctx* ctx, int* rank, int* world) {
+  XTPB_API_BEGIN
+  if (rank) *rank = ctx->impl.rank;
+  if (world) *world = ctx->impl.world;
+  XTPB_API_END
+}
 int xtpb_host_alloc(unsigned long long bytes, void** out) {
   XTPB_API_BEGIN
   XTPB_REQUIRE(out != nullptr, "null output pointer");
@@ -83,7 +101,7 @@ int xtpb_tc_sizes(const xtpb_tc* tc, xtpb_index* auxsize, xtpb_index* msize, xtp
   XTPB_API_BEGIN
   if (auxsize) *auxsize = tc->impl.naux;
   if (msize) *msize = tc->impl.mtotal;
-  if (nsize) *nsize = tc->impl.ntotal;
+  if (nsize) *nsize = tc->impl.ntotal_glob;
   XTPB_API_END
 }
 int xtpb_tc_set_raw(xtpb_tc* tc, const double* M_host) {
@@ -115,6 +133,19 @@ int xtpb_tc_fill_block_packed(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const d
 int xtpb_tc_fill_block_packed_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_packed_dev) {
   XTPB_API_BEGIN
   tc->impl.fill_block_packed_dev(P0, nP, ao3c_packed_dev);
+  XTPB_API_END
+}
+int xtpb_tc_local_aux_range(xtpb_tc* tc, xtpb_index* P0, xtpb_index* nP) {
+  XTPB_API_BEGIN
+  long long lo, hi;
+  tc->impl.aux_range(tc->impl.rank, lo, hi);
+  if (P0) *P0 = lo;
+  if (nP) *nP = hi - lo;
+  XTPB_API_END
+}
+int xtpb_tc_fill_sharded_packed(xtpb_tc* tc, const double* ao3c_packed_local, int on_device) {
+  XTPB_API_BEGIN
+  tc->impl.fill_sharded_packed(ao3c_packed_local, on_device != 0);
   XTPB_API_END
 }
 int xtpb_tc_fill_block_dev(xtpb_tc* tc, xtpb_index P0, xtpb_index nP, const double* ao3c_dev, xtpb_index ld_ao) {

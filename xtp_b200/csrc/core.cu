@@ -36,6 +36,7 @@ Context::Context(int dev) : device(dev) {
 }
 
 Context::~Context() {
+  comm_destroy();
   if (solver) cusolverDnDestroy(solver);
   if (dev_info) cudaFree(dev_info);
   if (ev0) cudaEventDestroy(ev0);

@@ -20,6 +20,7 @@ GW::GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host
   qptotal = o.qpmax - o.qpmin + 1;
   rpatotal = o.rpamax - o.rpamin + 1;
   n_occ = o.homo - o.rpamin + 1;
+  n_occ_loc = t->nloc_below(n_occ);
   q0 = o.qpmin - o.rpamin;
   dft_energies.assign(e, e + ne);
   vxc.resize((size_t)(qptotal * qptotal));
@@ -35,6 +36,7 @@ GW::GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host
 void GW::set_rpa_energies(const double* e) {
   rpa_energies.assign(e, e + rpatotal);
   ctx->h2d(energies_dev.p, rpa_energies.data(), (size_t)rpatotal);
+  e_loc = tc->local_energies(energies_dev.p, energies_loc_dev);
   ctx->sync();
 }
 
@@ -46,9 +48,11 @@ void GW::exchange(double* out_host) {
   g.A = GemmOperand{tc->slab_ptr(q0), tc->slab, 1, tc->ldn, 0};
   g.B = g.A;
   g.C = S.p; g.c_sm = 1; g.c_sn = qptotal;
-  g.M = (int)qptotal; g.N = (int)qptotal; g.K = (int)n_occ; g.n_outer = (int)tc->naux; g.n_batch = 1;
+  g.M = (int)qptotal; g.N = (int)qptotal; g.K = (int)n_occ_loc; g.n_outer = (int)tc->naux; g.n_batch = 1;
   g.alpha = -1.0; g.beta = 0.0; g.lower = 1;
-  contract(g, ctx->ws, ctx->stream);
+  if (n_occ_loc > 0) contract(g, ctx->ws, ctx->stream);
+  else S.zero(ctx->stream);
+  ctx->allreduce_sum(S.p, (size_t)(qptotal * qptotal));     // partial sums over the local occupied levels
   symmetrize_from_lower(S.p, (int)qptotal, qptotal, 0.0, ctx->stream);
   ctx->d2h(out_host, S.p, (size_t)(qptotal * qptotal));
 }
@@ -138,8 +142,9 @@ void GW::sigma_c_diag_elements(long long n, const long long* levels, const doubl
     double* partial = der + n + (n + 1) / 2 + 1;
     ctx->h2d(om, freqs, (size_t)n);
     XTPB_CUDA(cudaMemcpyAsync(sl, slabs.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    k_sigma_ppm_pairs(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ, energies_dev.p,
+    k_sigma_ppm_pairs(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ_loc, e_loc,
                       ppm_freq_dev.p, ppm_fac_dev.p, sl, om, (int)n, val, der, partial, ctx->stream);
+    ctx->allreduce_sum(val, (size_t)(2 * n));               // values and derivatives are adjacent
     ctx->d2h(values, val, (size_t)n);
     if (derivs) ctx->d2h(derivs, der, (size_t)n);
     return;
@@ -165,9 +170,10 @@ void GW::grid_scan(const std::vector<double>& f0, std::vector<double>& values) {
     int* sl = reinterpret_cast<int*>(om + qptotal);
     ctx->h2d(om, om0.data(), (size_t)qptotal);
     XTPB_CUDA(cudaMemcpyAsync(sl, slabs.data(), (size_t)qptotal * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    k_sigma_ppm_grid(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ, energies_dev.p,
+    k_sigma_ppm_grid(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ_loc, e_loc,
                      ppm_freq_dev.p, ppm_fac_dev.p, sl, om, opt.qp_grid_spacing, (int)steps, (int)qptotal, val,
                      ctx->stream);
+    ctx->allreduce_sum(val, (size_t)(qptotal * steps));
     ctx->d2h(values.data(), val, (size_t)(qptotal * steps));
     return;
   }
@@ -396,8 +402,8 @@ void GW::sigma_c_offdiag(const double* freqs, double* out_host) {
   ctx->h2d(om.p, freqs, (size_t)q);
   for (long long p0 = 0; p0 < na; p0 += pchunk) {
     const long long pc = std::min(pchunk, na - p0);
-    k_sigma_ppm_weighted_slab(W.p, tc->M.p, ldn, tc->slab, (int)tc->ntotal, (int)p0, (int)pc, (int)n_occ,
-                              energies_dev.p, ppm_freq_dev.p, ppm_fac_dev.p, (int)q0, (int)q, om.p, ctx->stream);
+    k_sigma_ppm_weighted_slab(W.p, tc->M.p, ldn, tc->slab, (int)tc->ntotal, (int)p0, (int)pc, (int)n_occ_loc,
+                              e_loc, ppm_freq_dev.p, ppm_fac_dev.p, (int)q0, (int)q, om.p, ctx->stream);
     GemmParams g{};
     g.A = GemmOperand{W.p, pc * ldn, 1, ldn, 0};
     g.B = GemmOperand{tc->slab_ptr(q0) + p0 * ldn, tc->slab, 1, ldn, 0};
@@ -406,6 +412,7 @@ void GW::sigma_c_offdiag(const double* freqs, double* out_host) {
     g.alpha = 1.0; g.beta = p0 == 0 ? 0.0 : 1.0;
     contract(g, ctx->ws, ctx->stream);
   }
+  ctx->allreduce_sum(S.p, (size_t)(q * q));
   std::vector<double> s((size_t)(q * q));
   ctx->d2h(s.data(), S.p, (size_t)(q * q));
   for (long long j = 0; j < q; ++j)

@@ -24,6 +24,11 @@ struct Context {
   double solver_seconds = 0.0;
   int solver_prof_slot = -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // multi-GPU: one process per GPU, this context is rank `rank` of `world` (comm.cu).  world == 1: no collectives.
+  int rank = 0, world = 1;
+  void* nccl = nullptr;         // ncclComm_t
+  cudaStream_t comm_stream = nullptr;
+  double comm_seconds = 0.0;    // not timed per call; collectives are stream-ordered
 
   explicit Context(int dev);
   ~Context();
@@ -48,11 +53,17 @@ struct Context {
   void general_inverse(int n, double* A, long long lda, double* Ainv, long long ldi);   // A destroyed
   void solver_begin();
   void solver_end();
+  // collectives on `st` (default: the compute stream), FP64, in place; no-ops when world == 1
+  void comm_init(const char* unique_id_128, int rank_, int world_);
+  void comm_destroy();
+  void allreduce_sum(double* buf, size_t count, cudaStream_t st = nullptr);
+  void allgather(const double* send, double* recv, size_t count_per_rank, cudaStream_t st = nullptr);
 };
+void comm_unique_id(char* out_128);
 
 // ---------------------------------------------------------------- small kernels (kernels.cu)
-void k_chi0_weights(double* d, const double* energies, int n_occ, int a0, int K, const double* omegas, int n_omega,
-                    bool imag, double eta, double gamma_extra, cudaStream_t s);
+void k_chi0_weights(double* d, const double* e_m, const double* e_n, int n_occ, int n_occ_n, int a0, int K,
+                    const double* omegas, int n_omega, bool imag, double eta, cudaStream_t s);
 void k_set_identity(double* A, int n, long long ld, cudaStream_t s);
 void k_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s);
 void k_scale_columns(double* A, int rows, int cols, long long ld, const double* scale, cudaStream_t s);  // A(:,j)*=scale[j]
@@ -87,12 +98,29 @@ void k_unit_vectors(double* V, long long ld, long long n, const long long* idx, 
 // full[b](mu,nu) = full[b](nu,mu) = packed[b][mu(mu+1)/2 + nu] (nu <= mu), b < count
 void k_unpack_symmetric(double* full, long long ld, long long full_slice, const double* packed, long long pk_slice,
                         int n, int count, cudaStream_t s);
+// dst[j] = src[first + j*stride], j < n  /  dst[first + j*stride] = src[j]
+void k_gather_strided(double* dst, const double* src, long long first, long long stride, long long n, cudaStream_t s);
+// cyclic column maps between a full row layout (ld_full, global columns) and a local one (ld_loc): rows = naux*count
+void k_cols_full_to_local(double* loc, long long ld_loc, const double* full, long long ld_full, long long rows,
+                          long long ncols_loc, int rank, int world, cudaStream_t s);
+void k_cols_local_to_full(double* full, long long ld_full, const double* loc, long long ld_loc, long long rows,
+                          long long ncols_loc, int rank, int world, cudaStream_t s);
+// BSE window re-shard: dst[i][Ql][j] = G[s(j)][i][P0+Ql][jl(j)], gathered blocks of [mcnt][naux][ldl]
+void k_window_from_gathered(double* dst, long long dst_ld, long long dst_slab, const double* G, long long ldl,
+                            int mcnt, int naux, int P0, int pcnt, int n0, int ncnt, int world, cudaStream_t s);
 
 // ---------------------------------------------------------------- TCMatrix_gwbse
 struct TCMatrix {
   Context* ctx;
   long long naux, mmin, mmax, nmin, nmax, mtotal, ntotal;
   long long ldn, slab;          // device layout [m][P][ldn], ldn = ntotal rounded up to even
+  // Multi-GPU: the second index is distributed cyclically, rank r holds the columns n = r, r + world, ... of
+  // nmin..nmax.  `ntotal` is the LOCAL column count (== ntotal_glob when world == 1); every stage that sums over
+  // the second index produces a partial result that is all-reduced.
+  int rank = 0, world = 1;
+  long long ntotal_glob;
+  long long nloc_below(long long g) const { return g > rank ? (g - rank + world - 1) / world : 0; }
+  long long nglob(long long jl) const { return rank + jl * world; }
   DBuf M;
   // Fill state
   long long n_basis = 0, ldc = 0;
@@ -109,6 +137,12 @@ struct TCMatrix {
   void fill_block_dev(long long P0, long long nP, const double* ao_dev, long long ld_ao);
   void fill_block_host(long long P0, long long nP, const double* ao_host, long long ld_ao, bool packed);
   void fill_block_packed_dev(long long P0, long long nP, const double* packed_dev);
+  // collective Fill3cMO: this rank contributes the packed AO slices of its canonical aux range
+  // [naux*rank/world, naux*(rank+1)/world) (host or device pointer); half-transformed blocks are all-gathered
+  void fill_sharded_packed(const double* packed, bool on_device);
+  void aux_range(int r, long long& lo, long long& hi) const { lo = naux * r / world; hi = naux * (r + 1) / world; }
+  // energies of the local second-index columns (returns e_glob_dev itself when world == 1)
+  const double* local_energies(const double* e_glob_dev, DBuf& tmp);
   ~TCMatrix();
   TCMatrix(TCMatrix&&) = delete;
   // M[m] <- M[m] * R for all m (R on the device, naux x naux, ld = ldr)
@@ -128,6 +162,9 @@ struct GW {
   TCMatrix* tc;
   xtpb_gw_options opt;
   long long qptotal, rpatotal, n_occ, q0;     // q0 = qpmin - rpamin (slab offset of gw level 0)
+  long long n_occ_loc = 0;                    // occupied levels among this rank's second-index columns
+  DBuf energies_loc_dev;                      // RPA energies of the local columns (multi-GPU only)
+  const double* e_loc = nullptr;              // == energies_dev.p on a single GPU
   std::vector<double> vxc, dft_energies, rpa_energies, sigma_x, sigma_c;   // host copies (q x q col-major)
   DBuf energies_dev;
   bool screening_ready = false;

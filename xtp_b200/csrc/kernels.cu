@@ -43,19 +43,43 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return r;
 }
 
+// FP64 reciprocal without the library slow path: MUFU.RCP64H seed (rel. error <= 2^-23, PTX rcp.approx.ftz.f64)
+// refined by one cubic step r(1 + e + e^2), e = 1 - x r  ->  rel. error ~2^-69 + rounding (3 DFMA, <= 2 ulp).
+// Valid for finite normal x; x = 0 gives inf (callers route |x| < 0.25 through the damped branch).
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
+}
+
+// damped branch of the Rohlfing-stabilised inverse: 0.5 (1 - cos 4 pi x) / x = sin^2(2 pi x) / x  (no cancellation);
+// Taylor limit 4 pi^2 x below the range where 1/x is finite.
+__device__ __noinline__ double ppm_ginv_damped(double x) {
+  if (fabs(x) < 1e-100) return (0.25 * kFourPi * kFourPi) * x;
+  const double s = sinpi(2.0 * x);
+  return s * s * rcp_fast(x);
+}
+
+// |x| < 0.25, read from the exponent word on the integer pipe (the FP64 pipe only carries subtract/refine/accumulate)
+__device__ __forceinline__ bool ppm_in_window(double x) {
+  return (static_cast<unsigned>(__double2hiint(x)) & 0x7fffffffu) < 0x3fd00000u;
+}
+
 // Rohlfing-stabilised inverse, upstream Sigma_PPM::Stabilize (sigma_ppm.cc): 1/x for |x| >= 0.25,
 // 0.5 (1 - cos 4 pi x) / x otherwise (-> 0 at x = 0).
 __device__ __forceinline__ double ppm_ginv(double x) {
-  const double ax = fabs(x);
-  if (ax >= 0.25) return 1.0 / x;
-  if (x == 0.0) return 0.0;
-  return 0.5 * (1.0 - cos(kFourPi * x)) / x;
+  return ppm_in_window(x) ? ppm_ginv_damped(x) : rcp_fast(x);
 }
 
 // ------------------------------------------------------------------ chi0 weights
 // d[w][m][k], k <-> level a = a0 + k (relative to rpamin); zero for a < n_occ (alignment padding).
 // Upstream: the `denom` vector of RPA::calculate_epsilon<imag> (rpa.cc).
-__global__ void chi0_weights_kernel(double* __restrict__ d, const double* __restrict__ e, int n_occ, int a0, int K,
+// e_m: energies by first index (all levels); e_n: energies of the second-index columns held by this rank
+// (n_occ_n of them occupied); identical arrays on a single GPU.
+__global__ void chi0_weights_kernel(double* __restrict__ d, const double* __restrict__ e_m,
+                                    const double* __restrict__ e_n, int n_occ, int n_occ_n, int a0, int K,
                                     const double* __restrict__ omegas, int n_omega, int imag, double eta) {
   const long long total = (long long)n_omega * n_occ * K;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -65,8 +89,8 @@ __global__ void chi0_weights_kernel(double* __restrict__ d, const double* __rest
     const int w = (int)(idx / ((long long)K * n_occ));
     const int a = a0 + k;
     double v = 0.0;
-    if (a >= n_occ) {
-      const double dE = e[a] - e[m];
+    if (a >= n_occ_n) {
+      const double dE = e_n[a] - e_m[m];
       const double om = omegas[w];
       if (imag) {
         v = 4.0 * dE / (dE * dE + om * om);
@@ -217,8 +241,23 @@ __global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
 #pragma unroll 4
       for (int t = 0; t < cnt; ++t) {
         const double2 el = tile[t];
+        // branch-free fast path for the NW frequencies of this thread (independent chains); poles inside the
+        // damping window contribute 0 here and are added by the rare branch below
+        double x[kGridNW];
+        bool any = false;
 #pragma unroll
-        for (int w = 0; w < kGridNW; ++w) acc[w] += el.x * ppm_ginv(om[w] - el.y);
+        for (int w = 0; w < kGridNW; ++w) {
+          x[w] = om[w] - el.y;
+          const bool win = ppm_in_window(x[w]);
+          const double r = rcp_fast(x[w]);
+          acc[w] = fma(el.x, win ? 0.0 : r, acc[w]);
+          any |= win;
+        }
+        if (any) {
+#pragma unroll
+          for (int w = 0; w < kGridNW; ++w)
+            if (ppm_in_window(x[w])) acc[w] = fma(el.x, ppm_ginv_damped(x[w]), acc[w]);
+        }
       }
     }
   }
@@ -420,14 +459,54 @@ __global__ void unit_vectors_kernel(double* V, long long ld, const long long* __
   if (c < cols) V[idx[c] + (long long)c * ld] = 1.0;
 }
 
+
+// ------------------------------------------------------------------ multi-GPU index maps (cyclic second index)
+__global__ void gather_strided_kernel(double* __restrict__ dst, const double* __restrict__ src, long long first,
+                                      long long stride, long long n) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+    dst[j] = src[first + j * stride];
+}
+template <bool TO_LOCAL>
+__global__ void cyclic_cols_kernel(double* __restrict__ dst, long long ld_dst, const double* __restrict__ src,
+                                   long long ld_src, long long rows, long long ncols_loc, int rank, int world) {
+  const long long total = rows * ncols_loc;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long jl = idx % ncols_loc, r = idx / ncols_loc;
+    const long long g = rank + jl * world;
+    if (TO_LOCAL) dst[r * ld_dst + jl] = src[r * ld_src + g];
+    else dst[r * ld_dst + g] = src[r * ld_src + jl];
+  }
+}
+// dst[i][Ql][j] <- G[s][i][P0+Ql][jl], global column g = n0 + j held by rank s = g % world at local window
+// position jl = g / world - (first local column of s inside the window)
+__global__ void window_from_gathered_kernel(double* __restrict__ dst, long long dst_ld, long long dst_slab,
+                                            const double* __restrict__ G, long long ldl, int mcnt, int naux, int P0,
+                                            int pcnt, int n0, int ncnt, int world) {
+  const long long total = (long long)mcnt * pcnt * ncnt;
+  const long long block = (long long)mcnt * naux * ldl;      // one rank's gathered block
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % ncnt);
+    const int Ql = (int)((idx / ncnt) % pcnt);
+    const int i = (int)(idx / ((long long)ncnt * pcnt));
+    const int g = n0 + j;
+    const int s = g % world;
+    const int first = n0 > s ? (n0 - s + world - 1) / world : 0;
+    const int jl = g / world - first;
+    dst[(long long)i * dst_slab + (long long)Ql * dst_ld + j] =
+        G[(long long)s * block + ((long long)i * naux + P0 + Ql) * ldl + jl];
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ host wrappers
-void k_chi0_weights(double* d, const double* energies, int n_occ, int a0, int K, const double* omegas_dev, int n_omega,
-                    bool imag, double eta, double, cudaStream_t s) {
+void k_chi0_weights(double* d, const double* e_m, const double* e_n, int n_occ, int n_occ_n, int a0, int K,
+                    const double* omegas_dev, int n_omega, bool imag, double eta, cudaStream_t s) {
   const long long total = (long long)n_omega * n_occ * K;
-  chi0_weights_kernel<<<blocks_for(total, 256, 4096), 256, 0, s>>>(d, energies, n_occ, a0, K, omegas_dev, n_omega,
-                                                                   imag ? 1 : 0, eta);
+  chi0_weights_kernel<<<blocks_for(total, 256, 4096), 256, 0, s>>>(d, e_m, e_n, n_occ, n_occ_n, a0, K, omegas_dev,
+                                                                   n_omega, imag ? 1 : 0, eta);
   LAUNCH_CHECK();
 }
 void k_set_identity(double* A, int n, long long ld, cudaStream_t s) {
@@ -561,6 +640,32 @@ void k_unpack_symmetric(double* full, long long ld, long long full_slice, const 
 }
 void k_unit_vectors(double* V, long long ld, long long, const long long* idx, int cols, cudaStream_t s) {
   unit_vectors_kernel<<<blocks_for(cols, 128), 128, 0, s>>>(V, ld, idx, cols);
+  LAUNCH_CHECK();
+}
+
+void k_gather_strided(double* dst, const double* src, long long first, long long stride, long long n, cudaStream_t s) {
+  if (n == 0) return;
+  gather_strided_kernel<<<blocks_for(n, 256, 1024), 256, 0, s>>>(dst, src, first, stride, n);
+  LAUNCH_CHECK();
+}
+void k_cols_full_to_local(double* loc, long long ld_loc, const double* full, long long ld_full, long long rows,
+                          long long ncols_loc, int rank, int world, cudaStream_t s) {
+  cyclic_cols_kernel<true><<<blocks_for(rows * ncols_loc, 256, 8192), 256, 0, s>>>(loc, ld_loc, full, ld_full, rows,
+                                                                                   ncols_loc, rank, world);
+  LAUNCH_CHECK();
+}
+void k_cols_local_to_full(double* full, long long ld_full, const double* loc, long long ld_loc, long long rows,
+                          long long ncols_loc, int rank, int world, cudaStream_t s) {
+  cyclic_cols_kernel<false><<<blocks_for(rows * ncols_loc, 256, 8192), 256, 0, s>>>(full, ld_full, loc, ld_loc, rows,
+                                                                                    ncols_loc, rank, world);
+  LAUNCH_CHECK();
+}
+void k_window_from_gathered(double* dst, long long dst_ld, long long dst_slab, const double* G, long long ldl,
+                            int mcnt, int naux, int P0, int pcnt, int n0, int ncnt, int world, cudaStream_t s) {
+  const long long total = (long long)mcnt * pcnt * ncnt;
+  if (total == 0) return;
+  window_from_gathered_kernel<<<blocks_for(total, 256, 16384), 256, 0, s>>>(dst, dst_ld, dst_slab, G, ldl, mcnt, naux,
+                                                                           P0, pcnt, n0, ncnt, world);
   LAUNCH_CHECK();
 }
 

@@ -10,7 +10,11 @@ TCMatrix::TCMatrix(Context* c, long long auxsize, long long mmin_, long long mma
     : ctx(c), naux(auxsize), mmin(mmin_), mmax(mmax_), nmin(nmin_), nmax(nmax_) {
   XTPB_REQUIRE(auxsize > 0 && mmax_ >= mmin_ && nmax_ >= nmin_ && mmin_ >= 0 && nmin_ >= 0, "bad TCMatrix ranges");
   mtotal = mmax - mmin + 1;
-  ntotal = nmax - nmin + 1;
+  ntotal_glob = nmax - nmin + 1;
+  rank = c->rank;
+  world = c->world;
+  XTPB_REQUIRE(ntotal_glob >= world, "fewer second-index levels than ranks");
+  ntotal = nloc_below(ntotal_glob);
   ldn = round_up(ntotal, 2);
   slab = naux * ldn;
   M.alloc((size_t)(mtotal * slab));
@@ -26,13 +30,39 @@ TCMatrix::~TCMatrix() {
 }
 
 void TCMatrix::set_raw(const double* host) {
-  ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
+  if (world == 1) {
+    ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
+    ctx->sync();
+    return;
+  }
+  // every rank is handed the whole tensor and keeps its cyclic share of the columns
+  DBuf full((size_t)(naux * ntotal_glob));
+  for (long long m = 0; m < mtotal; ++m) {
+    ctx->h2d(full.p, host + m * naux * ntotal_glob, (size_t)(naux * ntotal_glob));
+    k_cols_full_to_local(slab_ptr(m), ldn, full.p, ntotal_glob, naux, ntotal, rank, world, ctx->stream);
+  }
   ctx->sync();
 }
 
 void TCMatrix::get_slab(long long m, double* host) {
   XTPB_REQUIRE(m >= 0 && m < mtotal, "slab index out of range");
-  ctx->d2h_2d(host, ntotal, slab_ptr(m), ldn, ntotal, naux);
+  if (world == 1) {
+    ctx->d2h_2d(host, ntotal, slab_ptr(m), ldn, ntotal, naux);
+    return;
+  }
+  // collective: local columns scattered into a zeroed full slab, summed over ranks
+  DBuf full((size_t)(naux * ntotal_glob));
+  full.zero(ctx->stream);
+  k_cols_local_to_full(full.p, ntotal_glob, slab_ptr(m), ldn, naux, ntotal, rank, world, ctx->stream);
+  ctx->allreduce_sum(full.p, (size_t)(naux * ntotal_glob));
+  ctx->d2h(host, full.p, (size_t)(naux * ntotal_glob));
+}
+
+const double* TCMatrix::local_energies(const double* e_glob_dev, DBuf& tmp) {
+  if (world == 1) return e_glob_dev;
+  tmp.ensure((size_t)ntotal);
+  k_gather_strided(tmp.p, e_glob_dev, rank, world, ntotal, ctx->stream);
+  return tmp.p;
 }
 
 void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host) {
@@ -44,7 +74,8 @@ void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host
   Cm.zero(ctx->stream);
   Cn.zero(ctx->stream);
   ctx->h2d_2d(Cm.p, ldc, C_host + mmin * ldc_host, ldc_host, nb, mtotal);
-  ctx->h2d_2d(Cn.p, ldc, C_host + nmin * ldc_host, ldc_host, nb, ntotal);
+  // local second-index columns: host columns nmin + rank, nmin + rank + world, ... (pitch world*ldc_host)
+  ctx->h2d_2d(Cn.p, ldc, C_host + (nmin + rank) * ldc_host, ldc_host * world, nb, ntotal);
   ctx->sync();
 }
 
@@ -53,6 +84,7 @@ void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host
 //   M[m][P][:] = C_n^T * W_P    (ntotal x mtotal)       2 ntotal n_basis mtotal flops per P
 void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long long ld_ao) {
   XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill_block");
+  XTPB_REQUIRE(world == 1, "with more than one rank use the collective fill (xtpb_tc_fill_sharded_packed)");
   XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux && ld_ao >= n_basis, "bad aux block");
   ProfScope prof(PROF_FILL);
   const long long ldw = round_up(n_basis, 2);
@@ -146,6 +178,120 @@ void TCMatrix::fill_block_packed_dev(long long P0, long long nP, const double* p
   }
 }
 
+// Collective Fill3cMO over all ranks (one process per GPU).  Rank r holds the packed AO slices of its aux range;
+// per round every rank half-transforms up to `B` of its slices (W_P = T_P C_m, the n_basis^2 m part of the work,
+// split over P), the W blocks are all-gathered over NVLink on the communication stream, and every rank finishes
+// all gathered aux functions for its own share of the second index (M[m][P][n_loc] = C_nloc^T W_P, split over n).
+// The all-gather of round i overlaps the first half of round i+1 and the second half of round i-1.
+void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
+  XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill");
+  long long lo, hi;
+  aux_range(rank, lo, hi);
+  if (world == 1) {
+    if (on_device) fill_block_packed_dev(lo, hi - lo, packed);
+    else fill_block_host(lo, hi - lo, packed, 0, true);
+    ctx->sync();
+    return;
+  }
+  const long long ldt = round_up(n_basis, 2);
+  const long long full_slice = ldt * n_basis, pk_slice = n_basis * (n_basis + 1) / 2;
+  const long long ldw = ldt, wslice = ldw * mtotal;
+  long long maxcnt = 0;
+  for (int r = 0; r < world; ++r) {
+    long long a, b;
+    aux_range(r, a, b);
+    maxcnt = std::max(maxcnt, b - a);
+  }
+  // round size: bounded gather buffer (2 x world x B x wslice doubles <= ~4 GiB) and unpack scratch
+  long long B = std::min<long long>(32, std::max<long long>(1, (1LL << 28) / (world * wslice)));
+  B = std::min(B, std::max<long long>(1, (1LL << 26) / full_slice));
+  B = std::min(B, maxcnt);
+  const long long rounds = (maxcnt + B - 1) / B;
+  DBuf wsend[2], wall[2];
+  for (int b = 0; b < 2; ++b) {
+    wsend[b].alloc((size_t)(B * wslice));
+    wsend[b].zero(ctx->stream);
+    wall[b].alloc((size_t)(world * B * wslice));
+  }
+  unpacked.ensure((size_t)(B * full_slice));
+  if (!on_device) for (int b = 0; b < 2; ++b) stage2[b].ensure((size_t)(B * pk_slice));
+  if (!copy_stream) {
+    XTPB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      XTPB_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+      XTPB_CUDA(cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming));
+    }
+  }
+  cudaEvent_t ev_w[2], ev_g[2], ev_free[2];
+  for (int b = 0; b < 2; ++b) {
+    XTPB_CUDA(cudaEventCreateWithFlags(&ev_w[b], cudaEventDisableTiming));
+    XTPB_CUDA(cudaEventCreateWithFlags(&ev_g[b], cudaEventDisableTiming));
+    XTPB_CUDA(cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming));
+    XTPB_CUDA(cudaEventRecord(ev_free[b], ctx->stream));
+    XTPB_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
+  }
+  cudaStream_t cs = ctx->comm_stream;
+  auto second_half = [&](long long i) {      // consumes wall[i&1]
+    const int b = (int)(i & 1);
+    XTPB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_g[b], 0));
+    ProfScope prof(PROF_FILL);
+    for (int s = 0; s < world; ++s) {
+      long long a, e;
+      aux_range(s, a, e);
+      const long long p0 = a + i * B;
+      const long long cnt = std::min(B, e - p0);
+      if (cnt <= 0) continue;
+      GemmParams h{};
+      h.A = GemmOperand{Cn.p, ldc, 1, 0, 0};
+      h.B = GemmOperand{wall[b].p + (long long)s * B * wslice, ldw, 1, 0, wslice};
+      h.C = M.p + p0 * ldn; h.c_sm = 1; h.c_sn = slab; h.c_batch = ldn;
+      h.M = (int)ntotal; h.N = (int)mtotal; h.K = (int)n_basis; h.n_outer = 1; h.n_batch = (int)cnt;
+      h.alpha = 1.0; h.beta = 0.0;
+      contract(h, ctx->ws, ctx->stream);
+    }
+    XTPB_CUDA(cudaEventRecord(ev_free[b], ctx->stream));
+  };
+  for (long long i = 0; i < rounds; ++i) {
+    const int b = (int)(i & 1);
+    const long long p0 = lo + i * B;
+    const long long cnt = std::max<long long>(0, std::min(B, hi - p0));
+    if (cnt > 0) {
+      const double* src = packed + (p0 - lo) * pk_slice;
+      if (!on_device) {
+        XTPB_CUDA(cudaStreamWaitEvent(copy_stream, ev_consumed[b], 0));
+        XTPB_CUDA(cudaMemcpyAsync(stage2[b].p, src, (size_t)(cnt * pk_slice) * 8, cudaMemcpyHostToDevice, copy_stream));
+        XTPB_CUDA(cudaEventRecord(ev_copied[b], copy_stream));
+        XTPB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
+        src = stage2[b].p;
+      }
+      k_unpack_symmetric(unpacked.p, ldt, full_slice, src, pk_slice, (int)n_basis, (int)cnt, ctx->stream);
+      if (!on_device) XTPB_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
+      ProfScope prof(PROF_FILL);
+      GemmParams g{};
+      g.A = GemmOperand{unpacked.p, ldt, 1, 0, full_slice};
+      g.B = GemmOperand{Cm.p, ldc, 1, 0, 0};
+      g.C = wsend[b].p; g.c_sm = 1; g.c_sn = ldw; g.c_batch = wslice;
+      g.M = (int)n_basis; g.N = (int)mtotal; g.K = (int)n_basis; g.n_outer = 1; g.n_batch = (int)cnt;
+      g.alpha = 1.0; g.beta = 0.0;
+      contract(g, ctx->ws, ctx->stream);
+    }
+    XTPB_CUDA(cudaEventRecord(ev_w[b], ctx->stream));
+    XTPB_CUDA(cudaStreamWaitEvent(cs, ev_w[b], 0));
+    XTPB_CUDA(cudaStreamWaitEvent(cs, ev_free[b], 0));
+    ctx->allgather(wsend[b].p, wall[b].p, (size_t)(B * wslice), cs);
+    XTPB_CUDA(cudaEventRecord(ev_g[b], cs));
+    if (i > 0) second_half(i - 1);
+  }
+  second_half(rounds - 1);
+  ctx->sync();
+  XTPB_CUDA(cudaStreamSynchronize(cs));
+  for (int b = 0; b < 2; ++b) {
+    cudaEventDestroy(ev_w[b]);
+    cudaEventDestroy(ev_g[b]);
+    cudaEventDestroy(ev_free[b]);
+  }
+}
+
 // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]; A rows-contiguous (j), B = R K-contiguous (column Q of R).
 void TCMatrix::rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
                              const double* R_dev, long long ldr) {
@@ -184,21 +330,32 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
                      int n_omega, bool imag, double, double* out_dev) {
   Context* ctx = tc.ctx;
   ProfScope prof(PROF_EPSILON);
-  XTPB_REQUIRE(n_occ > 0 && n_occ < tc.ntotal && n_occ <= tc.mtotal, "RPA needs occupied and unoccupied levels");
-  const int a0 = (int)(n_occ & ~1LL);          // 16-byte aligned start of the contraction range
+  XTPB_REQUIRE(n_occ > 0 && n_occ < tc.ntotal_glob && n_occ <= tc.mtotal, "RPA needs occupied and unoccupied levels");
+  // second index: the local (cyclic) share of the unoccupied levels; first index: all occupied levels
+  const long long n_occ_loc = tc.nloc_below(n_occ);
+  const int a0 = (int)(n_occ_loc & ~1LL);          // 16-byte aligned start of the contraction range
   const int K = (int)(tc.ntotal - a0);
-  DBuf d((size_t)n_omega * n_occ * K + n_omega);
-  double* om_dev = d.p + (size_t)n_omega * n_occ * K;
+  DBuf e_loc_buf;
+  const double* e_loc = tc.local_energies(energies_dev, e_loc_buf);
+  DBuf d((size_t)n_omega * n_occ * std::max(K, 1) + n_omega);
+  double* om_dev = d.p + (size_t)n_omega * n_occ * std::max(K, 1);
   ctx->h2d(om_dev, omegas_host, n_omega);
-  k_chi0_weights(d.p, energies_dev, (int)n_occ, a0, K, om_dev, n_omega, imag, eta, 0.0, ctx->stream);
-  GemmParams g{};
-  g.A = GemmOperand{tc.M.p + a0, tc.ldn, 1, tc.slab, 0};
-  g.B = g.A;
-  g.C = out_dev; g.c_sm = 1; g.c_sn = tc.naux; g.c_batch = tc.naux * tc.naux;
-  g.d = d.p; g.d_outer = K; g.d_batch = (long long)n_occ * K;
-  g.M = (int)tc.naux; g.N = (int)tc.naux; g.K = K; g.n_outer = (int)n_occ; g.n_batch = n_omega;
-  g.alpha = 1.0; g.beta = 0.0; g.lower = 1;
-  contract(g, ctx->ws, ctx->stream);
+  const size_t out_count = (size_t)n_omega * tc.naux * tc.naux;
+  if (K > 0) {
+    k_chi0_weights(d.p, energies_dev, e_loc, (int)n_occ, (int)n_occ_loc, a0, K, om_dev, n_omega, imag, eta,
+                   ctx->stream);
+    GemmParams g{};
+    g.A = GemmOperand{tc.M.p + a0, tc.ldn, 1, tc.slab, 0};
+    g.B = g.A;
+    g.C = out_dev; g.c_sm = 1; g.c_sn = tc.naux; g.c_batch = tc.naux * tc.naux;
+    g.d = d.p; g.d_outer = K; g.d_batch = (long long)n_occ * K;
+    g.M = (int)tc.naux; g.N = (int)tc.naux; g.K = K; g.n_outer = (int)n_occ; g.n_batch = n_omega;
+    g.alpha = 1.0; g.beta = 0.0; g.lower = 1;
+    contract(g, ctx->ws, ctx->stream);
+  } else {
+    XTPB_CUDA(cudaMemsetAsync(out_dev, 0, out_count * 8, ctx->stream));
+  }
+  ctx->allreduce_sum(out_dev, out_count);           // partial sums over the local unoccupied levels
   for (int w = 0; w < n_omega; ++w)
     symmetrize_from_lower(out_dev + (long long)w * tc.naux * tc.naux, (int)tc.naux, tc.naux, 1.0, ctx->stream);
   ctx->sync();   // d is freed on return
