@@ -178,14 +178,18 @@ class GwbseJob:
         w = torch.exp(-d / 32.0) * t
         w[il[0] == il[1]] *= np.sqrt(2.0)          # (G + G^T)/sqrt(2) on the diagonal has variance 2
         g = torch.Generator(device=self.dev)
-        chunk = 64
-        for p0 in range(self.p_lo, self.p_hi, chunk):
-            cnt = min(chunk, self.p_hi - p0)
-            g.manual_seed(1_000_003 * (20260101 + sz.n_basis if seed is None else seed) + p0)
-            blk = torch.randn((cnt, self.pk), dtype=torch.float64, device=self.dev, generator=g)
-            blk *= w[None, :]
-            self.ao_dev[p0 - self.p_lo:p0 - self.p_lo + cnt] = blk
+        chunk = 64        # seeded per GLOBAL chunk of 64 aux functions: the tensor is the same for every world size
+        base_seed = 1_000_003 * (20260101 + sz.n_basis if seed is None else seed)
+        for c0 in range(self.p_lo // chunk * chunk, self.p_hi, chunk):
+            g.manual_seed(base_seed + c0)
+            blk = torch.randn((chunk, self.pk), dtype=torch.float64, device=self.dev, generator=g)
+            lo, hi = max(c0, self.p_lo), min(c0 + chunk, self.p_hi, sz.n_aux)
+            self.ao_dev[lo - self.p_lo:hi - self.p_lo] = blk[lo - c0:hi - c0] * w[None, :]
         torch.cuda.synchronize(self.dev)
+
+    def close(self):
+        self.tc.close()
+        self.ctx.close()
 
     # ---- one step
     def run(self, resident=True):
@@ -300,6 +304,7 @@ def main():
         run_reference(args)
         return
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: xtp_b200 has no CPU fallback")
@@ -446,6 +451,10 @@ def main():
     assert np.all(np.isfinite(res["qp"])) and np.all(np.isfinite(res["singlets"]))
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        job.close()
+        tdist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -162,6 +162,9 @@ int xtpb_gw_sigma_c_diag_elements(xtpb_gw* gw, xtpb_index n, const xtpb_index* l
                                   const double* frequencies_host, double* values_host, double* derivs_host);
 /* Sigma_base::CalcCorrelationDiag(frequencies): one frequency per gw level */
 int xtpb_gw_sigma_c_diag(xtpb_gw* gw, const double* frequencies_host, double* values_host);
+/* Sigma_c of every gw level on its QP grid (the scan GW::SolveQP_Grid runs, and what GW::PlotSigma tabulates):
+ * values_host[level*qp_grid_steps + j] = Sigma_c(level, center[level] + (j - (steps-1)/2) * qp_grid_spacing) */
+int xtpb_gw_sigma_c_grid(xtpb_gw* gw, const double* center_frequencies_host, double* values_host);
 /* Sigma_base::CalcCorrelationOffDiag(frequencies): qptotal x qptotal, zero diagonal */
 int xtpb_gw_sigma_c_offdiag(xtpb_gw* gw, const double* frequencies_host, double* sigma_c_host);
 /* GW::CalculateGWPerturbation / CalculateHQP / getGWAResults / getHQP / DiagonalizeQPHamiltonian */

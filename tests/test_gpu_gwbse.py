@@ -180,6 +180,30 @@ def test_ppm_parameters_and_sigma_c(ctx, prob):
     np.testing.assert_allclose(off, gwo.sigma.CalcCorrelationOffDiag(fr), rtol=1e-8, atol=1e-11)
 
 
+def test_sigma_c_qp_grid(ctx, prob):
+    """The fused grid kernel (G poles per reciprocal, damped-window branch) against element-wise oracle evaluations:
+    every level, a 173-point grid (odd, ragged against the 512-frequency CTA chunk) that crosses many poles."""
+    sz = prob["sizes"]
+    steps, spacing = 173, 0.013
+    gw, gwo, _, _ = _gw_pair(ctx, prob, qp_grid_steps=steps, qp_grid_spacing=spacing)
+    gwo.rpa.setRPAInputEnergies(prob["energies"][sz.rpamin:sz.rpamax + 1])
+    gw.PrepareScreening()
+    gwo.sigma.PrepareScreening()
+    centers = prob["energies"][sz.qpmin:sz.qpmax + 1].copy()
+    grid = gw.CalcCorrelationGrid(centers)
+    assert grid.shape == (sz.qptotal, steps)
+    rng = np.random.default_rng(9)
+    for level in rng.choice(sz.qptotal, size=min(6, sz.qptotal), replace=False):
+        js = np.unique(np.concatenate([[0, steps - 1, steps // 2], rng.integers(0, steps, 20)]))
+        ref = np.array([gwo.sigma.CalcCorrelationDiagElement(int(level), centers[level] + (j - (steps - 1) / 2) * spacing)
+                        for j in js])
+        np.testing.assert_allclose(grid[level, js], ref, rtol=1e-9, atol=1e-11)
+    # the pair kernel and the grid kernel must agree where both are evaluated
+    lv = np.arange(sz.qptotal)
+    np.testing.assert_allclose(grid[:, (steps - 1) // 2], gw.CalcCorrelationDiagElements(lv, centers), rtol=1e-10,
+                               atol=1e-12)
+
+
 @pytest.mark.parametrize("solver", ["grid", "fixedpoint"])
 def test_g0w0_qp_energies(ctx, prob, solver):
     gw, gwo, _, _ = _gw_pair(ctx, prob, qp_solver=solver, qp_grid_steps=401)

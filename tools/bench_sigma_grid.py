@@ -1,0 +1,62 @@
+"""Times the fused Sigma_c PPM grid kernel (GW::SolveQP_Grid scan) for G = 1, 2, 4, 8 poles per reciprocal.
+Each variant runs in a fresh process (the group size is read once from XTPB_GRID_GROUP).
+    python tools/bench_sigma_grid.py [--workload synth-1000] [--out gpurun_out/sigma_grid.jsonl]"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def child(workload, reps):
+    import numpy as np
+
+    from xtp_b200 import api, synth
+    sz = synth.WORKLOADS[workload]
+    rng = np.random.default_rng(3)
+    ctx = api.Context(0)
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.set_raw(synth.make_M_direct(sz, rng))
+    e = synth.make_energies(sz, rng)
+    gw = api.GW(ctx, tc, synth.make_vxc(sz, rng), e)
+    gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax))
+    gw.PrepareScreening()
+    centers = e[sz.qpmin:sz.qpmax + 1].copy()
+    out = gw.CalcCorrelationGrid(centers)          # warm-up
+    api.profile_reset()
+    api.profile_enable(True)
+    for _ in range(reps):
+        out = gw.CalcCorrelationGrid(centers)
+    api.profile_enable(False)
+    p = api.profile_summary()["sigma_ppm_grid"]
+    print(json.dumps({"workload": workload, "group": int(os.environ.get("XTPB_GRID_GROUP", "8")),
+                      "ms": p["ms"] / reps, "gevals_per_s": p["work"] / (p["ms"] * 1e-3) * 1e-9,
+                      "checksum": float(np.abs(out).sum()), "sample": out[1, 498:503].tolist()}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="synth-1000")
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--out", default="gpurun_out/sigma_grid.jsonl")
+    ap.add_argument("--child", action="store_true")
+    args = ap.parse_args()
+    if args.child:
+        child(args.workload, args.reps)
+        return
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    with open(args.out, "w") as f:
+        for g in (1, 2, 4, 8):
+            env = dict(os.environ, XTPB_GRID_GROUP=str(g))
+            r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
+                                str(args.reps)], env=env, capture_output=True, text=True)
+            line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"group": g, "error": r.stderr[-400:]})
+            print(line, flush=True)
+            f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "xtpb_gw_get_ppm": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_sigma_c_diag_elements": (C.c_int, [vp, idx, iptr, dptr, dptr, dptr]),
     "xtpb_gw_sigma_c_diag": (C.c_int, [vp, dptr, dptr]),
+    "xtpb_gw_sigma_c_grid": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_sigma_c_offdiag": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_calculate_gw_perturbation": (C.c_int, [vp]),
     "xtpb_gw_calculate_hqp": (C.c_int, [vp]),

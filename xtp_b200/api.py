@@ -364,6 +364,14 @@ class GW:
         check(_lib.lib().xtpb_gw_sigma_c_diag(self._h, _d(fr), _d(out)))
         return out
 
+    def CalcCorrelationGrid(self, center_frequencies):
+        """Sigma_c of every gw level on its QP grid (GW::SolveQP_Grid's scan / GW::PlotSigma): (qptotal, steps)."""
+        fr = np.ascontiguousarray(center_frequencies, dtype=np.float64)
+        assert len(fr) == self.qptotal
+        out = np.empty((self.qptotal, int(self.opt.qp_grid_steps)))
+        check(_lib.lib().xtpb_gw_sigma_c_grid(self._h, _d(fr), _d(out)))
+        return out
+
     def CalcCorrelationOffDiag(self, frequencies):
         fr = np.ascontiguousarray(frequencies, dtype=np.float64)
         out = np.empty((self.qptotal, self.qptotal), order="F")

@@ -310,6 +310,15 @@ int xtpb_gw_sigma_c_diag(xtpb_gw* gw, const double* frequencies_host, double* va
   gw->impl.sigma_c_diag_elements((long long)lv.size(), lv.data(), frequencies_host, values_host, nullptr);
   XTPB_API_END
 }
+int xtpb_gw_sigma_c_grid(xtpb_gw* gw, const double* center_frequencies_host, double* values_host) {
+  XTPB_API_BEGIN
+  GW& g = gw->impl;
+  XTPB_REQUIRE(g.screening_ready, "PrepareScreening has not been called");
+  std::vector<double> f0(center_frequencies_host, center_frequencies_host + g.qptotal), v;
+  g.grid_scan(f0, v);
+  std::memcpy(values_host, v.data(), v.size() * 8);
+  XTPB_API_END
+}
 int xtpb_gw_sigma_c_offdiag(xtpb_gw* gw, const double* frequencies_host, double* sigma_c_host) {
   XTPB_API_BEGIN
   gw->impl.sigma_c_offdiag(frequencies_host, sigma_c_host);

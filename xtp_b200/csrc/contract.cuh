@@ -97,53 +97,59 @@ struct GemmCfg {
   static_assert(MF % 2 == 0 && NF % 2 == 0, "fragment pairs");
 };
 
-// ---- tile loader: one operand tile (R rows x 16 k) for k-tile starting at k0 of `outer` ----
+// ---- tile loader: one operand tile (R rows x 16 k) for k-tile starting at k0 of `outer`, in R*8/THREADS 16-byte
+// chunks per thread.  `load_operand_chunk` issues chunk `it` only, so the main loop can spread the address
+// arithmetic and the cp.async issue of the next tile between its DMMA groups. ----
+template <int R, int THREADS, bool KC>
+__device__ __forceinline__ void load_operand_chunk(int it, uint32_t sbase, const double* __restrict__ base,
+                                                   long long s_row, long long s_k, int rows_left, int k_left,
+                                                   bool vec, int tid) {
+  const int ci = tid + it * THREADS;
+  if (KC) {
+    const int c = ci & 7, row = ci >> 3;
+    const int k = 2 * c;
+    const uint32_t dst = sbase + row * ROW_BYTES + (((c ^ (row & 7)) & 7) << 4);
+    const bool rv = row < rows_left;
+    if (vec) {
+      int nb = rv ? (k_left - k) * 8 : 0;
+      nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+      const double* src = nb > 0 ? base + (long long)row * s_row + k : base;
+      cp_async16(dst, src, nb);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool v = rv && (k + e) < k_left;
+        const double* src = v ? base + (long long)row * s_row + (k + e) : base;
+        cp_async8(dst + 8 * e, src, v ? 8 : 0);
+      }
+    }
+  } else {
+    const int rg = ci % (R / 2), k = ci / (R / 2);
+    const int row = 2 * rg;
+    const uint32_t dst = sbase + (row >> 4) * (BK * ROW_BYTES) + k * ROW_BYTES + ((((rg & 7) ^ (k & 7)) & 7) << 4);
+    const bool kv = k < k_left;
+    if (vec) {
+      int nb = kv ? (rows_left - row) * 8 : 0;
+      nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+      const double* src = nb > 0 ? base + (long long)k * s_k + row : base;
+      cp_async16(dst, src, nb);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool v = kv && (row + e) < rows_left;
+        const double* src = v ? base + (long long)k * s_k + (row + e) : base;
+        cp_async8(dst + 8 * e, src, v ? 8 : 0);
+      }
+    }
+  }
+}
 template <int R, int THREADS, bool KC>
 __device__ __forceinline__ void load_operand_tile(uint32_t sbase, const double* __restrict__ base,
                                                   long long s_row, long long s_k, int rows_left, int k_left,
                                                   bool vec, int tid) {
-  constexpr int CHUNKS = R * 8;
 #pragma unroll
-  for (int it = 0; it < CHUNKS / THREADS; ++it) {
-    const int ci = tid + it * THREADS;
-    if (KC) {
-      const int c = ci & 7, row = ci >> 3;
-      const int k = 2 * c;
-      const uint32_t dst = sbase + row * ROW_BYTES + (((c ^ (row & 7)) & 7) << 4);
-      const bool rv = row < rows_left;
-      if (vec) {
-        int nb = rv ? (k_left - k) * 8 : 0;
-        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-        const double* src = nb > 0 ? base + (long long)row * s_row + k : base;
-        cp_async16(dst, src, nb);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const bool v = rv && (k + e) < k_left;
-          const double* src = v ? base + (long long)row * s_row + (k + e) : base;
-          cp_async8(dst + 8 * e, src, v ? 8 : 0);
-        }
-      }
-    } else {
-      const int rg = ci % (R / 2), k = ci / (R / 2);
-      const int row = 2 * rg;
-      const uint32_t dst = sbase + (row >> 4) * (BK * ROW_BYTES) + k * ROW_BYTES + ((((rg & 7) ^ (k & 7)) & 7) << 4);
-      const bool kv = k < k_left;
-      if (vec) {
-        int nb = kv ? (rows_left - row) * 8 : 0;
-        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-        const double* src = nb > 0 ? base + (long long)k * s_k + row : base;
-        cp_async16(dst, src, nb);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const bool v = kv && (row + e) < rows_left;
-          const double* src = v ? base + (long long)k * s_k + (row + e) : base;
-          cp_async8(dst + 8 * e, src, v ? 8 : 0);
-        }
-      }
-    }
-  }
+  for (int it = 0; it < R * 8 / THREADS; ++it)
+    load_operand_chunk<R, THREADS, KC>(it, sbase, base, s_row, s_k, rows_left, k_left, vec, tid);
 }
 
 template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D>
@@ -200,25 +206,35 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
     cp_async_commit();
   }
 
+  // Main loop.  One barrier per 16-wide k-tile; inside a tile the 2*MF "steps" (half h = 8 k values, one A fragment
+  // load feeding 2*NF DMMAs each) are software-pipelined by hand: A fragments are double-buffered in registers and
+  // loaded one step ahead, the B fragments (and their chi0 weights) of the second half are fetched and
+  // scaled while the first half is still issuing DMMAs, and the cp.async traffic of the tile STAGES-1 ahead is
+  // spread over the steps so that no warp ever sits in a long non-tensor instruction run.
+  constexpr int NA = BM * 8 / Cfg::THREADS, NB = BN * 8 / Cfg::THREADS, NCH = NA + NB, STEPS = 2 * Cfg::MF;
 #pragma unroll 1
   for (int it = 0; it < nkt; ++it) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int nxt = it + STAGES - 1;
-      if (nxt < nkt) load_tile(nxt % STAGES, kt_begin + nxt);
-      cp_async_commit();
-    }
+    const int nxt = it + STAGES - 1;
+    const bool do_load = nxt < nkt;
+    // next tile's loader state (uniform)
+    const int l_kt = kt_begin + nxt;
+    const int l_outer = l_kt / tpo, l_k0 = (l_kt - l_outer * tpo) * BK;
+    const int l_kleft = p.K - l_k0;
+    const uint32_t lA = smem + (nxt % STAGES) * Cfg::STAGE_BYTES, lB = lA + Cfg::A_BYTES, lD = lB + Cfg::B_BYTES;
+
     const int stage = it % STAGES;
     const uint32_t sA = smem + stage * Cfg::STAGE_BYTES, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      double bf[Cfg::NF][2];
+
+    double bf[2][Cfg::NF][2];
+    double af[2][2];
+    auto load_b = [&](int h, double (&b)[Cfg::NF][2]) {
       if (B_KC) {
 #pragma unroll
         for (int nf = 0; nf < Cfg::NF; ++nf) {
           const int row = wn0 + kc_slot_row(nf, li);
-          lds128(sB + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), bf[nf][0], bf[nf][1]);
+          lds128(sB + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), b[nf][0], b[nf][1]);
         }
       } else {
 #pragma unroll
@@ -227,48 +243,85 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
           for (int j = 0; j < 2; ++j) {
             const int k = slot_k(h, lt, j);
             const int rb = (wn0 >> 4) + np;
-            lds128(sB + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), bf[2 * np][j],
-                   bf[2 * np + 1][j]);
+            lds128(sB + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), b[2 * np][j],
+                   b[2 * np + 1][j]);
           }
       }
-      if (HAS_D) {
-        double d0, d1;
-        lds128(sD + (8 * h + 2 * lt) * 8, d0, d1);
+    };
+    auto scale_b = [&](double d0, double d1, double (&b)[Cfg::NF][2]) {
 #pragma unroll
-        for (int nf = 0; nf < Cfg::NF; ++nf) {
-          bf[nf][0] *= d0;
-          bf[nf][1] *= d1;
+      for (int nf = 0; nf < Cfg::NF; ++nf) {
+        b[nf][0] *= d0;
+        b[nf][1] *= d1;
+      }
+    };
+    // A fragment of step s = h*MF + i:  K-contig: i = mf, (a0,a1) = two k sub-steps of fragment mf;
+    //                                   M-contig: i = 2*mp + j, (a0,a1) = fragments 2mp, 2mp+1 at k sub-step j
+    auto load_a = [&](int s, double (&a)[2]) {
+      const int h = s / Cfg::MF, i = s % Cfg::MF;
+      if (A_KC) {
+        const int row = wm0 + kc_slot_row(i, li);
+        lds128(sA + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), a[0], a[1]);
+      } else {
+        const int mp = i >> 1, j = i & 1;
+        const int k = slot_k(h, lt, j);
+        const int rb = (wm0 >> 4) + mp;
+        lds128(sA + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), a[0], a[1]);
+      }
+    };
+
+    double dn0 = 1.0, dn1 = 1.0;
+    load_b(0, bf[0]);
+    if (HAS_D) {
+      double d0, d1;
+      lds128(sD + (2 * lt) * 8, d0, d1);
+      scale_b(d0, d1, bf[0]);
+    }
+    load_a(0, af[0]);
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const int h = s / Cfg::MF, i = s % Cfg::MF;
+      if (s + 1 < STEPS) load_a(s + 1, af[(s + 1) & 1]);   // one step (2*NF DMMAs) ahead of its use
+      if (s == 0) {
+        load_b(1, bf[1]);
+        if (HAS_D) lds128(sD + (8 + 2 * lt) * 8, dn0, dn1);
+      }
+      if (do_load) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (c * STEPS / NCH != s) continue;
+          if (c < NA)
+            load_operand_chunk<BM, Cfg::THREADS, A_KC>(
+                c, lA, Ab + (long long)l_outer * p.A.s_outer + (long long)l_k0 * p.A.s_k, p.A.s_row, p.A.s_k, m_left,
+                l_kleft, p.a_vec != 0, tid);
+          else
+            load_operand_chunk<BN, Cfg::THREADS, B_KC>(
+                c - NA, lB, Bb + (long long)l_outer * p.B.s_outer + (long long)l_k0 * p.B.s_k, p.B.s_row, p.B.s_k,
+                n_left, l_kleft, p.b_vec != 0, tid);
+        }
+        if (HAS_D && s == STEPS - 1 && tid < BK) {
+          const bool v = tid < l_kleft;
+          const double* src = v ? Db + (long long)l_outer * p.d_outer + l_k0 + tid : Db;
+          cp_async8(lD + tid * 8, src, v ? 8 : 0);
         }
       }
+      const double a0 = af[s & 1][0], a1 = af[s & 1][1];
       if (A_KC) {
 #pragma unroll
-        for (int mf = 0; mf < Cfg::MF; ++mf) {
-          double a0, a1;
-          const int row = wm0 + kc_slot_row(mf, li);
-          lds128(sA + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), a0, a1);
+        for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[i][nf][0], acc[i][nf][1], a0, bf[h][nf][0]);
 #pragma unroll
-          for (int nf = 0; nf < Cfg::NF; ++nf) {
-            dmma884(acc[mf][nf][0], acc[mf][nf][1], a0, bf[nf][0]);
-            dmma884(acc[mf][nf][0], acc[mf][nf][1], a1, bf[nf][1]);
-          }
-        }
+        for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[i][nf][0], acc[i][nf][1], a1, bf[h][nf][1]);
       } else {
+        const int mp = i >> 1, j = i & 1;
 #pragma unroll
-        for (int mp = 0; mp < Cfg::MF / 2; ++mp)
+        for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[2 * mp][nf][0], acc[2 * mp][nf][1], a0, bf[h][nf][j]);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            double a0, a1;
-            const int k = slot_k(h, lt, j);
-            const int rb = (wm0 >> 4) + mp;
-            lds128(sA + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), a0, a1);
-#pragma unroll
-            for (int nf = 0; nf < Cfg::NF; ++nf) {
-              dmma884(acc[2 * mp][nf][0], acc[2 * mp][nf][1], a0, bf[nf][j]);
-              dmma884(acc[2 * mp + 1][nf][0], acc[2 * mp + 1][nf][1], a1, bf[nf][j]);
-            }
-          }
+        for (int nf = 0; nf < Cfg::NF; ++nf)
+          dmma884(acc[2 * mp + 1][nf][0], acc[2 * mp + 1][nf][1], a1, bf[h][nf][j]);
       }
+      if (HAS_D && s == Cfg::MF / 2) scale_b(dn0, dn1, bf[1]);
     }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 

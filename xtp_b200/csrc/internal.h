@@ -193,12 +193,12 @@ struct GW {
   std::vector<double> gwa_results() const;
   std::vector<double> hqp() const;
   std::vector<double> solve_qp(const std::vector<double>& frequencies);
+  void grid_scan(const std::vector<double>& f0, std::vector<double>& values);   // values[level*steps + j]
 
  private:
   void prepare_ppm();
   void prepare_exact();
   void prepare_cda();
-  void grid_scan(const std::vector<double>& f0, std::vector<double>& values);   // values[level*steps + j]
   void sigma_c_diag_elements_other(long long n, const long long* levels, const double* freqs, double* values,
                                    double* derivs);   // exact / CDA
   void sigma_c_offdiag_other(const double* freqs, double* out_host);

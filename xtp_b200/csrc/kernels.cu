@@ -203,13 +203,20 @@ __global__ void __launch_bounds__(256) unpack_symmetric_kernel(double* __restric
 //     is warp-coherent), the (P,m) elements of the level's slab stream through shared memory and are broadcast.
 //     Bound: FP64 ALU (one reciprocal per element and frequency); the slab is read once per 2*T*NW frequencies.
 constexpr int kGridThreads = 128, kGridNW = 4, kGridTile = 512;
+constexpr double kGridFar = 1.0e30;    // stand-in denominator: padding entries and poles inside the damping window
 
+// G poles share one reciprocal: sum_g w_g / x_g = N / D with D = prod x_g, N = sum_g w_g prod_{g' != g} x_g'
+// (pairwise tree, 4G+1 FP64 operations and ONE MUFU.RCP64H per G poles and frequency; |x| is in [0.25, ~20] outside
+// the damping window, so D stays far from over/underflow for G <= 8).  Poles inside the window get x = 1e30 here
+// (contribution ~1e-30 w) and are added exactly by the rare damped branch.
+template <int G>
 __global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
     const double* __restrict__ energies, const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac,
     const int* __restrict__ level_slab, const double* __restrict__ omega0, double domega, int n_omega,
     double* __restrict__ values) {
   __shared__ double2 tile[kGridTile];
+  static_assert(kGridTile % G == 0, "tile is consumed G poles at a time");
   const int level = blockIdx.y;
   const double* S = M + (long long)level_slab[level] * slab;
   const int jbase = blockIdx.x * (kGridThreads * kGridNW) + threadIdx.x;
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
       __syncthreads();
       for (int t = threadIdx.x; t < kGridTile; t += kGridThreads) {
         const int m = m0 + t;
-        double2 el = make_double2(0.0, 1.0e300);
+        double2 el = make_double2(0.0, -kGridFar);          // padding: weight 0, x = w + 1e30
         if (m < ntotal) {
           const double v = row[m];
           el.x = fac * v * v;
@@ -237,26 +244,42 @@ __global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
         tile[t] = el;
       }
       __syncthreads();
-      const int cnt = min(kGridTile, ntotal - m0);
-#pragma unroll 4
-      for (int t = 0; t < cnt; ++t) {
-        const double2 el = tile[t];
-        // branch-free fast path for the NW frequencies of this thread (independent chains); poles inside the
-        // damping window contribute 0 here and are added by the rare branch below
-        double x[kGridNW];
+      const int cnt = (min(kGridTile, ntotal - m0) + G - 1) / G * G;
+#pragma unroll 2
+      for (int t = 0; t < cnt; t += G) {
+        double2 el[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) el[g] = tile[t + g];
         bool any = false;
 #pragma unroll
         for (int w = 0; w < kGridNW; ++w) {
-          x[w] = om[w] - el.y;
-          const bool win = ppm_in_window(x[w]);
-          const double r = rcp_fast(x[w]);
-          acc[w] = fma(el.x, win ? 0.0 : r, acc[w]);
-          any |= win;
+          double num[G], den[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const double x = om[w] - el[g].y;
+            const bool win = ppm_in_window(x);
+            any |= win;
+            den[g] = win ? kGridFar : x;
+            num[g] = el[g].x;
+          }
+#pragma unroll
+          for (int width = G; width > 1; width >>= 1)
+#pragma unroll
+            for (int g = 0; g < width / 2; ++g) {
+              const double n0 = num[2 * g], n1 = num[2 * g + 1], d0 = den[2 * g], d1 = den[2 * g + 1];
+              num[g] = fma(n0, d1, n1 * d0);
+              den[g] = d0 * d1;
+            }
+          acc[w] = fma(num[0], rcp_fast(den[0]), acc[w]);
         }
         if (any) {
 #pragma unroll
-          for (int w = 0; w < kGridNW; ++w)
-            if (ppm_in_window(x[w])) acc[w] = fma(el.x, ppm_ginv_damped(x[w]), acc[w]);
+          for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int w = 0; w < kGridNW; ++w) {
+              const double x = om[w] - el[g].y;
+              if (ppm_in_window(x)) acc[w] = fma(el[g].x, ppm_ginv_damped(x), acc[w]);
+            }
         }
       }
     }
@@ -552,8 +575,22 @@ void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal
   dim3 grid((n_omega + per_block - 1) / per_block, n_levels);
   // work = pole evaluations (one reciprocal + ~6 flops each)
   const int slot = prof_begin(PROF_SIGMA_GRID, (double)ntotal * naux * (double)n_omega * n_levels, s);
-  sigma_ppm_grid_kernel<<<grid, kGridThreads, 0, s>>>(M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq, ppm_fac,
-                                                      level_slab, omega0, domega, n_omega, values);
+  // poles per reciprocal: 8 by default; XTPB_GRID_GROUP=1|2|4|8 selects another instance (tools/bench_sigma_grid.py)
+  static const int group = [] {
+    const char* e = getenv("XTPB_GRID_GROUP");
+    const int g = e ? atoi(e) : 8;
+    return (g == 1 || g == 2 || g == 4 || g == 8) ? g : 8;
+  }();
+#define XTPB_GRID_LAUNCH(G)                                                                                           \
+  sigma_ppm_grid_kernel<G><<<grid, kGridThreads, 0, s>>>(M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq,       \
+                                                         ppm_fac, level_slab, omega0, domega, n_omega, values)
+  switch (group) {
+    case 1: XTPB_GRID_LAUNCH(1); break;
+    case 2: XTPB_GRID_LAUNCH(2); break;
+    case 4: XTPB_GRID_LAUNCH(4); break;
+    default: XTPB_GRID_LAUNCH(8); break;
+  }
+#undef XTPB_GRID_LAUNCH
   LAUNCH_CHECK();
   prof_end(slot, s);
 }
