@@ -143,6 +143,10 @@ typedef struct xtpb_gw_options {   /* GW::options + Sigma_base::options, upstrea
 } xtpb_gw_options;
 void xtpb_gw_options_default(xtpb_gw_options* opt);
 
+/* GaussianQuadrature::configure + ScaledPoint/ScaledWeight (upstream gwbse/gaussian_quadrature.cc): the
+ * imaginary-axis nodes of Sigma_CDA mapped to (0, inf).  points/weights need room for `order` values (legendre,
+ * laguerre) or `order` positive nodes of a 2*order rule (hermite).  Host-only, needs no device. */
+int xtpb_gaussian_quadrature(int scheme, xtpb_index order, double* points, double* weights, xtpb_index* count);
 /* GW::GW(log, Mmn, vxc, dft_energies) + GW::configure(opt).  vxc is qptotal x qptotal. */
 int xtpb_gw_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_gw_options* opt, const double* vxc_host, xtpb_index ldv,
                    const double* dft_energies_host, xtpb_index n_energies, xtpb_gw** out);

@@ -46,3 +46,17 @@ def test_no_cpu_fallback():
     from xtp_b200 import api
     with pytest.raises(RuntimeError, match="no CUDA device"):
         api.Context(0)
+
+
+def test_gaussian_quadrature_matches_numpy():
+    """GaussianQuadrature is host code inside the library (no device needed): nodes/weights against numpy's rules
+    through the oracle's restatement."""
+    import numpy as np
+    from oracle import gwbse_oracle as orc
+    from xtp_b200 import api
+    for scheme in ("legendre", "laguerre", "hermite"):
+        for order in (8, 12, 16, 20, 40):
+            a, b = api.GaussianQuadrature(scheme, order), orc.GaussianQuadrature(scheme, order)
+            assert a.Order() == b.Order()
+            np.testing.assert_allclose(a.points, b.points, rtol=1e-11)
+            np.testing.assert_allclose(a.weights, b.weights, rtol=1e-10)

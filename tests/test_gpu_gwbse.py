@@ -204,6 +204,68 @@ def test_sigma_c_qp_grid(ctx, prob):
                                atol=1e-12)
 
 
+def test_sigma_exact(ctx, prob):
+    """Sigma_Exact: RPA::Diagonalize_H2p + residues + diagonal / derivative / off-diagonal elements."""
+    sz = prob["sizes"]
+    gw, gwo, _, _ = _gw_pair(ctx, prob, sigma_integration="exact")
+    gwo.rpa.setRPAInputEnergies(prob["energies"][sz.rpamin:sz.rpamax + 1])
+    gw.PrepareScreening()
+    gwo.sigma.PrepareScreening()
+    rng = np.random.default_rng(14)
+    levels = rng.integers(0, sz.qptotal, 24)
+    freqs = rng.uniform(-1.5, 1.5, 24)
+    val, der = gw.CalcCorrelationDiagElements(levels, freqs, derivative=True)
+    ref = np.array([gwo.sigma.CalcCorrelationDiagElement(int(l), float(x)) for l, x in zip(levels, freqs)])
+    refd = np.array([gwo.sigma.CalcCorrelationDiagElementDerivative(int(l), float(x)) for l, x in zip(levels, freqs)])
+    np.testing.assert_allclose(val, ref, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(der, refd, rtol=1e-7, atol=1e-8)
+    fr = prob["energies"][sz.qpmin:sz.qpmax + 1]
+    np.testing.assert_allclose(gw.CalcCorrelationOffDiag(fr), gwo.sigma.CalcCorrelationOffDiag(fr), rtol=1e-8, atol=1e-10)
+
+
+def test_g0w0_exact_qp_energies(ctx, prob):
+    gw, gwo, _, _ = _gw_pair(ctx, prob, sigma_integration="exact", qp_grid_steps=201)
+    gw.CalculateGWPerturbation()
+    gwo.CalculateGWPerturbation()
+    np.testing.assert_allclose(gw.getGWAResults(), gwo.getGWAResults(), rtol=0, atol=1e-6)
+    gw.CalculateHQP()
+    gwo.CalculateHQP()
+    np.testing.assert_allclose(gw.getHQP(), gwo.getHQP(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("scheme,order", [("legendre", 12), ("laguerre", 16), ("hermite", 10)])
+def test_sigma_cda(ctx, prob, scheme, order):
+    """Sigma_CDA: Gauss quadrature on the imaginary axis + residues of the enclosed poles + Gaussian tail."""
+    sz = prob["sizes"]
+    gw, gwo, _, _ = _gw_pair(ctx, prob, sigma_integration="cda", quadrature_scheme=scheme, order=order, alpha=1e-3)
+    gwo.rpa.setRPAInputEnergies(prob["energies"][sz.rpamin:sz.rpamax + 1])
+    gw.PrepareScreening()
+    gwo.sigma.PrepareScreening()
+    rng = np.random.default_rng(15)
+    e = prob["energies"][sz.qpmin:sz.qpmax + 1]
+    levels = rng.integers(0, sz.qptotal, 10)
+    freqs = np.concatenate([rng.uniform(-1.2, 1.2, 8), e[levels[8:]] + 0.05])    # some far from, some near the poles
+    val, der = gw.CalcCorrelationDiagElements(levels, freqs, derivative=True)
+    ref = np.array([gwo.sigma.CalcCorrelationDiagElement(int(l), float(x)) for l, x in zip(levels, freqs)])
+    np.testing.assert_allclose(val, ref, rtol=1e-8, atol=1e-10)
+    refd = np.array([gwo.sigma.CalcCorrelationDiagElementDerivative(int(l), float(x)) for l, x in zip(levels[:4], freqs[:4])])
+    np.testing.assert_allclose(der[:4], refd, rtol=1e-5, atol=1e-7)
+    assert np.all(gw.CalcCorrelationOffDiag(e) == 0.0)       # Sigma_CDA has no off-diagonal correlation upstream
+
+
+def test_g0w0_cda_qp_energies(ctx):
+    """G0W0 with the CDA self-energy on the tiny problem (fixed-point QP solver; residues need one eps^-1 each)."""
+    prob = synth.make_problem("tiny")
+    sz = prob["sizes"]
+    tc = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.Fill(prob["ao3c"], prob["C"], prob["aux_coulomb"])
+    prob["tc_o"] = tc
+    gw, gwo, _, _ = _gw_pair(ctx, prob, sigma_integration="cda", qp_solver="fixedpoint", qp_grid_steps=41)
+    gw.CalculateGWPerturbation()
+    gwo.CalculateGWPerturbation()
+    np.testing.assert_allclose(gw.getGWAResults(), gwo.getGWAResults(), rtol=0, atol=1e-6)
+
+
 @pytest.mark.parametrize("solver", ["grid", "fixedpoint"])
 def test_g0w0_qp_energies(ctx, prob, solver):
     gw, gwo, _, _ = _gw_pair(ctx, prob, qp_solver=solver, qp_grid_steps=401)
@@ -226,10 +288,13 @@ def test_evgw(ctx, prob):
     np.testing.assert_allclose(gw.RPAInputEnergies(), gwo.RPAInputEnergies(), rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("mode", ["dense", "factorised"])
 @pytest.mark.parametrize("name", list(orc.OPERATOR_TYPES))
-def test_bse_operator_matmul_diagonal(ctx, prob, name):
-    """BSE_OPERATOR<...>::matmul / diagonal / get_full_matrix vs the dense element-wise Hamiltonian."""
+def test_bse_operator_matmul_diagonal(ctx, prob, name, mode, monkeypatch):
+    """BSE_OPERATOR<...>::matmul / diagonal / get_full_matrix vs the dense element-wise Hamiltonian, for both
+    device strategies: H materialised once in HBM (default when it fits) and the factorised products."""
     from xtp_b200 import api
+    monkeypatch.setenv("XTPB_BSE_DENSE_MAX_GB", "32" if mode == "dense" else "0")
     sz = prob["sizes"]
     rng = np.random.default_rng(3)
     hq = rng.standard_normal((sz.vtotal + sz.ctotal,) * 2)

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "xtpb_tc_apply_coulomb_metric": (C.c_int, [vp, dptr, idx, dptr, idx, C.c_double, iptr]),
     "xtpb_rpa_epsilon": (C.c_int, [vp, dptr, idx, idx, idx, C.c_double, dptr, C.c_int, C.c_int, dptr]),
     "xtpb_gw_options_default": (None, [C.POINTER(GwOptions)]),
+    "xtpb_gaussian_quadrature": (C.c_int, [C.c_int, idx, dptr, dptr, iptr]),
     "xtpb_gw_create": (C.c_int, [vp, vp, C.POINTER(GwOptions), dptr, idx, dptr, idx, C.POINTER(vp)]),
     "xtpb_gw_destroy": (C.c_int, [vp]),
     "xtpb_gw_sigma_exchange": (C.c_int, [vp, dptr]),

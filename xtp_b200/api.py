@@ -275,6 +275,20 @@ QPSOLVER = {"grid": 0, "fixedpoint": 1}
 QUAD = {"legendre": 0, "laguerre": 1, "hermite": 2}
 
 
+class GaussianQuadrature:
+    """upstream xtp/src/libxtp/gwbse/gaussian_quadrature.cc (host code inside libxtpb200)"""
+
+    def __init__(self, scheme="legendre", order=12):
+        pts, wts, n = np.empty(2 * order + 2), np.empty(2 * order + 2), idx(0)
+        check(_lib.lib().xtpb_gaussian_quadrature(QUAD[scheme] if isinstance(scheme, str) else int(scheme), int(order),
+                                                  _d(pts), _d(wts), C.byref(n)))
+        self.points, self.weights = pts[:n.value].copy(), wts[:n.value].copy()
+
+    def Order(self): return len(self.points)
+    def ScaledPoint(self, j): return self.points[j]
+    def ScaledWeight(self, j): return self.weights[j]
+
+
 def gw_options(**kw):
     o = _lib.GwOptions()
     _lib.lib().xtpb_gw_options_default(C.byref(o))

@@ -122,21 +122,21 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
     XTPB_CUDA(cudaMemcpyAsync(Rs.p, R_dev, (size_t)(naux_glob * naux_glob) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     k_scale_columns(Rs.p, (int)naux_glob, (int)naux_glob, naux_glob, eps_inv_dev.p, ctx->stream);
   }
-  auto window = [&](DBuf& dst, long long& ld, long long& sl, int m0, int mcnt, int n0, int ncnt, bool screened) {
-    ld = round_up(ncnt, 2);
-    sl = naux * ld;
-    dst.alloc((size_t)(sl * mcnt));
-    dst.zero(ctx->stream);
+  // dst[i*dst_slab + Ql*dst_ld + j] = (rotated / screened) M[m0+i][Pbeg+Ql][n0+j], Ql < pcnt, j < ncnt (pure strides:
+  // [i][P][j] windows for the factorised operator, [P][i][j] "flat" operands for the dense build)
+  auto window_into = [&](double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
+                         bool screened, long long Pbeg, long long pcnt) {
     if (world == 1) {
+      XTPB_REQUIRE(Pbeg == 0 && pcnt == naux_glob, "single rank holds every aux function");
       if (R_dev)
-        tc->rotate_window(dst.p, ld, sl, m0, mcnt, n0, ncnt, screened ? Rs.p : R_dev, naux);
+        tc->rotate_window(dst, dst_ld, dst_slab, m0, mcnt, n0, ncnt, screened ? Rs.p : R_dev, naux_glob);
       else
-        k_extract_window(dst.p, ld, sl, tc->M.p, tc->ldn, tc->slab, m0, mcnt, n0, ncnt, (int)naux,
+        k_extract_window(dst, dst_ld, dst_slab, tc->M.p, tc->ldn, tc->slab, m0, mcnt, n0, ncnt, (int)naux_glob,
                          screened ? eps_inv_dev.p : nullptr, ctx->stream);
       return;
     }
-    // re-shard: the tensor is distributed over the second index, the operator over P.  Rotate / extract the local
-    // columns of the window for all P, all-gather the (small) window, keep this rank's P range.
+    // re-shard: the tensor is distributed over the second index, the operator over P (or, dense, over columns).
+    // Rotate / extract the local columns of the window for all P, all-gather the (small) window, keep what is asked.
     const long long jl0 = tc->nloc_below(n0), cl = tc->nloc_below(n0 + ncnt) - jl0;
     const long long ldl = round_up((ncnt + world - 1) / world + 1, 2), lslab = naux_glob * ldl;
     DBuf loc((size_t)(lslab * mcnt)), G((size_t)(lslab * mcnt * world));
@@ -149,10 +149,94 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
                          screened ? eps_inv_dev.p : nullptr, ctx->stream);
     }
     ctx->allgather(loc.p, G.p, (size_t)(lslab * mcnt));
-    k_window_from_gathered(dst.p, ld, sl, G.p, ldl, mcnt, (int)naux_glob, (int)P0, (int)naux, n0, ncnt, world,
+    k_window_from_gathered(dst, dst_ld, dst_slab, G.p, ldl, mcnt, (int)naux_glob, (int)Pbeg, (int)pcnt, n0, ncnt, world,
                            ctx->stream);
     ctx->sync();   // loc / G are freed on return
   };
+  auto window = [&](DBuf& dst, long long& ld, long long& sl, int m0, int mcnt, int n0, int ncnt, bool screened) {
+    ld = round_up(ncnt, 2);
+    sl = naux * ld;
+    dst.alloc((size_t)(sl * mcnt));
+    dst.zero(ctx->stream);
+    window_into(dst.p, ld, sl, m0, mcnt, n0, ncnt, screened, P0, naux);
+  };
+
+  // ---- dense mode: materialise H once (HBM is large: C60's 32 400^2 doubles are 8.4 GB) when it fits the budget.
+  // The reference rebuilds H row blocks on every matmul (2 v^2 c^2 N_aux flops per call); the factorised products
+  // below cost 2 N_aux k vc (v+c) per call; building H costs 2 v^2 c^2 N_aux (+ half of that for Hx) ONCE with
+  // long-K (K = N_aux) contractions, after which a matmul only streams H (HBM-bound).
+  {
+    const char* env = getenv("XTPB_BSE_DENSE_MAX_GB");
+    const double max_gb = env ? atof(env) : 32.0;
+    v2lo = vt * ctx->rank / world;
+    ns = vt * (ctx->rank + 1) / world - v2lo;
+    h_ld = round_up(size, 2);
+    const double gb = (double)h_ld * (double)(vt / world + 1) * (double)ct * 8e-9;
+    dense = (cx || cd || cd2) && gb <= max_gb && vt >= world && size <= 60000 &&
+            (double)std::max(vt, ct) * (double)std::max(vt, ct) < 2.0e9;
+  }
+  if (dense) {
+    const long long ncols = ns * ct;
+    H.alloc((size_t)(h_ld * std::max<long long>(ncols, 1)));
+    H.zero(ctx->stream);
+    ProfScope prof(PROF_BSE_MATMUL);
+    auto flat = [&](DBuf& F, long long& ldF, int m0, int mcnt, int n0, int ncnt, bool screened) {
+      ldF = round_up((long long)mcnt * ncnt, 2);
+      F.alloc((size_t)(ldF * naux_glob));
+      F.zero(ctx->stream);
+      window_into(F.p, ldF, ncnt, m0, mcnt, n0, ncnt, screened, 0, naux_glob);     // [P][i][j]
+    };
+    DBuf Fvc, Fa, Fb;
+    long long ldvcF = 0, ldA = 0, ldB = 0;
+    if (cx || cd2) flat(Fvc, ldvcF, v0, (int)vt, c0, (int)ct, false);
+    if (cd && ncols > 0) {
+      // Hd[(v1,c1),(v2,c2)] = sum_P Mcc[c2][P][c1] * (eps_inv_P Mvv[v1][P][v2])
+      flat(Fa, ldA, c0, (int)ct, c0, (int)ct, false);                      // rows (i = c2, j = c1)
+      flat(Fb, ldB, v0, (int)vt, v0 + (int)v2lo, (int)ns, true);           // rows (i = v1, j = v2 - v2lo)
+      GemmParams g{};
+      g.A = GemmOperand{Fa.p, 1, ldA, 0, 0};
+      g.B = GemmOperand{Fb.p, 1, ldB, 0, 0};
+      g.C = H.p;
+      g.c_m_inner = (int)ct; g.c_sm = 1; g.c_sm_outer = h_ld;              // row (c2, c1): c1 -> row, c2 -> column part
+      g.c_n_inner = (int)ns; g.c_sn = ct * h_ld; g.c_sn_outer = ct;        // col (v1, v2l): v2l -> column, v1 -> row part
+      g.M = (int)(ct * ct); g.N = (int)(vt * ns); g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
+      g.alpha = -(double)cd; g.beta = 1.0;
+      contract(g, ctx->ws, ctx->stream);
+      ctx->sync();
+      Fa.release();
+      Fb.release();
+    }
+    if (cd2 && ncols > 0) {
+      // Hd2[(v1,c1),(v2,c2)] = sum_P Mvc[v1][P][c2] * (eps_inv_P Mcv[c1][P][v2])
+      flat(Fb, ldB, c0, (int)ct, v0 + (int)v2lo, (int)ns, true);           // rows (i = c1, j = v2 - v2lo)
+      GemmParams g{};
+      g.A = GemmOperand{Fvc.p, 1, ldvcF, 0, 0};                            // rows (v1, c2)
+      g.B = GemmOperand{Fb.p, 1, ldB, 0, 0};
+      g.C = H.p;
+      g.c_m_inner = (int)ct; g.c_sm = h_ld; g.c_sm_outer = ct;             // c2 -> column part, v1 -> row part
+      g.c_n_inner = (int)ns; g.c_sn = ct * h_ld; g.c_sn_outer = 1;         // v2l -> column, c1 -> row part
+      g.M = (int)(vt * ct); g.N = (int)(ct * ns); g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
+      g.alpha = -(double)cd2; g.beta = 1.0;
+      contract(g, ctx->ws, ctx->stream);
+      ctx->sync();
+      Fb.release();
+    }
+    if (cx && ncols > 0) {
+      // Hx[(v1,c1),(v2,c2)] = sum_P Mvc[v1][P][c1] Mvc[v2][P][c2]
+      GemmParams g{};
+      g.A = GemmOperand{Fvc.p, 1, ldvcF, 0, 0};
+      g.B = GemmOperand{Fvc.p + v2lo * ct, 1, ldvcF, 0, 0};
+      g.C = H.p; g.c_sm = 1; g.c_sn = h_ld;
+      g.M = (int)size; g.N = (int)ncols; g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
+      g.alpha = (double)cx; g.beta = 1.0;
+      contract(g, ctx->ws, ctx->stream);
+    }
+    if (cqp && ncols > 0)
+      k_bse_add_hqp(H.p, h_ld, (int)vt, (int)ct, (int)v2lo, (int)ns, hqp_dev.p, hs, (double)cqp, ctx->stream);
+    ctx->sync();
+    ldvc = slabvc = ldvv = slabvv = ldcc = slabcc = ldcv = slabcv = 0;
+    return;
+  }
   ldvc = slabvc = ldvv = slabvv = ldcc = slabcc = ldcv = slabcv = 0;
   if (cx || cd2) window(Mvc, ldvc, slabvc, v0, (int)vt, c0, (int)ct, false);
   if (cd) {
@@ -164,6 +248,12 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
 }
 
 void BseOperator::diagonal_dev(double* d) {
+  if (dense) {      // the owned columns' diagonal entries, zero elsewhere; summed over ranks
+    XTPB_CUDA(cudaMemsetAsync(d, 0, (size_t)size * 8, ctx->stream));
+    if (ns > 0) k_extract_diagonal(H.p + v2lo * ct, (int)(ns * ct), h_ld, d + v2lo * ct, ctx->stream);
+    ctx->allreduce_sum(d, (size_t)size);
+    return;
+  }
   // partial sums over the local aux range; the P-independent Hqp part is contributed by rank 0 only
   k_bse_diagonal(d, (int)vt, (int)ct, (int)naux, Mvc.p, ldvc, slabvc, Mvv.p, ldvv, slabvv, Mcc.p, ldcc, slabcc, Mcv.p,
                  ldcv, slabcv, eps_inv_dev.p, hqp_diag_dev.p, ctx->rank == 0 ? cqp : 0, cx, cd, cd2, ctx->stream);
@@ -179,6 +269,21 @@ void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, l
   const long long hs = vt + ct;
 
   XTPB_REQUIRE(k <= 8192, "more than 8192 trial vectors per matmul are not supported");
+
+  if (dense) {      // Y = H[:, owned columns] X[owned rows, :]  (one HBM-bound pass over H), summed over ranks
+    if (ns > 0) {
+      GemmParams g{};
+      g.A = GemmOperand{H.p, 1, h_ld, 0, 0};
+      g.B = GemmOperand{X + v2lo * ct, ldx, 1, 0, 0};
+      g.C = Y; g.c_sm = 1; g.c_sn = ldy;
+      g.M = (int)size; g.N = k; g.K = (int)(ns * ct); g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0; g.beta = 0.0;
+      contract(g, ctx->ws, st);
+    } else {
+      XTPB_CUDA(cudaMemset2DAsync(Y, ldy * 8, 0, size * 8, k, st));
+    }
+    ctx->allreduce_sum(Y, (size_t)(ldy * (k - 1) + size));
+    return;
+  }
 
   if (cqp && ctx->rank == 0) {   // P-independent term: one rank contributes it, the all-reduce below spreads it
     // Y_k(c,v) = cqp * sum_c2 Hc(c,c2) X_k(c2,v)          (Hqp symmetric: K-contiguous view of the cc block)

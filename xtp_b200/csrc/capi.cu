@@ -258,6 +258,15 @@ void xtpb_gw_options_default(xtpb_gw_options* o) {
   o->gw_mixing_order = 0; o->gw_mixing_alpha = 0.7; o->quadrature_scheme = XTPB_QUAD_LEGENDRE; o->order = 12;
   o->alpha = 1e-3;
 }
+int xtpb_gaussian_quadrature(int scheme, xtpb_index order, double* points, double* weights, xtpb_index* count) {
+  XTPB_API_BEGIN
+  std::vector<double> x, w;
+  gaussian_quadrature(scheme, order, x, w);
+  if (count) *count = (xtpb_index)x.size();
+  if (points) std::memcpy(points, x.data(), x.size() * 8);
+  if (weights) std::memcpy(weights, w.data(), w.size() * 8);
+  XTPB_API_END
+}
 int xtpb_gw_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_gw_options* opt, const double* vxc_host, xtpb_index ldv,
                    const double* dft_energies_host, xtpb_index n_energies, xtpb_gw** out) {
   XTPB_API_BEGIN

@@ -74,10 +74,10 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D>
-void launch_cfg(const GemmParams& p, cudaStream_t stream) {
+template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D, bool VEC>
+void launch_cfg2(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BM, BN, WM, WN, A_KC, B_KC, kStages>;
-  auto kern = contract_kernel<Cfg, BM, BN, WM, WN, A_KC, B_KC, kStages, HAS_D>;
+  auto kern = contract_kernel<Cfg, BM, BN, WM, WN, A_KC, B_KC, kStages, HAS_D, VEC>;
   static bool attr_set = false;
   if (!attr_set) {
     XTPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -88,6 +88,13 @@ void launch_cfg(const GemmParams& p, cudaStream_t stream) {
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   XTPB_CUDA(cudaGetLastError());
   ++g_launch_count;
+}
+
+// 16-byte cp.async needs both operands 16-byte aligned in their contiguous direction; otherwise the 8-byte instance
+template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D>
+void launch_cfg(const GemmParams& p, cudaStream_t stream) {
+  if (p.a_vec && p.b_vec) launch_cfg2<BM, BN, WM, WN, A_KC, B_KC, HAS_D, true>(p, stream);
+  else launch_cfg2<BM, BN, WM, WN, A_KC, B_KC, HAS_D, false>(p, stream);
 }
 
 template <bool A_KC, bool B_KC, bool HAS_D>
@@ -190,8 +197,10 @@ int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, in
   if (splits <= 0) {
     splits = 1;
     const int sms = num_sms();
-    if (tiles < sms && nkt >= 16) {
-      splits = (int)std::min<long long>({(2LL * sms + tiles - 1) / tiles, nkt / 8, 64LL});
+    // fewer than two waves of tiles: split the contraction index so that ~3 waves of CTAs are in flight (tail
+    // balance for the tensor-bound shapes, bytes in flight for the HBM-bound tall-skinny ones)
+    if (tiles < 2LL * sms && nkt >= 16) {
+      splits = (int)std::min<long long>({(3LL * sms + tiles - 1) / tiles, nkt / 8, 64LL});
       if (splits < 1) splits = 1;
     }
   }

@@ -97,62 +97,76 @@ struct GemmCfg {
   static_assert(MF % 2 == 0 && NF % 2 == 0, "fragment pairs");
 };
 
-// ---- tile loader: one operand tile (R rows x 16 k) for k-tile starting at k0 of `outer`, in R*8/THREADS 16-byte
-// chunks per thread.  `load_operand_chunk` issues chunk `it` only, so the main loop can spread the address
-// arithmetic and the cp.async issue of the next tile between its DMMA groups. ----
-template <int R, int THREADS, bool KC>
-__device__ __forceinline__ void load_operand_chunk(int it, uint32_t sbase, const double* __restrict__ base,
-                                                   long long s_row, long long s_k, int rows_left, int k_left,
-                                                   bool vec, int tid) {
-  const int ci = tid + it * THREADS;
-  if (KC) {
-    const int c = ci & 7, row = ci >> 3;
-    const int k = 2 * c;
-    const uint32_t dst = sbase + row * ROW_BYTES + (((c ^ (row & 7)) & 7) << 4);
-    const bool rv = row < rows_left;
-    if (vec) {
-      int nb = rv ? (k_left - k) * 8 : 0;
-      nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-      const double* src = nb > 0 ? base + (long long)row * s_row + k : base;
-      cp_async16(dst, src, nb);
+// ---- per-thread loader with all index arithmetic hoisted out of the k-loop ----
+// Chunk `c` (c < CHUNKS) of this thread:
+//   K-contig : 16-byte column cc = tid & 7 (k = 2cc, 2cc+1) of row r0 + c*RSTEP;   r0 = tid >> 3, RSTEP = THREADS/8
+//              (RSTEP is a multiple of 8, so the swizzle term (cc ^ (row & 7)) is the same for every chunk)
+//   row-contig: row pair rg = tid % (R/2) (rows 2rg, 2rg+1) of k-row k0 + c*KSTEP; k0 = tid / (R/2), KSTEP = THREADS/(R/2)
+// VEC: both operands allow 16-byte cp.async (compile-time, so the 8-byte path costs nothing when it is not needed).
+template <int R, int THREADS, bool KC, bool VEC>
+struct OperandLoader {
+  static constexpr int CHUNKS = R * 8 / THREADS;
+  static constexpr int RSTEP = THREADS / 8, KSTEP = THREADS / (R / 2);
+  static_assert(RSTEP % 8 == 0 && THREADS % (R / 2) == 0, "chunk steps must preserve the swizzle phase");
+  long long g_off0;           // element offset of chunk 0 from the tile base
+  long long g_step;           // per-chunk increment (RSTEP rows / KSTEP k-rows)
+  uint32_t s_off0;            // K-contig: smem offset of chunk 0;  row-contig: row-group part of the smem offset
+  int first;                  // K-contig: k of the chunk (2cc);  row-contig: k-row of chunk 0
+  int rows_ok;                // K-contig: rows_left - r0;  row-contig: valid bytes of the row pair (0, 8, 16)
+  int rgsw;                   // row-contig: (rg & 7) swizzle phase
+  __device__ __forceinline__ OperandLoader(long long s_row, long long s_k, int rows_left, int tid) {
+    if (KC) {
+      const int cc = tid & 7, r0 = tid >> 3;
+      first = 2 * cc;
+      rows_ok = rows_left - r0;                       // chunk c valid iff c*RSTEP < rows_ok
+      g_off0 = (long long)r0 * s_row + first;
+      g_step = (long long)RSTEP * s_row;
+      s_off0 = (uint32_t)(r0 * ROW_BYTES + (((cc ^ (r0 & 7)) & 7) << 4));
+      rgsw = 0;
     } else {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool v = rv && (k + e) < k_left;
-        const double* src = v ? base + (long long)row * s_row + (k + e) : base;
-        cp_async8(dst + 8 * e, src, v ? 8 : 0);
-      }
+      const int rg = tid % (R / 2), k0 = tid / (R / 2), row = 2 * rg;
+      first = k0;
+      int nb = (rows_left - row) * 8;
+      rows_ok = nb < 0 ? 0 : (nb > 16 ? 16 : nb);     // valid bytes of this row pair (constant over tiles)
+      g_off0 = (long long)k0 * s_k + row;
+      g_step = (long long)KSTEP * s_k;
+      s_off0 = (uint32_t)((row >> 4) * (BK * ROW_BYTES));
+      rgsw = rg & 7;
     }
-  } else {
-    const int rg = ci % (R / 2), k = ci / (R / 2);
-    const int row = 2 * rg;
-    const uint32_t dst = sbase + (row >> 4) * (BK * ROW_BYTES) + k * ROW_BYTES + ((((rg & 7) ^ (k & 7)) & 7) << 4);
-    const bool kv = k < k_left;
-    if (vec) {
-      int nb = kv ? (rows_left - row) * 8 : 0;
-      nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-      const double* src = nb > 0 ? base + (long long)k * s_k + row : base;
-      cp_async16(dst, src, nb);
+  }
+  // valid bytes along k of this thread's chunk column in a tile with k_left valid k values (K-contig only)
+  __device__ __forceinline__ int k_bytes(int k_left) const {
+    const int nb = (k_left - first) * 8;
+    return nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+  }
+  // issue chunk c of the tile whose first element is `base` into the stage operand area `sbase`;
+  // kb = k_bytes(k_left) for K-contig operands, k_left itself for row-contig ones
+  __device__ __forceinline__ void issue(int c, uint32_t sbase, const double* __restrict__ base, int kb) const {
+    const double* src = base + g_off0 + c * g_step;
+    if (KC) {
+      const uint32_t dst = sbase + s_off0 + c * (RSTEP * ROW_BYTES);
+      const int nb = c * RSTEP < rows_ok ? kb : 0;
+      if (VEC) {
+        cp_async16(dst, nb > 0 ? src : base, nb);
+      } else {
+        cp_async8(dst, nb >= 8 ? src : base, nb >= 8 ? 8 : 0);
+        cp_async8(dst + 8, nb >= 16 ? src + 1 : base, nb >= 16 ? 8 : 0);
+      }
     } else {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool v = kv && (row + e) < rows_left;
-        const double* src = v ? base + (long long)k * s_k + (row + e) : base;
-        cp_async8(dst + 8 * e, src, v ? 8 : 0);
+      const int k = first + c * KSTEP;
+      const uint32_t dst = sbase + s_off0 + k * ROW_BYTES + (((rgsw ^ (k & 7)) & 7) << 4);
+      const int nb = k < kb ? rows_ok : 0;
+      if (VEC) {
+        cp_async16(dst, nb > 0 ? src : base, nb);
+      } else {
+        cp_async8(dst, nb >= 8 ? src : base, nb >= 8 ? 8 : 0);
+        cp_async8(dst + 8, nb >= 16 ? src + 1 : base, nb >= 16 ? 8 : 0);
       }
     }
   }
-}
-template <int R, int THREADS, bool KC>
-__device__ __forceinline__ void load_operand_tile(uint32_t sbase, const double* __restrict__ base,
-                                                  long long s_row, long long s_k, int rows_left, int k_left,
-                                                  bool vec, int tid) {
-#pragma unroll
-  for (int it = 0; it < R * 8 / THREADS; ++it)
-    load_operand_chunk<R, THREADS, KC>(it, sbase, base, s_row, s_k, rows_left, k_left, vec, tid);
-}
+};
 
-template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D>
+template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D, bool VEC>
 __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
@@ -179,17 +193,35 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
   const double* Db = HAS_D ? p.d + (long long)batch * p.d_batch : nullptr;
   const int m_left = p.M - m0, n_left = p.N - n0;
 
-  auto load_tile = [&](int stage, int kt) {
-    const int outer = kt / tpo, k0 = (kt - outer * tpo) * BK;
+  // ---- loader state, computed once per thread -------------------------------------------------------------
+  // Each thread owns chunk column/row (its 16-byte chunk position inside a tile) for every k-tile; only the tile
+  // base pointer changes from tile to tile.  Chunk `it` of an operand differs from chunk 0 by a constant row
+  // (K-contig) or k (row-contig) step, so its shared-memory offset and its global offset are chunk 0's plus a
+  // multiple of a per-thread constant: no index arithmetic is left in the main loop.
+  const OperandLoader<BM, Cfg::THREADS, A_KC, VEC> ldA(p.A.s_row, p.A.s_k, m_left, tid);
+  const OperandLoader<BN, Cfg::THREADS, B_KC, VEC> ldB(p.B.s_row, p.B.s_k, n_left, tid);
+  constexpr int NA = OperandLoader<BM, Cfg::THREADS, A_KC, VEC>::CHUNKS;
+  constexpr int NB = OperandLoader<BN, Cfg::THREADS, B_KC, VEC>::CHUNKS;
+
+  // tile -> (outer, k0) walked incrementally (no division in the loop)
+  int l_outer = kt_begin / tpo, l_k0 = (kt_begin - l_outer * tpo) * BK;
+  auto advance_tile = [&]() {
+    l_k0 += BK;
+    if (l_k0 >= p.K) { l_k0 = 0; ++l_outer; }
+  };
+  auto load_tile_full = [&](int stage) {      // prologue: whole tile at once
     const uint32_t sA = smem + stage * Cfg::STAGE_BYTES, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
-    const int k_left = p.K - k0;
-    load_operand_tile<BM, Cfg::THREADS, A_KC>(sA, Ab + (long long)outer * p.A.s_outer + (long long)k0 * p.A.s_k,
-                                              p.A.s_row, p.A.s_k, m_left, k_left, p.a_vec != 0, tid);
-    load_operand_tile<BN, Cfg::THREADS, B_KC>(sB, Bb + (long long)outer * p.B.s_outer + (long long)k0 * p.B.s_k,
-                                              p.B.s_row, p.B.s_k, n_left, k_left, p.b_vec != 0, tid);
+    const int k_left = p.K - l_k0;
+    const double* gA = Ab + (long long)l_outer * p.A.s_outer + (long long)l_k0 * p.A.s_k;
+    const double* gB = Bb + (long long)l_outer * p.B.s_outer + (long long)l_k0 * p.B.s_k;
+    const int kbA = A_KC ? ldA.k_bytes(k_left) : k_left, kbB = B_KC ? ldB.k_bytes(k_left) : k_left;
+#pragma unroll
+    for (int c = 0; c < NA; ++c) ldA.issue(c, sA, gA, kbA);
+#pragma unroll
+    for (int c = 0; c < NB; ++c) ldB.issue(c, sB, gB, kbB);
     if (HAS_D && tid < BK) {
       const bool v = tid < k_left;
-      const double* src = v ? Db + (long long)outer * p.d_outer + k0 + tid : Db;
+      const double* src = v ? Db + (long long)l_outer * p.d_outer + l_k0 + tid : Db;
       cp_async8(sD + tid * 8, src, v ? 8 : 0);
     }
   };
@@ -202,27 +234,49 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nkt) load_tile(s, kt_begin + s);
+    if (s < nkt) {
+      load_tile_full(s);
+      advance_tile();
+    }
     cp_async_commit();
   }
+
+  // ---- fragment addressing, computed once per thread ---------------------------------------------------------
+  // K-contig operand: fragment f, half h:  (w0 + rl)*128 + (((4h + lt) ^ rl) << 4) + f*1024, rl = row & 7 of the slot
+  // row-contig operand: pair q, half h, sub-step j: (w0/16 + q)*2048 + (8h + 2lt + j)*128 + ((li ^ (2lt + j)) << 4)
+  // -> two per-thread bases per operand (index h for K-contig, j for row-contig) plus compile-time immediates.
+  uint32_t a_off[2], b_off[2];
+  {
+    const int rl = (li >> 1) + 4 * (li & 1);
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      a_off[x] = A_KC ? (uint32_t)((wm0 + rl) * ROW_BYTES + ((((4 * x + lt) ^ rl) & 7) << 4))
+                      : (uint32_t)((wm0 >> 4) * (BK * ROW_BYTES) + (2 * lt + x) * ROW_BYTES + (((li ^ (2 * lt + x)) & 7) << 4));
+      b_off[x] = B_KC ? (uint32_t)((wn0 + rl) * ROW_BYTES + ((((4 * x + lt) ^ rl) & 7) << 4))
+                      : (uint32_t)((wn0 >> 4) * (BK * ROW_BYTES) + (2 * lt + x) * ROW_BYTES + (((li ^ (2 * lt + x)) & 7) << 4));
+    }
+  }
+  const uint32_t d_off = (uint32_t)(2 * lt * 8);
 
   // Main loop.  One barrier per 16-wide k-tile; inside a tile the 2*MF "steps" (half h = 8 k values, one A fragment
   // load feeding 2*NF DMMAs each) are software-pipelined by hand: A fragments are double-buffered in registers and
   // loaded one step ahead, the B fragments (and their chi0 weights) of the second half are fetched and
   // scaled while the first half is still issuing DMMAs, and the cp.async traffic of the tile STAGES-1 ahead is
   // spread over the steps so that no warp ever sits in a long non-tensor instruction run.
-  constexpr int NA = BM * 8 / Cfg::THREADS, NB = BN * 8 / Cfg::THREADS, NCH = NA + NB, STEPS = 2 * Cfg::MF;
+  constexpr int NCH = NA + NB, STEPS = 2 * Cfg::MF;
 #pragma unroll 1
   for (int it = 0; it < nkt; ++it) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     const int nxt = it + STAGES - 1;
     const bool do_load = nxt < nkt;
-    // next tile's loader state (uniform)
-    const int l_kt = kt_begin + nxt;
-    const int l_outer = l_kt / tpo, l_k0 = (l_kt - l_outer * tpo) * BK;
-    const int l_kleft = p.K - l_k0;
+    // next tile's loader state (uniform): stage bases and global tile bases
     const uint32_t lA = smem + (nxt % STAGES) * Cfg::STAGE_BYTES, lB = lA + Cfg::A_BYTES, lD = lB + Cfg::B_BYTES;
+    const int l_kleft = p.K - l_k0;
+    const double* gA = Ab + (long long)l_outer * p.A.s_outer + (long long)l_k0 * p.A.s_k;
+    const double* gB = Bb + (long long)l_outer * p.B.s_outer + (long long)l_k0 * p.B.s_k;
+    const double* gD = HAS_D ? Db + (long long)l_outer * p.d_outer + l_k0 : nullptr;
+    const int kbA = A_KC ? ldA.k_bytes(l_kleft) : l_kleft, kbB = B_KC ? ldB.k_bytes(l_kleft) : l_kleft;
 
     const int stage = it % STAGES;
     const uint32_t sA = smem + stage * Cfg::STAGE_BYTES, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
@@ -232,20 +286,13 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
     auto load_b = [&](int h, double (&b)[Cfg::NF][2]) {
       if (B_KC) {
 #pragma unroll
-        for (int nf = 0; nf < Cfg::NF; ++nf) {
-          const int row = wn0 + kc_slot_row(nf, li);
-          lds128(sB + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), b[nf][0], b[nf][1]);
-        }
+        for (int nf = 0; nf < Cfg::NF; ++nf) lds128(sB + b_off[h] + nf * (8 * ROW_BYTES), b[nf][0], b[nf][1]);
       } else {
 #pragma unroll
         for (int np = 0; np < Cfg::NF / 2; ++np)
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int k = slot_k(h, lt, j);
-            const int rb = (wn0 >> 4) + np;
-            lds128(sB + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), b[2 * np][j],
-                   b[2 * np + 1][j]);
-          }
+          for (int j = 0; j < 2; ++j)
+            lds128(sB + b_off[j] + h * (8 * ROW_BYTES) + np * (BK * ROW_BYTES), b[2 * np][j], b[2 * np + 1][j]);
       }
     };
     auto scale_b = [&](double d0, double d1, double (&b)[Cfg::NF][2]) {
@@ -259,22 +306,15 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
     //                                   M-contig: i = 2*mp + j, (a0,a1) = fragments 2mp, 2mp+1 at k sub-step j
     auto load_a = [&](int s, double (&a)[2]) {
       const int h = s / Cfg::MF, i = s % Cfg::MF;
-      if (A_KC) {
-        const int row = wm0 + kc_slot_row(i, li);
-        lds128(sA + row * ROW_BYTES + ((((4 * h + lt) ^ (row & 7)) & 7) << 4), a[0], a[1]);
-      } else {
-        const int mp = i >> 1, j = i & 1;
-        const int k = slot_k(h, lt, j);
-        const int rb = (wm0 >> 4) + mp;
-        lds128(sA + rb * (BK * ROW_BYTES) + k * ROW_BYTES + (((li ^ (k & 7)) & 7) << 4), a[0], a[1]);
-      }
+      if (A_KC) lds128(sA + a_off[h] + i * (8 * ROW_BYTES), a[0], a[1]);
+      else lds128(sA + a_off[i & 1] + h * (8 * ROW_BYTES) + (i >> 1) * (BK * ROW_BYTES), a[0], a[1]);
     };
 
     double dn0 = 1.0, dn1 = 1.0;
     load_b(0, bf[0]);
     if (HAS_D) {
       double d0, d1;
-      lds128(sD + (2 * lt) * 8, d0, d1);
+      lds128(sD + d_off, d0, d1);
       scale_b(d0, d1, bf[0]);
     }
     load_a(0, af[0]);
@@ -284,25 +324,18 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
       if (s + 1 < STEPS) load_a(s + 1, af[(s + 1) & 1]);   // one step (2*NF DMMAs) ahead of its use
       if (s == 0) {
         load_b(1, bf[1]);
-        if (HAS_D) lds128(sD + (8 + 2 * lt) * 8, dn0, dn1);
+        if (HAS_D) lds128(sD + d_off + 64, dn0, dn1);
       }
       if (do_load) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           if (c * STEPS / NCH != s) continue;
-          if (c < NA)
-            load_operand_chunk<BM, Cfg::THREADS, A_KC>(
-                c, lA, Ab + (long long)l_outer * p.A.s_outer + (long long)l_k0 * p.A.s_k, p.A.s_row, p.A.s_k, m_left,
-                l_kleft, p.a_vec != 0, tid);
-          else
-            load_operand_chunk<BN, Cfg::THREADS, B_KC>(
-                c - NA, lB, Bb + (long long)l_outer * p.B.s_outer + (long long)l_k0 * p.B.s_k, p.B.s_row, p.B.s_k,
-                n_left, l_kleft, p.b_vec != 0, tid);
+          if (c < NA) ldA.issue(c, lA, gA, kbA);
+          else ldB.issue(c - NA, lB, gB, kbB);
         }
         if (HAS_D && s == STEPS - 1 && tid < BK) {
           const bool v = tid < l_kleft;
-          const double* src = v ? Db + (long long)l_outer * p.d_outer + l_k0 + tid : Db;
-          cp_async8(lD + tid * 8, src, v ? 8 : 0);
+          cp_async8(lD + tid * 8, v ? gD + tid : Db, v ? 8 : 0);
         }
       }
       const double a0 = af[s & 1][0], a1 = af[s & 1][1];
@@ -322,6 +355,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
       if (HAS_D && s == Cfg::MF / 2) scale_b(dn0, dn1, bf[1]);
     }
     cp_async_commit();
+    if (do_load) advance_tile();
   }
   cp_async_wait<0>();
 

@@ -95,6 +95,9 @@ void k_residuals(double* res, long long ldr, const double* q, long long ldq, con
 void k_davidson_correction(double* out, const double* r, const double* x, const double* D, double lambda, long long n,
                            int olsen, double* scratch2, cudaStream_t s);
 void k_unit_vectors(double* V, long long ld, long long n, const long long* idx, int cols, cudaStream_t s);
+// dense BSE Hamiltonian: H[(v1,c1),(v2l,c2)] += cqp (Hqp[vt+c1,vt+c2] d(v1,v2) - Hqp[v1,v2] d(c1,c2)) for the local columns
+void k_bse_add_hqp(double* H, long long ld, int vt, int ct, int v2lo, int ns, const double* hqp, long long hs,
+                   double cqp, cudaStream_t s);
 // full[b](mu,nu) = full[b](nu,mu) = packed[b][mu(mu+1)/2 + nu] (nu <= mu), b < count
 void k_unpack_symmetric(double* full, long long ld, long long full_slice, const double* packed, long long pk_slice,
                         int n, int count, cudaStream_t s);
@@ -174,11 +177,14 @@ struct GW {
   DBuf ppm_freq_dev, ppm_fac_dev;
   // exact
   std::vector<double> rpa_omegas;
-  DBuf residues;                // [level][s][m]  (m fastest, ld = rpatotal)
+  DBuf residues;                // [level][s][m]  (m fastest, ld = tc->ldn)
+  DBuf exact_omega_dev;
   long long rpasize = 0;
   // CDA
   std::vector<double> quad_points, quad_weights;
   DBuf cda_kernels;             // (order+1) matrices naux x naux: dielinv_j ..., kappa0 last
+  DBuf cda_points_dev;          // points, then weights
+  DBuf cda_q;                   // quadratic forms Q[level][j][m] (j = order: kappa0), ld = tc->ldn
   DBuf backup;                  // un-rotated tensor for evGW (stands in for TCMatrix_gwbse::Rebuild)
 
   GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host, long long ldv, const double* e,
@@ -202,7 +208,10 @@ struct GW {
   void sigma_c_diag_elements_other(long long n, const long long* levels, const double* freqs, double* values,
                                    double* derivs);   // exact / CDA
   void sigma_c_offdiag_other(const double* freqs, double* out_host);
+  void cda_values(long long n, const long long* levels, const double* freqs, double* values);
 };
+// GaussianQuadrature (gaussian_quadrature.cc): scaled points / weights on (0, inf); host code
+void gaussian_quadrature(int scheme, long long order, std::vector<double>& points, std::vector<double>& weights);
 
 // ---------------------------------------------------------------- operators + Davidson
 struct Operator {
@@ -232,6 +241,11 @@ struct BseOperator : Operator {
   DBuf Mvv_raw_diag, Mcc_diag;      // not used (diagonal kernel reads windows directly)
   DBuf eps_inv_dev, hqp_dev, hqp_diag_dev;   // hqp_dev: (vt+ct)^2 col-major
   DBuf T, U;
+  // dense mode: the BSE Hamiltonian itself, built once from the windows (three long-K contractions) and kept in HBM;
+  // matmul is then a single HBM-bound GEMM.  Rank r owns the columns (v2, c2) with v2 in [v2lo, v2lo + ns).
+  bool dense = false;
+  DBuf H;
+  long long h_ld = 0, v2lo = 0, ns = 0;
   // windows are built from tc (optionally rotated by R_dev)
   BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpamin, long long vmin, long long cmax,
               const double* eps_inv_host, const double* hqp_host, long long ldh, int cqp_, int cx_, int cd_, int cd2_,

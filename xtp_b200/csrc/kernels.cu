@@ -1,5 +1,7 @@
 // Element-wise and reduction kernels of the GW-BSE path (everything that is not a contraction):
 // chi0 weights, Sigma_c plasmon-pole sums (FP64 ALU / HBM bound), BSE diagonal, Davidson vector ops.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace xtpb {
@@ -54,12 +56,28 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return fma(r, t, r);
 }
 
+// sin(2 pi x) for |x| <= 0.25 (argument in [-pi/2, pi/2]): odd Taylor polynomial through theta^21
+// (truncation < 2e-18), Horner in theta^2 -- 12 FP64 operations, no range reduction, no slow path.
+__device__ __forceinline__ double sin2pi_quarter(double x) {
+  const double t = 6.283185307179586476925286766559 * x, t2 = t * t;
+  double p = -1.9572941063391261230e-20;        // -1/21!
+  p = fma(p, t2, 8.2206352466243297170e-18);    //  1/19!
+  p = fma(p, t2, -2.8114572543455207632e-15);   // -1/17!
+  p = fma(p, t2, 7.6471637318198164759e-13);    //  1/15!
+  p = fma(p, t2, -1.6059043836821614599e-10);   // -1/13!
+  p = fma(p, t2, 2.5052108385441718775e-08);    //  1/11!
+  p = fma(p, t2, -2.7557319223985890653e-06);   // -1/9!
+  p = fma(p, t2, 1.9841269841269841270e-04);    //  1/7!
+  p = fma(p, t2, -8.3333333333333333333e-03);   // -1/5!
+  p = fma(p, t2, 1.6666666666666666667e-01);    //  1/3!  (sign folded below)
+  return fma(-t * t2, p, t);                    // t - t^3 (1/3! - t^2/5! + ...)
+}
+
 // damped branch of the Rohlfing-stabilised inverse: 0.5 (1 - cos 4 pi x) / x = sin^2(2 pi x) / x  (no cancellation);
-// Taylor limit 4 pi^2 x below the range where 1/x is finite.
-__device__ __noinline__ double ppm_ginv_damped(double x) {
-  if (fabs(x) < 1e-100) return (0.25 * kFourPi * kFourPi) * x;
-  const double s = sinpi(2.0 * x);
-  return s * s * rcp_fast(x);
+// r = 1/x is already at hand; Taylor limit 4 pi^2 x below the range where r is finite.
+__device__ __forceinline__ double ppm_ginv_damped(double x, double r) {
+  const double s = sin2pi_quarter(x);
+  return fabs(x) < 1e-100 ? (0.25 * kFourPi * kFourPi) * x : s * s * r;
 }
 
 // |x| < 0.25, read from the exponent word on the integer pipe (the FP64 pipe only carries subtract/refine/accumulate)
@@ -70,7 +88,8 @@ __device__ __forceinline__ bool ppm_in_window(double x) {
 // Rohlfing-stabilised inverse, upstream Sigma_PPM::Stabilize (sigma_ppm.cc): 1/x for |x| >= 0.25,
 // 0.5 (1 - cos 4 pi x) / x otherwise (-> 0 at x = 0).
 __device__ __forceinline__ double ppm_ginv(double x) {
-  return ppm_in_window(x) ? ppm_ginv_damped(x) : rcp_fast(x);
+  const double r = rcp_fast(x);
+  return ppm_in_window(x) ? ppm_ginv_damped(x, r) : r;
 }
 
 // ------------------------------------------------------------------ chi0 weights
@@ -202,31 +221,33 @@ __global__ void __launch_bounds__(256) unpack_symmetric_kernel(double* __restric
 //     frequencies (NW each, held in registers, consecutive lanes = consecutive grid points so the |x|<0.25 branch
 //     is warp-coherent), the (P,m) elements of the level's slab stream through shared memory and are broadcast.
 //     Bound: FP64 ALU (one reciprocal per element and frequency); the slab is read once per 2*T*NW frequencies.
-constexpr int kGridThreads = 128, kGridNW = 4, kGridTile = 512;
-constexpr double kGridFar = 1.0e30;    // stand-in denominator: padding entries and poles inside the damping window
+constexpr int kGridThreads = 128, kGridNW = 4, kGridTile = 512, kGridEl = 2;
 
-// G poles share one reciprocal: sum_g w_g / x_g = N / D with D = prod x_g, N = sum_g w_g prod_{g' != g} x_g'
-// (pairwise tree, 4G+1 FP64 operations and ONE MUFU.RCP64H per G poles and frequency; |x| is in [0.25, ~20] outside
-// the damping window, so D stays far from over/underflow for G <= 8).  Poles inside the window get x = 1e30 here
-// (contribution ~1e-30 w) and are added exactly by the rare damped branch.
-template <int G>
+// Per pole and frequency: 1 subtract, 1 MUFU.RCP64H seed + 3 DFMA refinement, 1 DFMA accumulate, and an integer
+// window test; the reciprocals of the kGridEl*NW evaluations of one step are independent chains.  If any of them
+// falls inside the damping window the (rare, warp-coherent: lanes are consecutive grid points) branch replaces those
+// reciprocals by sin^2(2 pi x)/x before the accumulate -- no selects on the common path.
+// blockIdx.z splits the aux range so that small level counts still fill the machine; partial sums are reduced in a
+// fixed order by sigma_ppm_grid_reduce (deterministic).
 __global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
     const double* __restrict__ energies, const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac,
     const int* __restrict__ level_slab, const double* __restrict__ omega0, double domega, int n_omega,
-    double* __restrict__ values) {
+    double* __restrict__ out, long long out_split_stride) {
   __shared__ double2 tile[kGridTile];
-  static_assert(kGridTile % G == 0, "tile is consumed G poles at a time");
+  static_assert(kGridTile % kGridEl == 0, "tile is consumed kGridEl poles at a time");
   const int level = blockIdx.y;
   const double* S = M + (long long)level_slab[level] * slab;
   const int jbase = blockIdx.x * (kGridThreads * kGridNW) + threadIdx.x;
+  const int p_per = (naux + gridDim.z - 1) / gridDim.z;
+  const int p_begin = blockIdx.z * p_per, p_end = min(naux, p_begin + p_per);
   double om[kGridNW], acc[kGridNW];
 #pragma unroll
   for (int w = 0; w < kGridNW; ++w) {
     om[w] = omega0[level] + domega * (double)(jbase + w * kGridThreads);
     acc[w] = 0.0;
   }
-  for (int P = 0; P < naux; ++P) {
+  for (int P = p_begin; P < p_end; ++P) {
     const double fac = ppm_fac[P];
     if (fac == 0.0) continue;     // uniform across the block
     const double Om = ppm_freq[P];
@@ -235,7 +256,7 @@ __global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
       __syncthreads();
       for (int t = threadIdx.x; t < kGridTile; t += kGridThreads) {
         const int m = m0 + t;
-        double2 el = make_double2(0.0, -kGridFar);          // padding: weight 0, x = w + 1e30
+        double2 el = make_double2(0.0, -1.0e30);            // padding: weight 0, far away
         if (m < ntotal) {
           const double v = row[m];
           el.x = fac * v * v;
@@ -244,50 +265,48 @@ __global__ void __launch_bounds__(kGridThreads) sigma_ppm_grid_kernel(
         tile[t] = el;
       }
       __syncthreads();
-      const int cnt = (min(kGridTile, ntotal - m0) + G - 1) / G * G;
+      const int cnt = (min(kGridTile, ntotal - m0) + kGridEl - 1) / kGridEl * kGridEl;
 #pragma unroll 2
-      for (int t = 0; t < cnt; t += G) {
-        double2 el[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) el[g] = tile[t + g];
+      for (int t = 0; t < cnt; t += kGridEl) {
+        double2 el[kGridEl];
+        double x[kGridEl][kGridNW], r[kGridEl][kGridNW];
         bool any = false;
 #pragma unroll
-        for (int w = 0; w < kGridNW; ++w) {
-          double num[G], den[G];
+        for (int g = 0; g < kGridEl; ++g) {
+          el[g] = tile[t + g];
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const double x = om[w] - el[g].y;
-            const bool win = ppm_in_window(x);
-            any |= win;
-            den[g] = win ? kGridFar : x;
-            num[g] = el[g].x;
+          for (int w = 0; w < kGridNW; ++w) {
+            x[g][w] = om[w] - el[g].y;
+            r[g][w] = rcp_fast(x[g][w]);
+            any |= ppm_in_window(x[g][w]);
           }
-#pragma unroll
-          for (int width = G; width > 1; width >>= 1)
-#pragma unroll
-            for (int g = 0; g < width / 2; ++g) {
-              const double n0 = num[2 * g], n1 = num[2 * g + 1], d0 = den[2 * g], d1 = den[2 * g + 1];
-              num[g] = fma(n0, d1, n1 * d0);
-              den[g] = d0 * d1;
-            }
-          acc[w] = fma(num[0], rcp_fast(den[0]), acc[w]);
         }
         if (any) {
 #pragma unroll
-          for (int g = 0; g < G; ++g)
+          for (int g = 0; g < kGridEl; ++g)
 #pragma unroll
-            for (int w = 0; w < kGridNW; ++w) {
-              const double x = om[w] - el[g].y;
-              if (ppm_in_window(x)) acc[w] = fma(el[g].x, ppm_ginv_damped(x), acc[w]);
-            }
+            for (int w = 0; w < kGridNW; ++w)
+              if (ppm_in_window(x[g][w])) r[g][w] = ppm_ginv_damped(x[g][w], r[g][w]);
         }
+#pragma unroll
+        for (int g = 0; g < kGridEl; ++g)
+#pragma unroll
+          for (int w = 0; w < kGridNW; ++w) acc[w] = fma(el[g].x, r[g][w], acc[w]);
       }
     }
   }
 #pragma unroll
   for (int w = 0; w < kGridNW; ++w) {
     const int j = jbase + w * kGridThreads;
-    if (j < n_omega) values[(long long)level * n_omega + j] = acc[w];
+    if (j < n_omega) out[(long long)blockIdx.z * out_split_stride + (long long)level * n_omega + j] = acc[w];
+  }
+}
+__global__ void sigma_ppm_grid_reduce(double* __restrict__ values, const double* __restrict__ partial, long long n,
+                                      int splits) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int s = 0; s < splits; ++s) v += partial[(long long)s * n + i];
+    values[i] = v;
   }
 }
 
@@ -522,6 +541,22 @@ __global__ void window_from_gathered_kernel(double* __restrict__ dst, long long 
   }
 }
 
+
+// ------------------------------------------------------------------ dense BSE Hamiltonian: Hqp part
+// part 0: rows (v2, c1) of column (v2l, c2) += cqp * Hqp[vt+c1, vt+c2];  part 1: rows (v1, c2) -= cqp * Hqp[v1, v2]
+__global__ void bse_add_hqp_kernel(double* __restrict__ H, long long ld, int vt, int ct, int v2lo, int ns,
+                                   const double* __restrict__ hqp, long long hs, double cqp, int part) {
+  const int per = part == 0 ? ct : vt;
+  const long long total = (long long)ns * ct * per;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % per);
+    const long long col = idx / per;
+    const int c2 = (int)(col % ct), v2 = v2lo + (int)(col / ct);
+    if (part == 0) H[(long long)v2 * ct + t + col * ld] += cqp * hqp[(vt + t) + (long long)(vt + c2) * hs];
+    else H[(long long)t * ct + c2 + col * ld] -= cqp * hqp[t + (long long)v2 * hs];
+  }
+}
 }  // namespace
 
 // ------------------------------------------------------------------ host wrappers
@@ -572,27 +607,31 @@ void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal
                       const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
                       const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s) {
   const int per_block = kGridThreads * kGridNW;
-  dim3 grid((n_omega + per_block - 1) / per_block, n_levels);
-  // work = pole evaluations (one reciprocal + ~6 flops each)
+  const int bx = (n_omega + per_block - 1) / per_block;
+  // ~8 resident CTAs per SM: split the aux range when there are few (level, frequency-chunk) blocks
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int splits = (8 * sms + bx * n_levels - 1) / (bx * n_levels);
+  splits = std::min(splits, 16);
+  splits = std::min(splits, naux / 64 > 0 ? naux / 64 : 1);
+  splits = std::max(splits, 1);
+  dim3 grid(bx, n_levels, splits);
+  const long long n = (long long)n_levels * n_omega;
+  DBuf partial;
+  if (splits > 1) partial.alloc((size_t)(n * splits));
+  // work = pole evaluations (one reciprocal + 5 FP64 operations each)
   const int slot = prof_begin(PROF_SIGMA_GRID, (double)ntotal * naux * (double)n_omega * n_levels, s);
-  // poles per reciprocal: 8 by default; XTPB_GRID_GROUP=1|2|4|8 selects another instance (tools/bench_sigma_grid.py)
-  static const int group = [] {
-    const char* e = getenv("XTPB_GRID_GROUP");
-    const int g = e ? atoi(e) : 8;
-    return (g == 1 || g == 2 || g == 4 || g == 8) ? g : 8;
-  }();
-#define XTPB_GRID_LAUNCH(G)                                                                                           \
-  sigma_ppm_grid_kernel<G><<<grid, kGridThreads, 0, s>>>(M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq,       \
-                                                         ppm_fac, level_slab, omega0, domega, n_omega, values)
-  switch (group) {
-    case 1: XTPB_GRID_LAUNCH(1); break;
-    case 2: XTPB_GRID_LAUNCH(2); break;
-    case 4: XTPB_GRID_LAUNCH(4); break;
-    default: XTPB_GRID_LAUNCH(8); break;
-  }
-#undef XTPB_GRID_LAUNCH
+  sigma_ppm_grid_kernel<<<grid, kGridThreads, 0, s>>>(M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq, ppm_fac,
+                                                      level_slab, omega0, domega, n_omega,
+                                                      splits > 1 ? partial.p : values, n);
   LAUNCH_CHECK();
+  if (splits > 1) {
+    sigma_ppm_grid_reduce<<<blocks_for(n, 256, 2048), 256, 0, s>>>(values, partial.p, n, splits);
+    LAUNCH_CHECK();
+  }
   prof_end(slot, s);
+  if (splits > 1) XTPB_CUDA(cudaStreamSynchronize(s));   // partial is freed on return
 }
 void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                        const double* energies, const double* ppm_freq, const double* ppm_fac, const int* pair_slab,
@@ -704,6 +743,16 @@ void k_window_from_gathered(double* dst, long long dst_ld, long long dst_slab, c
   window_from_gathered_kernel<<<blocks_for(total, 256, 16384), 256, 0, s>>>(dst, dst_ld, dst_slab, G, ldl, mcnt, naux,
                                                                            P0, pcnt, n0, ncnt, world);
   LAUNCH_CHECK();
+}
+
+void k_bse_add_hqp(double* H, long long ld, int vt, int ct, int v2lo, int ns, const double* hqp, long long hs,
+                   double cqp, cudaStream_t s) {
+  for (int part = 0; part < 2; ++part) {
+    const long long total = (long long)ns * ct * (part == 0 ? ct : vt);
+    if (total == 0) continue;
+    bse_add_hqp_kernel<<<blocks_for(total, 256, 8192), 256, 0, s>>>(H, ld, vt, ct, v2lo, ns, hqp, hs, cqp, part);
+    LAUNCH_CHECK();
+  }
 }
 
 }  // namespace xtpb
