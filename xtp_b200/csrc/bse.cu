@@ -93,6 +93,7 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
                          int cd2_, const double* R_dev)
     : cqp(cqp_), cx(cx_), cd(cd_), cd2(cd2_) {
   ctx = c;
+  tc->flush();
   XTPB_REQUIRE(!(cd != 0 && cd2 != 0), "Hamiltonian cannot contain Hd and Hd2 at the same time");
   XTPB_REQUIRE(vmin >= rpamin && vmin <= homo && cmax > homo && cmax <= tc->mmax && cmax <= tc->nmax,
                "BSE window outside the TCMatrix");
@@ -406,7 +407,7 @@ namespace {
 struct DavidsonWork {
   Context* ctx;
   long long n, ld, cap;
-  DBuf V, AV, Q, R, small, vec;   // Q: Ritz vectors, R: residuals
+  DBuf V, AV, Q, R, small, vec, tmp;   // Q: Ritz vectors, R: residuals, tmp: block being re-orthonormalised
 };
 
 // C(s x k) = V[:, :s]^T W[:, :k]
@@ -432,7 +433,7 @@ void gemm_nn(Context* ctx, const double* V, long long ldv, int s, const double* 
 
 // two-pass Gram-Schmidt of columns nstart..ncols-1 of V against all kept previous ones; dependent columns are
 // dropped (kept columns are compacted).  Returns the new column count.
-int gram_schmidt(DavidsonWork& w, int nstart, int ncols) {
+int gram_schmidt_columns(DavidsonWork& w, int nstart, int ncols) {
   Context* ctx = w.ctx;
   int kept = nstart;
   double* coef = w.small.p;       // up to cap doubles
@@ -455,6 +456,64 @@ int gram_schmidt(DavidsonWork& w, int nstart, int ncols) {
     ++kept;
   }
   return kept;
+}
+
+
+// Block version used on the hot path: two classical Gram-Schmidt passes of the whole new block against the kept
+// basis (2 GEMMs each), then Cholesky-QR (twice) inside the block -- a handful of launches and one small D2H per
+// call instead of ~8 launches and a host sync per column.  A (near-)dependent block (tiny Cholesky pivot) falls
+// back to the column-by-column routine above, which drops dependent columns.
+int gram_schmidt(DavidsonWork& w, int nstart, int ncols) {
+  Context* ctx = w.ctx;
+  const int k = ncols - nstart;
+  if (k <= 0) return nstart;
+  if (k == 1 || k > 64) return gram_schmidt_columns(w, nstart, ncols);
+  double* W = w.V.p + (long long)nstart * w.ld;
+  double* coef = w.small.p;                      // nstart x k (<= cap*cap)
+  if (nstart > 0) {
+    for (int pass = 0; pass < 2; ++pass) {
+      gemm_tn(ctx, w.V.p, w.ld, nstart, W, w.ld, k, w.n, coef, nstart);
+      gemm_nn(ctx, w.V.p, w.ld, nstart, coef, nstart, k, w.n, W, w.ld, -1.0, 1.0);
+    }
+  }
+  std::vector<double> G((size_t)k * k), S((size_t)k * k);
+  for (int pass = 0; pass < 2; ++pass) {
+    gemm_tn(ctx, W, w.ld, k, W, w.ld, k, w.n, coef, k);
+    ctx->d2h(G.data(), coef, (size_t)k * k);
+    // Cholesky G = L L^T (lower), then S = L^{-T} (upper) so that W S is orthonormal
+    std::vector<double> L((size_t)k * k, 0.0);
+    double dmax = 0.0;
+    for (int j = 0; j < k; ++j) dmax = std::max(dmax, G[j + (size_t)j * k]);
+    bool ok = dmax > 0.0 && std::isfinite(dmax);
+    for (int j = 0; j < k && ok; ++j) {
+      double d = G[j + (size_t)j * k];
+      for (int t = 0; t < j; ++t) d -= L[j + (size_t)t * k] * L[j + (size_t)t * k];
+      if (!(d > 1e-12 * G[j + (size_t)j * k]) || !(G[j + (size_t)j * k] > 1e-20)) { ok = false; break; }
+      const double ljj = std::sqrt(d);
+      L[j + (size_t)j * k] = ljj;
+      for (int i = j + 1; i < k; ++i) {
+        double v = G[i + (size_t)j * k];
+        for (int t = 0; t < j; ++t) v -= L[i + (size_t)t * k] * L[j + (size_t)t * k];
+        L[i + (size_t)j * k] = v / ljj;
+      }
+    }
+    if (!ok) return gram_schmidt_columns(w, nstart, ncols);
+    // S = (L^{-1})^T: solve L X = I column by column (X lower), S(i,j) = X(j,i)
+    std::fill(S.begin(), S.end(), 0.0);
+    for (int c = 0; c < k; ++c) {
+      std::vector<double> x((size_t)k, 0.0);
+      for (int i = c; i < k; ++i) {
+        double v = i == c ? 1.0 : 0.0;
+        for (int t = c; t < i; ++t) v -= L[i + (size_t)t * k] * x[t];
+        x[i] = v / L[i + (size_t)i * k];
+      }
+      for (int i = c; i < k; ++i) S[c + (size_t)i * k] = x[i];      // S(c, i) = X(i, c)
+    }
+    ctx->h2d(coef, S.data(), (size_t)k * k);
+    gemm_nn(ctx, W, w.ld, k, coef, k, k, w.n, w.tmp.p, w.ld, 1.0, 0.0);
+    k_copy_2d(W, w.ld, w.tmp.p, w.ld, (int)w.n, k, ctx->stream);
+  }
+  return ncols;
 }
 
 }  // namespace
@@ -486,6 +545,7 @@ void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& 
   w.AV.alloc((size_t)(w.ld * w.cap));
   w.Q.alloc((size_t)(w.ld * su));
   w.R.alloc((size_t)(w.ld * su));
+  w.tmp.alloc((size_t)(w.ld * std::max<long long>(su, 1)));
   w.small.alloc((size_t)(w.cap * (w.cap + 4) + 16));
   w.vec.alloc((size_t)(2 * n + 1024));
   w.V.zero(ctx->stream);

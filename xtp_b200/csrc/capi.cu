@@ -228,7 +228,7 @@ int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index l
     contract(g, ctx->ws, ctx->stream);
     R = A.p;
   }
-  t.rotate(R, na);
+  t.set_pending(R, na);       // deferred: folded into the next full rotation (see TCMatrix::set_pending)
   ctx->sync();
   if (removed_functions) *removed_functions = removed;
   XTPB_API_END

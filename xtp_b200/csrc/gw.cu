@@ -42,6 +42,7 @@ void GW::set_rpa_energies(const double* e) {
 
 // Sigma_x(n,n') = - sum_{m occ} sum_P M[n](m,P) M[n'](m,P)   (upstream Sigma_base::CalcExchangeMatrix)
 void GW::exchange(double* out_host) {
+  tc->flush();
   ProfScope prof(PROF_SIGMA_X);
   DBuf S((size_t)(qptotal * qptotal));
   GemmParams g{};
@@ -128,6 +129,7 @@ void GW::sigma_c_diag_elements(long long n, const long long* levels, const doubl
                                double* derivs) {
   XTPB_REQUIRE(screening_ready, "PrepareScreening has not been called");
   if (n == 0) return;
+  tc->flush();
   if (opt.sigma_integration == XTPB_SIGMA_PPM) {
     std::vector<int> slabs((size_t)n);
     for (long long i = 0; i < n; ++i) {
@@ -157,6 +159,7 @@ void GW::grid_scan(const std::vector<double>& f0, std::vector<double>& values) {
   const long long steps = opt.qp_grid_steps;
   const double range = opt.qp_grid_spacing * double(steps - 1) / 2.0;
   values.resize((size_t)(qptotal * steps));
+  tc->flush();
   if (opt.sigma_integration == XTPB_SIGMA_PPM) {
     std::vector<int> slabs((size_t)qptotal);
     std::vector<double> om0((size_t)qptotal);
@@ -331,14 +334,22 @@ static std::vector<double> update_rpa_energies(const std::vector<double>& dft, c
 // GW::CalculateGWPerturbation (gw.cc)
 void GW::calculate_gw_perturbation() {
   const long long q = qptotal;
-  exchange(sigma_x.data());
-  for (auto& v : sigma_x) v *= (1.0 - opt.ScaHFX);
   std::vector<double> shifted = dft_energies;          // ScissorShift_DFTlevel
   for (size_t i = (size_t)opt.homo + 1; i < shifted.size(); ++i) shifted[i] += opt.shift;
   std::vector<double> init(shifted.begin() + opt.rpamin, shifted.begin() + opt.rpamax + 1);
   set_rpa_energies(init.data());
   std::vector<double> freqs(shifted.begin() + opt.qpmin, shifted.begin() + opt.qpmin + q);
   const bool evgw = opt.gw_sc_max_iterations > 1;
+  // G0W0 with the plasmon-pole model and a deferred Coulomb-metric rotation on the tensor: build the screening first
+  // so that V^-1/2 and the PPM eigenvectors reach the tensor as ONE rotation; Sigma_x is invariant under the
+  // (orthogonal) PPM rotation, so evaluating it afterwards changes nothing.
+  bool screening_done = false;
+  if (tc->pending && !evgw && opt.sigma_integration == XTPB_SIGMA_PPM) {
+    prepare_screening();
+    screening_done = true;
+  }
+  exchange(sigma_x.data());
+  for (auto& v : sigma_x) v *= (1.0 - opt.ScaHFX);
   if (evgw && backup.n == 0) {     // stands in for TCMatrix_gwbse::Rebuild: restore the un-rotated tensor
     backup.alloc(tc->M.n);
     XTPB_CUDA(cudaMemcpyAsync(backup.p, tc->M.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -346,7 +357,7 @@ void GW::calculate_gw_perturbation() {
   for (long long i_gw = 0; i_gw < opt.gw_sc_max_iterations; ++i_gw) {
     if (i_gw % opt.reset_3c == 0 && i_gw != 0)
       XTPB_CUDA(cudaMemcpyAsync(tc->M.p, backup.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    prepare_screening();
+    if (!(screening_done && i_gw == 0)) prepare_screening();
     freqs = solve_qp(freqs);
     if (evgw) {
       const std::vector<double> old = rpa_energies;
@@ -389,6 +400,7 @@ std::vector<double> GW::hqp() const {
 // Sigma_base::CalcCorrelationOffDiag; for the PPM as one weighted contraction per aux chunk (see kernels.cu (3)).
 void GW::sigma_c_offdiag(const double* freqs, double* out_host) {
   XTPB_REQUIRE(screening_ready, "PrepareScreening has not been called");
+  tc->flush();
   ProfScope prof(PROF_SIGMA_OFFDIAG);
   const long long q = qptotal;
   if (opt.sigma_integration != XTPB_SIGMA_PPM) {

@@ -150,6 +150,14 @@ struct TCMatrix {
   TCMatrix(TCMatrix&&) = delete;
   // M[m] <- M[m] * R for all m (R on the device, naux x naux, ld = ldr)
   void rotate(const double* R_dev, long long ldr);
+  // Deferred aux rotation.  The Coulomb-metric factor V^-1/2 (xtpb_tc_apply_coulomb_metric) is not applied to the
+  // 29 GB tensor at once: the next full rotation (the PPM eigenvectors) is folded into it (M <- M (Rp R), one pass
+  // instead of two), epsilon is formed from the un-rotated tensor and sandwiched (Rp^T E Rp, two N_aux^3 products),
+  // and every other consumer calls flush() first, so the observable tensor is unchanged.
+  DBuf pendR;
+  bool pending = false;
+  void set_pending(const double* R_dev, long long ldr);
+  void flush();
   // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]   (window rotation into a caller-owned buffer)
   void rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
                      const double* R_dev, long long ldr);

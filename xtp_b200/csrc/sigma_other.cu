@@ -320,6 +320,7 @@ void gaussian_quadrature(int scheme, long long order, std::vector<double>& point
 
 // ================================================================ Sigma_Exact
 void GW::prepare_exact() {
+  tc->flush();
   ProfScope prof(PROF_EXACT);
   XTPB_REQUIRE(ctx->world == 1, "Sigma_Exact holds a dense (o*u)^2 matrix and runs on a single GPU");
   const long long na = tc->naux, nocc = n_occ, nun = rpatotal - n_occ;
@@ -383,6 +384,7 @@ void GW::prepare_exact() {
 
 // ================================================================ Sigma_CDA
 void GW::prepare_cda() {
+  tc->flush();
   ProfScope prof(PROF_CDA);
   const long long na = tc->naux, nn = na * na;
   gaussian_quadrature(opt.quadrature_scheme, opt.order, quad_points, quad_weights);

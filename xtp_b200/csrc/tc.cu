@@ -30,6 +30,7 @@ TCMatrix::~TCMatrix() {
 }
 
 void TCMatrix::set_raw(const double* host) {
+  pending = false;
   if (world == 1) {
     ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
     ctx->sync();
@@ -46,6 +47,7 @@ void TCMatrix::set_raw(const double* host) {
 
 void TCMatrix::get_slab(long long m, double* host) {
   XTPB_REQUIRE(m >= 0 && m < mtotal, "slab index out of range");
+  flush();
   if (world == 1) {
     ctx->d2h_2d(host, ntotal, slab_ptr(m), ldn, ntotal, naux);
     return;
@@ -67,6 +69,7 @@ const double* TCMatrix::local_energies(const double* e_glob_dev, DBuf& tmp) {
 
 void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host) {
   XTPB_REQUIRE(nb > 0 && ldc_host >= nb, "bad MO coefficient matrix");
+  pending = false;            // a new fill starts from the un-rotated tensor
   n_basis = nb;
   ldc = round_up(nb, 2);
   Cm.alloc((size_t)(ldc * mtotal));
@@ -295,6 +298,7 @@ void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
 // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]; A rows-contiguous (j), B = R K-contiguous (column Q of R).
 void TCMatrix::rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
                              const double* R_dev, long long ldr) {
+  flush();
   ProfScope prof(PROF_ROTATE);
   GemmParams g{};
   g.A = GemmOperand{M.p + (long long)m0 * slab + n0, 1, ldn, 0, slab};
@@ -312,7 +316,39 @@ void TCMatrix::rotate_window(double* dst, long long dst_ld, long long dst_slab, 
 }
 
 // MultiplyRightWithAuxMatrix: out of place through a bounded scratch of `chunk` slabs, copied back.
+void TCMatrix::set_pending(const double* R_dev, long long ldr) {
+  flush();
+  static const bool lazy = [] { const char* e = getenv("XTPB_LAZY_METRIC"); return !(e && e[0] == '0'); }();
+  if (!lazy) {
+    rotate(R_dev, ldr);
+    return;
+  }
+  pendR.ensure((size_t)(naux * naux));
+  k_copy_2d(pendR.p, naux, R_dev, ldr, (int)naux, naux, ctx->stream);
+  pending = true;
+}
+
+void TCMatrix::flush() {
+  if (!pending) return;
+  pending = false;
+  rotate(pendR.p, naux);
+}
+
 void TCMatrix::rotate(const double* R_dev, long long ldr) {
+  DBuf folded;
+  if (pending) {      // M <- M (Rp R): fold the deferred factor into this rotation
+    pending = false;
+    folded.alloc((size_t)(naux * naux));
+    ProfScope prof(PROF_DENSE_AUX);
+    GemmParams g{};
+    g.A = op_rows_contig(pendR.p, naux);
+    g.B = op_k_contig(R_dev, ldr);
+    g.C = folded.p; g.c_sm = 1; g.c_sn = naux;
+    g.M = g.N = g.K = (int)naux; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+    R_dev = folded.p;
+    ldr = naux;
+  }
   const long long budget = 1LL << 29;   // doubles (4 GiB)
   const long long chunk = std::max<long long>(1, std::min<long long>(mtotal, budget / slab));
   ctx->scratch_b.ensure((size_t)(chunk * slab));
@@ -322,6 +358,7 @@ void TCMatrix::rotate(const double* R_dev, long long ldr) {
     // padding column (ldn > ntotal) of the scratch is never written; copy only the payload rows
     k_copy_2d(slab_ptr(m), ldn, ctx->scratch_b.p, ldn, (int)ntotal, cnt * naux, ctx->stream);
   }
+  if (folded.p) ctx->sync();      // folded is freed on return
 }
 
 // eps(w) = 1 + sum_{m occ} A_m^T diag(d_m(w)) A_m with A_m = M[m](unocc, :)   (upstream RPA::calculate_epsilon)
@@ -356,6 +393,28 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
     XTPB_CUDA(cudaMemsetAsync(out_dev, 0, out_count * 8, ctx->stream));
   }
   ctx->allreduce_sum(out_dev, out_count);           // partial sums over the local unoccupied levels
+  if (tc.pending) {
+    // the tensor still lacks the deferred aux rotation Rp: eps = 1 + Rp^T E Rp with E from the un-rotated tensor
+    const long long na = tc.naux;
+    DBuf T((size_t)(na * na));
+    for (int w = 0; w < n_omega; ++w) {
+      double* E = out_dev + (long long)w * na * na;
+      symmetrize_from_lower(E, (int)na, na, 0.0, ctx->stream);
+      GemmParams g{};
+      g.A = op_k_contig(E, na);                      // E symmetric
+      g.B = op_k_contig(tc.pendR.p, na);
+      g.C = T.p; g.c_sm = 1; g.c_sn = na;
+      g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+      contract(g, ctx->ws, ctx->stream);
+      GemmParams h{};
+      h.A = op_k_contig(tc.pendR.p, na);
+      h.B = op_k_contig(T.p, na);
+      h.C = E; h.c_sm = 1; h.c_sn = na;
+      h.M = h.N = h.K = (int)na; h.n_outer = 1; h.n_batch = 1; h.alpha = 1.0; h.lower = 1;
+      contract(h, ctx->ws, ctx->stream);
+    }
+    ctx->sync();   // T is freed at scope exit
+  }
   for (int w = 0; w < n_omega; ++w)
     symmetrize_from_lower(out_dev + (long long)w * tc.naux * tc.naux, (int)tc.naux, tc.naux, 1.0, ctx->stream);
   ctx->sync();   // d is freed on return
