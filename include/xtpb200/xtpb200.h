@@ -38,6 +38,8 @@ const char* xtpb_last_error(void);
 int xtpb_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 long long xtpb_launch_count(void);
+/* of which launches of the contraction engine's TMA-fed instance (cp.async.bulk.tensor + mbarrier pipeline) */
+long long xtpb_tma_launch_count(void);
 
 /* ---- context: one CUDA device + stream + scratch.  Replaces OpenMP_CUDA / CudaPipeline
  *      (upstream xtp/src/libxtp/openmp_cuda.cc, cudapipeline.cc). ---- */
@@ -244,7 +246,7 @@ typedef struct xtpb_contract_desc {
   xtpb_index c_row, c_col, c_batch, c_len, c_col_inner, c_col_outer;
   xtpb_index d_outer, d_batch, d_len;   /* d_len = 0: no weights */
   double alpha, beta;
-  int lower, force_cfg, force_splits;
+  int lower, force_cfg, force_splits;   /* force_cfg: -1 auto; 0..2 tile; 4..7 cp.async instance; 8..10 TMA instance */
 } xtpb_contract_desc;
 int xtpb_contract_host(xtpb_ctx* ctx, const xtpb_contract_desc* desc, const double* A_host, const double* B_host,
                        const double* d_host, double* C_host);

@@ -123,3 +123,40 @@ def test_two_level_output_column(ctx):
 def test_multi_tile_grid(ctx):
     run_case(ctx, 700, 530, 96, True, True, seed=14)
     run_case(ctx, 700, 530, 96, False, True, seed=15)
+
+
+# ---- the TMA-fed instance (cp.async.bulk.tensor + mbarrier pipeline): force_cfg 8..10 bypasses the size threshold
+def _tma_case(ctx, *a, **kw):
+    from xtp_b200 import api
+    before = api.tma_launch_count()
+    run_case(ctx, *a, **kw)
+    assert api.tma_launch_count() > before, "the TMA instance was not used (tensor map refused?)"
+
+
+@pytest.mark.parametrize("a_kc,b_kc", LAYOUTS)
+@pytest.mark.parametrize("cfg", [8, 9, 10])
+def test_tma_full_and_ragged_tiles(ctx, a_kc, b_kc, cfg):
+    _tma_case(ctx, 256, 128, 64, a_kc, b_kc, cfg=cfg, seed=20)
+    _tma_case(ctx, 134, 78, 46, a_kc, b_kc, cfg=cfg, seed=21)          # ragged rows/cols and a k tail (46 = 2*16 + 14)
+    _tma_case(ctx, 700, 530, 98, a_kc, b_kc, cfg=cfg, seed=22)         # multi-tile grid, more k-tiles than stages
+
+
+@pytest.mark.parametrize("a_kc,b_kc", LAYOUTS)
+def test_tma_weights_outer_batch_lower(ctx, a_kc, b_kc):
+    _tma_case(ctx, 96, 72, 30, a_kc, b_kc, n_outer=3, n_batch=2, use_d=True, cfg=8, seed=23)
+    _tma_case(ctx, 300, 300, 50, a_kc, b_kc, lower=True, n_outer=2, use_d=True, cfg=8, seed=24)
+    _tma_case(ctx, 100, 60, 400, a_kc, b_kc, splits=3, alpha=1.5, beta=0.5, cfg=9, seed=25)
+    _tma_case(ctx, 90, 60, 20, a_kc, b_kc, col_inner=12, cfg=10, seed=26)
+
+
+def test_tma_long_pipeline(ctx):
+    """many k-tiles per CTA: every stage and both mbarrier parities are reused many times"""
+    _tma_case(ctx, 128, 128, 4096, True, True, cfg=8, seed=27)
+    _tma_case(ctx, 200, 64, 1000, False, True, n_outer=5, use_d=True, cfg=9, seed=28)
+
+
+def test_large_problem_takes_tma_automatically(ctx):
+    from xtp_b200 import api
+    before = api.tma_launch_count()
+    run_case(ctx, 1024, 512, 512, True, True, seed=29)
+    assert api.tma_launch_count() > before

@@ -190,17 +190,20 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
     DBuf Fvc, Fa, Fb;
     long long ldvcF = 0, ldA = 0, ldB = 0;
     if (cx || cd2) flat(Fvc, ldvcF, v0, (int)vt, c0, (int)ct, false);
+    // NOTE (multi-GPU): every flat() is a collective re-shard, so all ranks must ask for the SAME window; the
+    // column range a rank owns is then a contiguous row range of the flat operand (first index = v2), which is why
+    // the symmetric partners M[v2][P][v1] = M[v1][P][v2] and M[v2][P][c1] = M[c1][P][v2] are used below.
     if (cd && ncols > 0) {
-      // Hd[(v1,c1),(v2,c2)] = sum_P Mcc[c2][P][c1] * (eps_inv_P Mvv[v1][P][v2])
+      // Hd[(v1,c1),(v2,c2)] = sum_P Mcc[c2][P][c1] * (eps_inv_P Mvv[v2][P][v1])
       flat(Fa, ldA, c0, (int)ct, c0, (int)ct, false);                      // rows (i = c2, j = c1)
-      flat(Fb, ldB, v0, (int)vt, v0 + (int)v2lo, (int)ns, true);           // rows (i = v1, j = v2 - v2lo)
+      flat(Fb, ldB, v0, (int)vt, v0, (int)vt, true);                       // rows (i = v2, j = v1), all v2
       GemmParams g{};
       g.A = GemmOperand{Fa.p, 1, ldA, 0, 0};
-      g.B = GemmOperand{Fb.p, 1, ldB, 0, 0};
+      g.B = GemmOperand{Fb.p + v2lo * vt, 1, ldB, 0, 0};                   // this rank's v2 range
       g.C = H.p;
       g.c_m_inner = (int)ct; g.c_sm = 1; g.c_sm_outer = h_ld;              // row (c2, c1): c1 -> row, c2 -> column part
-      g.c_n_inner = (int)ns; g.c_sn = ct * h_ld; g.c_sn_outer = ct;        // col (v1, v2l): v2l -> column, v1 -> row part
-      g.M = (int)(ct * ct); g.N = (int)(vt * ns); g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
+      g.c_n_inner = (int)vt; g.c_sn = ct; g.c_sn_outer = ct * h_ld;        // col (v2l, v1): v1 -> row part, v2l -> column
+      g.M = (int)(ct * ct); g.N = (int)(ns * vt); g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
       g.alpha = -(double)cd; g.beta = 1.0;
       contract(g, ctx->ws, ctx->stream);
       ctx->sync();
@@ -208,15 +211,15 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
       Fb.release();
     }
     if (cd2 && ncols > 0) {
-      // Hd2[(v1,c1),(v2,c2)] = sum_P Mvc[v1][P][c2] * (eps_inv_P Mcv[c1][P][v2])
-      flat(Fb, ldB, c0, (int)ct, v0 + (int)v2lo, (int)ns, true);           // rows (i = c1, j = v2 - v2lo)
+      // Hd2[(v1,c1),(v2,c2)] = sum_P Mvc[v1][P][c2] * (eps_inv_P Mvc[v2][P][c1])
+      flat(Fb, ldB, v0, (int)vt, c0, (int)ct, true);                       // rows (i = v2, j = c1), all v2, screened
       GemmParams g{};
       g.A = GemmOperand{Fvc.p, 1, ldvcF, 0, 0};                            // rows (v1, c2)
-      g.B = GemmOperand{Fb.p, 1, ldB, 0, 0};
+      g.B = GemmOperand{Fb.p + v2lo * ct, 1, ldB, 0, 0};
       g.C = H.p;
       g.c_m_inner = (int)ct; g.c_sm = h_ld; g.c_sm_outer = ct;             // c2 -> column part, v1 -> row part
-      g.c_n_inner = (int)ns; g.c_sn = ct * h_ld; g.c_sn_outer = 1;         // v2l -> column, c1 -> row part
-      g.M = (int)(vt * ct); g.N = (int)(ct * ns); g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
+      g.c_n_inner = (int)ct; g.c_sn = 1; g.c_sn_outer = ct * h_ld;         // c1 -> row part, v2l -> column
+      g.M = (int)(vt * ct); g.N = (int)(ns * ct); g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
       g.alpha = -(double)cd2; g.beta = 1.0;
       contract(g, ctx->ws, ctx->stream);
       ctx->sync();

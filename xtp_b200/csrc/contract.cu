@@ -9,6 +9,7 @@
 namespace xtpb {
 
 long long g_launch_count = 0;
+long long g_tma_launch_count = 0;
 
 // ------------------------------------------------------------------ event-pair profiler
 namespace {
@@ -90,11 +91,88 @@ void launch_cfg2(const GemmParams& p, cudaStream_t stream) {
   ++g_launch_count;
 }
 
-// 16-byte cp.async needs both operands 16-byte aligned in their contiguous direction; otherwise the 8-byte instance
+// ---- TMA path: tensor maps are encoded per launch through the driver entry point (no link-time libcuda) ----
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+bool tma_enabled() {
+  static const bool on = [] { const char* e = getenv("XTPB_TMA"); return !(e && e[0] == '0'); }();
+  return on && encode_tiled_fn() != nullptr;
+}
+// K-contig operand: dims (k, row, outer, batch), box (16, rows_box, 1, 1); row-contig: dims (row, k, outer, batch),
+// box (16, 16, 1, 1).  Dimensions with a zero stride (broadcast) or extent 1 are dropped to extent 1 and the kernel
+// multiplies their coordinate by 0.  Returns false when the operand cannot be described (falls back to cp.async).
+bool make_tensor_map(CUtensorMap* map, const GemmOperand& o, bool kc, int rows, int rows_box, int K, int n_outer,
+                     int n_batch, int* use_outer, int* use_batch) {
+  *use_outer = (n_outer > 1 && o.s_outer != 0) ? 1 : 0;
+  *use_batch = (n_batch > 1 && o.s_batch != 0) ? 1 : 0;
+  if (reinterpret_cast<uintptr_t>(o.p) % 16) return false;
+  const long long s_other = kc ? o.s_row : o.s_k;
+  if (s_other <= 0 || s_other % 2 || (*use_outer && (o.s_outer <= 0 || o.s_outer % 2)) ||
+      (*use_batch && (o.s_batch <= 0 || o.s_batch % 2)))
+    return false;
+  cuuint64_t dims[4] = {(cuuint64_t)(kc ? K : rows), (cuuint64_t)(kc ? rows : K),
+                        (cuuint64_t)(*use_outer ? n_outer : 1), (cuuint64_t)(*use_batch ? n_batch : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)s_other * 8, (cuuint64_t)(*use_outer ? o.s_outer * 8 : 16),
+                           (cuuint64_t)(*use_batch ? o.s_batch * 8 : 16)};
+  cuuint32_t box[4] = {16u, (cuuint32_t)(kc ? rows_box : 16), 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] >= (1ULL << 40)) return false;
+  const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(o.p), dims, strides,
+                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D>
+bool launch_tma(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BM, BN, WM, WN, A_KC, B_KC, kStages>;
+  alignas(64) CUtensorMap mapA, mapB;
+  TmaCoords tc{};
+  if (!make_tensor_map(&mapA, p.A, A_KC, p.M, BM, p.K, p.n_outer, p.n_batch, &tc.a_outer, &tc.a_batch)) return false;
+  if (!make_tensor_map(&mapB, p.B, B_KC, p.N, BN, p.K, p.n_outer, p.n_batch, &tc.b_outer, &tc.b_batch)) return false;
+  auto kern = contract_tma_kernel<Cfg, BM, BN, WM, WN, A_KC, B_KC, kStages, HAS_D>;
+  constexpr int smem_bytes = kStages * (Cfg::A_BYTES + Cfg::B_BYTES + 1024) + 2 * kStages * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XTPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  dim3 grid(tiles_m * tiles_n, 1, p.n_batch * p.splits);
+  kern<<<grid, Cfg::THREADS, smem_bytes, stream>>>(p, tc, mapA, mapB);
+  XTPB_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return true;
+}
+
+// TMA instance when both operands are 16-byte aligned with even strides (and the problem is big enough to amortise
+// the two descriptor encodes); 16-byte cp.async instance otherwise; 8-byte cp.async instance for odd alignments.
 template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D>
 void launch_cfg(const GemmParams& p, cudaStream_t stream) {
-  if (p.a_vec && p.b_vec) launch_cfg2<BM, BN, WM, WN, A_KC, B_KC, HAS_D, true>(p, stream);
-  else launch_cfg2<BM, BN, WM, WN, A_KC, B_KC, HAS_D, false>(p, stream);
+  if (p.a_vec && p.b_vec) {
+    const double work = (double)p.M * p.N * (double)p.K * p.n_outer * p.n_batch;
+    if (p.use_tma && (p.use_tma == 2 || work >= 1.0e8) && tma_enabled() &&
+        launch_tma<BM, BN, WM, WN, A_KC, B_KC, HAS_D>(p, stream)) {
+      ++g_tma_launch_count;
+      return;
+    }
+    launch_cfg2<BM, BN, WM, WN, A_KC, B_KC, HAS_D, true>(p, stream);
+  } else {
+    launch_cfg2<BM, BN, WM, WN, A_KC, B_KC, HAS_D, false>(p, stream);
+  }
 }
 
 template <bool A_KC, bool B_KC, bool HAS_D>
@@ -177,6 +255,14 @@ int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, in
   const bool b_kc = p.B.s_k == 1;
   XTPB_REQUIRE(a_kc || p.A.s_row == 1, "operand A needs a unit stride");
   XTPB_REQUIRE(b_kc || p.B.s_row == 1, "operand B needs a unit stride");
+  p.use_tma = 1;
+  if (force_cfg >= 8) {        // 8..10: tile 0..2 on the TMA instance whatever the problem size (tests)
+    p.use_tma = 2;
+    force_cfg -= 8;
+  } else if (force_cfg >= 4) { // 4..6: tile 0..2 on the cp.async instance, 7: automatic tile on cp.async (tests, A/B runs)
+    p.use_tma = 0;
+    force_cfg = force_cfg == 7 ? -1 : force_cfg - 4;
+  }
   p.a_vec = aligned16(p.A, a_kc, p.n_outer, p.n_batch) ? 1 : 0;
   p.b_vec = aligned16(p.B, b_kc, p.n_outer, p.n_batch) ? 1 : 0;
 

@@ -14,6 +14,7 @@
 // K_total = n_outer x K (each outer block is zero-padded to a multiple of 16).
 // B likewise with row = output column.  C is written with arbitrary (c_sm, c_sn).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -38,6 +39,7 @@ struct GemmParams {
   double alpha, beta;
   int lower;                // 1: skip tiles strictly above the diagonal (SYRK-style output)
   int a_vec, b_vec;         // 1: 16-byte cp.async legal for that operand
+  int use_tma;              // 0: stay on the cp.async instance even when TMA is possible
   double* ws;               // split-K workspace: [batch][split][N][M] (M fastest)
 };
 
@@ -166,6 +168,130 @@ struct OperandLoader {
   }
 };
 
+// ---- fragment addressing, computed once per thread ---------------------------------------------------------
+// K-contig operand: fragment f, half h:  (w0 + rl)*128 + (((4h + lt) ^ rl) << 4) + f*1024, rl = row & 7 of the slot
+// row-contig operand: pair q, half h, sub-step j: (w0/16 + q)*2048 + (8h + 2lt + j)*128 + ((li ^ (2lt + j)) << 4)
+// -> two per-thread bases per operand (index h for K-contig, j for row-contig) plus compile-time immediates.
+template <bool KC>
+__device__ __forceinline__ void frag_offsets(uint32_t (&off)[2], int w0, int li, int lt) {
+  const int rl = (li >> 1) + 4 * (li & 1);
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+    off[x] = KC ? (uint32_t)((w0 + rl) * ROW_BYTES + ((((4 * x + lt) ^ rl) & 7) << 4))
+                : (uint32_t)((w0 >> 4) * (BK * ROW_BYTES) + (2 * lt + x) * ROW_BYTES + (((li ^ (2 * lt + x)) & 7) << 4));
+}
+
+// ---- one 16-wide k-tile of DMMAs for this warp -------------------------------------------------------------
+// The 2*MF "steps" (half h = 8 k values, one A fragment load feeding 2*NF DMMAs each) are software-pipelined by
+// hand: A fragments are double-buffered in registers and loaded one step ahead, the B fragments (and their chi0
+// weights) of the second half are fetched and scaled while the first half is still issuing DMMAs.  `hook(s)` is
+// called once per step so the caller can spread its producer work (cp.async chunks or the TMA issue) between the
+// DMMA groups; no warp ever sits in a long non-tensor instruction run.
+template <typename Cfg, bool A_KC, bool B_KC, bool HAS_D, typename Hook>
+__device__ __forceinline__ void consume_tile(double (&acc)[Cfg::MF][Cfg::NF][2], uint32_t sA, uint32_t sB, uint32_t sD,
+                                             const uint32_t (&a_off)[2], const uint32_t (&b_off)[2], uint32_t d_off,
+                                             Hook&& hook) {
+  constexpr int STEPS = 2 * Cfg::MF;
+  double bf[2][Cfg::NF][2];
+  double af[2][2];
+  auto load_b = [&](int h, double (&b)[Cfg::NF][2]) {
+    if (B_KC) {
+#pragma unroll
+      for (int nf = 0; nf < Cfg::NF; ++nf) lds128(sB + b_off[h] + nf * (8 * ROW_BYTES), b[nf][0], b[nf][1]);
+    } else {
+#pragma unroll
+      for (int np = 0; np < Cfg::NF / 2; ++np)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          lds128(sB + b_off[j] + h * (8 * ROW_BYTES) + np * (BK * ROW_BYTES), b[2 * np][j], b[2 * np + 1][j]);
+    }
+  };
+  auto scale_b = [&](double d0, double d1, double (&b)[Cfg::NF][2]) {
+#pragma unroll
+    for (int nf = 0; nf < Cfg::NF; ++nf) {
+      b[nf][0] *= d0;
+      b[nf][1] *= d1;
+    }
+  };
+  // A fragment of step s = h*MF + i:  K-contig: i = mf, (a0,a1) = two k sub-steps of fragment mf;
+  //                                   M-contig: i = 2*mp + j, (a0,a1) = fragments 2mp, 2mp+1 at k sub-step j
+  auto load_a = [&](int s, double (&a)[2]) {
+    const int h = s / Cfg::MF, i = s % Cfg::MF;
+    if (A_KC) lds128(sA + a_off[h] + i * (8 * ROW_BYTES), a[0], a[1]);
+    else lds128(sA + a_off[i & 1] + h * (8 * ROW_BYTES) + (i >> 1) * (BK * ROW_BYTES), a[0], a[1]);
+  };
+
+  double dn0 = 1.0, dn1 = 1.0;
+  load_b(0, bf[0]);
+  if (HAS_D) {
+    double d0, d1;
+    lds128(sD + d_off, d0, d1);
+    scale_b(d0, d1, bf[0]);
+  }
+  load_a(0, af[0]);
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s) {
+    const int h = s / Cfg::MF, i = s % Cfg::MF;
+    if (s + 1 < STEPS) load_a(s + 1, af[(s + 1) & 1]);   // one step (2*NF DMMAs) ahead of its use
+    if (s == 0) {
+      load_b(1, bf[1]);
+      if (HAS_D) lds128(sD + d_off + 64, dn0, dn1);
+    }
+    hook(s);
+    const double a0 = af[s & 1][0], a1 = af[s & 1][1];
+    if (A_KC) {
+#pragma unroll
+      for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[i][nf][0], acc[i][nf][1], a0, bf[h][nf][0]);
+#pragma unroll
+      for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[i][nf][0], acc[i][nf][1], a1, bf[h][nf][1]);
+    } else {
+      const int mp = i >> 1, j = i & 1;
+#pragma unroll
+      for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[2 * mp][nf][0], acc[2 * mp][nf][1], a0, bf[h][nf][j]);
+#pragma unroll
+      for (int nf = 0; nf < Cfg::NF; ++nf)
+        dmma884(acc[2 * mp + 1][nf][0], acc[2 * mp + 1][nf][1], a1, bf[h][nf][j]);
+    }
+    if (HAS_D && s == Cfg::MF / 2) scale_b(dn0, dn1, bf[1]);
+  }
+}
+
+// ---- epilogue: registers -> C (or the split-K workspace) through the two-level output maps ----
+template <typename Cfg, bool A_KC, bool B_KC>
+__device__ __forceinline__ void store_tile(const GemmParams& p, const double (&acc)[Cfg::MF][Cfg::NF][2], int m0, int n0,
+                                           int wm0, int wn0, int li, int lt, int split, int batch) {
+  const bool to_ws = p.splits > 1;
+  double* Cb = to_ws ? p.ws + ((long long)batch * p.splits + split) * (long long)p.M * p.N
+                     : p.C + (long long)batch * p.c_batch;
+  const long long csm = to_ws ? 1 : p.c_sm, csn = to_ws ? (long long)p.M : p.c_sn;
+  const double alpha = to_ws ? 1.0 : p.alpha, beta = to_ws ? 0.0 : p.beta;
+#pragma unroll
+  for (int mf = 0; mf < Cfg::MF; ++mf) {
+    const int r = m0 + wm0 + (A_KC ? kc_slot_row(mf, li) : mc_slot_row(mf, li));
+    if (r >= p.M) continue;
+    const long long roff = (!to_ws && p.c_m_inner > 0)
+                               ? (long long)(r / p.c_m_inner) * p.c_sm_outer + (long long)(r % p.c_m_inner) * csm
+                               : (long long)r * csm;
+#pragma unroll
+    for (int nf = 0; nf < Cfg::NF; ++nf)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int s = 2 * lt + e;
+        const int c = n0 + wn0 + (B_KC ? kc_slot_row(nf, s) : mc_slot_row(nf, s));
+        if (c >= p.N) continue;
+        if (p.lower && c > r) continue;
+        const long long coff = (!to_ws && p.c_n_inner > 0)
+                                   ? (long long)(c / p.c_n_inner) * p.c_sn_outer + (long long)(c % p.c_n_inner) * csn
+                                   : (long long)c * csn;
+        double* dst = Cb + roff + coff;
+        double v = alpha * acc[mf][nf][e];
+        if (beta != 0.0) v += beta * (*dst);
+        *dst = v;
+      }
+  }
+}
+
+// ============================================================ cp.async instance (any alignment, any strides)
 template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D, bool VEC>
 __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -193,11 +319,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
   const double* Db = HAS_D ? p.d + (long long)batch * p.d_batch : nullptr;
   const int m_left = p.M - m0, n_left = p.N - n0;
 
-  // ---- loader state, computed once per thread -------------------------------------------------------------
-  // Each thread owns chunk column/row (its 16-byte chunk position inside a tile) for every k-tile; only the tile
-  // base pointer changes from tile to tile.  Chunk `it` of an operand differs from chunk 0 by a constant row
-  // (K-contig) or k (row-contig) step, so its shared-memory offset and its global offset are chunk 0's plus a
-  // multiple of a per-thread constant: no index arithmetic is left in the main loop.
+  // loader state, computed once per thread: only the tile base pointer changes from tile to tile
   const OperandLoader<BM, Cfg::THREADS, A_KC, VEC> ldA(p.A.s_row, p.A.s_k, m_left, tid);
   const OperandLoader<BN, Cfg::THREADS, B_KC, VEC> ldB(p.B.s_row, p.B.s_k, n_left, tid);
   constexpr int NA = OperandLoader<BM, Cfg::THREADS, A_KC, VEC>::CHUNKS;
@@ -241,28 +363,12 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
     cp_async_commit();
   }
 
-  // ---- fragment addressing, computed once per thread ---------------------------------------------------------
-  // K-contig operand: fragment f, half h:  (w0 + rl)*128 + (((4h + lt) ^ rl) << 4) + f*1024, rl = row & 7 of the slot
-  // row-contig operand: pair q, half h, sub-step j: (w0/16 + q)*2048 + (8h + 2lt + j)*128 + ((li ^ (2lt + j)) << 4)
-  // -> two per-thread bases per operand (index h for K-contig, j for row-contig) plus compile-time immediates.
   uint32_t a_off[2], b_off[2];
-  {
-    const int rl = (li >> 1) + 4 * (li & 1);
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-      a_off[x] = A_KC ? (uint32_t)((wm0 + rl) * ROW_BYTES + ((((4 * x + lt) ^ rl) & 7) << 4))
-                      : (uint32_t)((wm0 >> 4) * (BK * ROW_BYTES) + (2 * lt + x) * ROW_BYTES + (((li ^ (2 * lt + x)) & 7) << 4));
-      b_off[x] = B_KC ? (uint32_t)((wn0 + rl) * ROW_BYTES + ((((4 * x + lt) ^ rl) & 7) << 4))
-                      : (uint32_t)((wn0 >> 4) * (BK * ROW_BYTES) + (2 * lt + x) * ROW_BYTES + (((li ^ (2 * lt + x)) & 7) << 4));
-    }
-  }
+  frag_offsets<A_KC>(a_off, wm0, li, lt);
+  frag_offsets<B_KC>(b_off, wn0, li, lt);
   const uint32_t d_off = (uint32_t)(2 * lt * 8);
 
-  // Main loop.  One barrier per 16-wide k-tile; inside a tile the 2*MF "steps" (half h = 8 k values, one A fragment
-  // load feeding 2*NF DMMAs each) are software-pipelined by hand: A fragments are double-buffered in registers and
-  // loaded one step ahead, the B fragments (and their chi0 weights) of the second half are fetched and
-  // scaled while the first half is still issuing DMMAs, and the cp.async traffic of the tile STAGES-1 ahead is
-  // spread over the steps so that no warp ever sits in a long non-tensor instruction run.
+  // Main loop: one barrier per k-tile; the cp.async traffic of the tile STAGES-1 ahead is spread over the steps.
   constexpr int NCH = NA + NB, STEPS = 2 * Cfg::MF;
 #pragma unroll 1
   for (int it = 0; it < nkt; ++it) {
@@ -270,62 +376,15 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
     __syncthreads();
     const int nxt = it + STAGES - 1;
     const bool do_load = nxt < nkt;
-    // next tile's loader state (uniform): stage bases and global tile bases
     const uint32_t lA = smem + (nxt % STAGES) * Cfg::STAGE_BYTES, lB = lA + Cfg::A_BYTES, lD = lB + Cfg::B_BYTES;
     const int l_kleft = p.K - l_k0;
     const double* gA = Ab + (long long)l_outer * p.A.s_outer + (long long)l_k0 * p.A.s_k;
     const double* gB = Bb + (long long)l_outer * p.B.s_outer + (long long)l_k0 * p.B.s_k;
     const double* gD = HAS_D ? Db + (long long)l_outer * p.d_outer + l_k0 : nullptr;
     const int kbA = A_KC ? ldA.k_bytes(l_kleft) : l_kleft, kbB = B_KC ? ldB.k_bytes(l_kleft) : l_kleft;
-
     const int stage = it % STAGES;
     const uint32_t sA = smem + stage * Cfg::STAGE_BYTES, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
-
-    double bf[2][Cfg::NF][2];
-    double af[2][2];
-    auto load_b = [&](int h, double (&b)[Cfg::NF][2]) {
-      if (B_KC) {
-#pragma unroll
-        for (int nf = 0; nf < Cfg::NF; ++nf) lds128(sB + b_off[h] + nf * (8 * ROW_BYTES), b[nf][0], b[nf][1]);
-      } else {
-#pragma unroll
-        for (int np = 0; np < Cfg::NF / 2; ++np)
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            lds128(sB + b_off[j] + h * (8 * ROW_BYTES) + np * (BK * ROW_BYTES), b[2 * np][j], b[2 * np + 1][j]);
-      }
-    };
-    auto scale_b = [&](double d0, double d1, double (&b)[Cfg::NF][2]) {
-#pragma unroll
-      for (int nf = 0; nf < Cfg::NF; ++nf) {
-        b[nf][0] *= d0;
-        b[nf][1] *= d1;
-      }
-    };
-    // A fragment of step s = h*MF + i:  K-contig: i = mf, (a0,a1) = two k sub-steps of fragment mf;
-    //                                   M-contig: i = 2*mp + j, (a0,a1) = fragments 2mp, 2mp+1 at k sub-step j
-    auto load_a = [&](int s, double (&a)[2]) {
-      const int h = s / Cfg::MF, i = s % Cfg::MF;
-      if (A_KC) lds128(sA + a_off[h] + i * (8 * ROW_BYTES), a[0], a[1]);
-      else lds128(sA + a_off[i & 1] + h * (8 * ROW_BYTES) + (i >> 1) * (BK * ROW_BYTES), a[0], a[1]);
-    };
-
-    double dn0 = 1.0, dn1 = 1.0;
-    load_b(0, bf[0]);
-    if (HAS_D) {
-      double d0, d1;
-      lds128(sD + d_off, d0, d1);
-      scale_b(d0, d1, bf[0]);
-    }
-    load_a(0, af[0]);
-#pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-      const int h = s / Cfg::MF, i = s % Cfg::MF;
-      if (s + 1 < STEPS) load_a(s + 1, af[(s + 1) & 1]);   // one step (2*NF DMMAs) ahead of its use
-      if (s == 0) {
-        load_b(1, bf[1]);
-        if (HAS_D) lds128(sD + d_off + 64, dn0, dn1);
-      }
+    consume_tile<Cfg, A_KC, B_KC, HAS_D>(acc, sA, sB, sD, a_off, b_off, d_off, [&](int s) {
       if (do_load) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -338,57 +397,170 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
           cp_async8(lD + tid * 8, v ? gD + tid : Db, v ? 8 : 0);
         }
       }
-      const double a0 = af[s & 1][0], a1 = af[s & 1][1];
-      if (A_KC) {
-#pragma unroll
-        for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[i][nf][0], acc[i][nf][1], a0, bf[h][nf][0]);
-#pragma unroll
-        for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[i][nf][0], acc[i][nf][1], a1, bf[h][nf][1]);
-      } else {
-        const int mp = i >> 1, j = i & 1;
-#pragma unroll
-        for (int nf = 0; nf < Cfg::NF; ++nf) dmma884(acc[2 * mp][nf][0], acc[2 * mp][nf][1], a0, bf[h][nf][j]);
-#pragma unroll
-        for (int nf = 0; nf < Cfg::NF; ++nf)
-          dmma884(acc[2 * mp + 1][nf][0], acc[2 * mp + 1][nf][1], a1, bf[h][nf][j]);
-      }
-      if (HAS_D && s == Cfg::MF / 2) scale_b(dn0, dn1, bf[1]);
-    }
+    });
     cp_async_commit();
     if (do_load) advance_tile();
   }
   cp_async_wait<0>();
+  store_tile<Cfg, A_KC, B_KC>(p, acc, m0, n0, wm0, wn0, li, lt, split, batch);
+}
 
-  // ---- epilogue ----
-  const bool to_ws = p.splits > 1;
-  double* Cb = to_ws ? p.ws + ((long long)batch * p.splits + split) * (long long)p.M * p.N
-                     : p.C + (long long)batch * p.c_batch;
-  const long long csm = to_ws ? 1 : p.c_sm, csn = to_ws ? (long long)p.M : p.c_sn;
-  const double alpha = to_ws ? 1.0 : p.alpha, beta = to_ws ? 0.0 : p.beta;
-#pragma unroll
-  for (int mf = 0; mf < Cfg::MF; ++mf) {
-    const int r = m0 + wm0 + (A_KC ? kc_slot_row(mf, li) : mc_slot_row(mf, li));
-    if (r >= p.M) continue;
-    const long long roff = (!to_ws && p.c_m_inner > 0)
-                               ? (long long)(r / p.c_m_inner) * p.c_sm_outer + (long long)(r % p.c_m_inner) * csm
-                               : (long long)r * csm;
-#pragma unroll
-    for (int nf = 0; nf < Cfg::NF; ++nf)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int s = 2 * lt + e;
-        const int c = n0 + wn0 + (B_KC ? kc_slot_row(nf, s) : mc_slot_row(nf, s));
-        if (c >= p.N) continue;
-        if (p.lower && c > r) continue;
-        const long long coff = (!to_ws && p.c_n_inner > 0)
-                                   ? (long long)(c / p.c_n_inner) * p.c_sn_outer + (long long)(c % p.c_n_inner) * csn
-                                   : (long long)c * csn;
-        double* dst = Cb + roff + coff;
-        double v = alpha * acc[mf][nf][e];
-        if (beta != 0.0) v += beta * (*dst);
-        *dst = v;
-      }
+// ============================================================ TMA instance (16-byte aligned operands)
+// Operand tiles arrive through cp.async.bulk.tensor (SWIZZLE_128B produces exactly the kc/mc tile layouts above;
+// out-of-range rows and the k tail of every outer block are zero-filled by the hardware), completion is tracked by
+// one "full" mbarrier per stage, and consumers hand a stage back through an "empty" mbarrier: there is no
+// __syncthreads and no address arithmetic in the main loop, and the warps of a CTA may drift up to STAGES-1 tiles
+// apart, which decouples their fragment-load and DMMA phases.  Lane 0 of warp 0 issues the copies for the tile
+// STAGES-1 ahead in the middle of its own DMMA stream (a dozen instructions per tile).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();     // a lost arrival becomes an error, never a hang
   }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+struct TmaCoords {        // per-operand multipliers: 0 when the tensor map has no outer / batch dimension
+  int a_outer, a_batch, b_outer, b_batch;
+};
+
+template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D>
+__global__ void __launch_bounds__(Cfg::THREADS) contract_tma_kernel(const GemmParams p, const TmaCoords tc,
+                                                                    const __grid_constant__ CUtensorMap mapA,
+                                                                    const __grid_constant__ CUtensorMap mapB) {
+  // stage = [A tile | B tile | d tile padded to 1 KiB]: every operand tile starts on a 1 KiB boundary (swizzle atom)
+  constexpr int TSTAGE = Cfg::A_BYTES + Cfg::B_BYTES + 1024;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const uint32_t bar_full = smem + STAGES * TSTAGE, bar_empty = bar_full + STAGES * 8;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp % Cfg::WARPS_M) * WM, wn0 = (warp / Cfg::WARPS_M) * WN;
+  const int li = lane >> 2, lt = lane & 3;
+
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  if (p.lower && tn * BN > tm * BM + BM - 1) return;
+  const int split = blockIdx.z % p.splits, batch = blockIdx.z / p.splits;
+
+  const int tpo = (p.K + BK - 1) / BK;
+  const int nkt_total = tpo * p.n_outer;
+  const int per = (nkt_total + p.splits - 1) / p.splits;
+  const int kt_begin = split * per;
+  const int kt_end = min(nkt_total, kt_begin + per);
+  const int nkt = max(0, kt_end - kt_begin);
+  const int m0 = tm * BM, n0 = tn * BN;
+  const double* Db = HAS_D ? p.d + (long long)batch * p.d_batch : nullptr;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, HAS_D ? 1 + BK : 1);       // expect_tx arrival (+ one per d element copy)
+      mbar_init(bar_empty + 8 * s, Cfg::THREADS / 32);       // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  int l_outer = kt_begin / tpo, l_k0 = (kt_begin - l_outer * tpo) * BK;
+  auto advance_tile = [&]() {
+    l_k0 += BK;
+    if (l_k0 >= p.K) { l_k0 = 0; ++l_outer; }
+  };
+  // warp 0 only: copies of tile (l_outer, l_k0) into `stage`
+  auto produce = [&](int stage) {
+    const uint32_t sA = smem + stage * TSTAGE, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
+    const uint32_t full = bar_full + 8 * stage;
+    if (HAS_D && lane < BK) {
+      const bool v = l_k0 + lane < p.K;
+      cp_async8(sD + lane * 8, v ? Db + (long long)l_outer * p.d_outer + l_k0 + lane : Db, v ? 8 : 0);
+      mbar_cp_async_arrive_noinc(full);
+    }
+    if (lane == 0) {
+      mbar_arrive_expect_tx(full, Cfg::A_BYTES + Cfg::B_BYTES);
+      if (A_KC) {
+        tma_load_4d(sA, &mapA, full, l_k0, m0, l_outer * tc.a_outer, batch * tc.a_batch);
+      } else {
+#pragma unroll
+        for (int g = 0; g < BM / 16; ++g)
+          tma_load_4d(sA + g * (BK * ROW_BYTES), &mapA, full, m0 + 16 * g, l_k0, l_outer * tc.a_outer, batch * tc.a_batch);
+      }
+      if (B_KC) {
+        tma_load_4d(sB, &mapB, full, l_k0, n0, l_outer * tc.b_outer, batch * tc.b_batch);
+      } else {
+#pragma unroll
+        for (int g = 0; g < BN / 16; ++g)
+          tma_load_4d(sB + g * (BK * ROW_BYTES), &mapB, full, n0 + 16 * g, l_k0, l_outer * tc.b_outer, batch * tc.b_batch);
+      }
+    }
+  };
+
+  double acc[Cfg::MF][Cfg::NF][2];
+#pragma unroll
+  for (int i = 0; i < Cfg::MF; ++i)
+#pragma unroll
+    for (int j = 0; j < Cfg::NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll 1
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nkt) {
+      if (warp == 0) produce(s);
+      advance_tile();
+    }
+  }
+
+  uint32_t a_off[2], b_off[2];
+  frag_offsets<A_KC>(a_off, wm0, li, lt);
+  frag_offsets<B_KC>(b_off, wn0, li, lt);
+  const uint32_t d_off = (uint32_t)(2 * lt * 8);
+  constexpr int STEPS = 2 * Cfg::MF;
+
+#pragma unroll 1
+  for (int it = 0; it < nkt; ++it) {
+    const int stage = it % STAGES;
+    const int nxt = it + STAGES - 1;
+    const bool do_load = nxt < nkt;
+    mbar_wait(bar_full + 8 * stage, (uint32_t)((it / STAGES) & 1));
+    const uint32_t sA = smem + stage * TSTAGE, sB = sA + Cfg::A_BYTES, sD = sB + Cfg::B_BYTES;
+    consume_tile<Cfg, A_KC, B_KC, HAS_D>(acc, sA, sB, sD, a_off, b_off, d_off, [&](int s) {
+      if (s == STEPS / 2 && warp == 0 && do_load) {
+        const int ns = nxt % STAGES;       // consumed as tile it-1: wait until every warp has handed it back
+        if (it > 0 && lane == 0) mbar_wait(bar_empty + 8 * ns, (uint32_t)(((it - 1) / STAGES) & 1));
+        __syncwarp();
+        produce(ns);
+      }
+    });
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+    if (do_load) advance_tile();
+  }
+  store_tile<Cfg, A_KC, B_KC>(p, acc, m0, n0, wm0, wn0, li, lt, split, batch);
 }
 
 }  // namespace xtpb

@@ -10,7 +10,9 @@ struct Workspace {
   double* get(size_t count) { buf.ensure(count); return buf.p; }
 };
 
-// Fills a_vec/b_vec/splits/ws and launches.  `force_cfg`: -1 auto, 0=128x128, 1=128x64, 2=128x32.
+// Fills a_vec/b_vec/splits/ws and launches.  `force_cfg`: -1 auto, 0=128x128, 1=128x64, 2=128x32 (TMA instance when
+// the operands allow it and the problem is large); 4..6 the same tiles on the cp.async instance, 7 automatic tile on
+// cp.async; 8..10 tile 0..2 on the TMA instance whatever the size.
 // `force_splits`: 0 auto.  Returns the number of kernels launched.
 int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg = -1, int force_splits = 0);
 
@@ -22,6 +24,7 @@ inline GemmOperand op_rows_contig(const double* p, long long ld) { return GemmOp
 inline GemmOperand op_k_contig(const double* p, long long ld) { return GemmOperand{p, ld, 1, 0, 0}; }      // A(row,k)=p[k+row*ld]
 
 extern long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
+extern long long g_tma_launch_count;   // of which contraction launches on the TMA instance
 
 // ---- in-library kernel timing (bench.py's roofline object): CUDA-event pairs on the launching stream around
 // every launch of a tagged kernel family; summed per tag.  Off by default (no events recorded).
