@@ -19,6 +19,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <array>
 #include <vector>
 
 #include "xtpb200.h"
@@ -70,9 +71,39 @@ class Context {
   Context& operator=(const Context&) = delete;
   xtpb_ctx* handle() const { return h_; }
   void sync() const { check(xtpb_ctx_sync(h_)); }
+  // multi-GPU (one process per GPU): rank 0 calls UniqueId(), the host program distributes the 128 bytes, every
+  // rank calls JoinCommunicator before creating its TCMatrix_gwbse.  No counterpart upstream (OpenMP threads there).
+  static std::array<char, 128> UniqueId() {
+    std::array<char, 128> id{};
+    check(xtpb_comm_unique_id(id.data()));
+    return id;
+  }
+  void JoinCommunicator(const std::array<char, 128>& id, int rank, int world) {
+    check(xtpb_ctx_comm_init(h_, id.data(), rank, world));
+  }
 
  private:
   xtpb_ctx* h_ = nullptr;
+};
+
+// ---- GaussianQuadrature (gaussian_quadrature.h): scaled nodes/weights of the Sigma_CDA imaginary-axis integral
+class GaussianQuadrature {
+ public:
+  struct options { Index order = 12; int qptype = XTPB_QUAD_LEGENDRE; };
+  void configure(const options& opt) {
+    points_.assign(static_cast<std::size_t>(2 * opt.order + 2), 0.0);
+    weights_ = points_;
+    Index n = 0;
+    check(xtpb_gaussian_quadrature(opt.qptype, opt.order, points_.data(), weights_.data(), &n));
+    points_.resize(static_cast<std::size_t>(n));
+    weights_.resize(static_cast<std::size_t>(n));
+  }
+  Index Order() const { return static_cast<Index>(points_.size()); }
+  double ScaledPoint(Index i) const { return points_[static_cast<std::size_t>(i)]; }
+  double ScaledWeight(Index i) const { return weights_[static_cast<std::size_t>(i)]; }
+
+ private:
+  std::vector<double> points_, weights_;
 };
 
 // ---- TCMatrix_gwbse (threecenter.h / threecenter_gwbse.cc)
@@ -242,6 +273,13 @@ class GW {
   void CalcCorrelationDiagElements(Index n, const Index* levels, const double* frequencies, double* values,
                                    double* derivatives = nullptr) const {
     check(xtpb_gw_sigma_c_diag_elements(h_, n, levels, frequencies, values, derivatives));
+  }
+  // Sigma_c of every gw level on its QP grid (what GW::SolveQP_Grid scans and GW::PlotSigma tabulates):
+  // result(level, j) = Sigma_c(level, center[level] + (j - (steps-1)/2) * qp_grid_spacing)
+  Matrix CalcCorrelationGrid(const Vector& center_frequencies) const {
+    Matrix rowmajor(opt_.qp_grid_steps, qptotal_);      // column `level` holds that level's grid (contiguous)
+    check(xtpb_gw_sigma_c_grid(h_, center_frequencies.data(), rowmajor.data()));
+    return rowmajor;
   }
   xtpb_gw* handle() const { return h_; }
 

@@ -1010,6 +1010,49 @@ class BSE:
     def Solve_triplets_TDA(self):
         return self.solve_hermitian(self.make_operator("TripletOperator_TDA"))
 
+    def solve_btda_dense(self, singlet=True):
+        """Full (non-TDA) BSE, upstream ``BSE::Solve_nonhermitian_Davidson`` / ``HamiltonianOperator<A,B>``:
+        [[A, B], [-B, -A]] [X; Y] = w [X; Y], solved densely through the symmetric reduction
+        (A-B)^{1/2} (A+B) (A-B)^{1/2} Z = w^2 Z.  Returns the lowest ``nmax`` positive energies and X, Y
+        normalised to X^T X - Y^T Y = 1."""
+        A = self.make_operator("SingletOperator_TDA" if singlet else "TripletOperator_TDA").get_full_matrix()
+        B = self.make_operator("SingletOperator_BTDA_B" if singlet else "TripletOperator_BTDA_B").get_full_matrix()
+        A, B = 0.5 * (A + A.T), 0.5 * (B + B.T)
+        lm, Um = np.linalg.eigh(A - B)
+        if lm.min() <= 0:
+            raise ValueError("A - B is not positive definite")
+        S = (Um * np.sqrt(lm)) @ Um.T
+        Si = (Um / np.sqrt(lm)) @ Um.T
+        w2, Z = np.linalg.eigh(S @ (A + B) @ S)
+        n = self.opt.nmax
+        w = np.sqrt(w2[:n])
+        XpY = (S @ Z[:, :n]) / np.sqrt(w)
+        XmY = (Si @ Z[:, :n]) * np.sqrt(w)
+        return w, 0.5 * (XpY + XmY), 0.5 * (XpY - XmY)
+
+    def Solve_singlets_BTDA(self):
+        return self.solve_btda_dense(True)
+
+    def Solve_triplets_BTDA(self):
+        return self.solve_btda_dense(False)
+
+    @staticmethod
+    def transition_dipoles(ao_dipoles, C, homo, vmin, cmax, X, Y=None):
+        """Upstream ``BSE::CalcCoupledTransition_Dipoles``: d_s = -sqrt(2) sum_vc (X+Y)_vc,s <v|r|c> with the
+        interlevel dipoles <v|r|c> = C_v^T r_AO C_c (``Orbitals::CalcFreeTransition_Dips``).  Returns (n_states, 3)."""
+        Cv, Cc = C[:, vmin:homo + 1], C[:, homo + 1:cmax + 1]
+        coef = X if Y is None else X + Y
+        out = np.zeros((coef.shape[1], 3))
+        for i in range(3):
+            D = (Cv.T @ ao_dipoles[i] @ Cc).reshape(-1)          # index v*ctotal + c
+            out[:, i] = -math.sqrt(2.0) * (D @ coef)
+        return out
+
+    @staticmethod
+    def oscillator_strengths(energies, dipoles):
+        """f_s = 2/3 E_s |d_s|^2 (upstream ``Orbitals::Oscillatorstrengths``)."""
+        return 2.0 / 3.0 * np.asarray(energies) * (np.asarray(dipoles) ** 2).sum(axis=1)
+
     def full_btda_matrix(self, singlet=True):
         """[[A, B], [-B, -A]] dense, for tests of the non-TDA problem."""
         A = self.make_operator("SingletOperator_TDA" if singlet else "TripletOperator_TDA").get_full_matrix()

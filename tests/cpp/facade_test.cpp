@@ -2,6 +2,7 @@
 // drives a tiny G0W0+BSE step the way GWBSE::Evaluate does (upstream xtp/src/libxtp/gwbse/gwbse.cc), reading its
 // inputs from a flat binary written by tests/test_cpp_facade.py and writing QP / BSE energies back as text.
 //   usage: facade_test <input.bin> <output.txt>      (no arguments: instantiate-only self check, exit 0)
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -24,6 +25,20 @@ static std::vector<double> read_all(const char* path) {
 
 int main(int argc, char** argv) {
   if (argc < 3) {   // nothing to run without a device; the templates above were instantiated at compile time
+    // GaussianQuadrature is host code: the Legendre weights mapped back to (-1,1) must sum to 2
+    GaussianQuadrature gq;
+    GaussianQuadrature::options qo;
+    qo.order = 12;
+    gq.configure(qo);
+    double sum = 0.0;
+    for (Index i = 0; i < gq.Order(); ++i) {      // w' = w / (1-x)^2 with omega = 0.5 (1+x)/(1-x)  =>  1-x = 1/(omega+0.5)
+      const double one_minus_x = 1.0 / (gq.ScaledPoint(i) + 0.5);
+      sum += gq.ScaledWeight(i) * one_minus_x * one_minus_x;
+    }
+    if (gq.Order() != 12 || std::abs(sum - 2.0) > 1e-12) {
+      std::printf("GaussianQuadrature check failed: order %lld sum %.15f\n", (long long)gq.Order(), sum);
+      return 1;
+    }
     std::printf("facade compiled; version %d\n", xtpb_version());
     return 0;
   }

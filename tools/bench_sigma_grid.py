@@ -1,5 +1,4 @@
-"""Times the fused Sigma_c PPM grid kernel (GW::SolveQP_Grid scan) for G = 1, 2, 4, 8 poles per reciprocal.
-Each variant runs in a fresh process (the group size is read once from XTPB_GRID_GROUP).
+"""Times the fused Sigma_c PPM grid kernel (GW::SolveQP_Grid scan) on a synthetic tensor.
     python tools/bench_sigma_grid.py [--workload synth-1000] [--out gpurun_out/sigma_grid.jsonl]"""
 import argparse
 import json
@@ -32,7 +31,7 @@ def child(workload, reps):
         out = gw.CalcCorrelationGrid(centers)
     api.profile_enable(False)
     p = api.profile_summary()["sigma_ppm_grid"]
-    print(json.dumps({"workload": workload, "group": int(os.environ.get("XTPB_GRID_GROUP", "8")),
+    print(json.dumps({"workload": workload, 
                       "ms": p["ms"] / reps, "gevals_per_s": p["work"] / (p["ms"] * 1e-3) * 1e-9,
                       "checksum": float(np.abs(out).sum()), "sample": out[1, 498:503].tolist()}), flush=True)
 
@@ -49,8 +48,8 @@ def main():
         return
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
-        for g in (1, 2, 4, 8):
-            env = dict(os.environ, XTPB_GRID_GROUP=str(g))
+        for g in (1,):
+            env = dict(os.environ)
             r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
                                 str(args.reps)], env=env, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"group": g, "error": r.stderr[-400:]})
