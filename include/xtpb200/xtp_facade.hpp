@@ -15,6 +15,7 @@
 //
 // Error behaviour: the reference throws std::runtime_error; so does this facade (message from xtpb_last_error()).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -428,6 +429,28 @@ class BSE {
   struct Result { Vector energies; Matrix eigenvectors; int info; Index iterations; };
   Result Solve_singlets() const { return solve(1, 2, 1, 0); }     // TDA
   Result Solve_triplets() const { return solve(1, 0, 1, 0); }     // TDA
+  // useTDA = false (upstream Solve_nonhermitian_Davidson): X = coefficients, Y = coefficients_AR, X^T X - Y^T Y = 1
+  struct FullResult { Vector energies; Matrix X, Y; int info; Index iterations; };
+  FullResult Solve_singlets_BTDA() const { return solve_full(1); }
+  FullResult Solve_triplets_BTDA() const { return solve_full(0); }
+  // BSE::CalcCoupledTransition_Dipoles: 3 x n_states (column s = dipole of state s); ao_dipoles = x, y, z matrices
+  Matrix CalcCoupledTransition_Dipoles(const Matrix& dft_orbitals, const std::array<Matrix, 3>& ao_dipoles,
+                                       const Matrix& X, const Matrix* Y = nullptr) const {
+    const Index nb = dft_orbitals.rows();
+    std::vector<double> r(static_cast<std::size_t>(3 * nb * nb));
+    for (int i = 0; i < 3; ++i)
+      std::copy(ao_dipoles[i].data(), ao_dipoles[i].data() + nb * nb, r.begin() + static_cast<std::size_t>(i) * nb * nb);
+    Matrix d(3, X.cols());
+    check(xtpb_bse_transition_dipoles(h_, nb, dft_orbitals.data(), nb, r.data(), X.cols(), X.data(),
+                                      Y ? Y->data() : nullptr, X.rows(), d.data()));
+    return d;
+  }
+  // Orbitals::Oscillatorstrengths
+  static Vector Oscillatorstrengths(const Vector& energies, const Matrix& dipoles) {
+    Vector f(energies.size());
+    check(xtpb_oscillator_strengths(energies.size(), energies.data(), dipoles.data(), f.data()));
+    return f;
+  }
 
  private:
   Result solve(int cqp, int cx, int cd, int cd2) const {
@@ -438,6 +461,15 @@ class BSE {
     ds.set_max_search_space(10 * opt_.nmax);
     ds.solve(H, opt_.nmax);
     return Result{ds.eigenvalues(), ds.eigenvectors(), ds.info(), ds.num_iterations()};
+  }
+  FullResult solve_full(int singlet) const {
+    xtpb_davidson_options o;
+    xtpb_davidson_options_default(&o);
+    o.max_search_space = 10 * opt_.nmax;
+    const Index n = (opt_.homo - opt_.vmin + 1) * (opt_.cmax - opt_.homo);
+    FullResult r{Vector(opt_.nmax), Matrix(n, opt_.nmax), Matrix(n, opt_.nmax), 1, 0};
+    check(xtpb_bse_solve_btda(h_, singlet, &o, r.energies.data(), r.X.data(), r.Y.data(), n, &r.info, &r.iterations));
+    return r;
   }
   TCMatrix_gwbse<Matrix>& Mmn_;
   options opt_{};

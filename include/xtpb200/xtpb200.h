@@ -236,6 +236,23 @@ void xtpb_davidson_options_default(xtpb_davidson_options* opt);
 int xtpb_davidson_solve(xtpb_op* op, xtpb_index neigen, const xtpb_davidson_options* opt, double* eigenvalues_host,
                         double* eigenvectors_host, xtpb_index ldv, int* info, xtpb_index* iterations);
 
+/* ---- full BSE, transition dipoles, oscillator strengths ---- */
+/* Full (non-TDA) BSE: BSE::Solve_singlets / Solve_triplets with useTDA = false (upstream bse.cc
+ * Solve_nonhermitian_Davidson over HamiltonianOperator<A,B>, A = *_TDA operator, B = *_BTDA_B operator).
+ * energies: nmax; X, Y: size x nmax (ld), normalised X^T X - Y^T Y = 1 (upstream BSE_*_coefficients / _AR).
+ * xtpb_davidson_options as for the TDA solver (tolerance on both residuals, iter_max, max_search_space). */
+int xtpb_bse_solve_btda(xtpb_bse* bse, int singlet, const xtpb_davidson_options* opt, double* energies_host,
+                        double* X_host, double* Y_host, xtpb_index ld, int* info, xtpb_index* iterations);
+/* BSE::CalcCoupledTransition_Dipoles (+ Orbitals::CalcFreeTransition_Dips): d_s = -sqrt(2) sum_vc (X+Y)_vc,s <v|r|c>
+ * from the three AO dipole matrices (3 x n_basis x n_basis, symmetric) and the MO coefficients.  Y may be NULL (TDA).
+ * dipoles_host: n_states x 3, state-major. */
+int xtpb_bse_transition_dipoles(xtpb_bse* bse, xtpb_index n_basis, const double* C_host, xtpb_index ldc,
+                                const double* ao_dipoles_host, xtpb_index n_states, const double* X_host,
+                                const double* Y_host, xtpb_index ld, double* dipoles_host);
+/* Orbitals::Oscillatorstrengths: f_s = 2/3 E_s |d_s|^2 (host arithmetic, no device needed) */
+int xtpb_oscillator_strengths(xtpb_index n_states, const double* energies_host, const double* dipoles_host,
+                              double* strengths_host);
+
 /* ---- engine-level hook used by the parity tests of the contraction kernel ----
  * C = alpha * sum_{outer,k} A(row,outer,k) d(outer,k) B(col,outer,k) + beta*C with every stride explicit
  * (element units, host buffers of the given lengths are copied to the device and back). */

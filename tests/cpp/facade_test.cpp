@@ -79,6 +79,14 @@ int main(int argc, char** argv) {
     bo.nmax = nmax; bo.use_Hqp_offdiag = 1;
     bse.configure(bo, gw.RPAInputEnergies(), Hqp);
     const auto singlets = bse.Solve_singlets();
+    // full BSE and oscillator strengths (unit "dipole" matrices are enough to exercise the call path)
+    const auto full = bse.Solve_singlets_BTDA();
+    std::array<DenseMatrix, 3> rdip{DenseMatrix(nb, nb), DenseMatrix(nb, nb), DenseMatrix(nb, nb)};
+    for (int k = 0; k < 3; ++k)
+      for (Index i = 0; i < nb; ++i)
+        for (Index j = 0; j < nb; ++j) rdip[k](i, j) = (i == j) ? 0.0 : 1.0 / double(1 + k + (i > j ? i - j : j - i));
+    const DenseMatrix dip = bse.CalcCoupledTransition_Dipoles(C, rdip, full.X, &full.Y);
+    const DenseVector fosc = BSE<>::Oscillatorstrengths(full.energies, dip);
 
     // operator-level check through the template typedefs: Hx via BSE_OPERATOR<0,1,0,0>
     DenseVector eps_inv = bse.epsilon_0_inv();
@@ -90,6 +98,8 @@ int main(int argc, char** argv) {
     for (Index i = 0; i < qp.size(); ++i) std::fprintf(out, "qp %.15e\n", qp(i));
     for (Index i = 0; i < singlets.energies.size(); ++i) std::fprintf(out, "singlet %.15e\n", singlets.energies(i));
     std::fprintf(out, "davidson_info %d\n", singlets.info);
+    for (Index i = 0; i < full.energies.size(); ++i) std::fprintf(out, "btda %.15e\n", full.energies(i));
+    for (Index i = 0; i < fosc.size(); ++i) std::fprintf(out, "fosc %.15e\n", fosc(i));
     std::fprintf(out, "hx_diag0 %.15e\n", d(0));
     std::fclose(out);
     return 0;

@@ -50,3 +50,6 @@ def test_facade_full_step_matches_oracle(tmp_path):
     np.testing.assert_allclose(vals["qp"], ref["qp_pert"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(vals["singlet"], ref["singlet_energies"], rtol=0, atol=1e-4)   # Davidson tol 'normal'
     assert vals["davidson_info"] == [0.0]
+    assert len(vals["btda"]) == nmax and len(vals["fosc"]) == nmax
+    assert np.all(np.array(vals["btda"]) <= np.array(vals["singlet"]) + 1e-6)      # full BSE lies below TDA
+    assert np.all(np.array(vals["fosc"]) >= 0.0)

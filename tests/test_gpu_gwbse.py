@@ -391,3 +391,64 @@ def test_full_gwbse_step(ctx, prob):
     gaps = np.diff(ref["singlet_energies"])
     if gaps.min() > 1e-4:
         np.testing.assert_allclose(ov, 1.0, atol=1e-5)
+
+
+def _bse_pair(ctx, prob, nmax=3):
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    gw, gwo, tc, tco = _gw_pair(ctx, prob, qp_grid_steps=201)
+    gw.CalculateGWPerturbation()
+    gw.CalculateHQP()
+    gwo.CalculateGWPerturbation()
+    gwo.CalculateHQP()
+    bse = api.BSE(ctx, tc)
+    bse.configure(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, nmax, gw.RPAInputEnergies(),
+                  gw.getHQP(), davidson_tolerance="lapack", davidson_maxiter=200)
+    bseo = orc.BSE(tco)
+    bseo.configure(orc.BSEOptions(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, nmax=nmax,
+                                  davidson_tolerance="lapack"), gwo.RPAInputEnergies(), gwo.getHQP())
+    return bse, bseo
+
+
+@pytest.mark.parametrize("singlet", [True, False])
+def test_full_bse_btda(ctx, prob, singlet):
+    """Full (non-TDA) BSE: subspace solver on the device vs the dense symmetric reduction of [[A,B],[-B,-A]]."""
+    bse, bseo = _bse_pair(ctx, prob)
+    e, X, Y = bse.Solve_singlets_BTDA() if singlet else bse.Solve_triplets_BTDA()
+    eo, Xo, Yo = bseo.solve_btda_dense(singlet)
+    assert bse.last_btda["info"] == "Success"
+    np.testing.assert_allclose(e, eo, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(np.diag(X.T @ X - Y.T @ Y), 1.0, atol=1e-8)
+    # eigenvectors up to sign (energies of the tiny problems are non-degenerate)
+    for j in range(len(e)):
+        sgn = np.sign(X[:, j] @ Xo[:, j])
+        np.testing.assert_allclose(sgn * X[:, j], Xo[:, j], atol=1e-5)
+        np.testing.assert_allclose(sgn * Y[:, j], Yo[:, j], atol=1e-5)
+    # the TDA energies lie above the full-BSE ones
+    etda, _ = bse.Solve_singlets_TDA() if singlet else bse.Solve_triplets_TDA()
+    assert np.all(e <= etda + 1e-9)
+
+
+def test_transition_dipoles_and_oscillator_strengths(ctx, prob):
+    """BSE::CalcCoupledTransition_Dipoles / Orbitals::Oscillatorstrengths (north_star: 1e-5 relative)."""
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    bse, bseo = _bse_pair(ctx, prob)
+    rng = np.random.default_rng(21)
+    r = rng.standard_normal((3, sz.n_basis, sz.n_basis))
+    r = 0.5 * (r + np.transpose(r, (0, 2, 1)))
+    e, X = bse.Solve_singlets_TDA()
+    d = bse.transition_dipoles(r, prob["C"], X)
+    dref = orc.BSE.transition_dipoles(r, prob["C"], sz.homo, sz.vmin, sz.cmax, X)
+    np.testing.assert_allclose(d, dref, rtol=1e-10, atol=1e-12)
+    f = api.oscillator_strengths(e, d)
+    np.testing.assert_allclose(f, orc.BSE.oscillator_strengths(e, dref), rtol=1e-10, atol=1e-14)
+    # against the oracle's own eigenvectors: oscillator strengths within 1e-5 relative (sign-invariant)
+    eo, Xo = bseo.Solve_singlets_TDA()
+    fo = orc.BSE.oscillator_strengths(eo, orc.BSE.transition_dipoles(r, prob["C"], sz.homo, sz.vmin, sz.cmax, Xo))
+    np.testing.assert_allclose(f, fo, rtol=1e-5, atol=1e-9)
+    # full BSE: X + Y enters
+    eb, Xb, Yb = bse.Solve_singlets_BTDA()
+    db = bse.transition_dipoles(r, prob["C"], Xb, Yb)
+    np.testing.assert_allclose(db, orc.BSE.transition_dipoles(r, prob["C"], sz.homo, sz.vmin, sz.cmax, Xb, Yb),
+                               rtol=1e-10, atol=1e-12)

@@ -111,6 +111,9 @@ PROTOTYPES = {
     "xtpb_bse_operator_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "xtpb_bse_operator_create_raw": (C.c_int, [vp, vp, idx, idx, idx, idx, dptr, dptr, idx, C.c_int, C.c_int,
                                                C.c_int, C.c_int, C.POINTER(vp)]),
+    "xtpb_bse_solve_btda": (C.c_int, [vp, C.c_int, C.POINTER(DavidsonOptions), dptr, dptr, dptr, idx, C.POINTER(C.c_int), iptr]),
+    "xtpb_bse_transition_dipoles": (C.c_int, [vp, idx, dptr, idx, dptr, idx, dptr, dptr, idx, dptr]),
+    "xtpb_oscillator_strengths": (C.c_int, [idx, dptr, dptr, dptr]),
     "xtpb_dense_operator_create": (C.c_int, [vp, dptr, idx, idx, C.POINTER(vp)]),
     "xtpb_op_destroy": (C.c_int, [vp]),
     "xtpb_op_size": (C.c_int, [vp, iptr]),

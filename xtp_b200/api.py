@@ -597,6 +597,51 @@ class BSE:
         finally:
             op.close()
 
+    def _solve_btda(self, singlet):
+        """Full BSE (useTDA = false): energies, X, Y with X^T X - Y^T Y = 1 (upstream Solve_nonhermitian_Davidson)."""
+        ds = DavidsonSolver()
+        corr, tol, upd, maxiter = self.davidson
+        ds.set_tolerance(tol)
+        ds.set_iter_max(maxiter)
+        ds.set_max_search_space(10 * int(self.opt.nmax))
+        n, k = self.size(), int(self.opt.nmax)
+        e = np.empty(k)
+        X, Y = np.empty((n, k), order="F"), np.empty((n, k), order="F")
+        info, iters = C.c_int(0), idx(0)
+        check(_lib.lib().xtpb_bse_solve_btda(self._h, int(singlet), C.byref(ds.opt), _d(e), _d(X), _d(Y), n,
+                                             C.byref(info), C.byref(iters)))
+        self.last_btda = {"info": "Success" if info.value == 0 else "NoConvergence", "iterations": int(iters.value)}
+        return e, X, Y
+
+    def Solve_singlets_BTDA(self):
+        return self._solve_btda(True)
+
+    def Solve_triplets_BTDA(self):
+        return self._solve_btda(False)
+
+    def size(self):
+        return int((self.opt.homo - self.opt.vmin + 1) * (self.opt.cmax - self.opt.homo))
+
+    def transition_dipoles(self, ao_dipoles, C_mo, X, Y=None):
+        """BSE::CalcCoupledTransition_Dipoles: (n_states, 3) from AO dipole matrices (3, nb, nb) and MO coefficients."""
+        Cf = _f(C_mo)
+        R = np.ascontiguousarray(ao_dipoles, dtype=np.float64)
+        Xf = _f(X)
+        Yf = _f(Y) if Y is not None else None
+        out = np.empty((Xf.shape[1], 3))
+        check(_lib.lib().xtpb_bse_transition_dipoles(self._h, Cf.shape[0], _d(Cf), Cf.shape[0], _d(R), Xf.shape[1],
+                                                     _d(Xf), _d(Yf) if Yf is not None else None, Xf.shape[0], _d(out)))
+        return out
+
+
+def oscillator_strengths(energies, dipoles):
+    """Orbitals::Oscillatorstrengths: f = 2/3 E |d|^2."""
+    e = np.ascontiguousarray(energies, dtype=np.float64)
+    d = np.ascontiguousarray(dipoles, dtype=np.float64)
+    out = np.empty(len(e))
+    check(_lib.lib().xtpb_oscillator_strengths(len(e), _d(e), _d(d), _d(out)))
+    return out
+
 
 def contract_host(ctx: Context, desc: "_lib.ContractDesc", A, B, d, Cmat):
     """Engine-level test hook: raw strided contraction on host buffers (flat float64 arrays)."""

@@ -651,4 +651,197 @@ void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& 
   ctx->sync();
 }
 
+
+// ------------------------------------------------------------------ full (non-TDA) BSE
+// upstream BSE::Solve_nonhermitian_Davidson / HamiltonianOperator<A,B> / DavidsonSolver "HAM" mode:
+//   [[A, B], [-B, -A]] [X; Y] = w [X; Y].
+// Solved in the symmetric-product form: with M+ = A + B, M- = A - B and an orthonormal basis b of the vc-dimensional
+// space, the reduced matrices m+- = b^T M+- b give (m-)^1/2 m+ (m-)^1/2 z = w^2 z; |X+Y> = b (m-)^1/2 z / sqrt(w),
+// |X-Y> = b (m-)^-1/2 z sqrt(w) (so (X+Y)^T (X-Y) = X^T X - Y^T Y = 1); residuals M+|X+Y> - w|X-Y> and
+// M-|X-Y> - w|X+Y> feed the diagonally preconditioned corrections.  Two operator applications (A, B) per new basis
+// vector; the subspace algebra (<= max_search_space) is small dense work (cuSOLVER eigh + host products).
+namespace {
+
+// symmetric s x s (host, col-major): A <- eigenvectors, w <- ascending eigenvalues
+void small_eigh(Context* ctx, int n, std::vector<double>& A, std::vector<double>& w, DBuf& dA, DBuf& dw) {
+  dA.ensure((size_t)n * n);
+  dw.ensure((size_t)n);
+  ctx->h2d(dA.p, A.data(), (size_t)n * n);
+  ctx->eigh(n, dA.p, n, dw.p);
+  w.resize((size_t)n);
+  ctx->d2h(w.data(), dw.p, (size_t)n);
+  ctx->d2h(A.data(), dA.p, (size_t)n * n);
+}
+// C = A * B for s x s host matrices (col-major)
+std::vector<double> small_mm(int n, const std::vector<double>& A, const std::vector<double>& B) {
+  std::vector<double> C((size_t)n * n, 0.0);
+  for (int j = 0; j < n; ++j)
+    for (int k = 0; k < n; ++k) {
+      const double b = B[k + (size_t)j * n];
+      if (b == 0.0) continue;
+      for (int i = 0; i < n; ++i) C[i + (size_t)j * n] += A[i + (size_t)k * n] * b;
+    }
+  return C;
+}
+
+}  // namespace
+
+void btda_solve(Operator& A, Operator& B, long long neigen, const xtpb_davidson_options& opt, BtdaResult& out) {
+  Context* ctx = A.ctx;
+  ProfScope prof(PROF_DAVIDSON);
+  const long long n = A.size;
+  XTPB_REQUIRE(B.size == n, "A and B operators differ in size");
+  XTPB_REQUIRE(neigen >= 1 && 2 * neigen <= n, "neigen out of range");
+  const int k = (int)neigen;
+  long long max_space = opt.max_search_space;
+  if (max_space < 4 * neigen) max_space = 10 * neigen;
+  max_space = std::min(max_space, n);
+  long long guess = opt.size_initial_guess == 0 ? 2 * neigen : opt.size_initial_guess;
+  guess = std::min(guess, n);
+
+  DavidsonWork w;
+  w.ctx = ctx;
+  w.n = n;
+  w.ld = round_up(n, 2);
+  w.cap = std::min<long long>(n, max_space + 2 * k) + guess + 2;
+  w.V.alloc((size_t)(w.ld * w.cap));
+  w.V.zero(ctx->stream);
+  w.small.alloc((size_t)(w.cap * (w.cap + 4) + 16));
+  w.vec.alloc((size_t)(2 * n + 1024));
+  w.tmp.alloc((size_t)(w.ld * 2 * k));
+  DBuf P((size_t)(w.ld * w.cap)), Q((size_t)(w.ld * w.cap)), T1((size_t)(w.ld * w.cap)), T2((size_t)(w.ld * w.cap));
+  DBuf XpY((size_t)(w.ld * k)), XmY((size_t)(w.ld * k)), RL((size_t)(w.ld * k)), RR((size_t)(w.ld * k));
+  DBuf D((size_t)n), dsmall, dw, Ldev((size_t)(w.cap * k)), Rdev((size_t)(w.cap * k)), omdev((size_t)k), nrm((size_t)(2 * k));
+  A.diagonal_dev(D.p);
+  {
+    std::vector<double> Dh((size_t)n);
+    ctx->d2h(Dh.data(), D.p, (size_t)n);
+    std::vector<long long> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0LL);
+    std::stable_sort(order.begin(), order.end(), [&](long long a, long long b) { return Dh[a] < Dh[b]; });
+    DBuf idx((size_t)guess);
+    XTPB_CUDA(cudaMemcpyAsync(idx.p, order.data(), (size_t)guess * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_unit_vectors(w.V.p, w.ld, n, reinterpret_cast<const long long*>(idx.p), (int)guess, ctx->stream);
+    ctx->sync();
+  }
+  auto apply = [&](int from, int to) {      // P, Q columns [from, to) = (A +- B) V
+    const int cnt = to - from;
+    if (cnt <= 0) return;
+    const long long off = (long long)from * w.ld;
+    A.matmul_dev(w.V.p + off, w.ld, cnt, T1.p, w.ld);
+    B.matmul_dev(w.V.p + off, w.ld, cnt, T2.p, w.ld);
+    const long long len = w.ld * (cnt - 1) + n;
+    XTPB_CUDA(cudaMemcpyAsync(P.p + off, T1.p, (size_t)len * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    XTPB_CUDA(cudaMemcpyAsync(Q.p + off, T1.p, (size_t)len * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_axpby(P.p + off, T2.p, len, 1.0, 1.0, ctx->stream);
+    k_axpby(Q.p + off, T2.p, len, -1.0, 1.0, ctx->stream);
+  };
+
+  int s = (int)guess, applied = 0;
+  std::vector<double> omega((size_t)k, 0.0), rn((size_t)(2 * k));
+  out.info = 1;
+  out.iterations = 0;
+  for (long long it = 0; it < opt.iter_max; ++it) {
+    out.iterations = it + 1;
+    apply(applied, s);
+    applied = s;
+    // reduced matrices
+    std::vector<double> mp((size_t)s * s), mm((size_t)s * s);
+    gemm_tn(ctx, w.V.p, w.ld, s, P.p, w.ld, s, n, w.small.p, s);
+    ctx->d2h(mp.data(), w.small.p, (size_t)s * s);
+    gemm_tn(ctx, w.V.p, w.ld, s, Q.p, w.ld, s, n, w.small.p, s);
+    ctx->d2h(mm.data(), w.small.p, (size_t)s * s);
+    for (int j = 0; j < s; ++j)
+      for (int i = 0; i < j; ++i) {
+        mp[i + (size_t)j * s] = mp[j + (size_t)i * s] = 0.5 * (mp[i + (size_t)j * s] + mp[j + (size_t)i * s]);
+        mm[i + (size_t)j * s] = mm[j + (size_t)i * s] = 0.5 * (mm[i + (size_t)j * s] + mm[j + (size_t)i * s]);
+      }
+    // (m-)^{+-1/2}
+    std::vector<double> U = mm, lam;
+    small_eigh(ctx, s, U, lam, dsmall, dw);
+    XTPB_REQUIRE(lam[0] > 0.0, "full BSE: A - B is not positive definite in the search space (triplet instability?)");
+    std::vector<double> Sh((size_t)s * s, 0.0), Si((size_t)s * s, 0.0);
+    for (int j = 0; j < s; ++j)
+      for (int i = 0; i < s; ++i) {
+        double a = 0.0, b = 0.0;
+        for (int t = 0; t < s; ++t) {
+          const double uu = U[i + (size_t)t * s] * U[j + (size_t)t * s];
+          a += uu * std::sqrt(lam[t]);
+          b += uu / std::sqrt(lam[t]);
+        }
+        Sh[i + (size_t)j * s] = a;
+        Si[i + (size_t)j * s] = b;
+      }
+    std::vector<double> Cm = small_mm(s, small_mm(s, Sh, mp), Sh), w2;
+    for (int j = 0; j < s; ++j)
+      for (int i = 0; i < j; ++i) Cm[i + (size_t)j * s] = Cm[j + (size_t)i * s] = 0.5 * (Cm[i + (size_t)j * s] + Cm[j + (size_t)i * s]);
+    small_eigh(ctx, s, Cm, w2, dsmall, dw);            // Cm <- Z
+    const int kk = std::min(k, s);
+    std::vector<double> L((size_t)s * kk), R((size_t)s * kk);
+    for (int j = 0; j < kk; ++j) {
+      XTPB_REQUIRE(w2[j] > 0.0, "full BSE: non-positive squared excitation energy");
+      omega[j] = std::sqrt(w2[j]);
+      const double sq = std::sqrt(omega[j]);
+      for (int i = 0; i < s; ++i) {
+        double a = 0.0, b = 0.0;
+        for (int t = 0; t < s; ++t) {
+          a += Sh[i + (size_t)t * s] * Cm[t + (size_t)j * s];
+          b += Si[i + (size_t)t * s] * Cm[t + (size_t)j * s];
+        }
+        L[i + (size_t)j * s] = a / sq;
+        R[i + (size_t)j * s] = b * sq;
+      }
+    }
+    ctx->h2d(Ldev.p, L.data(), L.size());
+    ctx->h2d(Rdev.p, R.data(), R.size());
+    ctx->h2d(omdev.p, omega.data(), (size_t)kk);
+    gemm_nn(ctx, w.V.p, w.ld, s, Ldev.p, s, kk, n, XpY.p, w.ld, 1.0, 0.0);
+    gemm_nn(ctx, w.V.p, w.ld, s, Rdev.p, s, kk, n, XmY.p, w.ld, 1.0, 0.0);
+    gemm_nn(ctx, P.p, w.ld, s, Ldev.p, s, kk, n, RL.p, w.ld, 1.0, 0.0);      // M+ |X+Y>
+    gemm_nn(ctx, Q.p, w.ld, s, Rdev.p, s, kk, n, RR.p, w.ld, 1.0, 0.0);      // M- |X-Y>
+    k_residuals(RL.p, w.ld, XmY.p, w.ld, omdev.p, n, kk, ctx->stream);       //   - w |X-Y>
+    k_residuals(RR.p, w.ld, XpY.p, w.ld, omdev.p, n, kk, ctx->stream);       //   - w |X+Y>
+    k_col_norms(RL.p, w.ld, n, kk, nrm.p, ctx->stream);
+    k_col_norms(RR.p, w.ld, n, kk, nrm.p + kk, ctx->stream);
+    ctx->d2h(rn.data(), nrm.p, (size_t)(2 * kk));
+    bool converged = kk == k;
+    for (int j = 0; j < kk; ++j) converged = converged && rn[j] < opt.tolerance && rn[kk + j] < opt.tolerance;
+    if (converged) {
+      out.info = 0;
+      break;
+    }
+    if (it == opt.iter_max - 1) break;
+    if (s + 2 * kk > max_space) {       // restart from the current Ritz pairs
+      XTPB_CUDA(cudaMemcpyAsync(w.V.p, XpY.p, (size_t)(w.ld * kk) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      XTPB_CUDA(cudaMemcpyAsync(w.V.p + (long long)kk * w.ld, XmY.p, (size_t)(w.ld * kk) * 8, cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+      s = gram_schmidt_columns(w, 0, 2 * kk);
+      applied = 0;
+    }
+    int added = 0;
+    for (int side = 0; side < 2; ++side)
+      for (int j = 0; j < kk; ++j) {
+        if (rn[side * kk + j] < opt.tolerance) continue;
+        XTPB_REQUIRE(s + added < w.cap, "full BSE: search space overflow");
+        const double* r = (side == 0 ? RL.p : RR.p) + (long long)j * w.ld;
+        const double* x = (side == 0 ? XpY.p : XmY.p) + (long long)j * w.ld;
+        k_davidson_correction(w.V.p + (long long)(s + added) * w.ld, r, x, D.p, omega[j], n, 0, w.vec.p, ctx->stream);
+        ++added;
+      }
+    const int before = s;
+    s = gram_schmidt(w, before, before + added);
+    if (s == before) break;
+  }
+  out.evals.assign(omega.begin(), omega.end());
+  out.X.alloc((size_t)(n * k));
+  out.Y.alloc((size_t)(n * k));
+  // X = (|X+Y> + |X-Y>)/2, Y = (|X+Y> - |X-Y>)/2
+  k_copy_2d(out.X.p, n, XpY.p, w.ld, (int)n, k, ctx->stream);
+  k_copy_2d(out.Y.p, n, XpY.p, w.ld, (int)n, k, ctx->stream);
+  k_copy_2d(w.tmp.p, n, XmY.p, w.ld, (int)n, k, ctx->stream);
+  k_axpby(out.X.p, w.tmp.p, n * k, 0.5, 0.5, ctx->stream);
+  k_axpby(out.Y.p, w.tmp.p, n * k, -0.5, 0.5, ctx->stream);
+  ctx->sync();
+}
+
 }  // namespace xtpb

@@ -1,4 +1,5 @@
 // extern "C" surface of libxtpb200 (include/xtpb200/xtpb200.h).
+#include <cmath>
 #include <cstring>
 
 #include "internal.h"
@@ -421,6 +422,81 @@ int xtpb_bse_operator_create_raw(xtpb_ctx* ctx, xtpb_tc* tc, xtpb_index homo, xt
   auto op = std::make_unique<BseOperator>(&ctx->impl, &tc->impl, homo, rpamin, vmin, cmax, eps_inv_host, hqp_host, ldh,
                                           cqp, cx, cd, cd2, nullptr);
   *out = new xtpb_op{std::move(op)};
+  XTPB_API_END
+}
+// BSE::Solve_singlets / Solve_triplets without the Tamm-Dancoff approximation (BSE::Solve_nonhermitian_Davidson)
+int xtpb_bse_solve_btda(xtpb_bse* bse, int singlet, const xtpb_davidson_options* opt, double* energies_host,
+                        double* X_host, double* Y_host, xtpb_index ld, int* info, xtpb_index* iterations) {
+  XTPB_API_BEGIN
+  BSE& b = bse->impl;
+  const int cx = singlet ? 2 : 0;
+  const double* R = bse->R ? bse->R->p : nullptr;
+  BseOperator A(b.ctx, b.tc, b.opt.homo, b.opt.rpamin, b.opt.vmin, b.opt.cmax, b.eps_inv.data(), b.hqp.data(),
+                b.vt + b.ct, 1, cx, 1, 0, R);
+  BseOperator B(b.ctx, b.tc, b.opt.homo, b.opt.rpamin, b.opt.vmin, b.opt.cmax, b.eps_inv.data(), b.hqp.data(),
+                b.vt + b.ct, 0, cx, 0, 1, R);
+  BtdaResult res;
+  btda_solve(A, B, b.opt.nmax, *opt, res);
+  std::memcpy(energies_host, res.evals.data(), res.evals.size() * 8);
+  XTPB_REQUIRE(ld >= A.size, "leading dimension smaller than the BSE size");
+  if (X_host) b.ctx->d2h_2d(X_host, ld, res.X.p, A.size, A.size, b.opt.nmax);
+  if (Y_host) b.ctx->d2h_2d(Y_host, ld, res.Y.p, A.size, A.size, b.opt.nmax);
+  if (info) *info = res.info;
+  if (iterations) *iterations = res.iterations;
+  XTPB_API_END
+}
+// BSE::CalcCoupledTransition_Dipoles with Orbitals::CalcFreeTransition_Dips folded in:
+//   d_s = -sqrt(2) sum_vc (X + Y)_vc,s  C_v^T r_AO C_c
+int xtpb_bse_transition_dipoles(xtpb_bse* bse, xtpb_index n_basis, const double* C_host, xtpb_index ldc,
+                                const double* ao_dipoles_host, xtpb_index n_states, const double* X_host,
+                                const double* Y_host, xtpb_index ld, double* dipoles_host) {
+  XTPB_API_BEGIN
+  BSE& b = bse->impl;
+  Context* ctx = b.ctx;
+  const long long nb = n_basis, vt = b.vt, ct = b.ct, size = b.size;
+  XTPB_REQUIRE(nb > 0 && ldc >= nb && n_states >= 1 && ld >= size, "bad transition dipole arguments");
+  const long long ldb = round_up(nb, 2), lds = round_up(size, 2);
+  DBuf Cv((size_t)(ldb * vt)), Cc((size_t)(ldb * ct)), Rm((size_t)(ldb * nb)), W((size_t)(ldb * vt)),
+      Dm((size_t)(3 * lds)), coef((size_t)(lds * n_states)), out((size_t)(3 * n_states));
+  Cv.zero(ctx->stream); Cc.zero(ctx->stream); Rm.zero(ctx->stream); Dm.zero(ctx->stream); coef.zero(ctx->stream);
+  ctx->h2d_2d(Cv.p, ldb, C_host + b.opt.vmin * ldc, ldc, nb, vt);
+  ctx->h2d_2d(Cc.p, ldb, C_host + (b.opt.homo + 1) * ldc, ldc, nb, ct);
+  std::vector<double> xy((size_t)(size * n_states));
+  for (long long s = 0; s < n_states; ++s)
+    for (long long i = 0; i < size; ++i) xy[i + s * size] = X_host[i + s * ld] + (Y_host ? Y_host[i + s * ld] : 0.0);
+  ctx->h2d_2d(coef.p, lds, xy.data(), size, size, n_states);
+  for (int i = 0; i < 3; ++i) {
+    ctx->h2d_2d(Rm.p, ldb, ao_dipoles_host + (long long)i * nb * nb, nb, nb, nb);
+    GemmParams g{};      // W(mu, v) = sum_nu r(mu,nu) Cv(nu,v)   (r symmetric)
+    g.A = op_k_contig(Rm.p, ldb);
+    g.B = op_k_contig(Cv.p, ldb);
+    g.C = W.p; g.c_sm = 1; g.c_sn = ldb;
+    g.M = (int)nb; g.N = (int)vt; g.K = (int)nb; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+    GemmParams h{};      // D_i[v*ct + c] = sum_mu Cc(mu,c) W(mu,v)
+    h.A = op_k_contig(Cc.p, ldb);
+    h.B = op_k_contig(W.p, ldb);
+    h.C = Dm.p + (long long)i * lds; h.c_sm = 1; h.c_sn = ct;
+    h.M = (int)ct; h.N = (int)vt; h.K = (int)nb; h.n_outer = 1; h.n_batch = 1; h.alpha = 1.0;
+    contract(h, ctx->ws, ctx->stream);
+  }
+  GemmParams t{};        // d(i, s) = -sqrt(2) sum_k D_i[k] (X+Y)[k, s]
+  t.A = op_k_contig(Dm.p, lds);
+  t.B = op_k_contig(coef.p, lds);
+  t.C = out.p; t.c_sm = 1; t.c_sn = 3;
+  t.M = 3; t.N = (int)n_states; t.K = (int)size; t.n_outer = 1; t.n_batch = 1; t.alpha = -std::sqrt(2.0);
+  contract(t, ctx->ws, ctx->stream);
+  ctx->d2h(dipoles_host, out.p, (size_t)(3 * n_states));
+  XTPB_API_END
+}
+// Orbitals::Oscillatorstrengths: f_s = 2/3 E_s |d_s|^2 (host arithmetic)
+int xtpb_oscillator_strengths(xtpb_index n_states, const double* energies_host, const double* dipoles_host,
+                              double* strengths_host) {
+  XTPB_API_BEGIN
+  for (long long s = 0; s < n_states; ++s) {
+    const double* d = dipoles_host + 3 * s;
+    strengths_host[s] = 2.0 / 3.0 * energies_host[s] * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  }
   XTPB_API_END
 }
 int xtpb_dense_operator_create(xtpb_ctx* ctx, const double* A_host, xtpb_index n, xtpb_index lda, xtpb_op** out) {

@@ -277,6 +277,14 @@ struct DavidsonResult {
   long long iterations = 0;
 };
 void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& opt, DavidsonResult& out);
+struct BtdaResult {
+  std::vector<double> evals;
+  DBuf X, Y;           // size x neigen each, X^T X - Y^T Y = 1
+  int info = 1;
+  long long iterations = 0;
+};
+// full BSE [[A, B], [-B, -A]] (upstream BSE::Solve_nonhermitian_Davidson); A, B symmetric operators of equal size
+void btda_solve(Operator& A, Operator& B, long long neigen, const xtpb_davidson_options& opt, BtdaResult& out);
 
 }  // namespace xtpb
 
