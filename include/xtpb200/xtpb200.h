@@ -171,6 +171,22 @@ int xtpb_gw_sigma_c_diag(xtpb_gw* gw, const double* frequencies_host, double* va
 /* Sigma_c of every gw level on its QP grid (the scan GW::SolveQP_Grid runs, and what GW::PlotSigma tabulates):
  * values_host[level*qp_grid_steps + j] = Sigma_c(level, center[level] + (j - (steps-1)/2) * qp_grid_spacing) */
 int xtpb_gw_sigma_c_grid(xtpb_gw* gw, const double* center_frequencies_host, double* values_host);
+/* How the last grid scan (xtpb_gw_sigma_c_grid, or the one inside GW::SolveQP_Grid) was evaluated on this rank:
+ * compressed = 1 when far poles went through Chebyshev moments (0: pole-by-pole kernel, e.g. XTPB_SIGMA_GRID=direct,
+ * unsorted RPA energies or a non-PPM Sigma), the bins of its plan, the (pole, frequency) evaluations actually
+ * performed one by one and the number the plain double sum needs.  Any pointer may be NULL. */
+int xtpb_gw_grid_scan_info(xtpb_gw* gw, int* compressed, xtpb_index* n_bins, double* direct_evaluations,
+                           double* equivalent_evaluations);
+/* Host-side plan of the compressed grid scan behind xtpb_gw_sigma_c_grid / GW::SolveQP_Grid (needs no device; exposed
+ * so that the bin/near-range logic can be tested on a CPU box).  The pole axis [zmin, zmax] is cut into n_bins bins
+ * (edges: n_bins + 1 ascending values); near_ranges[(level*n_chunks + chunk)*2 + {0,1}] is the inclusive range of bins
+ * whose poles are summed one by one for the chunk of 32 consecutive grid points starting at
+ * grid_start[level] + 32*chunk*spacing (lo > hi: none); every other bin enters through its Chebyshev moments.
+ * usable = 0: the scan falls back to the pole-by-pole kernel.  edges / near_ranges may be NULL to query the sizes
+ * (near_ranges needs 2*n_levels*n_chunks ints, n_chunks = ceil(steps/32)). */
+int xtpb_ppm_grid_plan(xtpb_index n_levels, const double* grid_start, double spacing, xtpb_index steps, double zmin,
+                       double zmax, xtpb_index edges_capacity, double* edges, xtpb_index* n_bins, int* near_ranges,
+                       xtpb_index* n_chunks, int* usable);
 /* Sigma_base::CalcCorrelationOffDiag(frequencies): qptotal x qptotal, zero diagonal */
 int xtpb_gw_sigma_c_offdiag(xtpb_gw* gw, const double* frequencies_host, double* sigma_c_host);
 /* GW::CalculateGWPerturbation / CalculateHQP / getGWAResults / getHQP / DiagonalizeQPHamiltonian */

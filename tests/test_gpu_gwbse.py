@@ -180,11 +180,15 @@ def test_ppm_parameters_and_sigma_c(ctx, prob):
     np.testing.assert_allclose(off, gwo.sigma.CalcCorrelationOffDiag(fr), rtol=1e-8, atol=1e-11)
 
 
-def test_sigma_c_qp_grid(ctx, prob):
-    """The fused grid kernel (G poles per reciprocal, damped-window branch) against element-wise oracle evaluations:
-    every level, a 173-point grid (odd, ragged against the 512-frequency CTA chunk) that crosses many poles."""
+@pytest.mark.parametrize("mode", ["compressed", "direct"])
+@pytest.mark.parametrize("steps,spacing", [(173, 0.013), (1001, 0.01)])
+def test_sigma_c_qp_grid(ctx, prob, mode, steps, spacing, monkeypatch):
+    """The grid scan of GW::SolveQP_Grid against element-wise oracle evaluations, both ways it can run: compressed
+    (far poles through Chebyshev moments, near poles one by one) and the plain pole-by-pole kernel (damped-window
+    branch).  Every level; a 173-point grid (odd, ragged against the 32-point chunks) that crosses many poles and the
+    reference's default 1001 x 0.01 Ha grid."""
     sz = prob["sizes"]
-    steps, spacing = 173, 0.013
+    monkeypatch.setenv("XTPB_SIGMA_GRID", mode)
     gw, gwo, _, _ = _gw_pair(ctx, prob, qp_grid_steps=steps, qp_grid_spacing=spacing)
     gwo.rpa.setRPAInputEnergies(prob["energies"][sz.rpamin:sz.rpamax + 1])
     gw.PrepareScreening()
@@ -192,6 +196,9 @@ def test_sigma_c_qp_grid(ctx, prob):
     centers = prob["energies"][sz.qpmin:sz.qpmax + 1].copy()
     grid = gw.CalcCorrelationGrid(centers)
     assert grid.shape == (sz.qptotal, steps)
+    info = gw.grid_scan_info()
+    assert info["compressed"] == (mode == "compressed")
+    assert 0 < info["direct_evaluations"] and info["equivalent_evaluations"] == sz.ntotal * sz.n_aux * steps * sz.qptotal
     rng = np.random.default_rng(9)
     for level in rng.choice(sz.qptotal, size=min(6, sz.qptotal), replace=False):
         js = np.unique(np.concatenate([[0, steps - 1, steps // 2], rng.integers(0, steps, 20)]))
@@ -202,6 +209,52 @@ def test_sigma_c_qp_grid(ctx, prob):
     lv = np.arange(sz.qptotal)
     np.testing.assert_allclose(grid[:, (steps - 1) // 2], gw.CalcCorrelationDiagElements(lv, centers), rtol=1e-10,
                                atol=1e-12)
+
+
+def test_sigma_c_qp_grid_compressed_vs_direct_large(ctx, monkeypatch):
+    """synth-500 shape (500 levels x 1500 aux functions, 100 QP levels, the default 1001-point grid): the compressed
+    scan against the pole-by-pole kernel on every grid point, against a numpy pole sum over the device's own rotated
+    slab on sampled points, with unsorted RPA energies (must fall back to pole by pole), and the saving it buys."""
+    from xtp_b200 import api
+    sz = synth.WORKLOADS["synth-500"]
+    rng = np.random.default_rng(3)
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.set_raw(synth.make_M_direct(sz, rng))
+    e = synth.make_energies(sz, rng)
+    gw = api.GW(ctx, tc, synth.make_vxc(sz, rng), e)
+    gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax))
+    gw.PrepareScreening()
+    centers = e[sz.qpmin:sz.qpmax + 1].copy()
+    monkeypatch.setenv("XTPB_SIGMA_GRID", "direct")
+    direct = gw.CalcCorrelationGrid(centers)
+    assert not gw.grid_scan_info()["compressed"]
+    monkeypatch.setenv("XTPB_SIGMA_GRID", "compressed")
+    comp = gw.CalcCorrelationGrid(centers)
+    info = gw.grid_scan_info()
+    assert info["compressed"] and info["bins"] > 8
+    assert info["direct_evaluations"] < 0.25 * info["equivalent_evaluations"]
+    scale = np.abs(direct).max()
+    assert np.abs(comp - direct).max() < 1e-11 * scale
+    # numpy pole sum over the rotated slab the device holds
+    weight, freq = gw.getPpm()
+    fac = np.where(weight < 1e-9, 0.0, 0.5 * weight * freq)
+    steps, spacing = 1001, 0.01
+    for level in (0, sz.homo, sz.homo + 1, sz.qptotal - 1):
+        slab = tc[level + sz.qpmin - sz.rpamin].T            # [P, m]
+        z = np.where(np.arange(sz.ntotal)[None, :] < sz.n_occ, e[None, :] - freq[:, None], e[None, :] + freq[:, None])
+        a = fac[:, None] * slab * slab
+        for j in (0, 137, 500, 731, 1000):
+            om = centers[level] + (j - (steps - 1) / 2) * spacing
+            ref = (a * orc.ppm_stabilized_inverse(om - z)).sum()
+            assert abs(comp[level, j] - ref) < 1e-10 * scale
+    # unsorted energies: bins are no longer contiguous m-ranges -> the scan must decline the compressed path
+    e2 = e[sz.rpamin:sz.rpamax + 1].copy()
+    e2[[sz.n_occ + 3, sz.n_occ + 4]] = e2[[sz.n_occ + 4, sz.n_occ + 3]]
+    gw.setRPAInputEnergies(e2)
+    unsorted_grid = gw.CalcCorrelationGrid(centers)
+    assert not gw.grid_scan_info()["compressed"]
+    monkeypatch.setenv("XTPB_SIGMA_GRID", "direct")
+    np.testing.assert_array_equal(unsorted_grid, gw.CalcCorrelationGrid(centers))
 
 
 def test_sigma_exact(ctx, prob):

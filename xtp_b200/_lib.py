@@ -99,6 +99,9 @@ PROTOTYPES = {
     "xtpb_gw_sigma_c_diag": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_sigma_c_grid": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_sigma_c_offdiag": (C.c_int, [vp, dptr, dptr]),
+    "xtpb_gw_grid_scan_info": (C.c_int, [vp, C.POINTER(C.c_int), iptr, dptr, dptr]),
+    "xtpb_ppm_grid_plan": (C.c_int, [idx, dptr, C.c_double, idx, C.c_double, C.c_double, idx, dptr, iptr,
+                                     C.POINTER(C.c_int), iptr, C.POINTER(C.c_int)]),
     "xtpb_gw_calculate_gw_perturbation": (C.c_int, [vp]),
     "xtpb_gw_calculate_hqp": (C.c_int, [vp]),
     "xtpb_gw_get_gwa_results": (C.c_int, [vp, dptr]),

@@ -390,6 +390,14 @@ class GW:
         check(_lib.lib().xtpb_gw_sigma_c_grid(self._h, _d(fr), _d(out)))
         return out
 
+    def grid_scan_info(self):
+        """How the last QP-grid scan ran on this rank: compressed (far poles through Chebyshev moments) or pole by pole,
+        the bins of the plan, and evaluated / equivalent (pole, frequency) pairs (xtpb_gw_grid_scan_info)."""
+        comp, nb, direct, equiv = C.c_int(0), idx(0), C.c_double(0.0), C.c_double(0.0)
+        check(_lib.lib().xtpb_gw_grid_scan_info(self._h, C.byref(comp), C.byref(nb), C.byref(direct), C.byref(equiv)))
+        return {"compressed": bool(comp.value), "bins": nb.value, "direct_evaluations": direct.value,
+                "equivalent_evaluations": equiv.value}
+
     def CalcCorrelationOffDiag(self, frequencies):
         fr = np.ascontiguousarray(frequencies, dtype=np.float64)
         out = np.empty((self.qptotal, self.qptotal), order="F")

@@ -269,6 +269,32 @@ int xtpb_gaussian_quadrature(int scheme, xtpb_index order, double* points, doubl
   if (weights) std::memcpy(weights, w.data(), w.size() * 8);
   XTPB_API_END
 }
+int xtpb_gw_grid_scan_info(xtpb_gw* gw, int* compressed, xtpb_index* n_bins, double* direct_evaluations,
+                           double* equivalent_evaluations) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(gw, "null pointer");
+  if (compressed) *compressed = gw->impl.grid_compressed;
+  if (n_bins) *n_bins = gw->impl.grid_bins;
+  if (direct_evaluations) *direct_evaluations = gw->impl.grid_direct_evals;
+  if (equivalent_evaluations) *equivalent_evaluations = gw->impl.grid_equiv_evals;
+  XTPB_API_END
+}
+int xtpb_ppm_grid_plan(xtpb_index n_levels, const double* grid_start, double spacing, xtpb_index steps, double zmin,
+                       double zmax, xtpb_index edges_capacity, double* edges, xtpb_index* n_bins, int* near_ranges,
+                       xtpb_index* n_chunks, int* usable) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(grid_start && n_bins && n_chunks && usable, "null pointer");
+  PpmGridPlan plan;
+  *usable = ppm_grid_plan(grid_start, n_levels, spacing, steps, zmin, zmax, plan) ? 1 : 0;
+  *n_bins = *usable ? plan.nb : 0;
+  *n_chunks = *usable ? plan.n_chunks : 0;
+  if (*usable && edges) {
+    XTPB_REQUIRE(edges_capacity >= (xtpb_index)plan.edges.size(), "edges buffer too small");
+    std::memcpy(edges, plan.edges.data(), plan.edges.size() * sizeof(double));
+  }
+  if (*usable && near_ranges) std::memcpy(near_ranges, plan.near.data(), plan.near.size() * sizeof(int));
+  XTPB_API_END
+}
 int xtpb_gw_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_gw_options* opt, const double* vxc_host, xtpb_index ldv,
                    const double* dft_energies_host, xtpb_index n_energies, xtpb_gw** out) {
   XTPB_API_BEGIN

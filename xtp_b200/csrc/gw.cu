@@ -2,6 +2,8 @@
 // Upstream: xtp/src/libxtp/gwbse/{rpa,ppm,sigma_base,sigma_ppm,gw}.cc.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <limits>
 
 #include "internal.h"
@@ -154,6 +156,61 @@ void GW::sigma_c_diag_elements(long long n, const long long* levels, const doubl
   sigma_c_diag_elements_other(n, levels, freqs, values, derivs);
 }
 
+// Plan of the compressed grid scan (kernels.cu (1b)).  Bins of the pole axis: width = the damping half-window over the
+// range the grids of all levels cover (+ one bin either side), doubling widths beyond it (a bin of half-width h that
+// starts 2h + ... outside the targets keeps d = distance/h >= 3), clipped to [zmin, zmax].  A bin is FAR from a chunk
+// [wa, wb] of grid points when its centre is >= 3 h away (Chebyshev series of 1/(w-z) converges like 5.83^-j) and
+// >= h + window away (none of its poles is damped for any target of the chunk); everything between the first and the
+// last bin that is not far is evaluated pole by pole.
+bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing, long long steps, double zmin,
+                   double zmax, PpmGridPlan& plan) {
+  if (n_levels <= 0 || steps <= 0 || !(zmax >= zmin) || !std::isfinite(zmin) || !std::isfinite(zmax)) return false;
+  const double W = kPpmDampingWindow;
+  double t_lo = grid_start[0], t_hi = grid_start[0];
+  for (long long l = 0; l < n_levels; ++l) {
+    t_lo = std::min(t_lo, grid_start[l]);
+    t_hi = std::max(t_hi, grid_start[l] + spacing * double(steps - 1));
+  }
+  const long long kMaxBins = 2048;
+  if (!std::isfinite(t_lo) || !std::isfinite(t_hi) || (t_hi - t_lo) / W > double(kMaxBins - 128)) return false;
+  std::vector<double> down;                       // edges below the first core edge, descending
+  const double core_lo = t_lo - W, core_hi = t_hi + W;
+  const long long ncore = (long long)std::ceil((core_hi - core_lo) / W);
+  std::vector<double> edges;
+  for (long long i = 0; i <= ncore; ++i) edges.push_back(core_lo + W * double(i));
+  for (double w = W; edges.back() < zmax && edges.size() < (size_t)kMaxBins; w *= 2.0) edges.push_back(edges.back() + w);
+  for (double w = W, e = edges.front(); e > zmin && down.size() < (size_t)kMaxBins; w *= 2.0) {
+    e -= w;
+    down.push_back(e);
+  }
+  edges.insert(edges.begin(), down.rbegin(), down.rend());
+  // keep the bins that intersect [zmin, zmax]
+  size_t first = 0, last = edges.size() - 1;      // bins first .. last-1
+  while (first + 1 < last && edges[first + 1] <= zmin) ++first;
+  while (last > first + 1 && edges[last - 1] > zmax) --last;
+  plan.edges.assign(edges.begin() + (long)first, edges.begin() + (long)last + 1);
+  plan.nb = (int)plan.edges.size() - 1;
+  if (plan.nb < 1 || plan.nb > kMaxBins) return false;
+  plan.n_chunks = (int)((steps + kPpmGridChunk - 1) / kPpmGridChunk);
+  plan.near.assign((size_t)(2 * n_levels * plan.n_chunks), 0);
+  for (long long l = 0; l < n_levels; ++l)
+    for (int ch = 0; ch < plan.n_chunks; ++ch) {
+      const double wa = grid_start[l] + spacing * double((long long)ch * kPpmGridChunk);
+      const double wb = grid_start[l] + spacing * double((long long)(ch + 1) * kPpmGridChunk - 1);
+      auto is_far = [&](int b) {
+        const double c = 0.5 * (plan.edges[b] + plan.edges[b + 1]), h = 0.5 * (plan.edges[b + 1] - plan.edges[b]);
+        const double dist = std::max(std::max(wa - c, c - wb), 0.0);
+        return dist >= 3.0 * h && dist >= h + W;
+      };
+      int lo = 0, hi = plan.nb - 1;
+      while (lo <= hi && is_far(lo)) ++lo;
+      while (hi >= lo && is_far(hi)) --hi;
+      plan.near[(size_t)(2 * (l * plan.n_chunks + ch))] = lo;          // lo > hi: every bin is far
+      plan.near[(size_t)(2 * (l * plan.n_chunks + ch) + 1)] = hi;
+    }
+  return true;
+}
+
 // values[level*steps + j] = Sigma_c(level, f0[level] - range + j*spacing)
 void GW::grid_scan(const std::vector<double>& f0, std::vector<double>& values) {
   const long long steps = opt.qp_grid_steps;
@@ -173,9 +230,41 @@ void GW::grid_scan(const std::vector<double>& f0, std::vector<double>& values) {
     int* sl = reinterpret_cast<int*>(om + qptotal);
     ctx->h2d(om, om0.data(), (size_t)qptotal);
     XTPB_CUDA(cudaMemcpyAsync(sl, slabs.data(), (size_t)qptotal * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    k_sigma_ppm_grid(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ_loc, e_loc,
-                     ppm_freq_dev.p, ppm_fac_dev.p, sl, om, opt.qp_grid_spacing, (int)steps, (int)qptotal, val,
-                     ctx->stream);
+    // compressed scan (far poles through Chebyshev moments) whenever the poles of a bin are contiguous in m, i.e. the
+    // local occupied and unoccupied energies are each ascending; XTPB_SIGMA_GRID=direct forces the pole-by-pole kernel
+    PpmGridPlan plan;
+    bool compressed = false;
+    const char* mode = std::getenv("XTPB_SIGMA_GRID");
+    if (!(mode && std::strcmp(mode, "direct") == 0)) {
+      const long long nl = tc->ntotal;
+      std::vector<double> el((size_t)nl);
+      for (long long j = 0; j < nl; ++j) el[j] = rpa_energies[(size_t)tc->nglob(j)];
+      bool sorted = true;
+      for (long long j = 1; j < nl && sorted; ++j)
+        if (j != n_occ_loc && el[j] < el[j - 1]) sorted = false;
+      double om_lo = std::numeric_limits<double>::infinity(), om_hi = 0.0;
+      for (long long P = 0; P < tc->naux; ++P)
+        if (ppm_weight[P] >= 1e-9) { om_lo = std::min(om_lo, ppm_freq[P]); om_hi = std::max(om_hi, ppm_freq[P]); }
+      if (sorted && nl > 0 && om_lo <= om_hi) {
+        double zmin = std::numeric_limits<double>::infinity(), zmax = -zmin;
+        if (n_occ_loc > 0) { zmin = std::min(zmin, el[0] - om_hi); zmax = std::max(zmax, el[n_occ_loc - 1] - om_lo); }
+        if (n_occ_loc < nl) { zmin = std::min(zmin, el[n_occ_loc] + om_lo); zmax = std::max(zmax, el[nl - 1] + om_hi); }
+        compressed = ppm_grid_plan(om0.data(), qptotal, opt.qp_grid_spacing, steps, zmin, zmax, plan);
+      }
+    }
+    grid_compressed = compressed ? 1 : 0;
+    grid_bins = compressed ? plan.nb : 0;
+    grid_equiv_evals = double(tc->ntotal) * double(tc->naux) * double(steps) * double(qptotal);
+    grid_direct_evals = grid_equiv_evals;
+    if (compressed)
+      k_sigma_ppm_grid_compressed(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ_loc, e_loc,
+                                  ppm_freq_dev.p, ppm_fac_dev.p, sl, om, opt.qp_grid_spacing, (int)steps, (int)qptotal,
+                                  plan.edges.data(), plan.nb, plan.near.data(), plan.n_chunks, val, &grid_direct_evals,
+                                  ctx->stream);
+    else
+      k_sigma_ppm_grid(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ_loc, e_loc,
+                       ppm_freq_dev.p, ppm_fac_dev.p, sl, om, opt.qp_grid_spacing, (int)steps, (int)qptotal, val,
+                       ctx->stream);
     ctx->allreduce_sum(val, (size_t)(qptotal * steps));
     ctx->d2h(values.data(), val, (size_t)(qptotal * steps));
     return;

@@ -78,6 +78,25 @@ void k_extract_window(double* dst, long long dst_ld, long long dst_slab, const d
 void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                       const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
                       const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s);
+// compressed grid scan (kernels.cu (1b)): far bins of the pole axis through Chebyshev moments, near bins pole by pole;
+// edges_host: nb+1 bin edges, near_host: [level][chunk][2] inclusive near-bin ranges (ppm_grid_plan)
+void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                                 const double* energies, const double* ppm_freq, const double* ppm_fac,
+                                 const int* level_slab, const double* omega0, double domega, int n_omega, int n_levels,
+                                 const double* edges_host, int nb, const int* near_host, int n_chunks, double* values,
+                                 double* direct_evaluations, cudaStream_t s);
+// host plan of the compressed scan: bins of the pole axis and, per level and chunk of 32 grid points, the bins that
+// are too close for the series.  grid_start[level] = first grid frequency; [zmin, zmax] = range of the live poles.
+// Returns false when the scan should use the direct kernel (no poles, too many bins).
+struct PpmGridPlan {
+  std::vector<double> edges;    // nb + 1, ascending
+  std::vector<int> near;        // [level][chunk][2]
+  int nb = 0, n_chunks = 0;
+};
+constexpr double kPpmDampingWindow = 0.25;   // |x| below which Sigma_PPM::Stabilize damps 1/x (sigma_ppm.cc)
+constexpr int kPpmGridChunk = 32;            // grid points per warp of the compressed scan
+bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing, long long steps, double zmin,
+                   double zmax, PpmGridPlan& plan);
 void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                        const double* energies, const double* ppm_freq, const double* ppm_fac, const int* pair_slab,
                        const double* pair_omega, int n_pairs, double* values, double* derivs, double* partial,
@@ -182,6 +201,11 @@ struct GW {
   long long unconverged = 0;
   // PPM
   std::vector<double> ppm_weight, ppm_freq;
+  // last grid scan: 1 = compressed (far poles through Chebyshev moments), bins of its plan, pole evaluations it
+  // performed one by one and the number the direct sum would have needed (this rank's share)
+  int grid_compressed = 0;
+  long long grid_bins = 0;
+  double grid_direct_evals = 0.0, grid_equiv_evals = 0.0;
   DBuf ppm_freq_dev, ppm_fac_dev;
   // exact
   std::vector<double> rpa_omegas;
