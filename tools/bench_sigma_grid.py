@@ -31,7 +31,10 @@ def child(workload, reps):
         out = gw.CalcCorrelationGrid(centers)
     api.profile_enable(False)
     p = api.profile_summary()["sigma_ppm_grid"]
-    print(json.dumps({"workload": workload, 
+    info = gw.grid_scan_info()
+    print(json.dumps({"workload": workload, "compressed": info["compressed"], "bins": info["bins"],
+                      "evaluated_fraction": info["direct_evaluations"] / info["equivalent_evaluations"],
+
                       "ms": p["ms"] / reps, "gevals_per_s": p["work"] / (p["ms"] * 1e-3) * 1e-9,
                       "checksum": float(np.abs(out).sum()), "sample": out[1, 498:503].tolist()}), flush=True)
 
@@ -48,11 +51,17 @@ def main():
         return
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
-        for g in (1,):
-            env = dict(os.environ)
+        # the three ways the scan can run: pole by pole, compressed, compressed with paired reciprocals
+        for mode, rcp in (("direct", "single"), ("compressed", "single"), ("compressed", "pair")):
+            env = dict(os.environ, XTPB_SIGMA_GRID=mode, XTPB_GRID_RCP=rcp)
             r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
                                 str(args.reps)], env=env, capture_output=True, text=True)
-            line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"group": g, "error": r.stderr[-400:]})
+            if r.stdout.strip():
+                rec = json.loads(r.stdout.strip().splitlines()[-1])
+            else:
+                rec = {"error": r.stderr[-400:]}
+            rec.update({"mode": mode, "rcp": rcp})
+            line = json.dumps(rec)
             print(line, flush=True)
             f.write(line + "\n")
 

@@ -1,6 +1,8 @@
 // Element-wise and reduction kernels of the GW-BSE path (everything that is not a contraction):
 // chi0 weights, Sigma_c plasmon-pole sums (FP64 ALU / HBM bound), BSE diagonal, Davidson vector ops.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "internal.h"
 
@@ -407,7 +409,10 @@ __global__ void __launch_bounds__(kCmpMomentWarps * 32) ppm_moments_kernel(
 // One warp per (level, chunk of 32 consecutive grid points); blockIdx.z splits the aux range of the near field when few
 // warps would leave SMs idle (split 0 also adds the far field).  near_range[(level*n_chunks + chunk)*2 + {0,1}] is the
 // inclusive range of bins whose poles are evaluated one by one (lo > hi: none).
-__global__ void __launch_bounds__(kCmpWarps * 32) sigma_ppm_grid_compressed_kernel(
+// PAIR: one MUFU.RCP64H seed per two poles (r0 = x1 / (x0 x1), r1 = x0 / (x0 x1): the same six FP64 operations per
+// pair, half the SFU traffic); pairs with a member inside the damping window are redone one by one (x = 0 safe).
+template <bool PAIR>
+__global__ void __launch_bounds__(kCmpWarps * 32, 5) sigma_ppm_grid_compressed_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int naux, const double* __restrict__ energies,
     const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac, const int* __restrict__ level_slab,
     const double* __restrict__ omega0, double domega, int n_omega, const int* __restrict__ binstart,
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(kCmpWarps * 32) sigma_ppm_grid_compressed_kern
   const int b_hi = near_range[((long long)level * n_chunks + chunk) * 2 + 1];
   const int p_per = (naux + gridDim.z - 1) / gridDim.z;
   const int p_begin = blockIdx.z * p_per, p_end = min(naux, p_begin + p_per);
-  double acc = 0.0;
+  double acc4[4] = {0.0, 0.0, 0.0, 0.0};     // four independent accumulation chains, summed in a fixed order
   long long n_near = 0;                       // poles this warp evaluates one by one (bookkeeping for the reports)
   // ---- near field: the damped kernel, pole by pole (lanes = grid points, poles broadcast from shared memory)
   if (b_lo <= b_hi) {
@@ -440,14 +445,21 @@ __global__ void __launch_bounds__(kCmpWarps * 32) sigma_ppm_grid_compressed_kern
         const int lo = bs[b_lo], hi = bs[b_hi + 1];
         const double shift = seg ? Om : -Om;
         n_near += hi - lo;
-        for (int m0 = lo; m0 < hi; m0 += 32) {
+        // lane's pole of the tile that starts at m0 (weight, position z: x = w - z); padding: weight 0, far away
+        auto load_pole = [&](int m0) {
           const int m = m0 + lane;
-          double2 el = make_double2(0.0, -1.0e30);          // padding: weight 0, far away
+          double2 el = make_double2(0.0, -1.0e30);
           if (m < hi) {
             const double v = row[m];
             el.x = fac * v * v;
-            el.y = energies[m] + shift;                     // pole position z: x = w - z
+            el.y = energies[m] + shift;
           }
+          return el;
+        };
+        double2 next = load_pole(lo);
+        for (int m0 = lo; m0 < hi; m0 += 32) {
+          const double2 el = next;
+          if (m0 + 32 < hi) next = load_pole(m0 + 32);      // in flight while this tile is evaluated
           __syncwarp();
           tile[warp][lane] = el;
           __syncwarp();
@@ -460,21 +472,40 @@ __global__ void __launch_bounds__(kCmpWarps * 32) sigma_ppm_grid_compressed_kern
             for (int g = 0; g < kCmpG; ++g) {
               e[g] = tile[warp][t + g];
               x[g] = om - e[g].y;
-              r[g] = rcp_fast(x[g]);
               any |= ppm_in_window(x[g]);
             }
+            if (PAIR) {
+#pragma unroll
+              for (int g = 0; g < kCmpG; g += 2) {
+                const double rp = rcp_fast(x[g] * x[g + 1]);
+                r[g] = x[g + 1] * rp;
+                r[g + 1] = x[g] * rp;
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < kCmpG; ++g) r[g] = rcp_fast(x[g]);
+            }
             if (any) {
+              if (PAIR) {
+#pragma unroll
+                for (int g = 0; g < kCmpG; g += 2)
+                  if (ppm_in_window(x[g]) || ppm_in_window(x[g + 1])) {
+                    r[g] = rcp_fast(x[g]);
+                    r[g + 1] = rcp_fast(x[g + 1]);
+                  }
+              }
 #pragma unroll
               for (int g = 0; g < kCmpG; ++g)
                 if (ppm_in_window(x[g])) r[g] = ppm_ginv_damped(x[g], r[g]);
             }
 #pragma unroll
-            for (int g = 0; g < kCmpG; ++g) acc = fma(e[g].x, r[g], acc);
+            for (int g = 0; g < kCmpG; ++g) acc4[g & 3] = fma(e[g].x, r[g], acc4[g & 3]);
           }
         }
       }
     }
   }
+  double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
   // ---- far field: Chebyshev series of the Cauchy kernel over the condensed bins
   if (blockIdx.z == 0) {
     const double* mom = moments + ((long long)level * nb) * kCmpOrder;
@@ -859,7 +890,11 @@ void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab,
     sigma_ppm_grid_reduce<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(mom_sum.p, mom_part.p, n_mom, slices);
     LAUNCH_CHECK();
   }
-  sigma_ppm_grid_compressed_kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
+  // XTPB_GRID_RCP=pair: one reciprocal seed per two poles in the near field (see the kernel)
+  const char* rcp_mode = std::getenv("XTPB_GRID_RCP");
+  const bool pair = rcp_mode && std::strcmp(rcp_mode, "pair") == 0;
+  auto kernel = pair ? sigma_ppm_grid_compressed_kernel<true> : sigma_ppm_grid_compressed_kernel<false>;
+  kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
       M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab, omega0, domega, n_omega, table_i, edges.p, nb,
       near_i, n_chunks, slices > 1 ? mom_sum.p : mom_part.p, splits > 1 ? partial.p : values, n,
       reinterpret_cast<unsigned long long*>(counter.p));
