@@ -369,8 +369,19 @@ def main():
     c_fl = sum(prof[t]["work"] for t in api.CONTRACTION_TAGS if t in prof)
     c_n = sum(prof[t]["launches"] for t in api.CONTRACTION_TAGS if t in prof)
     achieved = c_fl / (c_ms * 1e-3) * 1e-12 if c_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "xtpb::contract_kernel (FP64 DMMA m8n8k4)", "achieved": round(achieved, 3),
-                "peak": round(peak, 3), "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None,
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (one launch of one shape; the
+    # timed region mixes shapes, so `achieved` is the flop-weighted mean over all launches and `traffic` is per launch
+    # of the captured one, with its algorithmic bytes next to it)
+    traffic, traffic_detail = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_contract_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_detail = json.load(f)
+        traffic = traffic_detail["dram_bytes_per_launch"]
+    roofline = {"bound": "tensor", "kernel": "xtpb::contract_tma_kernel / contract_kernel (FP64 DMMA m8n8k4)",
+                "achieved": round(achieved, 3),
+                "peak": round(peak, 3), "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_detail": traffic_detail,
                 "peak_source": peak_src, "launches": c_n, "ms_per_step": round(c_ms / args.steps, 3),
                 "share_of_step": round(c_ms / args.steps / ms_per_step, 4),
                 "algorithmic_tflop_per_step": round(c_fl / args.steps * 1e-12, 3),

@@ -341,13 +341,15 @@ def test_evgw(ctx, prob):
     np.testing.assert_allclose(gw.RPAInputEnergies(), gwo.RPAInputEnergies(), rtol=0, atol=1e-6)
 
 
-@pytest.mark.parametrize("mode", ["dense", "factorised"])
+@pytest.mark.parametrize("mode", ["dense", "dense-hx", "factorised"])
 @pytest.mark.parametrize("name", list(orc.OPERATOR_TYPES))
 def test_bse_operator_matmul_diagonal(ctx, prob, name, mode, monkeypatch):
-    """BSE_OPERATOR<...>::matmul / diagonal / get_full_matrix vs the dense element-wise Hamiltonian, for both
-    device strategies: H materialised once in HBM (default when it fits) and the factorised products."""
+    """BSE_OPERATOR<...>::matmul / diagonal / get_full_matrix vs the dense element-wise Hamiltonian, for the three
+    device strategies: screened direct term materialised once in HBM with the rank-N_aux exchange term kept
+    factorised (default when H fits), everything in the dense H (XTPB_BSE_HX_DENSE=1), and all products factorised."""
     from xtp_b200 import api
-    monkeypatch.setenv("XTPB_BSE_DENSE_MAX_GB", "32" if mode == "dense" else "0")
+    monkeypatch.setenv("XTPB_BSE_DENSE_MAX_GB", "0" if mode == "factorised" else "32")
+    monkeypatch.setenv("XTPB_BSE_HX_DENSE", "1" if mode == "dense-hx" else "0")
     sz = prob["sizes"]
     rng = np.random.default_rng(3)
     hq = rng.standard_normal((sz.vtotal + sz.ctotal,) * 2)

@@ -51,16 +51,16 @@ def main():
         return
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
-        # the three ways the scan can run: pole by pole, compressed, compressed with paired reciprocals
-        for mode, rcp in (("direct", "single"), ("compressed", "single"), ("compressed", "pair")):
-            env = dict(os.environ, XTPB_SIGMA_GRID=mode, XTPB_GRID_RCP=rcp)
+        # the two ways the scan can run: pole by pole and compressed
+        for mode in ("direct", "compressed"):
+            env = dict(os.environ, XTPB_SIGMA_GRID=mode)
             r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
                                 str(args.reps)], env=env, capture_output=True, text=True)
             if r.stdout.strip():
                 rec = json.loads(r.stdout.strip().splitlines()[-1])
             else:
                 rec = {"error": r.stderr[-400:]}
-            rec.update({"mode": mode, "rcp": rcp})
+            rec.update({"mode": mode})
             line = json.dumps(rec)
             print(line, flush=True)
             f.write(line + "\n")

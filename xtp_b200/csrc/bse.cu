@@ -104,6 +104,7 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
   // keeps the windows for P in [P0, P0 + naux) and matmul/diagonal all-reduce their partial results.
   const int world = ctx->world;
   const long long naux_glob = tc->naux;
+  tc_naux_glob = naux_glob;
   const long long P0 = naux_glob * ctx->rank / world;
   naux = naux_glob * (ctx->rank + 1) / world - P0;
   XTPB_REQUIRE(naux > 0, "fewer auxiliary functions than ranks");
@@ -173,8 +174,16 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
     ns = vt * (ctx->rank + 1) / world - v2lo;
     h_ld = round_up(size, 2);
     const double gb = (double)h_ld * (double)(vt / world + 1) * (double)ct * 8e-9;
-    dense = (cx || cd || cd2) && gb <= max_gb && vt >= world && size <= 60000 &&
+    // The exchange term has rank N_aux: Hx X = Mvc (Mvc^T X) costs 4 vc N_aux k flops per call (two HBM-bound passes
+    // over the 1.4 GB operand at C60 size) while adding it to the dense H costs 2 (vc)^2 N_aux = 11.5 TFLOP once, as
+    // much as Hd itself.  So only the screened direct term (and Hqp) is materialised; XTPB_BSE_HX_DENSE=1 restores the
+    // fully dense H.
+    const char* hx_env = getenv("XTPB_BSE_HX_DENSE");
+    hx_factorised = cx != 0 && !(hx_env && hx_env[0] == '1');
+    const bool has_dense_terms = hx_factorised ? (cd || cd2) : (cx || cd || cd2);
+    dense = has_dense_terms && gb <= max_gb && vt >= world && size <= 60000 &&
             (double)std::max(vt, ct) * (double)std::max(vt, ct) < 2.0e9;
+    if (!dense) hx_factorised = false;        // the factorised operator below has its own exchange term
   }
   if (dense) {
     const long long ncols = ns * ct;
@@ -187,8 +196,8 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
       F.zero(ctx->stream);
       window_into(F.p, ldF, ncnt, m0, mcnt, n0, ncnt, screened, 0, naux_glob);     // [P][i][j]
     };
-    DBuf Fvc, Fa, Fb;
-    long long ldvcF = 0, ldA = 0, ldB = 0;
+    DBuf Fa, Fb;
+    long long ldA = 0, ldB = 0;
     if (cx || cd2) flat(Fvc, ldvcF, v0, (int)vt, c0, (int)ct, false);
     // NOTE (multi-GPU): every flat() is a collective re-shard, so all ranks must ask for the SAME window; the
     // column range a rank owns is then a contiguous row range of the flat operand (first index = v2), which is why
@@ -225,7 +234,7 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
       ctx->sync();
       Fb.release();
     }
-    if (cx && ncols > 0) {
+    if (cx && !hx_factorised && ncols > 0) {
       // Hx[(v1,c1),(v2,c2)] = sum_P Mvc[v1][P][c1] Mvc[v2][P][c2]
       GemmParams g{};
       g.A = GemmOperand{Fvc.p, 1, ldvcF, 0, 0};
@@ -238,6 +247,7 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
     if (cqp && ncols > 0)
       k_bse_add_hqp(H.p, h_ld, (int)vt, (int)ct, (int)v2lo, (int)ns, hqp_dev.p, hs, (double)cqp, ctx->stream);
     ctx->sync();
+    if (!hx_factorised) Fvc.release();         // the flat [P][(v,c)] operand stays for the exchange products
     ldvc = slabvc = ldvv = slabvv = ldcc = slabcc = ldcv = slabcv = 0;
     return;
   }
@@ -255,6 +265,9 @@ void BseOperator::diagonal_dev(double* d) {
   if (dense) {      // the owned columns' diagonal entries, zero elsewhere; summed over ranks
     XTPB_CUDA(cudaMemsetAsync(d, 0, (size_t)size * 8, ctx->stream));
     if (ns > 0) k_extract_diagonal(H.p + v2lo * ct, (int)(ns * ct), h_ld, d + v2lo * ct, ctx->stream);
+    if (hx_factorised && ns > 0)               // + cx sum_P Mvc[v][P][c]^2 for the owned entries
+      k_add_column_square_sums(d + v2lo * ct, Fvc.p + v2lo * ct, ldvcF, (int)tc_naux_glob, ns * ct, (double)cx,
+                               ctx->stream);
     ctx->allreduce_sum(d, (size_t)size);
     return;
   }
@@ -284,6 +297,24 @@ void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, l
       contract(g, ctx->ws, st);
     } else {
       XTPB_CUDA(cudaMemset2DAsync(Y, ldy * 8, 0, size * 8, k, st));
+    }
+    if (hx_factorised && ns > 0) {
+      // exchange, factorised: T(P,kk) = sum_{i owned} Mvc(i,P) X(i,kk);  Y(i,kk) += cx sum_P Mvc(i,P) T(P,kk).
+      // Linear in T, so the partial T of each rank goes straight into its partial Y (summed by the all-reduce below).
+      const long long na = tc_naux_glob;
+      T.ensure((size_t)(na * k));
+      GemmParams g{};
+      g.A = GemmOperand{Fvc.p + v2lo * ct, ldvcF, 1, 0, 0};
+      g.B = GemmOperand{X + v2lo * ct, ldx, 1, 0, 0};
+      g.C = T.p; g.c_sm = 1; g.c_sn = na;
+      g.M = (int)na; g.N = k; g.K = (int)(ns * ct); g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0; g.beta = 0.0;
+      contract(g, ctx->ws, st);
+      GemmParams h{};
+      h.A = GemmOperand{Fvc.p, 1, ldvcF, 0, 0};
+      h.B = GemmOperand{T.p, na, 1, 0, 0};
+      h.C = Y; h.c_sm = 1; h.c_sn = ldy;
+      h.M = (int)size; h.N = k; h.K = (int)na; h.n_outer = 1; h.n_batch = 1; h.alpha = (double)cx; h.beta = 1.0;
+      contract(h, ctx->ws, st);
     }
     ctx->allreduce_sum(Y, (size_t)(ldy * (k - 1) + size));
     return;

@@ -108,6 +108,9 @@ void k_bse_diagonal(double* diag, int vt, int ct, int naux, const double* Mvc, l
                     const double* Mvv, long long ldvv, long long slabvv, const double* Mcc, long long ldcc,
                     long long slabcc, const double* Mcv, long long ldcv, long long slabcv, const double* eps_inv,
                     const double* hqp_diag, int cqp, int cx, int cd, int cd2, cudaStream_t s);
+// d[i] += alpha * sum_{p < rows} F[p*ld + i]^2, i < n   (exchange part of the BSE diagonal from the flat operand)
+void k_add_column_square_sums(double* d, const double* F, long long ld, int rows, long long n, double alpha,
+                              cudaStream_t s);
 void k_col_norms(const double* A, long long ld, long long rows, int cols, double* out, cudaStream_t s);
 void k_residuals(double* res, long long ldr, const double* q, long long ldq, const double* lambda, long long rows,
                  int cols, cudaStream_t s);                            // res(:,j) -= lambda[j]*q(:,j)
@@ -278,6 +281,10 @@ struct BseOperator : Operator {
   bool dense = false;
   DBuf H;
   long long h_ld = 0, v2lo = 0, ns = 0;
+  // dense mode keeps the exchange term factorised (rank N_aux): flat operand Fvc[P][(v,c)] (ld ldvcF, all P, all rows)
+  bool hx_factorised = false;
+  DBuf Fvc;
+  long long ldvcF = 0, tc_naux_glob = 0;
   // windows are built from tc (optionally rotated by R_dev)
   BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpamin, long long vmin, long long cmax,
               const double* eps_inv_host, const double* hqp_host, long long ldh, int cqp_, int cx_, int cd_, int cd2_,

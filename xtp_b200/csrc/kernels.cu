@@ -82,6 +82,27 @@ __device__ __forceinline__ double ppm_ginv_damped(double x, double r) {
   return fabs(x) < 1e-100 ? (0.25 * kFourPi * kFourPi) * x : s * s * r;
 }
 
+// The damped branch without a reciprocal: sin^2(2 pi x)/x = x h(x^2), h(u) = sum_{k>=1} (-1)^(k+1) (4 pi)^(2k) u^(k-1) / (2 (2k)!)
+// (entire function; 13 terms leave < 1e-15 relative for u <= 1/16, checked against 40-digit arithmetic) -- 14 FP64
+// operations, x = 0 gives 0.  Used where whole warps sit inside the damping window (compressed grid scan).
+__device__ __forceinline__ double ppm_ginv_poly(double x) {
+  const double u = x * x;
+  double h = 4.7076855031461505630e+01;
+  h = fma(h, u, -1.9377648362907347975e+02);
+  h = fma(h, u, 6.7736136257549954211e+02);
+  h = fma(h, u, -1.9817217134061364861e+03);
+  h = fma(h, u, 4.7687717542357461594e+03);
+  h = fma(h, u, -9.2407715743593665354e+03);
+  h = fma(h, u, 1.4044288705238401560e+04);
+  h = fma(h, u, -1.6186442488460224111e+04);
+  h = fma(h, u, 1.3530243473087691496e+04);
+  h = fma(h, u, -7.7113140956002125264e+03);
+  h = fma(h, u, 2.7346181506141992876e+03);
+  h = fma(h, u, -5.1951515218134633193e+02);
+  h = fma(h, u, 3.9478417604357434475e+01);
+  return x * h;
+}
+
 // |x| < 0.25, read from the exponent word on the integer pipe (the FP64 pipe only carries subtract/refine/accumulate)
 __device__ __forceinline__ bool ppm_in_window(double x) {
   return (static_cast<unsigned>(__double2hiint(x)) & 0x7fffffffu) < 0x3fd00000u;
@@ -370,20 +391,43 @@ __global__ void __launch_bounds__(kCmpMomentWarps * 32) ppm_moments_kernel(
     double mu[kCmpOrder];
 #pragma unroll
     for (int j = 0; j < kCmpOrder; ++j) mu[j] = 0.0;
-    for (int P = p_begin; P < p_end; ++P) {
-      const double fac = ppm_fac[P];
-      if (fac == 0.0) continue;
-      const double Om = ppm_freq[P];
-      const double* row = S + (long long)P * ldn;
+    // two aux functions = four (P, segment) ranges per round, so that four independent table look-ups and slab loads
+    // are in flight per warp (the ranges of a core bin are only a few poles long: the loop is latency-bound)
+    for (int P0 = p_begin; P0 < p_end; P0 += 2) {
+      int lo[4], hi[4];
+      double fac[2], shift[4];
+      const double* row[2];
+      int iters = 0;
 #pragma unroll
-      for (int seg = 0; seg < 2; ++seg) {
-        const int* bs = binstart + ((long long)seg * naux + P) * (nb + 1);
-        const int lo = bs[b], hi = bs[b + 1];
-        const double shift = seg ? Om : -Om;
-        for (int m = lo + lane; m < hi; m += 32) {
-          const double v = row[m];
-          const double a = fac * v * v;
-          const double t = (energies[m] + shift - c) * hinv;
+      for (int u = 0; u < 2; ++u) {
+        const int P = min(P0 + u, p_end - 1);
+        fac[u] = P0 + u < p_end ? ppm_fac[P] : 0.0;
+        const double Om = ppm_freq[P];
+        row[u] = S + (long long)P * ldn;
+#pragma unroll
+        for (int seg = 0; seg < 2; ++seg) {
+          const int* bs = binstart + ((long long)seg * naux + P) * (nb + 1);
+          const int q = 2 * u + seg;
+          lo[q] = bs[b];
+          hi[q] = fac[u] != 0.0 ? bs[b + 1] : lo[q];
+          shift[q] = seg ? Om : -Om;
+          iters = max(iters, (hi[q] - lo[q] + 31) >> 5);
+        }
+      }
+      for (int it = 0; it < iters; ++it) {
+        double v[4], en[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = lo[q] + 32 * it + lane;
+          const bool ok = m < hi[q];
+          v[q] = ok ? row[q >> 1][m] : 0.0;
+          en[q] = ok ? energies[m] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (lo[q] + 32 * it >= hi[q]) continue;            // warp-uniform: this range is exhausted
+          const double a = fac[q >> 1] * v[q] * v[q];        // 0 for the lanes past the end of the range
+          const double t = v[q] != 0.0 ? (en[q] + shift[q] - c) * hinv : 0.0;
           const double t2 = t + t;
           double tm = 1.0, tc = t;
           mu[0] += a;
@@ -409,9 +453,6 @@ __global__ void __launch_bounds__(kCmpMomentWarps * 32) ppm_moments_kernel(
 // One warp per (level, chunk of 32 consecutive grid points); blockIdx.z splits the aux range of the near field when few
 // warps would leave SMs idle (split 0 also adds the far field).  near_range[(level*n_chunks + chunk)*2 + {0,1}] is the
 // inclusive range of bins whose poles are evaluated one by one (lo > hi: none).
-// PAIR: one MUFU.RCP64H seed per two poles (r0 = x1 / (x0 x1), r1 = x0 / (x0 x1): the same six FP64 operations per
-// pair, half the SFU traffic); pairs with a member inside the damping window are redone one by one (x = 0 safe).
-template <bool PAIR>
 __global__ void __launch_bounds__(kCmpWarps * 32, 5) sigma_ppm_grid_compressed_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int naux, const double* __restrict__ energies,
     const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac, const int* __restrict__ level_slab,
@@ -467,36 +508,30 @@ __global__ void __launch_bounds__(kCmpWarps * 32, 5) sigma_ppm_grid_compressed_k
           for (int t = 0; t < cnt; t += kCmpG) {
             double2 e[kCmpG];
             double x[kCmpG], r[kCmpG];
-            bool any = false;
+            bool in[kCmpG], any = false, all = true;
 #pragma unroll
             for (int g = 0; g < kCmpG; ++g) {
               e[g] = tile[warp][t + g];
               x[g] = om - e[g].y;
-              any |= ppm_in_window(x[g]);
+              in[g] = ppm_in_window(x[g]);
+              any |= in[g];
+              all &= in[g];
             }
-            if (PAIR) {
-#pragma unroll
-              for (int g = 0; g < kCmpG; g += 2) {
-                const double rp = rcp_fast(x[g] * x[g + 1]);
-                r[g] = x[g + 1] * rp;
-                r[g + 1] = x[g] * rp;
-              }
-            } else {
+            // the poles of a segment ascend, so a group of kCmpG is almost always of one kind for the whole warp:
+            // nobody damped (plain reciprocal), everybody damped (polynomial, no reciprocal), or -- at the two edges
+            // of the window -- mixed (both, selected per element).  Warp-uniform branches: no divergence.
+            if (!__any_sync(0xffffffffu, any)) {
 #pragma unroll
               for (int g = 0; g < kCmpG; ++g) r[g] = rcp_fast(x[g]);
-            }
-            if (any) {
-              if (PAIR) {
+            } else if (__all_sync(0xffffffffu, all)) {
 #pragma unroll
-                for (int g = 0; g < kCmpG; g += 2)
-                  if (ppm_in_window(x[g]) || ppm_in_window(x[g + 1])) {
-                    r[g] = rcp_fast(x[g]);
-                    r[g + 1] = rcp_fast(x[g + 1]);
-                  }
+              for (int g = 0; g < kCmpG; ++g) r[g] = ppm_ginv_poly(x[g]);
+            } else {
+#pragma unroll
+              for (int g = 0; g < kCmpG; ++g) {
+                const double plain = rcp_fast(x[g]), damped = ppm_ginv_poly(x[g]);
+                r[g] = in[g] ? damped : plain;
               }
-#pragma unroll
-              for (int g = 0; g < kCmpG; ++g)
-                if (ppm_in_window(x[g])) r[g] = ppm_ginv_damped(x[g], r[g]);
             }
 #pragma unroll
             for (int g = 0; g < kCmpG; ++g) acc4[g & 3] = fma(e[g].x, r[g], acc4[g & 3]);
@@ -607,6 +642,19 @@ __global__ void sigma_ppm_weighted_slab_kernel(double* __restrict__ W, const dou
       }
     }
     W[idx] = out;
+  }
+}
+
+// d[i] += alpha sum_p F[p*ld + i]^2: threads over i (coalesced), serial over the short p range
+__global__ void add_column_square_sums_kernel(double* __restrict__ d, const double* __restrict__ F, long long ld,
+                                              int rows, long long n, double alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int p = 0; p < rows; ++p) {
+      const double v = F[(long long)p * ld + i];
+      acc = fma(v, v, acc);
+    }
+    d[i] = fma(alpha, acc, d[i]);
   }
 }
 
@@ -822,6 +870,12 @@ void k_extract_window(double* dst, long long dst_ld, long long dst_slab, const d
   LAUNCH_CHECK();
 }
 
+void k_add_column_square_sums(double* d, const double* F, long long ld, int rows, long long n, double alpha,
+                              cudaStream_t s) {
+  if (n <= 0) return;
+  add_column_square_sums_kernel<<<blocks_for(n, 128, 4096), 128, 0, s>>>(d, F, ld, rows, n, alpha);
+  LAUNCH_CHECK();
+}
 void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                       const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
                       const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s) {
@@ -890,11 +944,7 @@ void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab,
     sigma_ppm_grid_reduce<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(mom_sum.p, mom_part.p, n_mom, slices);
     LAUNCH_CHECK();
   }
-  // XTPB_GRID_RCP=pair: one reciprocal seed per two poles in the near field (see the kernel)
-  const char* rcp_mode = std::getenv("XTPB_GRID_RCP");
-  const bool pair = rcp_mode && std::strcmp(rcp_mode, "pair") == 0;
-  auto kernel = pair ? sigma_ppm_grid_compressed_kernel<true> : sigma_ppm_grid_compressed_kernel<false>;
-  kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
+  sigma_ppm_grid_compressed_kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
       M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab, omega0, domega, n_omega, table_i, edges.p, nb,
       near_i, n_chunks, slices > 1 ? mom_sum.p : mom_part.p, splits > 1 ? partial.p : values, n,
       reinterpret_cast<unsigned long long*>(counter.p));
