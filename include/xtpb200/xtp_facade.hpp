@@ -476,4 +476,13 @@ class BSE {
   xtpb_bse* h_ = nullptr;
 };
 
+// ---- GWBSE::Initialize level ranges (gwbse.cc `ranges` option): default / factor / explicit / full + clamps
+inline xtpb_gwbse_ranges LevelRanges(int mode, Index n_levels, Index n_occ, double rpamax = 0, double qpmin = 0,
+                                     double qpmax = 0, double bsemin = 0, double bsemax = 0, Index n_core_ignored = 0) {
+  xtpb_gwbse_range_options o{mode, n_levels, n_occ, n_core_ignored, rpamax, qpmin, qpmax, bsemin, bsemax};
+  xtpb_gwbse_ranges r{};
+  check(xtpb_gwbse_level_ranges(&o, &r));
+  return r;
+}
+
 }  // namespace xtpb200

@@ -269,6 +269,29 @@ int xtpb_bse_transition_dipoles(xtpb_bse* bse, xtpb_index n_basis, const double*
 int xtpb_oscillator_strengths(xtpb_index n_states, const double* energies_host, const double* dipoles_host,
                               double* strengths_host);
 
+/* ---- GWBSE::Initialize level-range logic (upstream xtp/src/libxtp/gwbse/gwbse.cc) ----
+ * The `ranges` option of the dftgwbse calculator: which levels enter the RPA, the QP equation and the BSE.
+ *   default : rpamax = n_levels-1, qpmin = 0, qpmax = 2 homo + 1, bse vmin = 0, cmax = 2 homo + 1
+ *   factor  : rpamax = int(f_rpamax n_levels) - 1;  qpmin = n_occ - int(f_qpmin n_occ) - 1;
+ *             qpmax = n_occ + int(f_qpmax n_occ) - 1;  vmin, cmax likewise from f_bsemin, f_bsemax
+ *   explicit: the five values are level indices
+ *   full    : everything up to n_levels-1
+ * followed by the clamps (upper bounds to n_levels-1, lower bounds to 0 and to at most homo / at least homo+1) and
+ * rpamin = n_core_ignored (the `ignore_corelevels` option; 0 = keep all).  Host arithmetic, needs no device. */
+enum { XTPB_RANGES_DEFAULT = 0, XTPB_RANGES_FACTOR = 1, XTPB_RANGES_EXPLICIT = 2, XTPB_RANGES_FULL = 3 };
+typedef struct xtpb_gwbse_range_options {
+  int mode;                         /* XTPB_RANGES_* */
+  xtpb_index n_levels;              /* Orbitals::getBasisSetSize() */
+  xtpb_index n_occ;                 /* Orbitals::getNumberOfAlphaElectrons(); homo = n_occ - 1 */
+  xtpb_index n_core_ignored;        /* rpamin */
+  double rpamax, qpmin, qpmax, bsemin, bsemax;   /* factors (factor mode) or level indices (explicit mode) */
+} xtpb_gwbse_range_options;
+typedef struct xtpb_gwbse_ranges {
+  xtpb_index homo, rpamin, rpamax, qpmin, qpmax, vmin, cmax;
+  xtpb_index qptotal, rpatotal, bse_vtotal, bse_ctotal, bse_size;
+} xtpb_gwbse_ranges;
+int xtpb_gwbse_level_ranges(const xtpb_gwbse_range_options* opt, xtpb_gwbse_ranges* out);
+
 /* ---- engine-level hook used by the parity tests of the contraction kernel ----
  * C = alpha * sum_{outer,k} A(row,outer,k) d(outer,k) B(col,outer,k) + beta*C with every stride explicit
  * (element units, host buffers of the given lengths are copied to the device and back). */

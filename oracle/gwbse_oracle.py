@@ -1061,6 +1061,40 @@ class BSE:
 
 
 # --------------------------------------------------------------------------
+# GWBSE::Initialize level ranges        (upstream xtp/src/libxtp/gwbse/gwbse.cc)
+# --------------------------------------------------------------------------
+def gwbse_level_ranges(mode, n_levels, n_occ, rpamax=None, qpmin=None, qpmax=None, bsemin=None, bsemax=None,
+                       n_core_ignored=0):
+    """The ``ranges`` option of the dftgwbse calculator -> (homo, rpamin, rpamax, qpmin, qpmax, vmin, cmax).
+    ``default``: everything in the RPA, QP and BSE windows 0 .. 2*homo+1; ``factor``: multiples of the number of
+    levels (rpamax) / of occupied levels (the others); ``explicit``: level indices; ``full``: all levels.  Upper
+    bounds are clamped to the last level, lower bounds to rpamin, and every window keeps HOMO and LUMO."""
+    homo = n_occ - 1
+    if mode == "default":
+        rpamax, qpmin, qpmax, vmin, cmax = n_levels - 1, 0, 2 * homo + 1, 0, 2 * homo + 1
+    elif mode == "factor":
+        rpamax = int(rpamax * float(n_levels)) - 1
+        qpmin = n_occ - int(qpmin * float(n_occ)) - 1
+        qpmax = n_occ + int(qpmax * float(n_occ)) - 1
+        vmin = n_occ - int(bsemin * float(n_occ)) - 1
+        cmax = n_occ + int(bsemax * float(n_occ)) - 1
+    elif mode == "explicit":
+        rpamax, qpmin, qpmax, vmin, cmax = int(rpamax), int(qpmin), int(qpmax), int(bsemin), int(bsemax)
+    elif mode == "full":
+        rpamax, qpmin, qpmax, vmin, cmax = n_levels - 1, 0, n_levels - 1, 0, n_levels - 1
+    else:
+        raise ValueError(f"unknown ranges mode {mode}")
+    rpamin = n_core_ignored
+    clamp = lambda v, lo, hi: max(lo, min(hi, v))
+    rpamax = clamp(rpamax, homo + 1, n_levels - 1)
+    qpmax = clamp(qpmax, homo + 1, rpamax)
+    cmax = clamp(cmax, homo + 1, rpamax)
+    qpmin = clamp(qpmin, rpamin, homo)
+    vmin = clamp(vmin, rpamin, homo)
+    return dict(homo=homo, rpamin=rpamin, rpamax=rpamax, qpmin=qpmin, qpmax=qpmax, vmin=vmin, cmax=cmax)
+
+
+# --------------------------------------------------------------------------
 # whole step, the order GWBSE::Evaluate drives it (upstream gwbse/gwbse.cc)
 # --------------------------------------------------------------------------
 def run_gwbse(ao3c, C, dft_energies, vxc, aux_coulomb, gwopt: GWOptions, bseopt: BSEOptions,

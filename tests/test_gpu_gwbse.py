@@ -507,3 +507,32 @@ def test_transition_dipoles_and_oscillator_strengths(ctx, prob):
     db = bse.transition_dipoles(r, prob["C"], Xb, Yb)
     np.testing.assert_allclose(db, orc.BSE.transition_dipoles(r, prob["C"], sz.homo, sz.vmin, sz.cmax, Xb, Yb),
                                rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("ranges", ["default", "explicit"])
+def test_gwbse_driver_evaluate(ctx, ranges):
+    """GWBSE::Initialize + Evaluate (upstream gwbse/gwbse.cc): the driver mirror runs Fill -> G0W0 -> Hqp -> BSE singlets
+    and triplets in one call, with the level ranges coming from the `ranges` option, against the oracle's whole step.
+    `explicit` makes the BSE window stick out of the QP window on both sides (BSE::AdjustHqpSize extends Hqp with the
+    RPA input energies)."""
+    from xtp_b200 import api
+    prob = synth.make_problem("ch4-svp-shape")
+    sz = prob["sizes"]
+    kw = {} if ranges == "default" else dict(rpamax=sz.n_basis - 1, qpmin=1, qpmax=8, bsemin=0, bsemax=10)
+    drv = api.GWBSE(ctx).Initialize(sz.n_basis, sz.homo + 1, ranges=ranges, tasks=("gw", "singlets", "triplets"), nmax=3,
+                                    davidson_tolerance="lapack", **kw)
+    r = orc.gwbse_level_ranges(ranges, sz.n_basis, sz.homo + 1, **kw)
+    vxc = np.ascontiguousarray(prob["vxc"][r["qpmin"]:r["qpmax"] + 1, r["qpmin"]:r["qpmax"] + 1])   # QP-window block
+    out = drv.Evaluate(prob["ao3c"], prob["C"], prob["energies"], vxc, prob["aux_coulomb"])
+    assert {k: out["ranges"][k] for k in r} == r
+    gwopt = orc.GWOptions(r["homo"], r["qpmin"], r["qpmax"], r["rpamin"], r["rpamax"])
+    bseopt = orc.BSEOptions(r["homo"], r["rpamin"], r["rpamax"], r["qpmin"], r["qpmax"], r["vmin"], r["cmax"], nmax=3,
+                            davidson_tolerance="lapack")
+    ref = orc.run_gwbse(prob["ao3c"], prob["C"], prob["energies"], vxc, prob["aux_coulomb"], gwopt, bseopt,
+                        triplets=True)
+    np.testing.assert_allclose(out["QPpert_energies"], ref["qp_pert"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["Hqp"], ref["Hqp"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["QPdiag_energies"], ref["qp_diag"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["BSE_singlet_energies"], ref["singlet_energies"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["BSE_triplet_energies"], ref["triplet_energies"], rtol=0, atol=1e-6)
+    assert out["BSE_singlet_coefficients"].shape == ((r["homo"] - r["vmin"] + 1) * (r["cmax"] - r["homo"]), 3)

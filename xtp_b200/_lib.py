@@ -54,7 +54,18 @@ class ContractDesc(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol declared in include/xtpb200/xtpb200.h
+class GwbseRangeOptions(C.Structure):
+    _fields_ = [("mode", C.c_int), ("n_levels", idx), ("n_occ", idx), ("n_core_ignored", idx), ("rpamax", C.c_double),
+                ("qpmin", C.c_double), ("qpmax", C.c_double), ("bsemin", C.c_double), ("bsemax", C.c_double)]
+
+
+class GwbseRanges(C.Structure):
+    _fields_ = [(k, idx) for k in ("homo", "rpamin", "rpamax", "qpmin", "qpmax", "vmin", "cmax", "qptotal", "rpatotal",
+                                   "bse_vtotal", "bse_ctotal", "bse_size")]
+
+
 PROTOTYPES = {
+    "xtpb_gwbse_level_ranges": (C.c_int, [C.POINTER(GwbseRangeOptions), C.POINTER(GwbseRanges)]),
     "xtpb_last_error": (C.c_char_p, []),
     "xtpb_version": (C.c_int, []),
     "xtpb_launch_count": (C.c_longlong, []),

@@ -642,6 +642,72 @@ class BSE:
         return out
 
 
+RANGES = {"default": 0, "factor": 1, "explicit": 2, "full": 3}
+
+
+def gwbse_level_ranges(mode, n_levels, n_occ, rpamax=0.0, qpmin=0.0, qpmax=0.0, bsemin=0.0, bsemax=0.0,
+                       n_core_ignored=0):
+    """GWBSE::Initialize (upstream gwbse/gwbse.cc): level ranges from the ``ranges`` option (host code in libxtpb200)."""
+    o = _lib.GwbseRangeOptions(RANGES[mode], int(n_levels), int(n_occ), int(n_core_ignored), float(rpamax), float(qpmin),
+                               float(qpmax), float(bsemin), float(bsemax))
+    r = _lib.GwbseRanges()
+    check(_lib.lib().xtpb_gwbse_level_ranges(C.byref(o), C.byref(r)))
+    return {k: int(getattr(r, k)) for k, _ in _lib.GwbseRanges._fields_}
+
+
+class GWBSE:
+    """The driver of the path, upstream ``GWBSE`` (gwbse/gwbse.cc): ``Initialize`` fixes the level ranges and the
+    options, ``Evaluate`` runs Fill -> G0W0/evGW -> Hqp -> BSE in the reference's order and returns what the reference
+    stores into ``Orbitals`` (QPpert energies, Hqp, RPA input energies, BSE singlet/triplet energies and coefficients)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def Initialize(self, n_levels, n_occ, ranges="default", tasks=("gw", "singlets"), nmax=5, useTDA=True,
+                   sigma_integration="ppm", qp_solver="grid", davidson_tolerance="normal", gw_sc_max_iterations=1,
+                   **range_values):
+        self.r = gwbse_level_ranges(ranges, n_levels, n_occ, **range_values)
+        self.tasks, self.nmax, self.useTDA = tuple(tasks), int(nmax), bool(useTDA)
+        self.gwopt = dict(sigma_integration=sigma_integration, qp_solver=qp_solver,
+                          gw_sc_max_iterations=gw_sc_max_iterations)
+        self.davidson_tolerance = davidson_tolerance
+        return self
+
+    def Evaluate(self, ao3c, C_mo, dft_energies, vxc, aux_coulomb, aux_overlap=None):
+        r = self.r
+        tc = TCMatrix_gwbse(self.ctx).Initialize(np.asarray(ao3c).shape[0], r["rpamin"], max(r["qpmax"], r["cmax"]),
+                                                  r["rpamin"], r["rpamax"])
+        tc.Fill(ao3c, C_mo, aux_coulomb, aux_overlap)
+        out = {"ranges": dict(r)}
+        gw = GW(self.ctx, tc, vxc, dft_energies)
+        gw.configure(gw_options(homo=r["homo"], qpmin=r["qpmin"], qpmax=r["qpmax"], rpamin=r["rpamin"],
+                                rpamax=r["rpamax"], **self.gwopt))
+        gw.CalculateGWPerturbation()
+        out["QPpert_energies"] = gw.getGWAResults()
+        gw.CalculateHQP()
+        out["Hqp"] = gw.getHQP()
+        out["QPdiag_energies"], out["QPdiag_coefficients"] = gw.DiagonalizeQPHamiltonian()
+        out["RPA_input_energies"] = gw.RPAInputEnergies()
+        gw.close()
+        if "singlets" in self.tasks or "triplets" in self.tasks:
+            bse = BSE(self.ctx, tc)
+            bse.configure(r["homo"], r["rpamin"], r["rpamax"], r["qpmin"], r["qpmax"], r["vmin"], r["cmax"], self.nmax,
+                          out["RPA_input_energies"], out["Hqp"], davidson_tolerance=self.davidson_tolerance)
+            for task, singlet in (("singlets", True), ("triplets", False)):
+                if task not in self.tasks:
+                    continue
+                if self.useTDA:
+                    e, X = bse.Solve_singlets_TDA() if singlet else bse.Solve_triplets_TDA()
+                    out[f"BSE_{task[:-1]}_energies"], out[f"BSE_{task[:-1]}_coefficients"] = e, X
+                else:
+                    e, X, Y = bse.Solve_singlets_BTDA() if singlet else bse.Solve_triplets_BTDA()
+                    out[f"BSE_{task[:-1]}_energies"], out[f"BSE_{task[:-1]}_coefficients"] = e, X
+                    out[f"BSE_{task[:-1]}_coefficients_AR"] = Y
+            bse.close()
+        tc.close()
+        return out
+
+
 def oscillator_strengths(energies, dipoles):
     """Orbitals::Oscillatorstrengths: f = 2/3 E |d|^2."""
     e = np.ascontiguousarray(energies, dtype=np.float64)

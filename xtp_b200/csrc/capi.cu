@@ -525,6 +525,49 @@ int xtpb_oscillator_strengths(xtpb_index n_states, const double* energies_host, 
   }
   XTPB_API_END
 }
+// GWBSE::Initialize (gwbse.cc): level ranges from the `ranges` option
+int xtpb_gwbse_level_ranges(const xtpb_gwbse_range_options* o, xtpb_gwbse_ranges* r) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(o && r, "null pointer");
+  XTPB_REQUIRE(o->n_levels >= 2 && o->n_occ >= 1 && o->n_occ < o->n_levels, "need at least one occupied and one empty level");
+  const long long nl = o->n_levels, nocc = o->n_occ, homo = nocc - 1;
+  long long rpamax, qpmin, qpmax, vmin, cmax;
+  switch (o->mode) {
+    case XTPB_RANGES_DEFAULT:
+      rpamax = nl - 1; qpmin = 0; qpmax = 2 * homo + 1; vmin = 0; cmax = 2 * homo + 1;
+      break;
+    case XTPB_RANGES_FACTOR:
+      rpamax = (long long)(o->rpamax * double(nl)) - 1;
+      qpmin = nocc - (long long)(o->qpmin * double(nocc)) - 1;
+      qpmax = nocc + (long long)(o->qpmax * double(nocc)) - 1;
+      vmin = nocc - (long long)(o->bsemin * double(nocc)) - 1;
+      cmax = nocc + (long long)(o->bsemax * double(nocc)) - 1;
+      break;
+    case XTPB_RANGES_EXPLICIT:
+      rpamax = (long long)o->rpamax; qpmin = (long long)o->qpmin; qpmax = (long long)o->qpmax;
+      vmin = (long long)o->bsemin; cmax = (long long)o->bsemax;
+      break;
+    case XTPB_RANGES_FULL:
+      rpamax = nl - 1; qpmin = 0; qpmax = nl - 1; vmin = 0; cmax = nl - 1;
+      break;
+    default: throw Error("xtpb: unknown ranges mode");
+  }
+  const long long rpamin = o->n_core_ignored;
+  XTPB_REQUIRE(rpamin >= 0 && rpamin <= homo, "ignore_corelevels leaves no occupied level");
+  auto clamp = [](long long v, long long lo, long long hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  rpamax = clamp(rpamax, homo + 1, nl - 1);
+  qpmax = clamp(qpmax, homo + 1, rpamax);
+  cmax = clamp(cmax, homo + 1, rpamax);
+  qpmin = clamp(qpmin, rpamin, homo);
+  vmin = clamp(vmin, rpamin, homo);
+  r->homo = homo; r->rpamin = rpamin; r->rpamax = rpamax; r->qpmin = qpmin; r->qpmax = qpmax; r->vmin = vmin; r->cmax = cmax;
+  r->qptotal = qpmax - qpmin + 1;
+  r->rpatotal = rpamax - rpamin + 1;
+  r->bse_vtotal = homo - vmin + 1;
+  r->bse_ctotal = cmax - homo;
+  r->bse_size = r->bse_vtotal * r->bse_ctotal;
+  XTPB_API_END
+}
 int xtpb_dense_operator_create(xtpb_ctx* ctx, const double* A_host, xtpb_index n, xtpb_index lda, xtpb_op** out) {
   XTPB_API_BEGIN
   *out = new xtpb_op{std::make_unique<DenseOperator>(&ctx->impl, A_host, n, lda)};
