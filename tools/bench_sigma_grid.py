@@ -51,16 +51,18 @@ def main():
         return
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
-        # the two ways the scan can run: pole by pole and compressed
-        for mode in ("direct", "compressed"):
+        # the two ways the scan can run: pole by pole and compressed (the latter for several register/occupancy caps)
+        for mode, occ in (("direct", ""), ("compressed", "3"), ("compressed", "4"), ("compressed", "5"), ("compressed", "6")):
             env = dict(os.environ, XTPB_SIGMA_GRID=mode)
+            if occ:
+                env["XTPB_GRID_OCC"] = occ
             r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
                                 str(args.reps)], env=env, capture_output=True, text=True)
             if r.stdout.strip():
                 rec = json.loads(r.stdout.strip().splitlines()[-1])
             else:
                 rec = {"error": r.stderr[-400:]}
-            rec.update({"mode": mode})
+            rec.update({"mode": mode, "min_blocks_per_sm": occ})
             line = json.dumps(rec)
             print(line, flush=True)
             f.write(line + "\n")

@@ -346,7 +346,7 @@ __global__ void sigma_ppm_grid_reduce(double* __restrict__ values, const double*
 //     evaluated one by one, with the Rohlfing damping, exactly as in (1).  With sorted energies the poles of a bin are
 //     a contiguous m-range per aux function and occupied/unoccupied segment (ppm_bin_table_kernel), so both kernels
 //     stream contiguous pieces of the slab rows.  All sums run in a fixed order (deterministic).
-constexpr int kCmpOrder = 16, kCmpChunk = 32, kCmpWarps = 4, kCmpG = 8, kCmpMomentWarps = 8;
+constexpr int kCmpOrder = 16, kCmpChunk = 32, kCmpWarps = 4, kCmpG = 8, kCmpMomentWarps = 8, kCmpMinBlocks = 5;
 
 // binstart[(seg*naux + P)*(nb+1) + b] = first m of segment seg (0 occupied, 1 unoccupied) whose pole lies at or above
 // edges[b]; b = 0 -> segment start, b = nb -> segment end (the outermost bins take whatever lies beyond the edges).
@@ -453,7 +453,10 @@ __global__ void __launch_bounds__(kCmpMomentWarps * 32) ppm_moments_kernel(
 // One warp per (level, chunk of 32 consecutive grid points); blockIdx.z splits the aux range of the near field when few
 // warps would leave SMs idle (split 0 also adds the far field).  near_range[(level*n_chunks + chunk)*2 + {0,1}] is the
 // inclusive range of bins whose poles are evaluated one by one (lo > hi: none).
-__global__ void __launch_bounds__(kCmpWarps * 32, 5) sigma_ppm_grid_compressed_kernel(
+// MINB = resident CTAs per SM the register allocation is capped for (occupancy against unrolling depth; the launcher
+// picks kCmpMinBlocks unless XTPB_GRID_OCC says otherwise -- measured in profiles/r01_sigma_grid_variants_*.jsonl).
+template <int MINB>
+__global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compressed_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int naux, const double* __restrict__ energies,
     const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac, const int* __restrict__ level_slab,
     const double* __restrict__ omega0, double domega, int n_omega, const int* __restrict__ binstart,
@@ -475,15 +478,25 @@ __global__ void __launch_bounds__(kCmpWarps * 32, 5) sigma_ppm_grid_compressed_k
   long long n_near = 0;                       // poles this warp evaluates one by one (bookkeeping for the reports)
   // ---- near field: the damped kernel, pole by pole (lanes = grid points, poles broadcast from shared memory)
   if (b_lo <= b_hi) {
+    // m-ranges of the near bins for aux function P: {occupied lo, hi, unoccupied lo, hi}; the look-up of P + 1 is in
+    // flight while P is evaluated (the ranges of small systems are short: table latency would otherwise be exposed)
+    int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    auto ranges_of = [&](int P) {
+      const int* bs0 = binstart + (long long)P * (nb + 1);
+      const int* bs1 = binstart + ((long long)naux + P) * (nb + 1);
+      n0 = bs0[b_lo]; n1 = bs0[b_hi + 1]; n2 = bs1[b_lo]; n3 = bs1[b_hi + 1];
+    };
+    if (p_begin < p_end) ranges_of(p_begin);
     for (int P = p_begin; P < p_end; ++P) {
+      const int c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+      if (P + 1 < p_end) ranges_of(P + 1);
       const double fac = ppm_fac[P];
       if (fac == 0.0) continue;
       const double Om = ppm_freq[P];
       const double* row = S + (long long)P * ldn;
 #pragma unroll 1
       for (int seg = 0; seg < 2; ++seg) {
-        const int* bs = binstart + ((long long)seg * naux + P) * (nb + 1);
-        const int lo = bs[b_lo], hi = bs[b_hi + 1];
+        const int lo = seg ? c2 : c0, hi = seg ? c3 : c1;
         const double shift = seg ? Om : -Om;
         n_near += hi - lo;
         // lane's pole of the tile that starts at m0 (weight, position z: x = w - z); padding: weight 0, far away
@@ -944,7 +957,13 @@ void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab,
     sigma_ppm_grid_reduce<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(mom_sum.p, mom_part.p, n_mom, slices);
     LAUNCH_CHECK();
   }
-  sigma_ppm_grid_compressed_kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
+  const char* occ_env = std::getenv("XTPB_GRID_OCC");
+  const int occ = occ_env ? std::atoi(occ_env) : kCmpMinBlocks;
+  auto kernel = occ <= 3 ? sigma_ppm_grid_compressed_kernel<3>
+              : occ == 4 ? sigma_ppm_grid_compressed_kernel<4>
+              : occ == 5 ? sigma_ppm_grid_compressed_kernel<5>
+                         : sigma_ppm_grid_compressed_kernel<6>;
+  kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
       M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab, omega0, domega, n_omega, table_i, edges.p, nb,
       near_i, n_chunks, slices > 1 ? mom_sum.p : mom_part.p, splits > 1 ? partial.p : values, n,
       reinterpret_cast<unsigned long long*>(counter.p));
