@@ -346,7 +346,7 @@ __global__ void sigma_ppm_grid_reduce(double* __restrict__ values, const double*
 //     evaluated one by one, with the Rohlfing damping, exactly as in (1).  With sorted energies the poles of a bin are
 //     a contiguous m-range per aux function and occupied/unoccupied segment (ppm_bin_table_kernel), so both kernels
 //     stream contiguous pieces of the slab rows.  All sums run in a fixed order (deterministic).
-constexpr int kCmpOrder = 16, kCmpChunk = 32, kCmpWarps = 4, kCmpG = 8, kCmpMomentWarps = 8, kCmpMinBlocks = 5;
+constexpr int kCmpOrder = 16, kCmpChunk = 32, kCmpWarps = 4, kCmpG = 8, kCmpMomentWarps = 8, kCmpMinBlocks = 3;
 
 // binstart[(seg*naux + P)*(nb+1) + b] = first m of segment seg (0 occupied, 1 unoccupied) whose pole lies at or above
 // edges[b]; b = 0 -> segment start, b = nb -> segment end (the outermost bins take whatever lies beyond the edges).
