@@ -49,8 +49,29 @@ def clib():
         lib.unpack_symmetric.argtypes = [dp, C.c_int, dp, C.c_longlong]
         lib.unpack_symmetric.restype = None
         lib.oracle_num_threads.restype = C.c_int
+        lib.oracle_set_num_threads.argtypes = [C.c_int]
+        lib.oracle_set_num_threads.restype = None
         _LIB = lib
     return _LIB
+
+
+_THREADS_SET = False
+
+
+def use_all_host_threads():
+    """Make OpenBLAS (numpy) and the OpenMP C kernels use every core this process may run on, whatever
+    OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its ranks).  Returns the thread count in use."""
+    global _THREADS_SET
+    n = host_threads()
+    if not _THREADS_SET:
+        clib().oracle_set_num_threads(n)
+        try:
+            import threadpoolctl
+            threadpoolctl.threadpool_limits(limits=n)      # process-wide when not used as a context manager
+        except Exception:  # noqa: BLE001  (threadpoolctl missing: numpy keeps its start-up thread count)
+            pass
+        _THREADS_SET = True
+    return n
 
 
 def _dp(a):
@@ -93,6 +114,7 @@ def _timeit(fn, min_reps=1):
 def sampled_step(sz, davidson_matmul_calls=12, grid_steps=1001, triplets=False, scale=1.0, seed=7):
     """Estimated seconds per molecule for workload ``sz`` (xtp_b200.synth.Sizes), reference-structure CPU.
     ``scale`` multiplies every sample size (1.0 ~ 15-25 s of CPU work on 16 cores at C60 size)."""
+    use_all_host_threads()
     rng = np.random.default_rng(seed)
     nb, naux = sz.n_basis, sz.n_aux
     m, n, o = sz.mtotal, sz.ntotal, sz.n_occ

@@ -39,6 +39,12 @@ int main(int argc, char** argv) {
       std::printf("GaussianQuadrature check failed: order %lld sum %.15f\n", (long long)gq.Order(), sum);
       return 1;
     }
+    // GWBSE::Initialize level ranges are host code too: `default` on 17 levels / 5 occupied (methane, 3-21G-like)
+    const xtpb_gwbse_ranges r = LevelRanges(XTPB_RANGES_DEFAULT, 17, 5);
+    if (r.homo != 4 || r.rpamax != 16 || r.qpmin != 0 || r.qpmax != 9 || r.vmin != 0 || r.cmax != 9 || r.bse_size != 25) {
+      std::printf("LevelRanges check failed\n");
+      return 1;
+    }
     std::printf("facade compiled; version %d\n", xtpb_version());
     return 0;
   }

@@ -26,6 +26,10 @@ from oracle import gwbse_oracle as orc  # noqa: E402
 from xtp_b200 import synth  # noqa: E402
 
 CASES = ("tiny", "ch4-svp-shape")
+# BASELINE.json configs[1] at its full size (benzene/def2-TZVP shape: 222 basis functions, 1110 aux functions, G0W0 PPM
+# with the default 1001-point QP grid, 10 singlets + 10 triplets, Davidson "normal").  The numpy oracle needs ~7 minutes
+# for it, so only the generator and the GPU test touch this case (`python tests/golden/make_golden.py --large`).
+LARGE_CASES = ("benzene-tzvp-shape",)
 GRID_STEPS, GRID_SPACING = 65, 0.05
 
 
@@ -90,7 +94,29 @@ def compute(name):
     return out
 
 
+def compute_large(name, nmax=10):
+    """whole step only, small outputs only (the N_aux^2 matrices stay out of the repository)"""
+    prob = synth.make_problem(name)
+    sz = prob["sizes"]
+    gwopt = orc.GWOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax)
+    bseopt = orc.BSEOptions(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, nmax=nmax)
+    res = orc.run_gwbse(prob["ao3c"], prob["C"], prob["energies"], prob["vxc"], prob["aux_coulomb"], gwopt, bseopt,
+                        triplets=True)
+    out = {"input_checksums": np.array([np.abs(prob[k]).sum() for k in ("C", "energies", "ao3c", "aux_coulomb", "vxc")])}
+    for k in ("qp_pert", "qp_diag", "Hqp", "eps0_inv", "singlet_energies", "triplet_energies"):
+        out[k] = np.asarray(res[k])
+    out["davidson_iterations"] = np.array([res["davidson_iterations"]])
+    return out
+
+
 def main():
+    if "--large" in sys.argv:
+        for name in LARGE_CASES:
+            out = compute_large(name)
+            path = os.path.join(HERE, f"{name}.npz")
+            np.savez_compressed(path, **out)
+            print(path, os.path.getsize(path), "bytes;", ", ".join(f"{k}{list(v.shape)}" for k, v in out.items()))
+        return
     for name in CASES:
         out = compute(name)
         path = os.path.join(HERE, f"{name}.npz")

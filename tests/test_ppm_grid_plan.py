@@ -81,3 +81,24 @@ def test_compressed_scan_matches_direct_sum(seed, ntot, n_occ, naux, wide, steps
         np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-13)
     if steps == 1001 and not wide:
         assert counters["near"] < 0.35 * counters["all"]      # the point of the exercise
+
+
+def test_compressed_scan_sharded_over_two_ranks():
+    """Multi-GPU arithmetic of the scan: the second tensor index is distributed cyclically, every
+    rank plans and scans ITS columns (local energies, local occupied count, its own pole range and bins) and the partial
+    grids are summed (an all-reduce on the device).  Replayed here with the numpy mirror for world = 2."""
+    e, freq, fac, slab = _problem(11, 61, 11, 36, False)
+    n_occ, steps, spacing = 11, 1001, 0.01
+    level_energy = e[n_occ]
+    grid_start = np.array([level_energy - spacing * (steps - 1) / 2])
+    ref = mir.direct_values(slab, e, n_occ, freq, fac, grid_start[0], spacing, steps)
+    total = np.zeros(steps)
+    for rank in range(2):
+        cols = np.arange(rank, len(e), 2)                     # TCMatrix::nglob: n = rank + j * world
+        e_loc, slab_loc = e[cols], slab[:, cols]
+        n_occ_loc = int(np.count_nonzero(cols < n_occ))       # TCMatrix::nloc_below
+        zmin, zmax = mir.pole_range(e_loc, n_occ_loc, freq, fac)
+        pl = mir.plan(grid_start, spacing, steps, zmin, zmax)
+        assert pl is not None
+        total += mir.grid_values(slab_loc, e_loc, n_occ_loc, freq, fac, grid_start[0], spacing, steps, pl[0], pl[1][0])
+    np.testing.assert_allclose(total, ref, rtol=1e-11, atol=1e-13)
