@@ -343,6 +343,7 @@ def main():
     sampler.start()
     api.profile_reset()
     api.profile_enable(True)
+    api.alloc_stats(reset=True)
     launches0 = api.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -361,6 +362,7 @@ def main():
     host_s = max_over_ranks(time.perf_counter() - t_host)
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = api.launch_count() - launches0
+    alloc = api.alloc_stats()
     api.profile_enable(False)
     prof = api.profile_summary()
     clocks = sampler.stop()
@@ -469,6 +471,12 @@ def main():
                            sz.n_aux * job.pk * 8e-9, sz.mtotal * sz.n_aux * sz.ntotal * 8e-9)},
             "roofline": roofline, "other_kernels": other, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
+            # host/driver time between kernels: cudaMalloc + cudaFree of the library's scratch buffers, per step
+            "host_alloc": {"seconds_per_step": round(alloc["seconds"] / args.steps, 4),
+                           "calls_per_step": alloc["calls"] / args.steps,
+                           "block_cache": os.environ.get("XTPB_ALLOC_CACHE", "0") == "1",
+                           "cache_hits_per_step": alloc["cache_hits"] / args.steps,
+                           "cached_gb": round(alloc["cached_gb"], 3)},
             "stage_seconds": {k: round(v / args.steps, 4) for k, v in stage_acc.items()},
             "davidson": {"info": res["davidson_info"], "iterations": int(res["davidson_iterations"]),
                          "lowest_singlet_ha": float(res["singlets"][0])},

@@ -59,6 +59,12 @@ int xtpb_comm_unique_id(char* id_128);
 int xtpb_ctx_comm_init(xtpb_ctx* ctx, const char* id_128, int rank, int world);
 int xtpb_ctx_comm_info(xtpb_ctx* ctx, int* rank, int* world);
 
+/* Host seconds this process has spent inside cudaMalloc / cudaFree on behalf of the library, the number of device
+ * allocations, and -- with XTPB_ALLOC_CACHE=1 in the environment when the library is loaded: released blocks are kept
+ * in an exact-size cache instead of being returned to the driver -- cache hits and bytes currently cached.
+ * Any pointer may be NULL; reset != 0 zeroes the counters. */
+int xtpb_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, int reset);
+
 /* pinned (page-locked) host memory for the caller's AO-integral and result buffers: H2D/D2H copies from it run
  * asynchronously at PCIe rate and overlap the contractions (xtpb_tc_fill_block*). */
 int xtpb_host_alloc(unsigned long long bytes, void** out);

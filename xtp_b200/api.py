@@ -642,6 +642,14 @@ class BSE:
         return out
 
 
+def alloc_stats(reset=False):
+    """Host seconds inside cudaMalloc/cudaFree, allocation count, block-cache hits and cached GB (xtpb_alloc_stats)."""
+    sec, cached = C.c_double(0.0), C.c_double(0.0)
+    calls, hits = C.c_longlong(0), C.c_longlong(0)
+    check(_lib.lib().xtpb_alloc_stats(C.byref(sec), C.byref(calls), C.byref(hits), C.byref(cached), int(reset)))
+    return {"seconds": sec.value, "calls": calls.value, "cache_hits": hits.value, "cached_gb": cached.value * 1e-9}
+
+
 RANGES = {"default": 0, "factor": 1, "explicit": 2, "full": 3}
 
 

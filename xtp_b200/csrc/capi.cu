@@ -86,6 +86,12 @@ int xtpb_ctx_solver_seconds(xtpb_ctx* ctx, double* seconds, int reset) {
   XTPB_API_END
 }
 
+int xtpb_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, int reset) {
+  XTPB_API_BEGIN
+  device_alloc_stats(seconds, calls, cache_hits, cached_bytes, reset != 0);
+  XTPB_API_END
+}
+
 // ---------------------------------------------------------------- TCMatrix_gwbse
 int xtpb_tc_create(xtpb_ctx* ctx, xtpb_index auxsize, xtpb_index mmin, xtpb_index mmax, xtpb_index nmin,
                    xtpb_index nmax, xtpb_tc** out) {

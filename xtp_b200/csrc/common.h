@@ -43,6 +43,16 @@ struct Error : std::runtime_error {
     return 2;                                          \
   }
 
+// Device memory for DBuf (core.cu).  Host seconds spent inside cudaMalloc / cudaFree are accumulated (bench.py reports
+// them per step: they are pure host/driver time between kernels).  With XTPB_ALLOC_CACHE=1 released blocks are kept
+// in an exact-size cache instead of going back to the driver: a step allocates the same sizes again and again
+// (scratch for rotations, epsilon, the BSE operands), so after the first step almost every allocation is a cache hit.
+// release() then performs the device-wide synchronisation cudaFree would have implied, so that stream-ordering
+// assumptions of the callers are unchanged; the cache is flushed when cudaMalloc runs out of memory.
+void* device_alloc(size_t bytes);
+void device_free(void* p, size_t bytes);
+void device_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, bool reset);
+
 // Owning device allocation of doubles (or bytes via count*8).
 struct DBuf {
   double* p = nullptr;
@@ -60,11 +70,11 @@ struct DBuf {
   void alloc(size_t count) {
     release();
     if (count == 0) return;
-    XTPB_CUDA(cudaMalloc(&p, count * sizeof(double)));
+    p = static_cast<double*>(device_alloc(count * sizeof(double)));
     n = count;
   }
   void ensure(size_t count) { if (count > n) alloc(count); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) device_free(p, n * sizeof(double)); p = nullptr; n = 0; }
   void zero(cudaStream_t s) { if (p) XTPB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), s)); }
 };
 

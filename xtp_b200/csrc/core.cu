@@ -1,5 +1,9 @@
 // Context, error reporting, dense solver wrappers (cuSOLVER eigh / inverse; these are the
 // "serial-ish library calls" of SURVEY.md section 7 hard part 6 and are timed apart from the contractions).
+#include <chrono>
+#include <mutex>
+#include <unordered_map>
+
 #include "internal.h"
 
 namespace xtpb {
@@ -8,6 +12,83 @@ namespace {
 thread_local std::string g_last_error;
 }
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+// ---------------------------------------------------------------- device memory (see common.h)
+namespace {
+std::mutex g_alloc_mu;
+std::unordered_multimap<size_t, void*> g_block_cache;      // exact size -> released block
+double g_cached_bytes = 0.0, g_alloc_seconds = 0.0;
+long long g_alloc_calls = 0, g_cache_hits = 0;
+bool alloc_cache_on() {
+  static const bool on = [] { const char* e = getenv("XTPB_ALLOC_CACHE"); return e && e[0] == '1'; }();
+  return on;
+}
+double seconds_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+void flush_block_cache_locked() {
+  for (auto& kv : g_block_cache) cudaFree(kv.second);
+  g_block_cache.clear();
+  g_cached_bytes = 0.0;
+}
+}  // namespace
+
+void* device_alloc(size_t bytes) {
+  const auto t0 = std::chrono::steady_clock::now();
+  void* p = nullptr;
+  std::lock_guard<std::mutex> lock(g_alloc_mu);
+  if (alloc_cache_on()) {
+    auto it = g_block_cache.find(bytes);
+    if (it != g_block_cache.end()) {
+      p = it->second;
+      g_block_cache.erase(it);
+      g_cached_bytes -= (double)bytes;
+      ++g_cache_hits;
+    }
+  }
+  if (!p) {
+    cudaError_t err = cudaMalloc(&p, bytes);
+    if (err == cudaErrorMemoryAllocation && !g_block_cache.empty()) {
+      cudaGetLastError();                       // clear the sticky error, give the cached blocks back, try again
+      cudaDeviceSynchronize();
+      flush_block_cache_locked();
+      err = cudaMalloc(&p, bytes);
+    }
+    if (err != cudaSuccess)
+      throw Error(std::string("CUDA error ") + cudaGetErrorString(err) + " in cudaMalloc of " + std::to_string(bytes) +
+                  " bytes");
+  }
+  g_alloc_seconds += seconds_since(t0);
+  ++g_alloc_calls;
+  return p;
+}
+
+void device_free(void* p, size_t bytes) {
+  if (!p) return;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::lock_guard<std::mutex> lock(g_alloc_mu);
+  if (alloc_cache_on()) {
+    cudaDeviceSynchronize();                    // what cudaFree implies: nothing in flight may still use the block
+    g_block_cache.emplace(bytes, p);
+    g_cached_bytes += (double)bytes;
+  } else {
+    cudaFree(p);
+  }
+  g_alloc_seconds += seconds_since(t0);
+}
+
+void device_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, bool reset) {
+  std::lock_guard<std::mutex> lock(g_alloc_mu);
+  if (seconds) *seconds = g_alloc_seconds;
+  if (calls) *calls = g_alloc_calls;
+  if (cache_hits) *cache_hits = g_cache_hits;
+  if (cached_bytes) *cached_bytes = g_cached_bytes;
+  if (reset) {
+    g_alloc_seconds = 0.0;
+    g_alloc_calls = 0;
+    g_cache_hits = 0;
+  }
+}
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
 #define XTPB_SOLVER(expr)                                                                       \
