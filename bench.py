@@ -142,13 +142,26 @@ class GwbseJob:
         n_loc = self.p_hi - self.p_lo
         self.ao_dev = torch.empty((n_loc, self.pk), dtype=torch.float64, device=self.dev)
         self._generate_ao(sz, seed)
-        self.ao_host = None
-        if e2e:
-            self.ao_host = torch.empty((n_loc, self.pk), dtype=torch.float64, pin_memory=True)
-            self.ao_host.copy_(self.ao_dev)
-            torch.cuda.synchronize(self.dev)
+        self.ao_host = None       # pinned host copy of the AO slices: exists only during the e2e leg (pin_host_copy)
         self.block = 256
         self.last = {}
+
+    def pin_host_copy(self):
+        """The e2e leg's input: this rank's packed AO slices in page-locked host memory.  Created only when the e2e leg
+        starts: with the GB-sized pinned buffer alive, the host time between the kernels of the RESIDENT step grew by
+        0.5-1.3 s per step at identical kernel times (pentacene shape: 0.76 s per step without the buffer,
+        profiles/r01_bench_pentacene_cache0.json, against 1.30 / 2.06 s with it, r01_bench_pentacene_r9 / _r14.json) --
+        driver-side cost of allocation and mapping calls while that much memory is page-locked, which has no business
+        in the resident-input number."""
+        torch = self.torch
+        n_loc = self.p_hi - self.p_lo
+        self.ao_host = torch.empty((n_loc, self.pk), dtype=torch.float64, pin_memory=True)
+        self.ao_host.copy_(self.ao_dev)
+        torch.cuda.synchronize(self.dev)
+
+    def unpin_host_copy(self):
+        self.ao_host = None
+        self.torch.cuda.synchronize(self.dev)
 
     def _aux_range(self):
         lo, cnt = self.tc.local_aux_range()       # canonical contiguous split of the aux functions over ranks
@@ -306,6 +319,10 @@ def main():
         return
 
     os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
+    # single GPU: keep the library's released scratch blocks in its exact-size cache (read once when libxtpb200 loads), so
+    # that the steps after the first make no cudaMalloc/cudaFree calls at all; "host_alloc" in the JSON line reports it
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        os.environ.setdefault("XTPB_ALLOC_CACHE", "1")
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: xtp_b200 has no CPU fallback")
@@ -434,9 +451,11 @@ def main():
     # e2e: host buffers in, host results out, through the public API
     e2e = None
     if not args.no_e2e:
+        job.pin_host_copy()
         job.run(resident=False)
         barrier()
         n_e2e = max(1, min(args.steps, 2))
+        api.alloc_stats(reset=True)
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             job.run(resident=False)
@@ -444,7 +463,9 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0) / n_e2e
         e2e = {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(job.h2d_bytes(False)),
                "d2h_bytes_per_step": int(job.d2h_bytes()), "steps": n_e2e,
+               "host_alloc_seconds_per_step": round(api.alloc_stats()["seconds"] / n_e2e, 4),
                "stage_seconds": {k: round(v, 4) for k, v in job.last["stage_seconds"].items()}}
+        job.unpin_host_copy()
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:

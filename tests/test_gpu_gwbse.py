@@ -536,3 +536,47 @@ def test_gwbse_driver_evaluate(ctx, ranges):
     np.testing.assert_allclose(out["BSE_singlet_energies"], ref["singlet_energies"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(out["BSE_triplet_energies"], ref["triplet_energies"], rtol=0, atol=1e-6)
     assert out["BSE_singlet_coefficients"].shape == ((r["homo"] - r["vmin"] + 1) * (r["cmax"] - r["homo"]), 3)
+
+
+def test_block_cache_reuses_scratch_without_changing_results(tmp_path):
+    """XTPB_ALLOC_CACHE=1 (what bench.py turns on for one GPU): released scratch blocks are handed out again instead of
+    going back to the driver.  The switch is read when the library loads, so the check runs in a child process: two
+    identical G0W0+BSE steps; the second must be served from the cache and give bit-identical energies, equal to the
+    oracle's within the usual bounds."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import json, sys
+sys.path.insert(0, %r)
+import numpy as np
+from xtp_b200 import api, synth
+prob = synth.make_problem("ch4-svp-shape")
+sz = prob["sizes"]
+ctx = api.Context(0)
+res = []
+for step in range(2):
+    api.alloc_stats(reset=True)
+    drv = api.GWBSE(ctx).Initialize(sz.n_basis, sz.homo + 1, tasks=("gw", "singlets"), nmax=3, davidson_tolerance="lapack")
+    out = drv.Evaluate(prob["ao3c"], prob["C"], prob["energies"], prob["vxc"], prob["aux_coulomb"])
+    st = api.alloc_stats()
+    res.append({"qp": out["QPpert_energies"].tolist(), "s": out["BSE_singlet_energies"].tolist(), "calls": st["calls"],
+                "hits": st["cache_hits"]})
+print("RESULT " + json.dumps(res))
+""" % root
+    env = dict(os.environ, XTPB_ALLOC_CACHE="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert res[0]["qp"] == res[1]["qp"] and res[0]["s"] == res[1]["s"]
+    assert res[1]["calls"] > 0 and res[1]["hits"] >= 0.5 * res[1]["calls"]
+    prob = synth.make_problem("ch4-svp-shape")
+    sz = prob["sizes"]
+    gwopt = orc.GWOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax)
+    bseopt = orc.BSEOptions(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, nmax=3,
+                            davidson_tolerance="lapack")
+    ref = orc.run_gwbse(prob["ao3c"], prob["C"], prob["energies"], prob["vxc"], prob["aux_coulomb"], gwopt, bseopt)
+    np.testing.assert_allclose(res[1]["qp"], ref["qp_pert"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(res[1]["s"], ref["singlet_energies"], rtol=0, atol=1e-6)
