@@ -580,3 +580,35 @@ print("RESULT " + json.dumps(res))
     ref = orc.run_gwbse(prob["ao3c"], prob["C"], prob["energies"], prob["vxc"], prob["aux_coulomb"], gwopt, bseopt)
     np.testing.assert_allclose(res[1]["qp"], ref["qp_pert"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(res[1]["s"], ref["singlet_energies"], rtol=0, atol=1e-6)
+
+
+def test_bse_operator_properties_at_scale(ctx, monkeypatch):
+    """Size-independent properties at a size the numpy oracle would need minutes for (synth-500 shape: 1500 aux
+    functions, BSE size 2500): the three device strategies of BSE_OPERATOR::matmul (screened direct term dense +
+    factorised exchange, fully dense H, all factorised) agree with each other, and the operator is linear and symmetric."""
+    from xtp_b200 import api
+    sz = synth.WORKLOADS["synth-500"]
+    rng = np.random.default_rng(12)
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc.set_raw(synth.make_M_direct(sz, rng))
+    hs = sz.vtotal + sz.ctotal
+    hq = rng.standard_normal((hs, hs)) * 0.05
+    hq = 0.5 * (hq + hq.T) + np.diag(np.sort(rng.uniform(-1.0, 2.0, hs)))
+    eps_inv = rng.uniform(0.2, 1.0, sz.n_aux)
+    n = sz.bse_size
+    X, Y = rng.standard_normal((n, 7)), rng.standard_normal((n, 7))
+    results = {}
+    for mode in ("dense", "dense-hx", "factorised"):
+        monkeypatch.setenv("XTPB_BSE_DENSE_MAX_GB", "0" if mode == "factorised" else "32")
+        monkeypatch.setenv("XTPB_BSE_HX_DENSE", "1" if mode == "dense-hx" else "0")
+        op = api.BSE_OPERATOR(ctx, 1, 2, 1, 0, eps_inv, tc, hq, sz.homo, sz.rpamin, sz.vmin, sz.cmax)   # singlet TDA
+        hx, hy = op.matmul(X), op.matmul(Y)
+        results[mode] = (hx, op.diagonal())
+        scale = np.abs(hx).max()
+        assert np.abs(op.matmul(X - 0.7 * Y) - (hx - 0.7 * hy)).max() < 1e-10 * scale          # linear
+        assert np.abs(Y.T @ hx - hy.T @ X).max() < 1e-9 * scale * np.sqrt(n)                  # symmetric
+        op.close()
+    scale = np.abs(results["dense"][0]).max()
+    for mode in ("dense-hx", "factorised"):
+        assert np.abs(results[mode][0] - results["dense"][0]).max() < 1e-10 * scale * np.sqrt(n)
+        assert np.abs(results[mode][1] - results["dense"][1]).max() < 1e-11 * np.abs(results["dense"][1]).max()
