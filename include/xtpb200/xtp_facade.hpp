@@ -485,4 +485,92 @@ inline xtpb_gwbse_ranges LevelRanges(int mode, Index n_levels, Index n_occ, doub
   return r;
 }
 
+// ---- GWBSE (gwbse.h / gwbse.cc): the driver.  Initialize fixes level ranges and options, Evaluate runs
+//      Fill -> GW (G0W0 or evGW) -> Hqp -> BSE in the reference's order and returns what the reference stores into
+//      Orbitals (QPpert energies, Hqp, RPA input energies, BSE energies / coefficients).  The AO three-centre slices
+//      come from the caller's integral loop: `ao3c` holds auxsize symmetric n_basis x n_basis slices, full storage.
+template <class Matrix = DenseMatrix, class Vector = DenseVector>
+class GWBSE {
+ public:
+  struct options {
+    int ranges = XTPB_RANGES_DEFAULT;
+    double rpamax = 0, qpmin = 0, qpmax = 0, bsemin = 0, bsemax = 0;   // factors or level indices (see LevelRanges)
+    Index ignore_corelevels = 0;
+    bool do_singlets = true, do_triplets = false, useTDA = true;
+    Index nmax = 5;
+    xtpb_gw_options gw;                                                  // ranges are overwritten by Initialize
+    options() { xtpb_gw_options_default(&gw); }
+  };
+  struct Results {
+    xtpb_gwbse_ranges ranges;
+    Vector QPpert_energies, RPA_input_energies, QPdiag_energies;
+    Matrix Hqp, QPdiag_coefficients;
+    Vector BSE_singlet_energies, BSE_triplet_energies;
+    Matrix BSE_singlet_coefficients, BSE_singlet_coefficients_AR, BSE_triplet_coefficients, BSE_triplet_coefficients_AR;
+  };
+
+  explicit GWBSE(Context& ctx) : ctx_(ctx) {}
+  void Initialize(const options& opt, Index n_levels, Index n_occ) {
+    opt_ = opt;
+    ranges_ = LevelRanges(opt.ranges, n_levels, n_occ, opt.rpamax, opt.qpmin, opt.qpmax, opt.bsemin, opt.bsemax,
+                          opt.ignore_corelevels);
+    opt_.gw.homo = ranges_.homo; opt_.gw.qpmin = ranges_.qpmin; opt_.gw.qpmax = ranges_.qpmax;
+    opt_.gw.rpamin = ranges_.rpamin; opt_.gw.rpamax = ranges_.rpamax;
+  }
+  const xtpb_gwbse_ranges& ranges() const { return ranges_; }
+
+  // vxc: qptotal x qptotal block of the exchange-correlation matrix in the MO basis; dft_energies: all levels
+  Results Evaluate(const Matrix& dft_orbitals, const Vector& dft_energies, const Matrix& vxc, Index auxsize,
+                   const double* ao3c, const Matrix& aux_coulomb, const Matrix* aux_overlap = nullptr) const {
+    Results r;
+    r.ranges = ranges_;
+    TCMatrix_gwbse<Matrix> Mmn(ctx_);
+    const Index mmax = ranges_.qpmax > ranges_.cmax ? ranges_.qpmax : ranges_.cmax;
+    Mmn.Initialize(auxsize, ranges_.rpamin, mmax, ranges_.rpamin, ranges_.rpamax);
+    Mmn.Fill3cMO_begin(dft_orbitals);
+    Mmn.Fill3cMO_block(0, auxsize, ao3c, dft_orbitals.rows());
+    Mmn.ApplyCoulombMetric(aux_coulomb, aux_overlap);
+    GW<Matrix, Vector> gw(Mmn, vxc, dft_energies);
+    gw.configure(opt_.gw);
+    gw.CalculateGWPerturbation();
+    r.QPpert_energies = gw.getGWAResults();
+    gw.CalculateHQP();
+    r.Hqp = gw.getHQP();
+    r.RPA_input_energies = gw.RPAInputEnergies();
+    auto diag = gw.DiagonalizeQPHamiltonian();
+    r.QPdiag_energies = diag.first;
+    r.QPdiag_coefficients = diag.second;
+    if (opt_.do_singlets || opt_.do_triplets) {
+      BSE<Matrix, Vector> bse(Mmn);
+      xtpb_bse_options bo{ranges_.homo, ranges_.rpamin, ranges_.rpamax, ranges_.qpmin, ranges_.qpmax, ranges_.vmin,
+                          ranges_.cmax, opt_.nmax, 1};
+      bse.configure(bo, r.RPA_input_energies, r.Hqp);
+      if (opt_.do_singlets) {
+        if (opt_.useTDA) {
+          auto s = bse.Solve_singlets();
+          r.BSE_singlet_energies = s.energies; r.BSE_singlet_coefficients = s.eigenvectors;
+        } else {
+          auto s = bse.Solve_singlets_BTDA();
+          r.BSE_singlet_energies = s.energies; r.BSE_singlet_coefficients = s.X; r.BSE_singlet_coefficients_AR = s.Y;
+        }
+      }
+      if (opt_.do_triplets) {
+        if (opt_.useTDA) {
+          auto t = bse.Solve_triplets();
+          r.BSE_triplet_energies = t.energies; r.BSE_triplet_coefficients = t.eigenvectors;
+        } else {
+          auto t = bse.Solve_triplets_BTDA();
+          r.BSE_triplet_energies = t.energies; r.BSE_triplet_coefficients = t.X; r.BSE_triplet_coefficients_AR = t.Y;
+        }
+      }
+    }
+    return r;
+  }
+
+ private:
+  Context& ctx_;
+  options opt_{};
+  xtpb_gwbse_ranges ranges_{};
+};
+
 }  // namespace xtpb200

@@ -11,6 +11,9 @@
 
 using namespace xtpb200;
 
+// the driver template is compile-checked here (its members are the calls the step below makes one by one)
+template class xtpb200::GWBSE<>;
+
 static std::vector<double> read_all(const char* path) {
   FILE* f = std::fopen(path, "rb");
   if (!f) throw std::runtime_error("cannot open input");
