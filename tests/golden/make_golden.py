@@ -30,6 +30,9 @@ CASES = ("tiny", "ch4-svp-shape")
 # with the default 1001-point QP grid, 10 singlets + 10 triplets, Davidson "normal").  The numpy oracle needs ~7 minutes
 # for it, so only the generator and the GPU test touch this case (`python tests/golden/make_golden.py --large`).
 LARGE_CASES = ("benzene-tzvp-shape",)
+# a real molecule: water, RHF/STO-3G orbitals and integrals from xtp_b200/molecule.py (literature-pinned SCF), G0W0@HF
+# (ScaHFX = 1, Vxc = 0) with all 7 levels in every window, 4 singlets and triplets  (`--real`)
+REAL_CASES = ("h2o-sto3g",)
 GRID_STEPS, GRID_SPACING = 65, 0.05
 
 
@@ -109,7 +112,37 @@ def compute_large(name, nmax=10):
     return out
 
 
+def real_inputs(name):
+    from xtp_b200 import molecule as ml
+    assert name == "h2o-sto3g"
+    return ml.gwbse_inputs(ml.water())
+
+
+def compute_real(name, nmax=4):
+    inp = real_inputs(name)
+    r = orc.gwbse_level_ranges("full", inp["n_basis"], inp["n_occ"])
+    vxc = np.zeros((r["qpmax"] - r["qpmin"] + 1,) * 2)
+    gwopt = orc.GWOptions(r["homo"], r["qpmin"], r["qpmax"], r["rpamin"], r["rpamax"], ScaHFX=1.0)
+    bseopt = orc.BSEOptions(r["homo"], r["rpamin"], r["rpamax"], r["qpmin"], r["qpmax"], r["vmin"], r["cmax"], nmax=nmax,
+                            davidson_tolerance="lapack")
+    res = orc.run_gwbse(inp["ao3c"], inp["C"], inp["energies"], vxc, inp["aux_coulomb"], gwopt, bseopt, triplets=True)
+    out = {"input_checksums": np.array([np.abs(inp[k]).sum() for k in ("C", "energies", "ao3c", "aux_coulomb")]),
+           "rhf_energy": np.array([inp["scf"]["energy"]])}
+    for k in ("qp_pert", "qp_diag", "Hqp", "singlet_energies", "triplet_energies"):
+        out[k] = np.asarray(res[k])
+    d = orc.BSE.transition_dipoles(inp["ao_dipoles"], inp["C"], r["homo"], r["vmin"], r["cmax"], res["singlet_vectors"])
+    out["tda_oscillator_strengths"] = orc.BSE.oscillator_strengths(res["singlet_energies"], d)
+    return out
+
+
 def main():
+    if "--real" in sys.argv:
+        for name in REAL_CASES:
+            out = compute_real(name)
+            path = os.path.join(HERE, f"{name}.npz")
+            np.savez_compressed(path, **out)
+            print(path, os.path.getsize(path), "bytes;", ", ".join(f"{k}{list(v.shape)}" for k, v in out.items()))
+        return
     if "--large" in sys.argv:
         for name in LARGE_CASES:
             out = compute_large(name)

@@ -673,11 +673,11 @@ class GWBSE:
 
     def Initialize(self, n_levels, n_occ, ranges="default", tasks=("gw", "singlets"), nmax=5, useTDA=True,
                    sigma_integration="ppm", qp_solver="grid", davidson_tolerance="normal", gw_sc_max_iterations=1,
-                   **range_values):
+                   ScaHFX=0.0, **range_values):
         self.r = gwbse_level_ranges(ranges, n_levels, n_occ, **range_values)
         self.tasks, self.nmax, self.useTDA = tuple(tasks), int(nmax), bool(useTDA)
         self.gwopt = dict(sigma_integration=sigma_integration, qp_solver=qp_solver,
-                          gw_sc_max_iterations=gw_sc_max_iterations)
+                          gw_sc_max_iterations=gw_sc_max_iterations, ScaHFX=ScaHFX)
         self.davidson_tolerance = davidson_tolerance
         return self
 
