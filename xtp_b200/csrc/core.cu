@@ -2,7 +2,8 @@
 // "serial-ish library calls" of SURVEY.md section 7 hard part 6 and are timed apart from the contractions).
 #include <chrono>
 #include <mutex>
-#include <unordered_map>
+#include <map>
+#include <utility>
 
 #include "internal.h"
 
@@ -16,7 +17,12 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 // ---------------------------------------------------------------- device memory (see common.h)
 namespace {
 std::mutex g_alloc_mu;
-std::unordered_multimap<size_t, void*> g_block_cache;      // exact size -> released block
+std::multimap<std::pair<int, size_t>, void*> g_block_cache;   // (device, exact size) -> released block
+std::pair<int, size_t> cache_key(size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return {dev, bytes};
+}
 double g_cached_bytes = 0.0, g_alloc_seconds = 0.0;
 long long g_alloc_calls = 0, g_cache_hits = 0;
 bool alloc_cache_on() {
@@ -38,7 +44,7 @@ void* device_alloc(size_t bytes) {
   void* p = nullptr;
   std::lock_guard<std::mutex> lock(g_alloc_mu);
   if (alloc_cache_on()) {
-    auto it = g_block_cache.find(bytes);
+    auto it = g_block_cache.find(cache_key(bytes));
     if (it != g_block_cache.end()) {
       p = it->second;
       g_block_cache.erase(it);
@@ -69,7 +75,7 @@ void device_free(void* p, size_t bytes) {
   std::lock_guard<std::mutex> lock(g_alloc_mu);
   if (alloc_cache_on()) {
     cudaDeviceSynchronize();                    // what cudaFree implies: nothing in flight may still use the block
-    g_block_cache.emplace(bytes, p);
+    g_block_cache.emplace(cache_key(bytes), p);
     g_cached_bytes += (double)bytes;
   } else {
     cudaFree(p);
