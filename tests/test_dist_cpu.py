@@ -117,6 +117,33 @@ def _worker(rank, world, port, results):
         Hx = np.einsum('vpc,wpd->vcwd', Mvc_f, Mvc_f).reshape(vt * ct, vt * ct)
         Hd = np.einsum('vpw,p,cpd->vcwd', Mvv_f, eps_inv, Mcc_f).reshape(vt * ct, vt * ct)
         np.testing.assert_allclose(Y, (2.0 * Hx - Hd) @ X, rtol=0, atol=1e-11)
+
+        # ---- BSE operator, dense mode (bse.cu: BseOperator with H in HBM): rank r owns the columns (v2, c2) with v2 in
+        # [vt r / world, vt (r+1) / world); the screened direct term is the dense block H[:, owned], the exchange term
+        # stays factorised with the PARTIAL T of the owned rows (linear in T, so the all-reduce of Y completes it)
+        v2lo, v2hi = vt * rank // world, vt * (rank + 1) // world
+        own = slice(v2lo * ct, v2hi * ct)
+        Fvc = np.transpose(Mvc_f, (1, 0, 2)).reshape(sz.n_aux, vt * ct)           # flat operand [P][(v, c)]
+        T_part = Fvc[:, own] @ X[own]
+        Y_dense = _allreduce(-Hd[:, own] @ X[own] + 2.0 * Fvc.T @ T_part)
+        np.testing.assert_allclose(Y_dense, (2.0 * Hx - Hd) @ X, rtol=0, atol=1e-11)
+        d_part = np.zeros(vt * ct)
+        d_part[own] = -np.diag(Hd)[own] + 2.0 * (Fvc[:, own] ** 2).sum(axis=0)
+        np.testing.assert_allclose(_allreduce(d_part), np.diag(2.0 * Hx - Hd), rtol=0, atol=1e-12)
+
+        # ---- compressed QP-grid scan: every rank plans over ITS columns (own pole range, own bins) and the partial
+        # grids are summed; host plan from libxtpb200 (no device), kernels replayed by the numpy mirror
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import ppm_grid_mirror as mir
+        steps, spacing, level = 257, 0.02, q0 + 1
+        g0 = np.array([e[sz.qpmin - sz.rpamin + 1] - spacing * (steps - 1) / 2])
+        zmin, zmax = mir.pole_range(el, n_occ_loc, Om, fac)
+        pl = mir.plan(g0, spacing, steps, zmin, zmax)
+        assert pl is not None
+        part = mir.grid_values(np.ascontiguousarray(Ml[level]), el, n_occ_loc, Om, fac, g0[0], spacing, steps, pl[0], pl[1][0])
+        full = mir.direct_values(tc.M[level], e, n_occ, Om, fac, g0[0], spacing, steps)
+        np.testing.assert_allclose(_allreduce(part), full, rtol=1e-10, atol=1e-12)
         results[rank] = "ok"
     except Exception as exc:  # noqa: BLE001
         import traceback
