@@ -96,9 +96,12 @@ class TCMatrix_gwbse:
 
 
 def Pseudo_InvSqrt_GWBSE(V, S=None, etol=5e-7):
-    """Upstream ``AOCoulomb::Pseudo_InvSqrt_GWBSE`` (aomatrices/aocoulomb.cc):
-    S^{-1/2} (S^{-1/2} V S^{-1/2})^{-1/2} S^{-1/2} with eigenvalues < etol
-    dropped in both decompositions.  ``S=None`` means an orthonormal aux basis."""
+    """Upstream ``AOCoulomb::Pseudo_InvSqrt_GWBSE`` (aomatrices/aocoulomb.cc), which its own comment describes as
+    "converts V into ((S-1/2 V S-1/2)-1/2 S-1/2)T": R = S^{-1/2} (S^{-1/2} V S^{-1/2})^{-1/2}, eigenvalues < etol
+    dropped (and counted) in both decompositions.  [MATH] pin: R R^T = V^{-1} (pseudo-inverse on the kept space), which
+    is exactly what the RI identity sum_P M_mn^P M_kl^P = (mn|kl)_RI needs; any other placement of S^{-1/2} breaks it
+    for a non-orthonormal aux basis (tests/test_oracle_selfconsistency.py::test_metric_factor_inverts_coulomb_matrix).
+    ``S=None`` means an orthonormal aux basis (R = V^{-1/2})."""
     n = V.shape[0]
     removed = 0
     if S is None:
@@ -117,7 +120,7 @@ def Pseudo_InvSqrt_GWBSE(V, S=None, etol=5e-7):
     removed += int((~keep).sum())
     d[keep] = 1.0 / np.sqrt(w[keep])
     Vm1 = (U * d) @ U.T
-    return Ssqrt @ Vm1 @ Ssqrt, removed
+    return Ssqrt @ Vm1, removed
 
 
 # --------------------------------------------------------------------------
@@ -968,7 +971,10 @@ class BSE:
             occ_extra = o.qpmin - o.vmin
             idx = np.arange(occ_extra)
             H[idx, idx] = rpa_e[off:off + occ_extra]
-            H[occ_extra:occ_extra + gwsize, occ_extra:occ_extra + gwsize] = Hqp
+            # upstream copies the whole gwsize block here (Eigen asserts when cmax < qpmax); only the part of the QP
+            # window that lies inside the BSE window can be meant
+            cnt = min(gwsize, hsize - occ_extra)
+            H[occ_extra:occ_extra + cnt, occ_extra:occ_extra + cnt] = Hqp[:cnt, :cnt]
             if o.cmax > o.qpmax:
                 virtoffset = occ_extra + gwsize
                 extra = o.cmax - o.qpmax

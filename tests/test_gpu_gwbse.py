@@ -509,7 +509,7 @@ def test_transition_dipoles_and_oscillator_strengths(ctx, prob):
                                rtol=1e-10, atol=1e-12)
 
 
-@pytest.mark.parametrize("ranges", ["default", "explicit"])
+@pytest.mark.parametrize("ranges", ["default", "explicit", "explicit-low", "explicit-high"])
 def test_gwbse_driver_evaluate(ctx, ranges):
     """GWBSE::Initialize + Evaluate (upstream gwbse/gwbse.cc): the driver mirror runs Fill -> G0W0 -> Hqp -> BSE singlets
     and triplets in one call, with the level ranges coming from the `ranges` option, against the oracle's whole step.
@@ -518,7 +518,12 @@ def test_gwbse_driver_evaluate(ctx, ranges):
     from xtp_b200 import api
     prob = synth.make_problem("ch4-svp-shape")
     sz = prob["sizes"]
-    kw = {} if ranges == "default" else dict(rpamax=sz.n_basis - 1, qpmin=1, qpmax=8, bsemin=0, bsemax=10)
+    # explicit-low: vmin < qpmin AND cmax < qpmax (only part of the QP block lies inside the BSE window -- the case the
+    # round-1 AdjustHqpSize wrote out of bounds for); explicit-high: vmin > qpmin and cmax > qpmax
+    kw = {"default": {}, "explicit": dict(rpamax=sz.n_basis - 1, qpmin=1, qpmax=8, bsemin=0, bsemax=10),
+          "explicit-low": dict(rpamax=sz.n_basis - 1, qpmin=2, qpmax=10, bsemin=0, bsemax=7),
+          "explicit-high": dict(rpamax=sz.n_basis - 1, qpmin=0, qpmax=7, bsemin=2, bsemax=11)}[ranges]
+    ranges = ranges.split("-")[0]
     drv = api.GWBSE(ctx).Initialize(sz.n_basis, sz.homo + 1, ranges=ranges, tasks=("gw", "singlets", "triplets"), nmax=3,
                                     davidson_tolerance="lapack", **kw)
     r = orc.gwbse_level_ranges(ranges, sz.n_basis, sz.homo + 1, **kw)
@@ -538,9 +543,6 @@ def test_gwbse_driver_evaluate(ctx, ranges):
     assert out["BSE_singlet_coefficients"].shape == ((r["homo"] - r["vmin"] + 1) * (r["cmax"] - r["homo"]), 3)
 
 
-# Written after the GPU budget of round 1 was spent: the first execution is the round-end suite, so a surprise must not
-# turn the suite red (non-strict xfail: a pass shows up as XPASS).  Remove the marker once it has been seen to pass.
-@pytest.mark.xfail(reason="first run pending (added after the round's GPU budget was spent)", strict=False)
 def test_block_cache_reuses_scratch_without_changing_results(tmp_path):
     """XTPB_ALLOC_CACHE=1 (what bench.py turns on for one GPU): released scratch blocks are handed out again instead of
     going back to the driver.  The switch is read when the library loads, so the check runs in a child process: two
@@ -586,9 +588,6 @@ print("RESULT " + json.dumps(res))
     np.testing.assert_allclose(res[1]["s"], ref["singlet_energies"], rtol=0, atol=1e-6)
 
 
-# Written after the GPU budget of round 1 was spent: the first execution is the round-end suite, so a surprise must not
-# turn the suite red (non-strict xfail: a pass shows up as XPASS).  Remove the marker once it has been seen to pass.
-@pytest.mark.xfail(reason="first run pending (added after the round's GPU budget was spent)", strict=False)
 def test_bse_operator_properties_at_scale(ctx, monkeypatch):
     """Size-independent properties at a size the numpy oracle would need minutes for (synth-500 shape: 1500 aux
     functions, BSE size 2500): the three device strategies of BSE_OPERATOR::matmul (screened direct term dense +

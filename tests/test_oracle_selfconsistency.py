@@ -233,3 +233,68 @@ def test_full_pipeline_and_bse_vs_dense(prob):
     Ht = bse.make_operator("TripletOperator_TDA").get_full_matrix()
     np.testing.assert_allclose(out["triplet_energies"], np.linalg.eigvalsh(Ht)[:4], atol=1e-8)
     assert out["singlet_energies"][0] > 0
+
+
+def test_metric_factor_inverts_coulomb_matrix():
+    """[MATH] pin of AOCoulomb::Pseudo_InvSqrt_GWBSE: whatever the aux overlap S, the factor R applied to the tensor
+    must satisfy R R^T = V^-1 (pseudo-inverse on the kept space) -- that is what makes sum_P M_mn^P M_kl^P the RI
+    four-index integral.  With a rank-deficient V the product V R R^T V must give V back."""
+    rng = np.random.default_rng(11)
+    n = 23
+    A = rng.standard_normal((n, n))
+    V = A @ A.T / n + 0.3 * np.eye(n)
+    B = rng.standard_normal((n, n))
+    S = B @ B.T / n + 0.5 * np.eye(n)
+    for overlap in (None, S):
+        R, removed = orc.Pseudo_InvSqrt_GWBSE(V, overlap)
+        assert removed == 0
+        np.testing.assert_allclose(R @ R.T @ V, np.eye(n), atol=1e-10)
+    w, U = np.linalg.eigh(V)
+    w[:3] = 1e-9
+    Vd = (U * w) @ U.T
+    R, removed = orc.Pseudo_InvSqrt_GWBSE(Vd, None)
+    assert removed == 3
+    keep = (U[:, 3:] * w[3:]) @ U[:, 3:].T
+    np.testing.assert_allclose(keep @ R @ R.T @ keep, keep, atol=1e-10)
+
+
+def test_energies_do_not_depend_on_the_aux_overlap(prob):
+    """Consequence of R R^T = V^-1: two factors built with different aux overlaps differ by an orthogonal rotation of
+    the aux index only, so eps eigenvalues (and everything downstream) are identical."""
+    p, sz = prob, prob["sizes"]
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((sz.n_aux, sz.n_aux))
+    S = B @ B.T / sz.n_aux + 0.5 * np.eye(sz.n_aux)
+    tc2 = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    tc2.Fill(p["ao3c"], p["C"], p["aux_coulomb"], S)
+    e1 = np.linalg.eigvalsh(_rpa(p).calculate_epsilon_i(0.5))
+    e2 = np.linalg.eigvalsh(_rpa(p, tc2).calculate_epsilon_i(0.5))
+    np.testing.assert_allclose(e1, e2, rtol=1e-10)
+
+
+@pytest.mark.parametrize("window", [(2, 10, 0, 7), (0, 7, 2, 11), (1, 8, 0, 10), (0, 9, 1, 8)])
+def test_adjust_hqp_size_windows(window):
+    """BSE::AdjustHqpSize for every relative position of the QP and BSE windows (qpmin, qpmax, vmin, cmax): entries
+    inside both windows come from Hqp, the rest of the diagonal from the RPA input energies, nothing else is set."""
+    qpmin, qpmax, vmin, cmax = window
+    homo, rpamin, rpamax = 4, 0, 15
+    rng = np.random.default_rng(1)
+    gws = qpmax - qpmin + 1
+    Hqp = rng.standard_normal((gws, gws)); Hqp = Hqp + Hqp.T
+    e = rng.standard_normal(rpamax + 1)
+    b = orc.BSE.__new__(orc.BSE)
+    b.opt = orc.BSEOptions(homo, rpamin, rpamax, qpmin, qpmax, vmin, cmax)
+    b.vtotal, b.ctotal = homo - vmin + 1, cmax - homo
+    H = b.AdjustHqpSize(Hqp, e)
+    hs = cmax - vmin + 1
+    assert H.shape == (hs, hs)
+    for i in range(hs):
+        for j in range(hs):
+            li, lj = vmin + i, vmin + j
+            inside = qpmin <= li <= qpmax and qpmin <= lj <= qpmax
+            if inside:
+                assert H[i, j] == Hqp[li - qpmin, lj - qpmin]
+            elif i == j:
+                assert H[i, j] == e[li - rpamin]
+            else:
+                assert H[i, j] == 0.0

@@ -7,7 +7,9 @@
 //   Hd  X : U[k][c1][P][v2] = sum_c2 Mcc[c1][P][c2] X[k][v2,c2]              2 N_aux c^2 v k
 //           Y[k][v1,c1]    -= sum_{P,v2} eps_inv[P] Mvv[v1][P][v2] U[...]    2 N_aux v^2 c k
 //   Hqp X : two small products with the QP Hamiltonian blocks.
-// H itself is never materialised.
+// Two strategies (BseOperator): "factorised" applies the products above on every call and never holds H;
+// "dense" (XTPB_BSE_MODE=dense, or auto when it fits XTPB_BSE_DENSE_MAX_GB) builds the screened direct term + Hqp
+// once as a (vc)^2 matrix in HBM and streams it per call, the exchange term staying factorised.
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -51,8 +53,11 @@ BSE::BSE(Context* c, TCMatrix* t, const xtpb_bse_options& o, const double* rpa_e
   } else {
     const long long occ_extra = o.qpmin - o.vmin;
     for (long long i = 0; i < occ_extra; ++i) H[i + i * hsize] = rpa_e[off + i];
-    for (long long j = 0; j < gwsize; ++j)
-      for (long long i = 0; i < gwsize; ++i) H[(occ_extra + i) + (occ_extra + j) * hsize] = Hq(i, j);
+    // upstream copies the whole gwsize block (an Eigen assertion when cmax < qpmax); only the part of the QP window
+    // inside the BSE window can be meant
+    const long long cnt = std::min(gwsize, hsize - occ_extra);
+    for (long long j = 0; j < cnt; ++j)
+      for (long long i = 0; i < cnt; ++i) H[(occ_extra + i) + (occ_extra + j) * hsize] = Hq(i, j);
     if (o.cmax > o.qpmax) {
       const long long virtoffset = occ_extra + gwsize, extra = o.cmax - o.qpmax;
       for (long long i = 0; i < extra; ++i) {

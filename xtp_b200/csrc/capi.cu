@@ -227,14 +227,9 @@ int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index l
   inv_sqrt(A.p, Vm1.p);
   double* R = Vm1.p;
   if (S_host) {
+    // R = S^-1/2 (S^-1/2 V S^-1/2)^-1/2  ("((S-1/2 V S-1/2)-1/2 S-1/2)T" in upstream's words): R R^T = V^-1
     mm(Ssqrt.p, true, Vm1.p, Cc.p);      // Cc = Ssqrt * Vm1
-    GemmParams g{};
-    g.A = op_rows_contig(Cc.p, na);
-    g.B = op_k_contig(Ssqrt.p, na);
-    g.C = A.p; g.c_sm = 1; g.c_sn = na;
-    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
-    contract(g, ctx->ws, ctx->stream);
-    R = A.p;
+    R = Cc.p;
   }
   t.set_pending(R, na);       // deferred: folded into the next full rotation (see TCMatrix::set_pending)
   ctx->sync();

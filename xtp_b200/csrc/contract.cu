@@ -64,26 +64,37 @@ ProfScope::~ProfScope() { t_prof_tag = prev; }
 namespace {
 
 constexpr int kStages = 4;
-int g_num_sms = 0;
+constexpr int kMaxDevices = 64;
+int g_num_sms[kMaxDevices] = {};
 
+int current_device() {
+  int dev = 0;
+  XTPB_CUDA(cudaGetDevice(&dev));
+  return dev;
+}
+// per-device state (one process may hold contexts on several devices): SM count, and which kernel instances have had
+// their dynamic shared memory opt-in applied on which device
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    XTPB_CUDA(cudaGetDevice(&dev));
-    XTPB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return g_num_sms;
+  const int dev = current_device();
+  int& n = g_num_sms[dev % kMaxDevices];
+  if (n == 0) XTPB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return n;
+}
+template <class Kern>
+void ensure_smem_optin(Kern kern, int bytes, unsigned long long& device_mask) {
+  const int dev = current_device();
+  const unsigned long long bit = 1ULL << (dev % kMaxDevices);
+  if (device_mask & bit) return;
+  XTPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  device_mask |= bit;
 }
 
 template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D, bool VEC>
 void launch_cfg2(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BM, BN, WM, WN, A_KC, B_KC, kStages>;
   auto kern = contract_kernel<Cfg, BM, BN, WM, WN, A_KC, B_KC, kStages, HAS_D, VEC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XTPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static unsigned long long optin_mask = 0;
+  ensure_smem_optin(kern, Cfg::SMEM_BYTES, optin_mask);
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   dim3 grid(tiles_m * tiles_n, 1, p.n_batch * p.splits);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
@@ -145,11 +156,8 @@ bool launch_tma(const GemmParams& p, cudaStream_t stream) {
   if (!make_tensor_map(&mapB, p.B, B_KC, p.N, BN, p.K, p.n_outer, p.n_batch, &tc.b_outer, &tc.b_batch)) return false;
   auto kern = contract_tma_kernel<Cfg, BM, BN, WM, WN, A_KC, B_KC, kStages, HAS_D>;
   constexpr int smem_bytes = kStages * (Cfg::A_BYTES + Cfg::B_BYTES + 1024) + 2 * kStages * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XTPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  static unsigned long long optin_mask = 0;
+  ensure_smem_optin(kern, smem_bytes, optin_mask);
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   dim3 grid(tiles_m * tiles_n, 1, p.n_batch * p.splits);
   kern<<<grid, Cfg::THREADS, smem_bytes, stream>>>(p, tc, mapA, mapB);

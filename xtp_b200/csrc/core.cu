@@ -124,6 +124,23 @@ Context::Context(int dev) : device(dev) {
 
 Context::~Context() {
   comm_destroy();
+  solver_work.release();
+  scratch_a.release();
+  scratch_b.release();
+  ws.buf.release();
+  {   // blocks cached for this device go back to the driver with the context
+    std::lock_guard<std::mutex> lock(g_alloc_mu);
+    cudaDeviceSynchronize();
+    for (auto it = g_block_cache.begin(); it != g_block_cache.end();) {
+      if (it->first.first == device) {
+        cudaFree(it->second);
+        g_cached_bytes -= (double)it->first.second;
+        it = g_block_cache.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
   if (solver) cusolverDnDestroy(solver);
   if (dev_info) cudaFree(dev_info);
   if (ev0) cudaEventDestroy(ev0);

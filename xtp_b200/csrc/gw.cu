@@ -19,6 +19,12 @@ GW::GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host
   XTPB_REQUIRE(o.qpmin >= o.rpamin && o.qpmax <= t->mmax && o.qpmax >= o.qpmin, "QP range outside the TCMatrix m-range");
   XTPB_REQUIRE(o.homo >= o.qpmin && o.homo + 1 <= o.qpmax, "QP range must contain HOMO and LUMO");
   XTPB_REQUIRE(ne > o.rpamax, "dft_energies shorter than rpamax");
+  XTPB_REQUIRE(o.reset_3c >= 1, "reset_3c must be at least 1");
+  XTPB_REQUIRE(o.qp_grid_steps >= 2, "qp_grid_steps must be at least 2");
+  XTPB_REQUIRE(o.gw_sc_max_iterations >= 1 && o.g_sc_max_iterations >= 1, "iteration limits must be at least 1");
+  XTPB_REQUIRE(o.gw_mixing_order >= 0 && o.gw_mixing_order <= 25, "gw_mixing_order out of range (0..25)");
+  XTPB_REQUIRE(o.gw_mixing_alpha > 0.0 && o.gw_mixing_alpha <= 1.0, "gw_mixing_alpha must be in (0, 1]");
+  XTPB_REQUIRE(o.qp_grid_spacing > 0.0, "qp_grid_spacing must be positive");
   qptotal = o.qpmax - o.qpmin + 1;
   rpatotal = o.rpamax - o.rpamin + 1;
   n_occ = o.homo - o.rpamin + 1;
