@@ -210,6 +210,7 @@ class GwbseJob:
         t = {}
         t0 = time.perf_counter()
         tc = self.tc
+        tc.coulomb_metric_begin(self.V)     # TCMatrix_gwbse::Fill = Fill3cMO + metric: the metric's eigensolver runs underneath
         tc.fill_begin(self.C)
         n_loc = self.p_hi - self.p_lo
         if self.world > 1:
@@ -319,11 +320,8 @@ def main():
         return
 
     os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
-    # single GPU: keep the library's released scratch blocks in its exact-size cache (read once when libxtpb200 loads), so
-    # that the steps after the first make no cudaMalloc/cudaFree calls at all; "host_alloc" in the JSON line reports it
-    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and "XTPB_ALLOC_CACHE" not in os.environ:
-        os.environ["XTPB_ALLOC_CACHE"] = "1"
-        os.environ["XTPB_BENCH_CACHE_DEFAULTED"] = "1"      # lets __main__ fall back to a run without the cache
+    # the library keeps released scratch blocks in its exact-size cache (default; XTPB_ALLOC_CACHE=0 turns it off), so the
+    # steps after the first make no cudaMalloc/cudaFree calls at all, at any world size; "host_alloc" reports it
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: xtp_b200 has no CPU fallback")
@@ -496,7 +494,7 @@ def main():
             # host/driver time between kernels: cudaMalloc + cudaFree of the library's scratch buffers, per step
             "host_alloc": {"seconds_per_step": round(alloc["seconds"] / args.steps, 4),
                            "calls_per_step": alloc["calls"] / args.steps,
-                           "block_cache": os.environ.get("XTPB_ALLOC_CACHE", "0") == "1",
+                           "block_cache": os.environ.get("XTPB_ALLOC_CACHE", "1") != "0",
                            "cache_hits_per_step": alloc["cache_hits"] / args.steps,
                            "cached_gb": round(alloc["cached_gb"], 3)},
             "stage_seconds": {k: round(v / args.steps, 4) for k, v in stage_acc.items()},
@@ -514,16 +512,4 @@ def main():
 
 
 if __name__ == "__main__":
-    try:
-        main()
-    except Exception:  # noqa: BLE001
-        # safety net for the one switch this script turns on by itself: if a single-GPU run fails with the block cache
-        # that bench.py (not the user) enabled, say so and run once more without it; anything else propagates
-        if os.environ.get("XTPB_BENCH_CACHE_DEFAULTED") == "1" and os.environ.get("XTPB_ALLOC_CACHE") == "1":
-            import traceback
-            traceback.print_exc()
-            print("bench.py: run with XTPB_ALLOC_CACHE=1 failed; repeating without the block cache", file=sys.stderr,
-                  flush=True)
-            env = dict(os.environ, XTPB_ALLOC_CACHE="0", XTPB_BENCH_CACHE_DEFAULTED="0")
-            os.execve(sys.executable, [sys.executable] + sys.argv, env)
-        raise
+    main()

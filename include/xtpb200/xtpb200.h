@@ -116,6 +116,12 @@ int xtpb_tc_multiply_right_with_aux_matrix(xtpb_tc* tc, const double* A_host, xt
  * MultiplyRightWithAuxMatrix.  S_host may be NULL (orthonormal aux basis). */
 int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
                                  xtpb_index lds, double etol, xtpb_index* removed_functions);
+/* Optional: start the first eigendecomposition of that step (of S when given, else of V) on a helper thread, stream
+ * and cuSOLVER handle NOW, so that it runs underneath the xtpb_tc_fill_* calls that follow (the two halves of
+ * TCMatrix_gwbse::Fill have independent inputs).  The same pointers must then be passed to
+ * xtpb_tc_apply_coulomb_metric, which joins the helper; the host matrices must stay valid until it returns. */
+int xtpb_tc_coulomb_metric_begin(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
+                                 xtpb_index lds);
 
 /* ---- RPA (upstream xtp/src/libxtp/gwbse/rpa.cc) ---- */
 /* RPA::calculate_epsilon_i / calculate_epsilon_r for n_omega frequencies in one call.
@@ -219,6 +225,10 @@ int xtpb_bse_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_bse_options* opt, con
                     const double* hqp_host, xtpb_index ldh, int rotate_full_tc, xtpb_bse** out);
 int xtpb_bse_destroy(xtpb_bse* bse);
 int xtpb_bse_get_epsilon_0_inv(xtpb_bse* bse, double* eps_inv_host);
+/* eps0_reused = 1 when SetupDirectInteractionOperator found the tensor already in the eigenbasis of epsilon(0) for
+ * exactly these RPA input energies (G0W0 after Sigma_PPM::PrepareScreening rotated it there) and read the eigenvalues
+ * instead of recomputing epsilon(0), its eigensolver and the rotation.  XTPB_BSE_REUSE_EPS0=0 disables the shortcut. */
+int xtpb_bse_screening_info(xtpb_bse* bse, int* eps0_reused);
 /* BSE_OPERATOR<cqp,cx,cd,cd2>(epsilon_0_inv, Mmn, Hqp) + configure(BSEOperator_Options).
  * Typedefs upstream: SingletOperator_TDA <1,2,1,0>, TripletOperator_TDA <1,0,1,0>, SingletOperator_BTDA_B <0,2,0,1>,
  * TripletOperator_BTDA_B <0,0,0,1>, HxOperator <0,1,0,0>, HdOperator <0,0,1,0>, Hd2Operator <0,0,0,1>, HqpOperator <1,0,0,0>. */
@@ -257,6 +267,12 @@ void xtpb_davidson_options_default(xtpb_davidson_options* opt);
  * info: 0 = Eigen::Success, 1 = Eigen::NoConvergence.  iterations: num_iterations(). */
 int xtpb_davidson_solve(xtpb_op* op, xtpb_index neigen, const xtpb_davidson_options* opt, double* eigenvalues_host,
                         double* eigenvectors_host, xtpb_index ldv, int* info, xtpb_index* iterations);
+
+/* The dense symmetric eigensolver the Davidson solvers apply to their projected matrices (upstream:
+ * Eigen::SelfAdjointEigenSolver inside DavidsonSolver::getRitz, davidsonsolver.cc): Householder tridiagonalisation +
+ * implicit QL on the host.  A_host (n x n, ld = lda, lower triangle read) is overwritten by the eigenvectors,
+ * w_host receives the ascending eigenvalues.  Host-only, needs no device. */
+int xtpb_host_eigh(xtpb_index n, double* A_host, xtpb_index lda, double* w_host);
 
 /* ---- full BSE, transition dipoles, oscillator strengths ---- */
 /* Full (non-TDA) BSE: BSE::Solve_singlets / Solve_triplets with useTDA = false (upstream bse.cc

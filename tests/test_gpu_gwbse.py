@@ -543,8 +543,72 @@ def test_gwbse_driver_evaluate(ctx, ranges):
     assert out["BSE_singlet_coefficients"].shape == ((r["homo"] - r["vmin"] + 1) * (r["cmax"] - r["homo"]), 3)
 
 
+def test_bse_reuses_ppm_eigenbasis_of_epsilon0(ctx, prob, monkeypatch):
+    """G0W0 + PPM leaves the tensor in the eigenbasis of eps(0) at the RPA input energies BSE::configure is then given:
+    the library reads the eigenvalues instead of recomputing eps(0) + eigensolver + rotation.  Both ways must give the
+    same screening and the same excitation energies (and the oracle's, which recomputes like upstream)."""
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    out = {}
+    for reuse in ("1", "0"):
+        monkeypatch.setenv("XTPB_BSE_REUSE_EPS0", reuse)
+        gw, gwo, tc, tco = _gw_pair(ctx, prob, qp_grid_steps=201)
+        gw.CalculateGWPerturbation()
+        gw.CalculateHQP()
+        bse = api.BSE(ctx, tc)
+        bse.configure(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, 3, gw.RPAInputEnergies(),
+                      gw.getHQP(), davidson_tolerance="lapack", davidson_maxiter=200)
+        assert bse.eps0_reused() == (reuse == "1")
+        out[reuse] = (bse.epsilon_0_inv(), bse.Solve_singlets_TDA()[0], bse.Solve_triplets_TDA()[0])
+        bse.close()
+    np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=1e-9)
+    np.testing.assert_allclose(out["1"][1], out["0"][1], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(out["1"][2], out["0"][2], rtol=0, atol=1e-9)
+    # a rotation of the tensor, or other energies, invalidate the shortcut
+    gw, gwo, tc, tco = _gw_pair(ctx, prob, qp_grid_steps=201)
+    monkeypatch.setenv("XTPB_BSE_REUSE_EPS0", "1")
+    gw.CalculateGWPerturbation()
+    gw.CalculateHQP()
+    e = gw.RPAInputEnergies().copy()
+    e[-1] += 1e-3
+    bse = api.BSE(ctx, tc)
+    bse.configure(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, 3, e, gw.getHQP())
+    assert not bse.eps0_reused()
+    bse.close()
+    tc.MultiplyRightWithAuxMatrix(np.eye(sz.n_aux))
+    bse.configure(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, 3, gw.RPAInputEnergies(),
+                  gw.getHQP())
+    assert not bse.eps0_reused()
+    bse.close()
+
+
+def test_coulomb_metric_prefetch_matches_synchronous_path(ctx, prob):
+    """xtpb_tc_coulomb_metric_begin starts the first eigendecomposition of the metric step on the helper thread before
+    Fill3cMO (what TCMatrix_gwbse.Fill does); the tensor must equal the one of the synchronous call sequence, with and
+    without an aux overlap, and mismatched matrices must be refused."""
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    rng = np.random.default_rng(9)
+    B = rng.standard_normal((sz.n_aux, sz.n_aux))
+    S = B @ B.T / sz.n_aux + 0.5 * np.eye(sz.n_aux)
+    for overlap in (None, S):
+        a = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+        a.Fill(prob["ao3c"], prob["C"], prob["aux_coulomb"], overlap)           # prefetch inside
+        b = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+        b.Fill3cMO(prob["ao3c"], prob["C"])
+        b.apply_coulomb_metric(prob["aux_coulomb"], overlap)                    # no prefetch
+        ref = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+        ref.Fill(prob["ao3c"], prob["C"], prob["aux_coulomb"], overlap)
+        assert rel(a.get_raw(), b.get_raw()) < 1e-11
+        assert rel(a.get_raw(), ref.M) < 1e-9
+    c = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    c.coulomb_metric_begin(prob["aux_coulomb"])
+    with pytest.raises(ValueError):
+        c.apply_coulomb_metric(S)
+
+
 def test_block_cache_reuses_scratch_without_changing_results(tmp_path):
-    """XTPB_ALLOC_CACHE=1 (what bench.py turns on for one GPU): released scratch blocks are handed out again instead of
+    """The exact-size block cache (library default; XTPB_ALLOC_CACHE=0 turns it off): released scratch blocks are handed out again instead of
     going back to the driver.  The switch is read when the library loads, so the check runs in a child process: two
     identical G0W0+BSE steps; the second must be served from the cache and give the same energies (1e-12), equal to the
     oracle's within the usual bounds."""

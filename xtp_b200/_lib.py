@@ -97,6 +97,7 @@ PROTOTYPES = {
     "xtpb_tc_fill_sharded_packed": (C.c_int, [vp, vp, C.c_int]),
     "xtpb_tc_multiply_right_with_aux_matrix": (C.c_int, [vp, dptr, idx]),
     "xtpb_tc_apply_coulomb_metric": (C.c_int, [vp, dptr, idx, dptr, idx, C.c_double, iptr]),
+    "xtpb_tc_coulomb_metric_begin": (C.c_int, [vp, dptr, idx, dptr, idx]),
     "xtpb_rpa_epsilon": (C.c_int, [vp, dptr, idx, idx, idx, C.c_double, dptr, C.c_int, C.c_int, dptr]),
     "xtpb_gw_options_default": (None, [C.POINTER(GwOptions)]),
     "xtpb_gaussian_quadrature": (C.c_int, [C.c_int, idx, dptr, dptr, iptr]),
@@ -122,6 +123,7 @@ PROTOTYPES = {
     "xtpb_gw_unconverged_levels": (C.c_int, [vp, iptr]),
     "xtpb_bse_create": (C.c_int, [vp, vp, C.POINTER(BseOptions), dptr, dptr, idx, C.c_int, C.POINTER(vp)]),
     "xtpb_bse_destroy": (C.c_int, [vp]),
+    "xtpb_bse_screening_info": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "xtpb_bse_get_epsilon_0_inv": (C.c_int, [vp, dptr]),
     "xtpb_bse_operator_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "xtpb_bse_operator_create_raw": (C.c_int, [vp, vp, idx, idx, idx, idx, dptr, dptr, idx, C.c_int, C.c_int,
@@ -137,6 +139,7 @@ PROTOTYPES = {
     "xtpb_op_get_full_matrix": (C.c_int, [vp, dptr, idx]),
     "xtpb_davidson_options_default": (None, [C.POINTER(DavidsonOptions)]),
     "xtpb_davidson_solve": (C.c_int, [vp, idx, C.POINTER(DavidsonOptions), dptr, dptr, idx, C.POINTER(C.c_int), iptr]),
+    "xtpb_host_eigh": (C.c_int, [idx, dptr, idx, dptr]),
     "xtpb_contract_host": (C.c_int, [vp, C.POINTER(ContractDesc), dptr, dptr, dptr, dptr]),
     "xtpb_contract_bench": (C.c_int, [vp, C.POINTER(ContractDesc), C.c_int, dptr]),
 }

@@ -227,12 +227,29 @@ class TCMatrix_gwbse:
         check(_lib.lib().xtpb_tc_multiply_right_with_aux_matrix(self._h, _d(Af), Af.shape[0]))
 
     def Fill(self, ao3c, C_mo, aux_coulomb, aux_overlap=None, etol=5e-7):
+        self.coulomb_metric_begin(aux_coulomb, aux_overlap)    # eigensolver of the metric runs underneath Fill3cMO
         self.Fill3cMO(ao3c, C_mo)
         self.removedfunctions = self.apply_coulomb_metric(aux_coulomb, aux_overlap, etol)
 
-    def apply_coulomb_metric(self, V, S=None, etol=5e-7):
+    def coulomb_metric_begin(self, V, S=None):
+        """Start the metric's first eigendecomposition on the library's helper thread (xtpb_tc_coulomb_metric_begin);
+        the matching apply_coulomb_metric(V, S) call joins it.  The column-major copies are kept alive here."""
         Vf = _f(V)
         Sf = _f(S) if S is not None else None
+        self._metric_inputs = (V, S, Vf, Sf)
+        check(_lib.lib().xtpb_tc_coulomb_metric_begin(self._h, _d(Vf), Vf.shape[0], _d(Sf) if Sf is not None else None,
+                                                      Sf.shape[0] if Sf is not None else 0))
+
+    def apply_coulomb_metric(self, V, S=None, etol=5e-7):
+        pre = getattr(self, "_metric_inputs", None)
+        self._metric_inputs = None
+        if pre is not None and pre[0] is V and pre[1] is S:
+            Vf, Sf = pre[2], pre[3]                # the very buffers the helper thread was given
+        else:
+            if pre is not None:
+                raise ValueError("coulomb_metric_begin was called with different matrices")
+            Vf = _f(V)
+            Sf = _f(S) if S is not None else None
         removed = idx(0)
         check(_lib.lib().xtpb_tc_apply_coulomb_metric(
             self._h, _d(Vf), Vf.shape[0], _d(Sf) if Sf is not None else None,
@@ -567,6 +584,12 @@ class BSE:
             self.close()
         except Exception:
             pass
+
+    def eps0_reused(self):
+        """True when BSE::configure took the eps(0) eigenvalues from the PPM rotation (xtpb_bse_screening_info)."""
+        flag = C.c_int(0)
+        check(_lib.lib().xtpb_bse_screening_info(self._h, C.byref(flag)))
+        return bool(flag.value)
 
     def epsilon_0_inv(self):
         out = np.empty(self.Mmn.auxsize())

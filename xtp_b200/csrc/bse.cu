@@ -11,7 +11,9 @@
 // "dense" (XTPB_BSE_MODE=dense, or auto when it fits XTPB_BSE_DENSE_MAX_GB) builds the screened direct term + Hqp
 // once as a (vc)^2 matrix in HBM and streams it per call, the exchange term staying factorised.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <numeric>
 
 #include "internal.h"
@@ -20,6 +22,7 @@ namespace xtpb {
 
 namespace {
 constexpr double kRpaEtaDefault = 1e-3;   // RPA object's eta when BSE builds its own screening (oracle: RPA.eta)
+constexpr int kHostEighMax = 768;         // projected eigenproblems up to this size are solved on the host
 }
 
 // ------------------------------------------------------------------ BSE::configure
@@ -79,11 +82,27 @@ std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e) {
   TCMatrix* tc = b.tc;
   Context* ctx = b.ctx;
   const long long na = tc->naux, rpatotal = tc->ntotal_glob;
+  const long long n_occ = b.opt.homo - b.opt.rpamin + 1;
+  // G0W0 after Sigma_PPM: the tensor is already in the eigenbasis of eps(0) at exactly these energies (upstream
+  // recomputes eps(0) from the rotated tensor and diagonalises a matrix that is diag(lambda) up to rounding).  Read the
+  // eigenvalues instead: no epsilon contraction, no N_aux^3 eigensolver, no window rotation (U = 1).
+  // XTPB_BSE_REUSE_EPS0=0 forces the full recomputation.
+  {
+    const char* env = getenv("XTPB_BSE_REUSE_EPS0");
+    const TCMatrix::Eps0Basis& z = tc->eps0;
+    if (!(env && env[0] == '0') && z.valid && !tc->pending && z.eta == kRpaEtaDefault && z.n_occ == n_occ &&
+        (long long)z.energies.size() == rpatotal && std::equal(z.energies.begin(), z.energies.end(), rpa_e)) {
+      b.eps_inv.resize((size_t)na);
+      for (long long i = 0; i < na; ++i) b.eps_inv[i] = z.lambda[i] > 1e-8 ? 1.0 / z.lambda[i] : 0.0;
+      b.eps0_reused = true;
+      return nullptr;
+    }
+  }
   DBuf e_dev((size_t)rpatotal), lam((size_t)na);
   ctx->h2d(e_dev.p, rpa_e, (size_t)rpatotal);
   auto U = std::make_unique<DBuf>((size_t)(na * na));
   const double w0 = 0.0;
-  rpa_epsilon_dev(*tc, e_dev.p, b.opt.homo - b.opt.rpamin + 1, kRpaEtaDefault, &w0, 1, false, 0.0, U->p);
+  rpa_epsilon_dev(*tc, e_dev.p, n_occ, kRpaEtaDefault, &w0, 1, false, 0.0, U->p);
   ctx->eigh((int)na, U->p, na, lam.p);
   std::vector<double> lambda((size_t)na);
   ctx->d2h(lambda.data(), lam.p, (size_t)na);
@@ -613,8 +632,22 @@ void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& 
   out.iterations = 0;
   std::vector<double> rn((size_t)su);
 
+  // XTPB_TRACE=1: host seconds per phase of the iteration (with a stream synchronisation at every phase boundary, so
+  // device time lands in the phase that issued it) on stderr -- a diagnostic, never on during a bench
+  static const bool trace = [] { const char* e = getenv("XTPB_TRACE"); return e && e[0] == '1'; }();
+  enum { PH_MATMUL, PH_PROJECT, PH_EIGH, PH_RITZ, PH_CORRECT, PH_ORTHO, PH_N };
+  double phase[PH_N] = {};
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto lap = [&](int ph, std::chrono::steady_clock::time_point& t0) {
+    if (!trace) return;
+    ctx->sync();
+    const auto t1 = tnow();
+    phase[ph] += std::chrono::duration<double>(t1 - t0).count();
+    t0 = t1;
+  };
   for (long long it = 0; it < opt.iter_max; ++it) {
     out.iterations = it + 1;
+    auto t0 = tnow();
     if (ncols > max_space && have_ritz) {
       // restart: V <- Ritz vectors, AV <- AV U, T <- V^T AV
       gemm_nn(ctx, w.AV.p, w.ld, nold, Udev.p, nold, (int)su, n, w.R.p, w.ld, 1.0, 0.0);   // R = AV U (temp)
@@ -629,6 +662,7 @@ void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& 
       // AV[:, nold:] = A V[:, nold:];  T[:, nold:] = V^T AV[:, nold:]
       const int nnew = ncols - nold;
       A.matmul_dev(w.V.p + (long long)nold * w.ld, w.ld, nnew, w.AV.p + (long long)nold * w.ld, w.ld);
+      lap(PH_MATMUL, t0);
       gemm_tn(ctx, w.V.p, w.ld, ncols, w.AV.p + (long long)nold * w.ld, w.ld, nnew, n, w.small.p, ncols);
       std::vector<double> Tn((size_t)ncols * nnew);
       ctx->d2h(Tn.data(), w.small.p, Tn.size());
@@ -643,22 +677,34 @@ void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& 
       T.swap(T2);
       nold = ncols;
     }
+    lap(PH_PROJECT, t0);
     // Ritz pairs of the symmetrised projected matrix
     {
       std::vector<double> Ts((size_t)ncols * ncols);
       for (int j = 0; j < ncols; ++j)
         for (int i = 0; i < ncols; ++i) Ts[i + (size_t)j * ncols] = 0.5 * (T[i + (size_t)j * ncols] + T[j + (size_t)i * ncols]);
-      ctx->h2d(Udev.p, Ts.data(), Ts.size());
-      ctx->eigh(ncols, Udev.p, ncols, lamdev.p);
       lam.resize((size_t)ncols);
-      ctx->d2h(lam.data(), lamdev.p, (size_t)ncols);
+      // the projected problem (<= max_search_space rows) is solved on the host, as upstream does with
+      // Eigen::SelfAdjointEigenSolver: no cuSOLVER launch chain, no extra synchronisation
+      if (ncols <= kHostEighMax && host_eigh(ncols, Ts.data(), lam.data())) {
+        ctx->h2d(Udev.p, Ts.data(), Ts.size());
+        ctx->h2d(lamdev.p, lam.data(), (size_t)ncols);
+      } else {
+        for (int j = 0; j < ncols; ++j)
+          for (int i = 0; i < ncols; ++i) Ts[i + (size_t)j * ncols] = 0.5 * (T[i + (size_t)j * ncols] + T[j + (size_t)i * ncols]);
+        ctx->h2d(Udev.p, Ts.data(), Ts.size());
+        ctx->eigh(ncols, Udev.p, ncols, lamdev.p);
+        ctx->d2h(lam.data(), lamdev.p, (size_t)ncols);
+      }
     }
+    lap(PH_EIGH, t0);
     const int nsu = (int)std::min<long long>(su, ncols);
     gemm_nn(ctx, w.V.p, w.ld, ncols, Udev.p, ncols, nsu, n, w.Q.p, w.ld, 1.0, 0.0);     // q = V U
     gemm_nn(ctx, w.AV.p, w.ld, ncols, Udev.p, ncols, nsu, n, w.R.p, w.ld, 1.0, 0.0);    // r = AV U
     k_residuals(w.R.p, w.ld, w.Q.p, w.ld, lamdev.p, n, nsu, ctx->stream);               //   - q lambda
     k_col_norms(w.R.p, w.ld, n, nsu, nrmdev.p, ctx->stream);
     ctx->d2h(rn.data(), nrmdev.p, (size_t)nsu);
+    lap(PH_RITZ, t0);
     have_ritz = true;
     bool converged = true;
     for (long long j = 0; j < neigen; ++j) converged = converged && (j < nsu) && rn[j] < opt.tolerance;
@@ -677,10 +723,16 @@ void davidson_solve(Operator& A, long long neigen, const xtpb_davidson_options& 
                             opt.correction == XTPB_DAVIDSON_OLSEN ? 1 : 0, w.vec.p, ctx->stream);
       ++added;
     }
+    lap(PH_CORRECT, t0);
     const int before = ncols;
     ncols = gram_schmidt(w, before, before + added);
+    lap(PH_ORTHO, t0);
     if (ncols == before) break;    // nothing independent left to add
   }
+  if (trace)
+    fprintf(stderr, "[xtpb trace] davidson n=%lld neigen=%lld iterations=%lld: matmul %.4f project %.4f eigh %.4f "
+            "ritz+residual %.4f correction %.4f orthogonalise %.4f s\n", n, neigen, out.iterations, phase[PH_MATMUL],
+            phase[PH_PROJECT], phase[PH_EIGH], phase[PH_RITZ], phase[PH_CORRECT], phase[PH_ORTHO]);
   out.evals.assign(lam.begin(), lam.begin() + std::min<size_t>((size_t)neigen, lam.size()));
   out.evecs.alloc((size_t)(n * neigen));
   k_copy_2d(out.evecs.p, n, w.Q.p, w.ld, (int)n, neigen, ctx->stream);
@@ -700,6 +752,12 @@ namespace {
 
 // symmetric s x s (host, col-major): A <- eigenvectors, w <- ascending eigenvalues
 void small_eigh(Context* ctx, int n, std::vector<double>& A, std::vector<double>& w, DBuf& dA, DBuf& dw) {
+  w.resize((size_t)n);
+  if (n <= kHostEighMax) {
+    std::vector<double> keep = A;
+    if (host_eigh(n, A.data(), w.data())) return;
+    A.swap(keep);
+  }
   dA.ensure((size_t)n * n);
   dw.ensure((size_t)n);
   ctx->h2d(dA.p, A.data(), (size_t)n * n);

@@ -171,6 +171,14 @@ int xtpb_tc_multiply_right_with_aux_matrix(xtpb_tc* tc, const double* A_host, xt
   XTPB_API_END
 }
 // AOCoulomb::Pseudo_InvSqrt_GWBSE (upstream xtp/src/libxtp/aomatrices/aocoulomb.cc) + MultiplyRightWithAuxMatrix
+int xtpb_tc_coulomb_metric_begin(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
+                                 xtpb_index lds) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(tc && V_host, "null pointer");
+  if (S_host) tc->impl.metric_prefetch_begin(S_host, lds, true);
+  else tc->impl.metric_prefetch_begin(V_host, ldv, false);
+  XTPB_API_END
+}
 int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
                                  xtpb_index lds, double etol, xtpb_index* removed_functions) {
   XTPB_API_BEGIN
@@ -189,10 +197,22 @@ int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index l
     g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
     contract(g, ctx->ws, ctx->stream);
   };
+  // the first decomposition may have been started before Fill3cMO (xtpb_tc_coulomb_metric_begin)
+  bool prefetched = t.metric_prefetch_join();
+  if (prefetched) {
+    XTPB_REQUIRE(t.prefetch.of_overlap == (S_host != nullptr) && t.prefetch.src == (S_host ? S_host : V_host),
+                 "xtpb_tc_coulomb_metric_begin was given different matrices than xtpb_tc_apply_coulomb_metric");
+  }
   // f(X) = U diag(1/sqrt(lambda) | 0) U^T for symmetric X (eigenvalues < etol dropped)
   auto inv_sqrt = [&](double* X, double* out) {
-    ctx->eigh((int)na, X, na, w.p);              // X <- U
-    ctx->d2h(lam.data(), w.p, (size_t)na);
+    if (prefetched) {                            // eigenvectors / eigenvalues are already there
+      prefetched = false;
+      XTPB_CUDA(cudaMemcpyAsync(X, t.prefetch.U.p, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      lam = t.prefetch.lam;
+    } else {
+      ctx->eigh((int)na, X, na, w.p);            // X <- U
+      ctx->d2h(lam.data(), w.p, (size_t)na);
+    }
     for (long long i = 0; i < na; ++i) {
       if (lam[i] < etol) { ++removed; sc[i] = 0.0; } else sc[i] = 1.0 / std::sqrt(lam[i]);
     }
@@ -207,11 +227,11 @@ int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index l
     g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
     contract(g, ctx->ws, ctx->stream);
   };
-  ctx->h2d_2d(A.p, na, V_host, ldv, na, na);
+  if (S_host || !prefetched) ctx->h2d_2d(A.p, na, V_host, ldv, na, na);
   if (S_host) {
     Ssqrt.alloc((size_t)(na * na));
     DBuf S((size_t)(na * na));
-    ctx->h2d_2d(S.p, na, S_host, lds, na, na);
+    if (!prefetched) ctx->h2d_2d(S.p, na, S_host, lds, na, na);
     inv_sqrt(S.p, Ssqrt.p);
     // ortho = Ssqrt V Ssqrt  (all symmetric)
     mm(Ssqrt.p, true, A.p, Cc.p);
@@ -411,7 +431,7 @@ int xtpb_bse_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_bse_options* opt, con
                          nullptr};
   try {
     b->R = bse_setup_screening(b->impl, rpa_input_energies_host);
-    if (rotate_full_tc) {
+    if (rotate_full_tc && b->R) {
       tc->impl.rotate(b->R->p, tc->impl.naux);
       ctx->impl.sync();
       b->R.reset();
@@ -426,6 +446,11 @@ int xtpb_bse_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_bse_options* opt, con
 int xtpb_bse_destroy(xtpb_bse* bse) {
   XTPB_API_BEGIN
   delete bse;
+  XTPB_API_END
+}
+int xtpb_bse_screening_info(xtpb_bse* bse, int* eps0_reused) {
+  XTPB_API_BEGIN
+  if (eps0_reused) *eps0_reused = bse->impl.eps0_reused ? 1 : 0;
   XTPB_API_END
 }
 int xtpb_bse_get_epsilon_0_inv(xtpb_bse* bse, double* eps_inv_host) {
@@ -629,6 +654,18 @@ int xtpb_davidson_solve(xtpb_op* op, xtpb_index neigen, const xtpb_davidson_opti
   if (eigenvectors_host) A.ctx->d2h_2d(eigenvectors_host, ldv, res.evecs.p, A.size, A.size, neigen);
   if (info) *info = res.info;
   if (iterations) *iterations = res.iterations;
+  XTPB_API_END
+}
+
+int xtpb_host_eigh(xtpb_index n, double* A_host, xtpb_index lda, double* w_host) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(n >= 1 && lda >= n && A_host && w_host, "bad eigenproblem arguments");
+  std::vector<double> A((size_t)(n * n));
+  for (long long j = 0; j < n; ++j)
+    for (long long i = 0; i < n; ++i) A[i + j * n] = A_host[i + j * lda];
+  XTPB_REQUIRE(host_eigh((int)n, A.data(), w_host), "QL iteration did not converge");
+  for (long long j = 0; j < n; ++j)
+    for (long long i = 0; i < n; ++i) A_host[i + j * lda] = A[i + j * n];
   XTPB_API_END
 }
 

@@ -44,8 +44,9 @@ struct Error : std::runtime_error {
   }
 
 // Device memory for DBuf (core.cu).  Host seconds spent inside cudaMalloc / cudaFree are accumulated (bench.py reports
-// them per step: they are pure host/driver time between kernels).  With XTPB_ALLOC_CACHE=1 released blocks are kept
-// in an exact-size cache instead of going back to the driver: a step allocates the same sizes again and again
+// them per step: they are pure host/driver time between kernels).  Unless XTPB_ALLOC_CACHE=0, released blocks are kept
+// in an exact-size cache (capped by XTPB_ALLOC_CACHE_MAX_GB, default 64) instead of going back to the driver: a step
+// allocates the same sizes again and again
 // (scratch for rotations, epsilon, the BSE operands), so after the first step almost every allocation is a cache hit.
 // release() then performs the device-wide synchronisation cudaFree would have implied, so that stream-ordering
 // assumptions of the callers are unchanged; the cache is flushed when cudaMalloc runs out of memory.

@@ -4,17 +4,19 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <mutex>
 #include <vector>
 
 namespace xtpb {
 
-long long g_launch_count = 0;
-long long g_tma_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
+std::atomic<long long> g_tma_launch_count{0};
 
 // ------------------------------------------------------------------ event-pair profiler
 namespace {
 struct ProfRec { cudaEvent_t e0, e1; int tag; double work; };
 bool g_prof_on = false;
+std::mutex g_prof_mu;                  // the Coulomb-metric prefetch thread may launch while the main thread does
 std::vector<ProfRec> g_prof_pool;      // events are created once and reused after prof_reset()
 size_t g_prof_used = 0;
 constexpr size_t kProfCap = 1 << 17;
@@ -25,7 +27,9 @@ void prof_enable(bool on) { g_prof_on = on; }
 bool prof_enabled() { return g_prof_on; }
 void prof_reset() { g_prof_used = 0; }
 int prof_begin(int tag, double work, cudaStream_t s) {
-  if (!g_prof_on || g_prof_used >= kProfCap) return -1;
+  if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (g_prof_used >= kProfCap) return -1;
   if (g_prof_used == g_prof_pool.size()) {
     ProfRec r{};
     XTPB_CUDA(cudaEventCreate(&r.e0));
@@ -40,7 +44,12 @@ int prof_begin(int tag, double work, cudaStream_t s) {
 }
 void prof_end(int slot, cudaStream_t s) {
   if (slot < 0) return;
-  XTPB_CUDA(cudaEventRecord(g_prof_pool[(size_t)slot].e1, s));
+  cudaEvent_t e1;
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    e1 = g_prof_pool[(size_t)slot].e1;
+  }
+  XTPB_CUDA(cudaEventRecord(e1, s));
 }
 void prof_get(int tag, double* ms, double* work, long long* launches) {
   double tms = 0.0, tw = 0.0;

@@ -1,5 +1,7 @@
 // Host API of the contraction engine (see contract.cuh for the index model).
 #pragma once
+#include <atomic>
+
 #include "common.h"
 #include "contract.cuh"
 
@@ -23,8 +25,8 @@ void symmetrize_from_lower(double* C, int n, long long ld, double diag_add, cuda
 inline GemmOperand op_rows_contig(const double* p, long long ld) { return GemmOperand{p, 1, ld, 0, 0}; }   // A(row,k)=p[row+k*ld]
 inline GemmOperand op_k_contig(const double* p, long long ld) { return GemmOperand{p, ld, 1, 0, 0}; }      // A(row,k)=p[k+row*ld]
 
-extern long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
-extern long long g_tma_launch_count;   // of which contraction launches on the TMA instance
+extern std::atomic<long long> g_launch_count;       // kernels launched by this library (bench.py's gpu_launches)
+extern std::atomic<long long> g_tma_launch_count;   // of which contraction launches on the TMA instance
 
 // ---- in-library kernel timing (bench.py's roofline object): CUDA-event pairs on the launching stream around
 // every launch of a tagged kernel family; summed per tag.  Off by default (no events recorded).

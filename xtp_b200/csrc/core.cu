@@ -25,9 +25,17 @@ std::pair<int, size_t> cache_key(size_t bytes) {
 }
 double g_cached_bytes = 0.0, g_alloc_seconds = 0.0;
 long long g_alloc_calls = 0, g_cache_hits = 0;
+// on unless XTPB_ALLOC_CACHE=0; at most XTPB_ALLOC_CACHE_MAX_GB (default 64) are kept
 bool alloc_cache_on() {
-  static const bool on = [] { const char* e = getenv("XTPB_ALLOC_CACHE"); return e && e[0] == '1'; }();
+  static const bool on = [] { const char* e = getenv("XTPB_ALLOC_CACHE"); return !(e && e[0] == '0'); }();
   return on;
+}
+double alloc_cache_cap_bytes() {
+  static const double cap = [] {
+    const char* e = getenv("XTPB_ALLOC_CACHE_MAX_GB");
+    return (e ? atof(e) : 64.0) * 1e9;
+  }();
+  return cap;
 }
 double seconds_since(std::chrono::steady_clock::time_point t0) {
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -73,7 +81,7 @@ void device_free(void* p, size_t bytes) {
   if (!p) return;
   const auto t0 = std::chrono::steady_clock::now();
   std::lock_guard<std::mutex> lock(g_alloc_mu);
-  if (alloc_cache_on()) {
+  if (alloc_cache_on() && g_cached_bytes + (double)bytes <= alloc_cache_cap_bytes()) {
     cudaDeviceSynchronize();                    // what cudaFree implies: nothing in flight may still use the block
     g_block_cache.emplace(cache_key(bytes), p);
     g_cached_bytes += (double)bytes;
@@ -124,6 +132,10 @@ Context::Context(int dev) : device(dev) {
 
 Context::~Context() {
   comm_destroy();
+  if (side_solver) cusolverDnDestroy(side_solver);
+  if (side_info) cudaFree(side_info);
+  if (side_stream) cudaStreamDestroy(side_stream);
+  side_work.release();
   solver_work.release();
   scratch_a.release();
   scratch_b.release();

@@ -120,6 +120,12 @@ void GW::prepare_ppm() {
   ctx->h2d(ppm_freq_dev.p, ppm_freq.data(), (size_t)na);
   ctx->h2d(ppm_fac_dev.p, fac.data(), (size_t)na);
   tc->rotate(phi, na);
+  // the tensor now lives in the eigenbasis of eps(0) at these energies (see TCMatrix::Eps0Basis)
+  tc->eps0.valid = true;
+  tc->eps0.energies = rpa_energies;
+  tc->eps0.lambda = lambda;
+  tc->eps0.eta = opt.eta;
+  tc->eps0.n_occ = n_occ;
   ctx->sync();
 }
 

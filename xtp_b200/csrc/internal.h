@@ -2,8 +2,10 @@
 #pragma once
 #include <cusolverDn.h>
 
+#include <exception>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/xtpb200/xtpb200.h"
@@ -30,6 +32,11 @@ struct Context {
   cudaStream_t comm_stream = nullptr;
   double comm_seconds = 0.0;    // not timed per call; collectives are stream-ordered
 
+  // helper-thread resources of TCMatrix::metric_prefetch_begin (created on first use)
+  cudaStream_t side_stream = nullptr;
+  cusolverDnHandle_t side_solver = nullptr;
+  DBuf side_work;
+  int* side_info = nullptr;
   explicit Context(int dev);
   ~Context();
   void sync() { XTPB_CUDA(cudaStreamSynchronize(stream)); }
@@ -60,6 +67,9 @@ struct Context {
   void allgather(const double* send, double* recv, size_t count_per_rank, cudaStream_t st = nullptr);
 };
 void comm_unique_id(char* out_128);
+// hostlinalg.cu: symmetric eigenproblem on the host (A: n x n col-major, lower triangle read; A <- eigenvectors,
+// w ascending).  false = QL iteration did not converge.
+bool host_eigh(int n, double* A, double* w);
 
 // ---------------------------------------------------------------- small kernels (kernels.cu)
 void k_chi0_weights(double* d, const double* e_m, const double* e_n, int n_occ, int n_occ_n, int a0, int K,
@@ -180,6 +190,29 @@ struct TCMatrix {
   bool pending = false;
   void set_pending(const double* R_dev, long long ldr);
   void flush();
+  // After the PPM rotation (Sigma_PPM::PrepareScreening) the aux basis of the tensor IS the eigenbasis of eps(0) for
+  // the RPA input energies of that call: eps(0) = diag(lambda).  G0W0 hands the same energies to
+  // BSE::SetupDirectInteractionOperator, whose eps(0) + eigensolver + rotation then reduce to reading lambda
+  // (bse_setup_screening).  Cleared by anything that changes the tensor's aux basis or contents.
+  struct Eps0Basis {
+    bool valid = false;
+    std::vector<double> energies, lambda;
+    double eta = 0.0;
+    long long n_occ = 0;
+  } eps0;
+  // First eigendecomposition of the Coulomb-metric step (of the aux overlap if one is given, else of the Coulomb
+  // matrix), started on a helper thread with its own stream and cuSOLVER handle BEFORE Fill3cMO so that the two
+  // overlap: their inputs are independent.  xtpb_tc_apply_coulomb_metric joins it.
+  struct MetricPrefetch {
+    std::thread th;
+    std::exception_ptr err;
+    DBuf U, w;
+    std::vector<double> lam;
+    bool active = false, of_overlap = false;
+    const double* src = nullptr;
+  } prefetch;
+  void metric_prefetch_begin(const double* X_host, long long ldx, bool of_overlap);
+  bool metric_prefetch_join();      // true when a prefetched decomposition is available in prefetch.U / lam
   // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]   (window rotation into a caller-owned buffer)
   void rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
                      const double* R_dev, long long ldr);
@@ -264,6 +297,7 @@ struct BSE {
   long long vt, ct, size, naux;
   std::vector<double> hqp;          // (vt+ct)^2 host, col-major
   std::vector<double> eps_inv;      // host
+  bool eps0_reused = false;         // eps(0) eigenvalues taken from the PPM rotation instead of being recomputed
   BSE(Context* c, TCMatrix* t, const xtpb_bse_options& o, const double* rpa_e, const double* hqp_in, long long ldh,
       bool rotate_full);
 };

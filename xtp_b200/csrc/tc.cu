@@ -22,6 +22,7 @@ TCMatrix::TCMatrix(Context* c, long long auxsize, long long mmin_, long long mma
 }
 
 TCMatrix::~TCMatrix() {
+  if (prefetch.th.joinable()) prefetch.th.join();
   for (int b = 0; b < 2; ++b) {
     if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
     if (ev_consumed[b]) cudaEventDestroy(ev_consumed[b]);
@@ -31,6 +32,7 @@ TCMatrix::~TCMatrix() {
 
 void TCMatrix::set_raw(const double* host) {
   pending = false;
+  eps0.valid = false;
   if (world == 1) {
     ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
     ctx->sync();
@@ -70,6 +72,7 @@ const double* TCMatrix::local_energies(const double* e_glob_dev, DBuf& tmp) {
 void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host) {
   XTPB_REQUIRE(nb > 0 && ldc_host >= nb, "bad MO coefficient matrix");
   pending = false;            // a new fill starts from the un-rotated tensor
+  eps0.valid = false;
   n_basis = nb;
   ldc = round_up(nb, 2);
   Cm.alloc((size_t)(ldc * mtotal));
@@ -315,9 +318,68 @@ void TCMatrix::rotate_window(double* dst, long long dst_ld, long long dst_slab, 
   }
 }
 
+// Coulomb-metric prefetch: A <- eigenvectors, w <- eigenvalues of the n_aux x n_aux host matrix, on a helper thread
+// with its own high-priority stream and cuSOLVER handle, so that the dense eigensolver (latency-bound, ~0.2 s at
+// N_aux 5500, replicated on every rank) runs underneath Fill3cMO instead of after it.
+void TCMatrix::metric_prefetch_begin(const double* X_host, long long ldx, bool of_overlap) {
+  XTPB_REQUIRE(X_host && ldx >= naux, "bad matrix for the Coulomb-metric prefetch");
+  if (prefetch.th.joinable()) prefetch.th.join();
+  prefetch.err = nullptr;
+  prefetch.active = true;
+  prefetch.of_overlap = of_overlap;
+  prefetch.src = X_host;
+  prefetch.U.ensure((size_t)(naux * naux));
+  prefetch.w.ensure((size_t)naux);
+  prefetch.lam.assign((size_t)naux, 0.0);
+  Context* c = ctx;
+  if (!c->side_stream) {
+    int lo = 0, hi = 0;
+    XTPB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    XTPB_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));
+    if (cusolverDnCreate(&c->side_solver) != CUSOLVER_STATUS_SUCCESS) throw Error("xtpb: cusolverDnCreate failed");
+    cusolverDnSetStream(c->side_solver, c->side_stream);
+    XTPB_CUDA(cudaMalloc(&c->side_info, sizeof(int)));
+  }
+  int lwork = 0;
+  if (cusolverDnDsyevd_bufferSize(c->side_solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)naux,
+                                  prefetch.U.p, (int)naux, prefetch.w.p, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    throw Error("xtpb: cusolverDnDsyevd_bufferSize failed");
+  c->side_work.ensure((size_t)lwork);
+  c->sync();      // buffers above may come out of the block cache: nothing on the main stream still uses them
+  const long long na = naux;
+  prefetch.th = std::thread([this, c, X_host, ldx, na, lwork] {
+    try {
+      XTPB_CUDA(cudaSetDevice(c->device));
+      XTPB_CUDA(cudaMemcpy2DAsync(prefetch.U.p, na * 8, X_host, ldx * 8, na * 8, na, cudaMemcpyHostToDevice,
+                                  c->side_stream));
+      const cusolverStatus_t st =
+          cusolverDnDsyevd(c->side_solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)na, prefetch.U.p,
+                           (int)na, prefetch.w.p, c->side_work.p, lwork, c->side_info);
+      if (st != CUSOLVER_STATUS_SUCCESS) throw Error("xtpb: cusolverDnDsyevd failed in the Coulomb-metric prefetch");
+      int info = 0;
+      XTPB_CUDA(cudaMemcpyAsync(prefetch.lam.data(), prefetch.w.p, (size_t)na * 8, cudaMemcpyDeviceToHost,
+                                c->side_stream));
+      XTPB_CUDA(cudaMemcpyAsync(&info, c->side_info, sizeof(int), cudaMemcpyDeviceToHost, c->side_stream));
+      XTPB_CUDA(cudaStreamSynchronize(c->side_stream));
+      if (info != 0) throw Error("xtpb: cuSOLVER devInfo " + std::to_string(info) + " in the Coulomb-metric prefetch");
+    } catch (...) {
+      prefetch.err = std::current_exception();
+    }
+  });
+}
+
+bool TCMatrix::metric_prefetch_join() {
+  if (!prefetch.active) return false;
+  if (prefetch.th.joinable()) prefetch.th.join();
+  prefetch.active = false;
+  if (prefetch.err) std::rethrow_exception(prefetch.err);
+  return true;
+}
+
 // MultiplyRightWithAuxMatrix: out of place through a bounded scratch of `chunk` slabs, copied back.
 void TCMatrix::set_pending(const double* R_dev, long long ldr) {
   flush();
+  eps0.valid = false;
   static const bool lazy = [] { const char* e = getenv("XTPB_LAZY_METRIC"); return !(e && e[0] == '0'); }();
   if (!lazy) {
     rotate(R_dev, ldr);
@@ -335,6 +397,7 @@ void TCMatrix::flush() {
 }
 
 void TCMatrix::rotate(const double* R_dev, long long ldr) {
+  eps0.valid = false;         // the caller re-validates when R is an eps(0) eigenbasis (GW::prepare_ppm)
   DBuf folded;
   if (pending) {      // M <- M (Rp R): fold the deferred factor into this rotation
     pending = false;
