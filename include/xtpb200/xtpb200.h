@@ -268,6 +268,12 @@ void xtpb_davidson_options_default(xtpb_davidson_options* opt);
 int xtpb_davidson_solve(xtpb_op* op, xtpb_index neigen, const xtpb_davidson_options* opt, double* eigenvalues_host,
                         double* eigenvectors_host, xtpb_index ldv, int* info, xtpb_index* iterations);
 
+/* Anderson::UpdateInput / UpdateOutput / MixHistory (upstream xtp/src/libxtp/anderson_mixing.cc), the mixer
+ * GW::CalculateGWPerturbation applies to the evGW iterates when gw_mixing_order > 0 (1 = linear mixing): feeds
+ * n_history (input, output) pairs of length n, oldest first (row h at inputs_host + h*n), through a mixer of the
+ * given order and returns the next guess.  Host-only, needs no device. */
+int xtpb_anderson_mix(xtpb_index order, double alpha, xtpb_index n, xtpb_index n_history, const double* inputs_host,
+                      const double* outputs_host, double* mixed_host);
 /* The dense symmetric eigensolver the Davidson solvers apply to their projected matrices (upstream:
  * Eigen::SelfAdjointEigenSolver inside DavidsonSolver::getRitz, davidsonsolver.cc): Householder tridiagonalisation +
  * implicit QL on the host.  A_host (n x n, ld = lda, lower triangle read) is overwritten by the eigenvectors,

@@ -511,6 +511,42 @@ class Sigma_CDA(Sigma_base):
 
 
 # --------------------------------------------------------------------------
+# a-8  Anderson mixing            (upstream xtp/src/libxtp/anderson_mixing.cc)
+# --------------------------------------------------------------------------
+class Anderson:
+    """History of the last ``order`` (input, output) pairs of the evGW map; ``MixHistory`` returns
+    alpha * Out + (1 - alpha) * In where Out/In are the history combinations that minimise the residual
+    |Out - In| (least squares over the affine span), order 1 == linear mixing."""
+
+    def __init__(self, order, alpha):
+        self.order, self.alpha = int(order), float(alpha)
+        self.input, self.output = [], []
+
+    def UpdateInput(self, x):
+        if len(self.input) > self.order - 1:
+            self.input.pop(0)
+        self.input.append(np.array(x, dtype=np.float64))
+
+    def UpdateOutput(self, x):
+        if len(self.output) > self.order - 1:
+            self.output.pop(0)
+        self.output.append(np.array(x, dtype=np.float64))
+
+    def MixHistory(self):
+        it = len(self.output)
+        used = it - 1
+        out, inp = self.output[-1].copy(), self.input[-1].copy()
+        if it > 1 and self.order > 1:
+            dN = out - inp
+            D = np.array([dN - self.output[used - m] + self.input[used - m] for m in range(1, it)])
+            coef = np.linalg.lstsq(D @ D.T, D @ dN, rcond=1e-12)[0]
+            for k in range(1, it):
+                out += coef[k - 1] * (self.output[used - k] - self.output[used])
+                inp += coef[k - 1] * (self.input[used - k] - self.input[used])
+        return self.alpha * out + (1.0 - self.alpha) * inp
+
+
+# --------------------------------------------------------------------------
 # a-8  GW                                    (upstream xtp/src/libxtp/gwbse/gw.cc)
 # --------------------------------------------------------------------------
 @dataclasses.dataclass
@@ -660,18 +696,20 @@ class GW:
         shifted = self.ScissorShift_DFTlevel(self.dft_energies)
         self.rpa.setRPAInputEnergies(shifted[o.rpamin:o.rpamax + 1])
         freqs = shifted[o.qpmin:o.qpmin + self.qptotal].copy()
+        mixing = Anderson(o.gw_mixing_order, o.gw_mixing_alpha) if o.gw_mixing_order > 0 else None
         for i_gw in range(o.gw_sc_max_iterations):
             if i_gw % o.reset_3c == 0 and i_gw != 0:
                 self.Mmn.Rebuild()
             self.sigma.PrepareScreening()
+            if mixing is not None and o.gw_sc_max_iterations > 1:
+                mixing.UpdateInput(freqs)
             freqs = self.SolveQP(freqs)
             if o.gw_sc_max_iterations > 1:
                 old = self.rpa.getRPAInputEnergies().copy()
+                if mixing is not None:      # order 1: linear mixing, > 1: Anderson (upstream anderson_mixing.cc)
+                    mixing.UpdateOutput(freqs)
+                    freqs = mixing.MixHistory()
                 self.rpa.UpdateRPAInputEnergies(self.dft_energies, freqs, o.qpmin)
-                if o.gw_mixing_order > 0 and i_gw > 0:
-                    mixed = o.gw_mixing_alpha * self.rpa.getRPAInputEnergies() + (1 - o.gw_mixing_alpha) * old
-                    self.rpa.setRPAInputEnergies(mixed)
-                    freqs = mixed[o.qpmin - o.rpamin:o.qpmin - o.rpamin + self.qptotal].copy()
                 diff = np.abs(old - self.rpa.getRPAInputEnergies())
                 if diff[o.qpmin - o.rpamin:o.qpmin - o.rpamin + self.qptotal].max() < o.gw_sc_limit:
                     break

@@ -95,3 +95,42 @@ def test_host_eigh_matches_numpy():
         np.testing.assert_allclose(U.T @ U, np.eye(n), atol=1e-13 * n)
         np.testing.assert_allclose(U @ np.diag(w) @ U.T, A, rtol=0, atol=1e-13 * scale * n)
         assert np.all(np.diff(w) >= 0)
+
+
+def test_anderson_mixing_matches_oracle():
+    """Anderson mixer of the evGW loop (host code): every order / history length against the oracle's least-squares
+    restatement, including a rank-deficient history (two identical residual differences) and the order-1 linear mix."""
+    import numpy as np
+    from oracle import gwbse_oracle as orc
+    from xtp_b200 import _lib
+    lib = _lib.lib()
+    rng = np.random.default_rng(3)
+    n = 17
+    for order in (1, 2, 3, 6):
+        for nh in (1, 2, 3, 5, 8):
+            ins = rng.standard_normal((nh, n))
+            outs = ins + 0.1 * rng.standard_normal((nh, n))
+            if nh >= 3:
+                outs[1] = ins[1] + (outs[0] - ins[0])            # duplicate residual: singular normal equations
+            ref = orc.Anderson(order, 0.6)
+            for a, b in zip(ins, outs):
+                ref.UpdateInput(a)
+                ref.UpdateOutput(b)
+            want = ref.MixHistory()
+            got = np.empty(n)
+            _lib.check(lib.xtpb_anderson_mix(order, 0.6, n, nh, ins.ctypes.data_as(_lib.dptr),
+                                             outs.ctypes.data_as(_lib.dptr), got.ctypes.data_as(_lib.dptr)))
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+            if order == 1:
+                np.testing.assert_allclose(got, 0.6 * outs[-1] + 0.4 * ins[-1], rtol=0, atol=1e-14)
+    # a linear fixed-point map x -> A x + b is solved exactly once the history spans the space
+    A = 0.5 * np.linalg.qr(rng.standard_normal((4, 4)))[0]
+    b = rng.standard_normal(4)
+    fixed = np.linalg.solve(np.eye(4) - A, b)
+    mix = orc.Anderson(6, 1.0)
+    x = np.zeros(4)
+    for _ in range(6):
+        mix.UpdateInput(x)
+        mix.UpdateOutput(A @ x + b)
+        x = mix.MixHistory()
+    np.testing.assert_allclose(x, fixed, atol=1e-9)

@@ -332,8 +332,11 @@ def test_g0w0_qp_energies(ctx, prob, solver):
     np.testing.assert_allclose(wq, gwo.DiagonalizeQPHamiltonian()[0], rtol=0, atol=1e-6)
 
 
-def test_evgw(ctx, prob):
-    gw, gwo, _, _ = _gw_pair(ctx, prob, gw_sc_max_iterations=4, qp_grid_steps=201)
+@pytest.mark.parametrize("mixing_order", [0, 1, 3])
+def test_evgw(ctx, prob, mixing_order):
+    """evGW iterates: plain update, linear mixing and Anderson mixing (upstream anderson_mixing.cc)."""
+    gw, gwo, _, _ = _gw_pair(ctx, prob, gw_sc_max_iterations=5, qp_grid_steps=201, gw_mixing_order=mixing_order,
+                             gw_mixing_alpha=0.7)
     gw.CalculateGWPerturbation()
     gwo.Mmn._fill_args = (prob["ao3c"], prob["C"], prob["aux_coulomb"], None, 5e-7)
     gwo.CalculateGWPerturbation()
@@ -521,7 +524,7 @@ def test_gwbse_driver_evaluate(ctx, ranges):
     # explicit-low: vmin < qpmin AND cmax < qpmax (only part of the QP block lies inside the BSE window -- the case the
     # round-1 AdjustHqpSize wrote out of bounds for); explicit-high: vmin > qpmin and cmax > qpmax
     kw = {"default": {}, "explicit": dict(rpamax=sz.n_basis - 1, qpmin=1, qpmax=8, bsemin=0, bsemax=10),
-          "explicit-low": dict(rpamax=sz.n_basis - 1, qpmin=2, qpmax=10, bsemin=0, bsemax=7),
+          "explicit-low": dict(rpamax=sz.n_basis - 1, qpmin=2, qpmax=9, bsemin=0, bsemax=7),
           "explicit-high": dict(rpamax=sz.n_basis - 1, qpmin=0, qpmax=7, bsemin=2, bsemax=11)}[ranges]
     ranges = ranges.split("-")[0]
     drv = api.GWBSE(ctx).Initialize(sz.n_basis, sz.homo + 1, ranges=ranges, tasks=("gw", "singlets", "triplets"), nmax=3,

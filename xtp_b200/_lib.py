@@ -139,6 +139,7 @@ PROTOTYPES = {
     "xtpb_op_get_full_matrix": (C.c_int, [vp, dptr, idx]),
     "xtpb_davidson_options_default": (None, [C.POINTER(DavidsonOptions)]),
     "xtpb_davidson_solve": (C.c_int, [vp, idx, C.POINTER(DavidsonOptions), dptr, dptr, idx, C.POINTER(C.c_int), iptr]),
+    "xtpb_anderson_mix": (C.c_int, [idx, C.c_double, idx, idx, dptr, dptr, dptr]),
     "xtpb_host_eigh": (C.c_int, [idx, dptr, idx, dptr]),
     "xtpb_contract_host": (C.c_int, [vp, C.POINTER(ContractDesc), dptr, dptr, dptr, dptr]),
     "xtpb_contract_bench": (C.c_int, [vp, C.POINTER(ContractDesc), C.c_int, dptr]),

@@ -785,7 +785,7 @@ void btda_solve(Operator& A, Operator& B, long long neigen, const xtpb_davidson_
   ProfScope prof(PROF_DAVIDSON);
   const long long n = A.size;
   XTPB_REQUIRE(B.size == n, "A and B operators differ in size");
-  XTPB_REQUIRE(neigen >= 1 && 2 * neigen <= n, "neigen out of range");
+  XTPB_REQUIRE(neigen >= 1 && neigen <= n, "neigen out of range");
   const int k = (int)neigen;
   long long max_space = opt.max_search_space;
   if (max_space < 4 * neigen) max_space = 10 * neigen;

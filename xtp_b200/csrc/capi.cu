@@ -657,6 +657,20 @@ int xtpb_davidson_solve(xtpb_op* op, xtpb_index neigen, const xtpb_davidson_opti
   XTPB_API_END
 }
 
+int xtpb_anderson_mix(xtpb_index order, double alpha, xtpb_index n, xtpb_index n_history, const double* inputs_host,
+                      const double* outputs_host, double* mixed_host) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(n >= 1 && n_history >= 1 && inputs_host && outputs_host && mixed_host, "bad Anderson arguments");
+  Anderson a;
+  a.configure((int)order, alpha);
+  for (long long h = 0; h < n_history; ++h) {
+    a.update_input(std::vector<double>(inputs_host + h * n, inputs_host + (h + 1) * n));
+    a.update_output(std::vector<double>(outputs_host + h * n, outputs_host + (h + 1) * n));
+  }
+  const std::vector<double> x = a.mix_history();
+  std::memcpy(mixed_host, x.data(), (size_t)n * 8);
+  XTPB_API_END
+}
 int xtpb_host_eigh(xtpb_index n, double* A_host, xtpb_index lda, double* w_host) {
   XTPB_API_BEGIN
   XTPB_REQUIRE(n >= 1 && lda >= n && A_host && w_host, "bad eigenproblem arguments");

@@ -455,19 +455,26 @@ void GW::calculate_gw_perturbation() {
     backup.alloc(tc->M.n);
     XTPB_CUDA(cudaMemcpyAsync(backup.p, tc->M.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  // GW::CalculateGWPerturbation's mixing of the evGW iterates: gw_mixing_order 0 = plain update, 1 = linear mixing
+  // with gw_mixing_alpha, > 1 = Anderson mixing over that many iterations (anderson_mixing.cc); the QP-window energies
+  // are mixed, the levels outside follow through UpdateRPAInputEnergies' rigid gap shift
+  Anderson mixing;
+  if (opt.gw_mixing_order > 0) mixing.configure((int)opt.gw_mixing_order, opt.gw_mixing_alpha);
   for (long long i_gw = 0; i_gw < opt.gw_sc_max_iterations; ++i_gw) {
-    if (i_gw % opt.reset_3c == 0 && i_gw != 0)
+    if (i_gw % opt.reset_3c == 0 && i_gw != 0) {
       XTPB_CUDA(cudaMemcpyAsync(tc->M.p, backup.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      tc->eps0.valid = false;
+    }
     if (!(screening_done && i_gw == 0)) prepare_screening();
+    if (evgw && opt.gw_mixing_order > 0) mixing.update_input(freqs);
     freqs = solve_qp(freqs);
     if (evgw) {
       const std::vector<double> old = rpa_energies;
-      std::vector<double> upd = update_rpa_energies(dft_energies, freqs, opt);
-      if (opt.gw_mixing_order > 0 && i_gw > 0) {
-        for (size_t i = 0; i < upd.size(); ++i)
-          upd[i] = opt.gw_mixing_alpha * upd[i] + (1.0 - opt.gw_mixing_alpha) * old[i];
-        for (long long l = 0; l < q; ++l) freqs[l] = upd[opt.qpmin - opt.rpamin + l];
+      if (opt.gw_mixing_order > 0) {
+        mixing.update_output(freqs);
+        freqs = mixing.mix_history();
       }
+      std::vector<double> upd = update_rpa_energies(dft_energies, freqs, opt);
       set_rpa_energies(upd.data());
       double diff = 0.0;
       for (long long l = 0; l < q; ++l)

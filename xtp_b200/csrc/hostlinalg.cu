@@ -185,3 +185,75 @@ bool host_eigh(int n, double* A, double* w) {
 }
 
 }  // namespace xtpb
+
+// ---------------------------------------------------------------------------------------------------------------
+// Anderson mixing of the evGW quasiparticle energies (upstream xtp/src/libxtp/anderson_mixing.cc, used by
+// GW::CalculateGWPerturbation when gw_mixing_order > 1).  History of the last `order` input / output vectors; the new
+// guess minimises |sum_j c_j (out_j - in_j)| over the affine combinations of the history and is then damped:
+//   x = alpha * Out_mixed + (1 - alpha) * In_mixed.
+// order 1 degenerates to linear mixing of the last pair.
+namespace xtpb {
+
+void Anderson::configure(int order, double alpha) {
+  XTPB_REQUIRE(order >= 1 && alpha > 0.0 && alpha <= 1.0, "Anderson mixing needs order >= 1 and 0 < alpha <= 1");
+  order_ = order;
+  alpha_ = alpha;
+  input_.clear();
+  output_.clear();
+}
+void Anderson::update_input(const std::vector<double>& x) {
+  if ((int)input_.size() > order_ - 1) input_.erase(input_.begin());
+  input_.push_back(x);
+}
+void Anderson::update_output(const std::vector<double>& x) {
+  if ((int)output_.size() > order_ - 1) output_.erase(output_.begin());
+  output_.push_back(x);
+}
+
+// minimum-norm least-squares solution of the symmetric positive semi-definite h x h system A c = b through the
+// eigendecomposition A = U diag(l) U^T: c = sum_i u_i (u_i . b) / l_i over l_i > 1e-12 l_max.  (Upstream solves with
+// Eigen's fullPivHouseholderQr; for a full-rank history the two agree, for a rank-deficient one -- repeated residuals
+// -- the minimum-norm choice is the reproducible one.)
+static std::vector<double> solve_psd_min_norm(int h, std::vector<double> A, const std::vector<double>& b) {
+  std::vector<double> lam((size_t)h), c((size_t)h, 0.0);
+  XTPB_REQUIRE(host_eigh(h, A.data(), lam.data()), "Anderson mixing: eigensolver did not converge");
+  const double lmax = std::max(std::fabs(lam.front()), std::fabs(lam.back()));
+  for (int i = 0; i < h; ++i) {
+    if (!(lam[i] > 1e-12 * lmax)) continue;
+    double ub = 0.0;
+    for (int k = 0; k < h; ++k) ub += A[(size_t)k + (size_t)i * h] * b[k];
+    for (int k = 0; k < h; ++k) c[k] += A[(size_t)k + (size_t)i * h] * ub / lam[i];
+  }
+  return c;
+}
+
+std::vector<double> Anderson::mix_history() const {
+  XTPB_REQUIRE(!output_.empty() && output_.size() == input_.size(), "Anderson mixing: input/output history out of step");
+  const int iteration = (int)output_.size(), used = iteration - 1;
+  std::vector<double> out = output_.back(), in = input_.back();
+  const size_t n = out.size();
+  if (iteration > 1 && order_ > 1) {
+    std::vector<double> dN(n);
+    for (size_t i = 0; i < n; ++i) dN[i] = out[i] - in[i];
+    // D_m = DeltaN - (out_{used-m} - in_{used-m}), m = 1 .. used
+    std::vector<std::vector<double>> D((size_t)used, std::vector<double>(n));
+    for (int m = 1; m <= used; ++m)
+      for (size_t i = 0; i < n; ++i) D[m - 1][i] = dN[i] - output_[used - m][i] + input_[used - m][i];
+    std::vector<double> A((size_t)used * used), c((size_t)used);
+    for (int m = 0; m < used; ++m) {
+      c[m] = std::inner_product(D[m].begin(), D[m].end(), dN.begin(), 0.0);
+      for (int j = 0; j < used; ++j) A[(size_t)m + (size_t)j * used] = std::inner_product(D[m].begin(), D[m].end(), D[j].begin(), 0.0);
+    }
+    const std::vector<double> coef = solve_psd_min_norm(used, A, c);
+    for (int k = 1; k <= used; ++k)
+      for (size_t i = 0; i < n; ++i) {
+        out[i] += coef[k - 1] * (output_[used - k][i] - output_[used][i]);
+        in[i] += coef[k - 1] * (input_[used - k][i] - input_[used][i]);
+      }
+  }
+  std::vector<double> x(n);
+  for (size_t i = 0; i < n; ++i) x[i] = alpha_ * out[i] + (1.0 - alpha_) * in[i];
+  return x;
+}
+
+}  // namespace xtpb

@@ -70,6 +70,18 @@ void comm_unique_id(char* out_128);
 // hostlinalg.cu: symmetric eigenproblem on the host (A: n x n col-major, lower triangle read; A <- eigenvectors,
 // w ascending).  false = QL iteration did not converge.
 bool host_eigh(int n, double* A, double* w);
+// hostlinalg.cu: Anderson mixing (upstream xtp/src/libxtp/anderson_mixing.cc)
+class Anderson {
+ public:
+  void configure(int order, double alpha);
+  void update_input(const std::vector<double>& x);
+  void update_output(const std::vector<double>& x);
+  std::vector<double> mix_history() const;
+ private:
+  int order_ = 1;
+  double alpha_ = 0.7;
+  std::vector<std::vector<double>> input_, output_;
+};
 
 // ---------------------------------------------------------------- small kernels (kernels.cu)
 void k_chi0_weights(double* d, const double* e_m, const double* e_n, int n_occ, int n_occ_n, int a0, int K,
