@@ -199,6 +199,12 @@ int xtpb_gw_grid_scan_info(xtpb_gw* gw, int* compressed, xtpb_index* n_bins, dou
 int xtpb_ppm_grid_plan(xtpb_index n_levels, const double* grid_start, double spacing, xtpb_index steps, double zmin,
                        double zmax, xtpb_index edges_capacity, double* edges, xtpb_index* n_bins, int* near_ranges,
                        xtpb_index* n_chunks, int* usable);
+/* GW::PlotSigma(filename, steps, spacing, states): for every listed gw level (0 = qpmin) the correlation self-energy
+ * on `steps` frequencies centred on the level's RPA input energy, as the steps x (2 n_states) column-major table
+ * upstream writes to the file: column 2i = frequency, column 2i+1 = Sigma_c(w) + e_KS + Sigma_x - Vxc (the curve
+ * whose intersection with w is the quasiparticle energy).  Needs PrepareScreening and Sigma_x (CalculateGWPerturbation). */
+int xtpb_gw_plot_sigma(xtpb_gw* gw, xtpb_index steps, double spacing, xtpb_index n_states,
+                       const xtpb_index* states_host, double* table_host);
 /* Sigma_base::CalcCorrelationOffDiag(frequencies): qptotal x qptotal, zero diagonal */
 int xtpb_gw_sigma_c_offdiag(xtpb_gw* gw, const double* frequencies_host, double* sigma_c_host);
 /* GW::CalculateGWPerturbation / CalculateHQP / getGWAResults / getHQP / DiagonalizeQPHamiltonian */
@@ -287,6 +293,15 @@ int xtpb_host_eigh(xtpb_index n, double* A_host, xtpb_index lda, double* w_host)
  * xtpb_davidson_options as for the TDA solver (tolerance on both residuals, iter_max, max_search_space). */
 int xtpb_bse_solve_btda(xtpb_bse* bse, int singlet, const xtpb_davidson_options* opt, double* energies_host,
                         double* X_host, double* Y_host, xtpb_index ld, int* info, xtpb_index* iterations);
+/* BSE::Perturbative_DynamicalScreening(type, orb): first-order correction of BSE energies for the frequency
+ * dependence of the screening in the direct term.  Per state s: E <- E_static + <s|Hd^(w = E)|s> - <s|Hd^(0)|s> with
+ * Hd^ = HdOperator built from epsilon(w) on the real axis (SetupDirectInteractionOperator at w), repeated until
+ * |dE| < dyn_tolerance or max_dyn_iter (upstream defaults 10 and 1e-5 Ha).  X (and Y for the full BSE, else NULL):
+ * size x n_states eigenvectors as returned by the solvers.  iterations_host may be NULL. */
+int xtpb_bse_perturbative_dynamical_screening(xtpb_bse* bse, xtpb_index n_states, const double* energies_static_host,
+                                              const double* X_host, const double* Y_host, xtpb_index ld,
+                                              xtpb_index max_dyn_iter, double dyn_tolerance,
+                                              double* energies_dynamic_host, xtpb_index* iterations_host);
 /* BSE::CalcCoupledTransition_Dipoles (+ Orbitals::CalcFreeTransition_Dips): d_s = -sqrt(2) sum_vc (X+Y)_vc,s <v|r|c>
  * from the three AO dipole matrices (3 x n_basis x n_basis, symmetric) and the MO coefficients.  Y may be NULL (TDA).
  * dipoles_host: n_states x 3, state-major. */

@@ -716,6 +716,20 @@ class GW:
         self.Sigma_c[np.diag_indices(self.qptotal)] = self.sigma.CalcCorrelationDiag(freqs)
         return freqs
 
+    def PlotSigma(self, steps, spacing, states):
+        """Upstream ``GW::PlotSigma``: (steps, 2*len(states)) table of (frequency, Sigma_c + intercept)."""
+        o = self.opt
+        freqs = self.rpa.getRPAInputEnergies()[o.qpmin - o.rpamin:o.qpmin - o.rpamin + self.qptotal]
+        intercept = (self.dft_energies[o.qpmin:o.qpmin + self.qptotal] + np.diag(self.Sigma_x) - np.diag(self.vxc))
+        mat = np.zeros((steps, 2 * len(states)))
+        for gp in range(steps):
+            offset = (gp - (steps - 1) / 2.0) * spacing
+            for i, l in enumerate(states):
+                w = freqs[l] + offset
+                mat[gp, 2 * i] = w
+                mat[gp, 2 * i + 1] = self.sigma.CalcCorrelationDiagElement(l, w) + intercept[l]
+        return mat
+
     def CalculateHQP(self):
         diag = np.diag(self.Sigma_c).copy()
         self.Sigma_c = self.sigma.CalcCorrelationOffDiag(self.getGWAResults())
@@ -1079,6 +1093,38 @@ class BSE:
 
     def Solve_triplets_BTDA(self):
         return self.solve_btda_dense(False)
+
+    def Perturbative_DynamicalScreening(self, RPAInputEnergies, energies, X, Y=None, max_dyn_iter=10,
+                                        dyn_tolerance=1e-5):
+        """Upstream ``BSE::Perturbative_DynamicalScreening``: per state
+        E <- E_static + <s|Hd^(w = E)|s> - <s|Hd^(0)|s>, Hd^ = HdOperator (= -Hd) rebuilt by
+        ``SetupDirectInteractionOperator(RPAInputEnergies, E)`` (eps on the real axis at E, eigenbasis rotation of the
+        tensor -- rotations accumulate, which leaves the operator unchanged), until |dE| < dyn_tolerance.  Full BSE:
+        expectation value X^T Hd^ X + Y^T Hd^ Y + 2 X^T Hd2^ Y.  Returns (energies, iterations)."""
+        def expectation(cols):
+            hd = self.make_operator("HdOperator")
+            v = np.einsum('ij,ij->j', X[:, cols], hd.matmul(X[:, cols]))
+            if Y is not None:
+                hd2 = self.make_operator("Hd2Operator")
+                v = v + np.einsum('ij,ij->j', Y[:, cols], hd.matmul(Y[:, cols]))
+                v = v + 2.0 * np.einsum('ij,ij->j', X[:, cols], hd2.matmul(Y[:, cols]))
+            return v
+        self.SetupDirectInteractionOperator(RPAInputEnergies, 0.0)
+        n = len(energies)
+        stat = expectation(slice(0, n))
+        out, iters = np.array(energies, dtype=np.float64), np.zeros(n, dtype=int)
+        for s in range(n):
+            e = energies[s]
+            for it in range(max_dyn_iter):
+                old = e
+                self.SetupDirectInteractionOperator(RPAInputEnergies, old)
+                e = energies[s] + expectation(slice(s, s + 1))[0] - stat[s]
+                iters[s] = it + 1
+                if abs(e - old) < dyn_tolerance:
+                    break
+            out[s] = e
+        self.SetupDirectInteractionOperator(RPAInputEnergies, 0.0)
+        return out, iters
 
     @staticmethod
     def transition_dipoles(ao_dipoles, C, homo, vmin, cmax, X, Y=None):

@@ -25,13 +25,13 @@ import numpy as np
 from scipy import integrate
 
 
-def two_level_system(n_aux=7, seed=5):
+def two_level_system(n_aux=7, seed=5, hqp_gap=0.83):
     """Random two-level problem in the oracle's conventions: M[m, P, n] with levels (v, c) = (0, 1)."""
     rng = np.random.default_rng(seed)
     M = rng.standard_normal((2, n_aux, 2)) * 0.35
     M = 0.5 * (M + M.transpose(2, 1, 0))                 # (mn|P) = (nm|P)
     energies = np.array([-0.45, 0.20])
-    hqp = np.array([[-0.52, 0.0], [0.0, 0.31]])
+    hqp = np.array([[-0.52, 0.0], [0.0, -0.52 + hqp_gap]])
     return {"M": np.ascontiguousarray(M), "energies": energies, "hqp": hqp, "n_aux": n_aux}
 
 
@@ -97,3 +97,27 @@ def sigma_c_imaginary_axis(M_level, M_occ_unocc, energies, n_occ, omega, limit=4
 
     val, err = integrate.quad(integrand, 0.0, np.inf, limit=limit, epsabs=1e-12, epsrel=1e-11)
     return -val / math.pi, err / math.pi
+
+
+def two_level_dynamical_screening(sysm, e_static, eta=1e-3, max_iter=10, tol=1e-5):
+    """Perturbative dynamical screening of the two-level TDA exciton (coefficient vector = [1]):
+    E <- E_static - [hd(E) - hd(0)],  hd(w) = a.b - d(w) (a.m)(b.m) / (1 + d(w) |m|^2),
+    d(w) = 2 [(D - w)/((D - w)^2 + eta^2) + (D + w)/((D + w)^2 + eta^2)]   (chi0 weight on the real axis)."""
+    M, en = sysm["M"], sysm["energies"]
+    m, a, b = M[0, :, 1], M[0, :, 0], M[1, :, 1]
+    D = en[1] - en[0]
+    m2, am, bm, ab = float(m @ m), float(a @ m), float(b @ m), float(a @ b)
+
+    def hd(w):
+        d = 2.0 * ((D - w) / ((D - w) ** 2 + eta * eta) + (D + w) / ((D + w) ** 2 + eta * eta))
+        lam = 1.0 + d * m2                      # the one eigenvalue of eps(w) that is not 1
+        inv = 1.0 / lam if lam > 1e-8 else 0.0  # BSE::SetupDirectInteractionOperator drops eigenvalues <= 1e-8 (w > D)
+        return ab - (1.0 - inv) * am * bm / m2
+
+    e, its = e_static, 0
+    for its in range(1, max_iter + 1):
+        old = e
+        e = e_static - (hd(old) - hd(0.0))
+        if abs(e - old) < tol:
+            break
+    return e, its

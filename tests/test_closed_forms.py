@@ -144,3 +144,19 @@ def test_h2_minimal_basis_cis_matches_szabo_ostlund():
     assert abs(out["TripletOperator_TDA"] - (d - 0.6636)) < 1e-3
     # and exactly (to rounding) against the same combination of the RI integrals
     np.testing.assert_allclose(out["SingletOperator_TDA"], inp["energies"][1] - inp["energies"][0] + 2 * K12 - J12, rtol=1e-12)
+
+
+@pytest.mark.parametrize("hqp_gap", [0.55, 0.83])
+def test_two_level_dynamical_screening_closed_form(hqp_gap):
+    """BSE::Perturbative_DynamicalScreening on the two-level exciton against the scalar fixed-point iteration
+    (hqp_gap 0.55: excitation below the KS transition; 0.83: above it, where eps(w) has a negative eigenvalue that
+    SetupDirectInteractionOperator drops)."""
+    sysm = cf.two_level_system(hqp_gap=hqp_gap)
+    bse = _two_level_bse(sysm)
+    for solve in (bse.Solve_singlets_TDA, bse.Solve_triplets_TDA):
+        e, X = solve()
+        dyn, its = bse.Perturbative_DynamicalScreening(sysm["energies"], e, X)
+        ref, ref_its = cf.two_level_dynamical_screening(sysm, float(e[0]))
+        np.testing.assert_allclose(dyn, [ref], rtol=0, atol=1e-10)
+        assert its[0] == ref_its
+        assert abs(dyn[0] - e[0]) > 1e-6          # the correction is not trivially zero

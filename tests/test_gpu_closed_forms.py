@@ -124,3 +124,19 @@ def test_h2_cis_matches_szabo_ostlund(ctx):
         op = api.BSE_OPERATOR(ctx, cqp, cx, cdd, cd2, ones, tc, hqp, 0, 0, 0, 1)
         assert abs(float(op.get_full_matrix()[0, 0]) - ref) < tol
         op.close()
+
+
+@pytest.mark.parametrize("hqp_gap", [0.55, 0.83])
+def test_two_level_dynamical_screening(ctx, hqp_gap):
+    from xtp_b200 import api
+    sysm = cf.two_level_system(hqp_gap=hqp_gap)
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sysm["n_aux"], 0, 1, 0, 1)
+    tc.set_raw(sysm["M"])
+    bse = api.BSE(ctx, tc)
+    bse.configure(0, 0, 1, 0, 1, 0, 1, 1, sysm["energies"], sysm["hqp"], davidson_tolerance="lapack")
+    for solve in (bse.Solve_singlets_TDA, bse.Solve_triplets_TDA):
+        e, X = solve()
+        dyn = bse.Perturbative_DynamicalScreening(e, X)
+        ref, ref_its = cf.two_level_dynamical_screening(sysm, float(e[0]))
+        np.testing.assert_allclose(dyn, [ref], rtol=0, atol=1e-9)
+        assert bse.dynamical_iterations[0] == ref_its

@@ -465,6 +465,7 @@ def _bse_pair(ctx, prob, nmax=3):
     bseo = orc.BSE(tco)
     bseo.configure(orc.BSEOptions(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, nmax=nmax,
                                   davidson_tolerance="lapack"), gwo.RPAInputEnergies(), gwo.getHQP())
+    bseo._rpa_energies_for_tests = gwo.RPAInputEnergies().copy()
     return bse, bseo
 
 
@@ -510,6 +511,36 @@ def test_transition_dipoles_and_oscillator_strengths(ctx, prob):
     db = bse.transition_dipoles(r, prob["C"], Xb, Yb)
     np.testing.assert_allclose(db, orc.BSE.transition_dipoles(r, prob["C"], sz.homo, sz.vmin, sz.cmax, Xb, Yb),
                                rtol=1e-10, atol=1e-12)
+
+
+def test_plot_sigma(ctx, prob):
+    """GW::PlotSigma table (frequency, Sigma_c + e_KS + Sigma_x - Vxc per state) against the oracle."""
+    gw, gwo, _, _ = _gw_pair(ctx, prob, qp_grid_steps=201)
+    gw.CalculateGWPerturbation()
+    gwo.CalculateGWPerturbation()
+    sz = prob["sizes"]
+    states = [0, sz.homo - sz.qpmin, sz.homo + 1 - sz.qpmin]
+    tab = gw.PlotSigma(41, 0.02, states)
+    ref = gwo.PlotSigma(41, 0.02, states)
+    np.testing.assert_allclose(tab[:, 0::2], ref[:, 0::2], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(tab[:, 1::2], ref[:, 1::2], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize("tda", [True, False])
+def test_perturbative_dynamical_screening(ctx, prob, tda):
+    """BSE::Perturbative_DynamicalScreening against the oracle, TDA and full BSE singlets."""
+    bse, bseo = _bse_pair(ctx, prob, nmax=3)
+    sz = prob["sizes"]
+    if tda:
+        e, X = bse.Solve_singlets_TDA()
+        Y = None
+    else:
+        e, X, Y = bse.Solve_singlets_BTDA()
+    dyn = bse.Perturbative_DynamicalScreening(e, X, Y)
+    ref, its = bseo.Perturbative_DynamicalScreening(bseo._rpa_energies_for_tests, e, X, Y)
+    np.testing.assert_allclose(dyn, ref, rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(bse.dynamical_iterations, its)
+    assert np.abs(dyn - e).max() > 1e-7
 
 
 @pytest.mark.parametrize("ranges", ["default", "explicit", "explicit-low", "explicit-high"])

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "xtpb_gw_sigma_c_diag_elements": (C.c_int, [vp, idx, iptr, dptr, dptr, dptr]),
     "xtpb_gw_sigma_c_diag": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_sigma_c_grid": (C.c_int, [vp, dptr, dptr]),
+    "xtpb_gw_plot_sigma": (C.c_int, [vp, idx, C.c_double, idx, iptr, dptr]),
     "xtpb_gw_sigma_c_offdiag": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_grid_scan_info": (C.c_int, [vp, C.POINTER(C.c_int), iptr, dptr, dptr]),
     "xtpb_ppm_grid_plan": (C.c_int, [idx, dptr, C.c_double, idx, C.c_double, C.c_double, idx, dptr, iptr,
@@ -129,6 +130,8 @@ PROTOTYPES = {
     "xtpb_bse_operator_create_raw": (C.c_int, [vp, vp, idx, idx, idx, idx, dptr, dptr, idx, C.c_int, C.c_int,
                                                C.c_int, C.c_int, C.POINTER(vp)]),
     "xtpb_bse_solve_btda": (C.c_int, [vp, C.c_int, C.POINTER(DavidsonOptions), dptr, dptr, dptr, idx, C.POINTER(C.c_int), iptr]),
+    "xtpb_bse_perturbative_dynamical_screening": (C.c_int, [vp, idx, dptr, dptr, dptr, idx, idx, C.c_double, dptr,
+                                                            iptr]),
     "xtpb_bse_transition_dipoles": (C.c_int, [vp, idx, dptr, idx, dptr, idx, dptr, dptr, idx, dptr]),
     "xtpb_oscillator_strengths": (C.c_int, [idx, dptr, dptr, dptr]),
     "xtpb_dense_operator_create": (C.c_int, [vp, dptr, idx, idx, C.POINTER(vp)]),

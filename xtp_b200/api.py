@@ -415,6 +415,18 @@ class GW:
         return {"compressed": bool(comp.value), "bins": nb.value, "direct_evaluations": direct.value,
                 "equivalent_evaluations": equiv.value}
 
+    def PlotSigma(self, steps, spacing, states, filename=None):
+        """GW::PlotSigma: (steps, 2*len(states)) table, columns (frequency, Sigma_c + e_KS + Sigma_x - Vxc) per state;
+        written to `filename` in upstream's text layout when one is given."""
+        st = np.ascontiguousarray(states, dtype=np.int64)
+        tab = np.empty((int(steps), 2 * len(st)), order="F")
+        check(_lib.lib().xtpb_gw_plot_sigma(self._h, int(steps), float(spacing), len(st), st.ctypes.data_as(iptr), _d(tab)))
+        if filename is not None:
+            qpmin = int(self.opt.qpmin)
+            head = "\t".join(f"#frequency_{qpmin + int(l)}\tSigma_c_{qpmin + int(l)}" for l in st)
+            np.savetxt(filename, tab, delimiter="\t", header=head, comments="")
+        return tab
+
     def CalcCorrelationOffDiag(self, frequencies):
         fr = np.ascontiguousarray(frequencies, dtype=np.float64)
         out = np.empty((self.qptotal, self.qptotal), order="F")
@@ -584,6 +596,19 @@ class BSE:
             self.close()
         except Exception:
             pass
+
+    def Perturbative_DynamicalScreening(self, energies, X, Y=None, max_dyn_iter=10, dyn_tolerance=1e-5):
+        """BSE::Perturbative_DynamicalScreening: dynamically screened energies (and iterations per state)."""
+        e = np.ascontiguousarray(energies, dtype=np.float64)
+        Xf = _f(X)
+        Yf = _f(Y) if Y is not None else None
+        out = np.empty(len(e))
+        its = np.zeros(len(e), dtype=np.int64)
+        check(_lib.lib().xtpb_bse_perturbative_dynamical_screening(
+            self._h, len(e), _d(e), _d(Xf), _d(Yf) if Yf is not None else None, Xf.shape[0], int(max_dyn_iter),
+            float(dyn_tolerance), _d(out), its.ctypes.data_as(iptr)))
+        self.dynamical_iterations = its
+        return out
 
     def eps0_reused(self):
         """True when BSE::configure took the eps(0) eigenvalues from the PPM rotation (xtpb_bse_screening_info)."""

@@ -78,7 +78,7 @@ BSE::BSE(Context* c, TCMatrix* t, const xtpb_bse_options& o, const double* rpa_e
 
 // BSE::SetupDirectInteractionOperator: eps(0) at the given energies -> eigenvectors U (returned, device) and
 // eps_inv = 1/lambda (lambda > 1e-8).
-std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e) {
+std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e, double omega) {
   TCMatrix* tc = b.tc;
   Context* ctx = b.ctx;
   const long long na = tc->naux, rpatotal = tc->ntotal_glob;
@@ -90,7 +90,7 @@ std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e) {
   {
     const char* env = getenv("XTPB_BSE_REUSE_EPS0");
     const TCMatrix::Eps0Basis& z = tc->eps0;
-    if (!(env && env[0] == '0') && z.valid && !tc->pending && z.eta == kRpaEtaDefault && z.n_occ == n_occ &&
+    if (omega == 0.0 && !(env && env[0] == '0') && z.valid && !tc->pending && z.eta == kRpaEtaDefault && z.n_occ == n_occ &&
         (long long)z.energies.size() == rpatotal && std::equal(z.energies.begin(), z.energies.end(), rpa_e)) {
       b.eps_inv.resize((size_t)na);
       for (long long i = 0; i < na; ++i) b.eps_inv[i] = z.lambda[i] > 1e-8 ? 1.0 / z.lambda[i] : 0.0;
@@ -101,7 +101,7 @@ std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e) {
   DBuf e_dev((size_t)rpatotal), lam((size_t)na);
   ctx->h2d(e_dev.p, rpa_e, (size_t)rpatotal);
   auto U = std::make_unique<DBuf>((size_t)(na * na));
-  const double w0 = 0.0;
+  const double w0 = omega;
   rpa_epsilon_dev(*tc, e_dev.p, n_occ, kRpaEtaDefault, &w0, 1, false, 0.0, U->p);
   ctx->eigh((int)na, U->p, na, lam.p);
   std::vector<double> lambda((size_t)na);
@@ -111,10 +111,75 @@ std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e) {
   return U;
 }
 
+// BSE::Perturbative_DynamicalScreening (bse.cc): first-order correction of the BSE energies for the frequency dependence
+// of the screening in the direct term.  With Hd(w) built from eps(w) (real axis) instead of eps(0),
+//   E_dyn,s = E_static,s + <s|Hd^(w = E_dyn,s)|s> - <s|Hd^(0)|s>,       Hd^ = HdOperator = -Hd,
+// iterated per state until |dE| < dyn_tolerance or max_dyn_iter.  Without the Tamm-Dancoff approximation the
+// expectation value is X^T Hd^ X + Y^T Hd^ Y + 2 X^T Hd2^ Y (the energy functional X^T A X + Y^T A Y + 2 X^T B Y).
+// Every evaluation is SetupDirectInteractionOperator at the new frequency (eps(w), eigensolver, window rotation)
+// followed by one factorised operator application to the state's vector, as upstream does per excitation.
+void bse_dynamical_screening(BSE& b, const double* R_static, const double* rpa_e, long long n_states,
+                             const double* e_static, const double* X_host, const double* Y_host, long long ld,
+                             long long max_iter, double tol, double* e_dyn, long long* iters) {
+  Context* ctx = b.ctx;
+  const long long size = b.size, lds = round_up(size, 2);
+  XTPB_REQUIRE(n_states >= 1 && ld >= size && max_iter >= 1 && tol > 0.0, "bad dynamical-screening arguments");
+  DBuf X((size_t)(lds * n_states)), Yv, HX((size_t)(lds * n_states)), HY, H2Y, dots((size_t)(3 * n_states));
+  X.zero(ctx->stream);
+  ctx->h2d_2d(X.p, lds, X_host, ld, size, n_states);
+  if (Y_host) {
+    Yv.alloc((size_t)(lds * n_states));
+    HY.alloc((size_t)(lds * n_states));
+    H2Y.alloc((size_t)(lds * n_states));
+    Yv.zero(ctx->stream);
+    ctx->h2d_2d(Yv.p, lds, Y_host, ld, size, n_states);
+  }
+  const std::vector<double> eps_static = b.eps_inv;
+  // <s|Hd^|s> for states [s0, s0 + cnt) with the screening (eps_inv, R)
+  auto expectation = [&](const std::vector<double>& eps_inv, const double* R, long long s0, long long cnt,
+                         std::vector<double>& out) {
+    BseOperator hd(ctx, b.tc, b.opt.homo, b.opt.rpamin, b.opt.vmin, b.opt.cmax, eps_inv.data(), b.hqp.data(),
+                   b.vt + b.ct, 0, 0, 1, 0, R, /*force_factorised=*/true);
+    hd.matmul_dev(X.p + s0 * lds, lds, (int)cnt, HX.p, lds);
+    k_column_dots(dots.p, X.p + s0 * lds, lds, HX.p, lds, size, (int)cnt, ctx->stream);
+    if (Y_host) {
+      hd.matmul_dev(Yv.p + s0 * lds, lds, (int)cnt, HY.p, lds);
+      k_column_dots(dots.p + n_states, Yv.p + s0 * lds, lds, HY.p, lds, size, (int)cnt, ctx->stream);
+      BseOperator hd2(ctx, b.tc, b.opt.homo, b.opt.rpamin, b.opt.vmin, b.opt.cmax, eps_inv.data(), b.hqp.data(),
+                      b.vt + b.ct, 0, 0, 0, 1, R, true);
+      hd2.matmul_dev(Yv.p + s0 * lds, lds, (int)cnt, H2Y.p, lds);
+      k_column_dots(dots.p + 2 * n_states, X.p + s0 * lds, lds, H2Y.p, lds, size, (int)cnt, ctx->stream);
+    }
+    std::vector<double> d((size_t)(3 * n_states), 0.0);
+    ctx->d2h(d.data(), dots.p, (size_t)(3 * n_states));
+    out.resize((size_t)cnt);
+    for (long long i = 0; i < cnt; ++i)
+      out[i] = d[i] + (Y_host ? d[n_states + i] + 2.0 * d[2 * n_states + i] : 0.0);
+  };
+  std::vector<double> stat;
+  expectation(eps_static, R_static, 0, n_states, stat);
+  for (long long s = 0; s < n_states; ++s) {
+    double e = e_static[s];
+    long long it = 0;
+    for (; it < max_iter; ++it) {
+      const double old = e;
+      std::unique_ptr<DBuf> U = bse_setup_screening(b, rpa_e, old);      // overwrites b.eps_inv
+      std::vector<double> dyn;
+      expectation(b.eps_inv, U ? U->p : nullptr, s, 1, dyn);
+      e = e_static[s] + dyn[0] - stat[s];
+      if (std::fabs(e - old) < tol) { ++it; break; }
+    }
+    e_dyn[s] = e;
+    if (iters) iters[s] = it;
+  }
+  b.eps_inv = eps_static;
+  ctx->sync();
+}
+
 // ------------------------------------------------------------------ BSE_OPERATOR
 BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpamin, long long vmin, long long cmax,
                          const double* eps_inv_host, const double* hqp_host, long long ldh, int cqp_, int cx_, int cd_,
-                         int cd2_, const double* R_dev)
+                         int cd2_, const double* R_dev, bool force_factorised)
     : cqp(cqp_), cx(cx_), cd(cd_), cd2(cd2_) {
   ctx = c;
   tc->flush();
@@ -205,7 +270,11 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
     const char* hx_env = getenv("XTPB_BSE_HX_DENSE");
     hx_factorised = cx != 0 && !(hx_env && hx_env[0] == '1');
     const bool has_dense_terms = hx_factorised ? (cd || cd2) : (cx || cd || cd2);
-    dense = has_dense_terms && gb <= max_gb && vt >= world && size <= 60000 &&
+    // XTPB_BSE_MODE=factorised never materialises H (the strategy BASELINE.json's north_star describes; mandatory
+    // when H does not fit); =dense insists on it when it fits; default: dense when it fits the budget
+    const char* mode = getenv("XTPB_BSE_MODE");
+    const bool want_factorised = force_factorised || (mode && mode[0] == 'f');
+    dense = !want_factorised && has_dense_terms && gb <= max_gb && vt >= world && size <= 60000 &&
             (double)std::max(vt, ct) * (double)std::max(vt, ct) < 2.0e9;
     if (!dense) hx_factorised = false;        // the factorised operator below has its own exchange term
   }

@@ -6,7 +6,10 @@
 
 namespace xtpb {
 const char* last_error_cstr();
-std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e);
+std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e, double omega);
+void bse_dynamical_screening(BSE& b, const double* R_static, const double* rpa_e, long long n_states,
+                             const double* e_static, const double* X_host, const double* Y_host, long long ld,
+                             long long max_iter, double tol, double* e_dyn, long long* iters);
 }
 using namespace xtpb;
 
@@ -377,6 +380,35 @@ int xtpb_gw_sigma_c_grid(xtpb_gw* gw, const double* center_frequencies_host, dou
   std::memcpy(values_host, v.data(), v.size() * 8);
   XTPB_API_END
 }
+// GW::PlotSigma(filename, steps, spacing, states): the table upstream writes to the file
+int xtpb_gw_plot_sigma(xtpb_gw* gw, xtpb_index steps, double spacing, xtpb_index n_states,
+                       const xtpb_index* states_host, double* table_host) {
+  XTPB_API_BEGIN
+  GW& g = gw->impl;
+  XTPB_REQUIRE(g.screening_ready, "PrepareScreening has not been called");
+  XTPB_REQUIRE(steps >= 1 && n_states >= 1 && states_host && table_host, "bad PlotSigma arguments");
+  const long long q = g.qptotal, off = g.opt.qpmin - g.opt.rpamin;
+  std::vector<long long> lv((size_t)(steps * n_states));
+  std::vector<double> fr(lv.size()), val(lv.size());
+  for (long long i = 0; i < n_states; ++i) {
+    XTPB_REQUIRE(states_host[i] >= 0 && states_host[i] < q, "PlotSigma: state outside the QP window");
+    for (long long gp = 0; gp < steps; ++gp) {
+      lv[(size_t)(i * steps + gp)] = states_host[i];
+      fr[(size_t)(i * steps + gp)] =
+          g.rpa_energies[(size_t)(off + states_host[i])] + (double(gp) - double(steps - 1) / 2.0) * spacing;
+    }
+  }
+  g.sigma_c_diag_elements((long long)lv.size(), lv.data(), fr.data(), val.data(), nullptr);
+  for (long long i = 0; i < n_states; ++i) {
+    const long long l = states_host[i];
+    const double intercept = g.dft_energies[(size_t)(g.opt.qpmin + l)] + g.sigma_x[(size_t)(l + l * q)] - g.vxc[(size_t)(l + l * q)];
+    for (long long gp = 0; gp < steps; ++gp) {
+      table_host[gp + (2 * i) * steps] = fr[(size_t)(i * steps + gp)];
+      table_host[gp + (2 * i + 1) * steps] = val[(size_t)(i * steps + gp)] + intercept;
+    }
+  }
+  XTPB_API_END
+}
 int xtpb_gw_sigma_c_offdiag(xtpb_gw* gw, const double* frequencies_host, double* sigma_c_host) {
   XTPB_API_BEGIN
   gw->impl.sigma_c_offdiag(frequencies_host, sigma_c_host);
@@ -428,9 +460,10 @@ int xtpb_bse_create(xtpb_ctx* ctx, xtpb_tc* tc, const xtpb_bse_options* opt, con
   XTPB_API_BEGIN
   XTPB_REQUIRE(ctx && tc && opt && out, "null pointer");
   auto* b = new xtpb_bse{BSE(&ctx->impl, &tc->impl, *opt, rpa_input_energies_host, hqp_host, ldh, rotate_full_tc != 0),
-                         nullptr};
+                         nullptr, {}};
   try {
-    b->R = bse_setup_screening(b->impl, rpa_input_energies_host);
+    b->rpa_energies.assign(rpa_input_energies_host, rpa_input_energies_host + tc->impl.ntotal_glob);
+    b->R = bse_setup_screening(b->impl, rpa_input_energies_host, 0.0);
     if (rotate_full_tc && b->R) {
       tc->impl.rotate(b->R->p, tc->impl.naux);
       ctx->impl.sync();
@@ -495,6 +528,18 @@ int xtpb_bse_solve_btda(xtpb_bse* bse, int singlet, const xtpb_davidson_options*
   if (Y_host) b.ctx->d2h_2d(Y_host, ld, res.Y.p, A.size, A.size, b.opt.nmax);
   if (info) *info = res.info;
   if (iterations) *iterations = res.iterations;
+  XTPB_API_END
+}
+// BSE::Perturbative_DynamicalScreening
+int xtpb_bse_perturbative_dynamical_screening(xtpb_bse* bse, xtpb_index n_states, const double* energies_static_host,
+                                              const double* X_host, const double* Y_host, xtpb_index ld,
+                                              xtpb_index max_dyn_iter, double dyn_tolerance,
+                                              double* energies_dynamic_host, xtpb_index* iterations_host) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(bse && energies_static_host && X_host && energies_dynamic_host, "null pointer");
+  bse_dynamical_screening(bse->impl, bse->R ? bse->R->p : nullptr, bse->rpa_energies.data(), n_states,
+                          energies_static_host, X_host, Y_host, ld, max_dyn_iter, dyn_tolerance, energies_dynamic_host,
+                          iterations_host);
   XTPB_API_END
 }
 // BSE::CalcCoupledTransition_Dipoles with Orbitals::CalcFreeTransition_Dips folded in:

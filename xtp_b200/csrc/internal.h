@@ -134,6 +134,9 @@ void k_bse_diagonal(double* diag, int vt, int ct, int naux, const double* Mvc, l
 void k_add_column_square_sums(double* d, const double* F, long long ld, int rows, long long n, double alpha,
                               cudaStream_t s);
 void k_col_norms(const double* A, long long ld, long long rows, int cols, double* out, cudaStream_t s);
+// out[j] = sum_i A[i + j*lda] * B[i + j*ldb], j < cols
+void k_column_dots(double* out, const double* A, long long lda, const double* B, long long ldb, long long rows, int cols,
+                   cudaStream_t s);
 void k_residuals(double* res, long long ldr, const double* q, long long ldq, const double* lambda, long long rows,
                  int cols, cudaStream_t s);                            // res(:,j) -= lambda[j]*q(:,j)
 void k_davidson_correction(double* out, const double* r, const double* x, const double* D, double lambda, long long n,
@@ -334,7 +337,7 @@ struct BseOperator : Operator {
   // windows are built from tc (optionally rotated by R_dev)
   BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpamin, long long vmin, long long cmax,
               const double* eps_inv_host, const double* hqp_host, long long ldh, int cqp_, int cx_, int cd_, int cd2_,
-              const double* R_dev);
+              const double* R_dev, bool force_factorised = false);
   void matmul_dev(const double* X, long long ldx, int k, double* Y, long long ldy) override;
   void diagonal_dev(double* d) override;
 };
@@ -368,5 +371,5 @@ void btda_solve(Operator& A, Operator& B, long long neigen, const xtpb_davidson_
 struct xtpb_ctx { xtpb::Context impl; explicit xtpb_ctx(int d) : impl(d) {} };
 struct xtpb_tc { xtpb::TCMatrix impl; };
 struct xtpb_gw { xtpb::GW impl; };
-struct xtpb_bse { xtpb::BSE impl; std::unique_ptr<xtpb::DBuf> R; };
+struct xtpb_bse { xtpb::BSE impl; std::unique_ptr<xtpb::DBuf> R; std::vector<double> rpa_energies; };
 struct xtpb_op { std::unique_ptr<xtpb::Operator> impl; };

@@ -722,6 +722,17 @@ __global__ void __launch_bounds__(256) col_norms_kernel(const double* __restrict
   s = block_sum<256>(s, sh);
   if (threadIdx.x == 0) out[blockIdx.x] = sqrt(s);
 }
+__global__ void __launch_bounds__(256) column_dots_kernel(const double* __restrict__ A, long long lda,
+                                                          const double* __restrict__ B, long long ldb, long long rows,
+                                                          double* out) {
+  __shared__ double sh[8];
+  const double* a = A + (long long)blockIdx.x * lda;
+  const double* b = B + (long long)blockIdx.x * ldb;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < rows; i += 256) s += a[i] * b[i];
+  s = block_sum<256>(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
 __global__ void residuals_kernel(double* res, long long ldr, const double* __restrict__ q, long long ldq,
                                  const double* __restrict__ lambda, long long rows, int cols) {
   const long long total = rows * cols;
@@ -1026,6 +1037,12 @@ void k_bse_diagonal(double* diag, int vt, int ct, int naux, const double* Mvc, l
 void k_col_norms(const double* A, long long ld, long long rows, int cols, double* out, cudaStream_t s) {
   if (cols == 0) return;
   col_norms_kernel<<<cols, 256, 0, s>>>(A, ld, rows, out);
+  LAUNCH_CHECK();
+}
+void k_column_dots(double* out, const double* A, long long lda, const double* B, long long ldb, long long rows, int cols,
+                   cudaStream_t s) {
+  if (cols == 0) return;
+  column_dots_kernel<<<cols, 256, 0, s>>>(A, lda, B, ldb, rows, out);
   LAUNCH_CHECK();
 }
 void k_residuals(double* res, long long ldr, const double* q, long long ldq, const double* lambda, long long rows,
