@@ -118,13 +118,23 @@ class ClockSampler:
 class GwbseJob:
     """One molecule's inputs plus the persistent device tensor; `run()` is one step."""
 
-    def __init__(self, workload, device, rank=0, world=1, comm=None, e2e=True, seed=None):
+    def __init__(self, workload, device, rank=0, world=1, comm=None, e2e=True, seed=None, sigma="ppm", evgw=1):
         import torch
 
         from xtp_b200 import api, dist, synth
         self.api, self.torch = api, torch
         self.sz = sz = synth.WORKLOADS[workload]
         self.workload = workload
+        # GW options beyond the level ranges: G0W0 with the plasmon-pole model and the 1001-point QP grid (defaults), or
+        # --sigma cda [--evgw N]: contour-deformation self-energy, Newton ("fixedpoint") QP solver, N evGW iterations
+        self.gw_kw = {}
+        if sigma == "cda":
+            # (the grid the solver falls back to for a level Newton cannot solve is kept small: with CDA every grid
+            # point costs one epsilon^-1 per enclosed pole)
+            self.gw_kw.update(sigma_integration="cda", qp_solver="fixedpoint", order=12, g_sc_max_iterations=20,
+                              qp_grid_steps=21, qp_grid_spacing=0.05)
+        if evgw > 1:
+            self.gw_kw.update(gw_sc_max_iterations=int(evgw))
         self.rank, self.world, self.comm = rank, world, comm
         self.dev = torch.device("cuda", device)
         rng = np.random.default_rng(20260101 + sz.n_basis if seed is None else seed)
@@ -239,7 +249,8 @@ class GwbseJob:
         t["metric"] = time.perf_counter() - t1
         t1 = time.perf_counter()
         gw = api.GW(self.ctx, tc, self.vxc, self.energies)
-        gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax))
+        gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax,
+                                    **self.gw_kw))
         gw.CalculateGWPerturbation()
         qp = gw.getGWAResults()
         t["gw_perturbation"] = time.perf_counter() - t1
@@ -317,6 +328,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c60-tzvp-shape")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sigma", default="ppm", choices=["ppm", "cda"], help="Sigma_c frequency integration")
+    ap.add_argument("--evgw", type=int, default=1, help="evGW iterations (1 = G0W0)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--davidson-calls", type=int, default=12, help="matmul calls assumed by the CPU sample")
@@ -336,7 +349,7 @@ def main():
     rank, world, local = dist.init_process_group_from_env("nccl")
     import torch.distributed as tdist
 
-    job = GwbseJob(args.workload, local, rank, world, e2e=not args.no_e2e)
+    job = GwbseJob(args.workload, local, rank, world, e2e=not args.no_e2e, sigma=args.sigma, evgw=args.evgw)
     sz = job.sz
 
     def barrier():
@@ -473,7 +486,7 @@ def main():
         job.unpin_host_copy()
 
     cpu = None
-    if not args.no_cpu_baseline and rank == 0 and world == 1:
+    if not args.no_cpu_baseline and rank == 0 and world == 1 and args.sigma == "ppm" and args.evgw <= 1:
         from oracle import cpu_reference as cr
         iters = int(job.last["davidson_iterations"])
         s = cr.sampled_step(sz, davidson_matmul_calls=iters)
@@ -489,7 +502,10 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n_basis": sz.n_basis, "n_aux": sz.n_aux, "homo": sz.homo,
                        "mtotal": sz.mtotal, "qptotal": sz.qptotal, "bse_size": sz.bse_size, "nmax": NMAX,
-                       "sigma": "ppm", "qp_solver": "grid(1001)", "bse": "singlets TDA, Davidson DPR tol 1e-4",
+                       "sigma": args.sigma, "gw": "G0W0" if args.evgw <= 1 else f"evGW({args.evgw} iterations max)",
+                       "qp_window": [int(sz.qpmin), int(sz.qpmax)],
+                       "qp_solver": "grid(1001)" if args.sigma == "ppm" else "fixedpoint (Newton)",
+                       "bse": "singlets TDA, Davidson DPR tol 1e-4",
                        "parallelism": ("single GPU" if world == 1 else
                                        f"{world} ranks: tensor split over its second index (cyclic), Fill3cMO and "
                                        f"BSE operator split over the aux index, NCCL all-reduce/all-gather"),

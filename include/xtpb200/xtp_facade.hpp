@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <stdexcept>
+#include <fstream>
 #include <string>
 #include <utility>
 #include <array>
@@ -282,6 +283,24 @@ class GW {
     check(xtpb_gw_sigma_c_grid(h_, center_frequencies.data(), rowmajor.data()));
     return rowmajor;
   }
+  // GW::PlotSigma(filename, steps, spacing, states): `states` are gw-level indices (0 = qpmin); writes upstream's
+  // tab-separated table (frequency / Sigma_c + e_KS + Sigma_x - Vxc column pair per state) and returns it
+  Matrix PlotSigma(const std::string& filename, Index steps, double spacing, const std::vector<Index>& states) const {
+    Matrix table(steps, 2 * static_cast<Index>(states.size()));
+    check(xtpb_gw_plot_sigma(h_, steps, spacing, static_cast<Index>(states.size()), states.data(), table.data()));
+    if (!filename.empty()) {
+      std::ofstream out(filename);
+      for (std::size_t i = 0; i < states.size(); ++i)
+        out << (i ? "\t" : "") << "#frequency_" << opt_.qpmin + states[i] << "\tSigma_c_" << opt_.qpmin + states[i];
+      out << "\n";
+      out.precision(12);
+      for (Index gp = 0; gp < steps; ++gp) {
+        for (Index c = 0; c < table.cols(); ++c) out << (c ? "\t" : "") << table.data()[gp + c * steps];
+        out << "\n";
+      }
+    }
+    return table;
+  }
   xtpb_gw* handle() const { return h_; }
 
  private:
@@ -444,6 +463,16 @@ class BSE {
     check(xtpb_bse_transition_dipoles(h_, nb, dft_orbitals.data(), nb, r.data(), X.cols(), X.data(),
                                       Y ? Y->data() : nullptr, X.rows(), d.data()));
     return d;
+  }
+  // BSE::Perturbative_DynamicalScreening(type, orb): dynamically screened excitation energies of the given states
+  // (X = coefficients, Y = coefficients_AR or nullptr for the TDA); upstream option names and defaults
+  Vector Perturbative_DynamicalScreening(const Vector& energies, const Matrix& X, const Matrix* Y = nullptr,
+                                         Index max_dyn_iter = 10, double dyn_tolerance = 1e-5) const {
+    Vector dyn(energies.size());
+    check(xtpb_bse_perturbative_dynamical_screening(h_, energies.size(), energies.data(), X.data(),
+                                                    Y ? Y->data() : nullptr, X.rows(), max_dyn_iter, dyn_tolerance,
+                                                    dyn.data(), nullptr));
+    return dyn;
   }
   // Orbitals::Oscillatorstrengths
   static Vector Oscillatorstrengths(const Vector& energies, const Matrix& dipoles) {

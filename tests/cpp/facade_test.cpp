@@ -97,6 +97,10 @@ int main(int argc, char** argv) {
     const DenseMatrix dip = bse.CalcCoupledTransition_Dipoles(C, rdip, full.X, &full.Y);
     const DenseVector fosc = BSE<>::Oscillatorstrengths(full.energies, dip);
 
+    // GW::PlotSigma table for HOMO and LUMO, BSE::Perturbative_DynamicalScreening of the TDA singlets
+    const DenseMatrix plot = gw.PlotSigma("", 11, 0.05, std::vector<Index>{homo, homo + 1});
+    const DenseVector dyn = bse.Perturbative_DynamicalScreening(singlets.energies, singlets.eigenvectors);
+
     // operator-level check through the template typedefs: Hx via BSE_OPERATOR<0,1,0,0>
     DenseVector eps_inv = bse.epsilon_0_inv();
     HxOperator<> hx(eps_inv, Mmn, Hqp);
@@ -110,6 +114,8 @@ int main(int argc, char** argv) {
     for (Index i = 0; i < full.energies.size(); ++i) std::fprintf(out, "btda %.15e\n", full.energies(i));
     for (Index i = 0; i < fosc.size(); ++i) std::fprintf(out, "fosc %.15e\n", fosc(i));
     std::fprintf(out, "hx_diag0 %.15e\n", d(0));
+    for (Index i = 0; i < dyn.size(); ++i) std::fprintf(out, "dynamic %.15e\n", dyn(i));
+    std::fprintf(out, "plot_rows %lld\n", (long long)plot.rows());
     std::fclose(out);
     return 0;
   } catch (const std::exception& ex) {

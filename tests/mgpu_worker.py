@@ -101,6 +101,36 @@ def main():
         assert torch.equal(t, t0), "results differ between ranks"
         gw.close()
         bse.close()
+
+        # -- Sigma_CDA with the quadrature nodes and the residue poles sharded over the ranks (BASELINE configs[2]):
+        #    kernel values at arbitrary (level, frequency) pairs incl. frequencies that enclose poles, then a G0W0
+        #    fixed-point solve, against the oracle to 1e-6 Ha
+        if name != "odd":
+            tco2 = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+            tco2.Fill(prob["ao3c"], prob["C"], prob["aux_coulomb"])
+            tc2 = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+            tc2.set_raw(tco2.M)
+            kw = dict(sigma_integration="cda", qp_solver="fixedpoint", qp_grid_steps=41, order=12)
+            gwc = api.GW(ctx, tc2, prob["vxc"], prob["energies"])
+            gwc.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin,
+                                         rpamax=sz.rpamax, **kw))
+            gwo = orc.GW(tco2, prob["vxc"], prob["energies"])
+            gwo.configure(orc.GWOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax, **kw))
+            gwc.PrepareScreening()
+            gwo.rpa.setRPAInputEnergies(prob["energies"][sz.rpamin:sz.rpamax + 1])
+            gwo.sigma.PrepareScreening()
+            e = prob["energies"]
+            rng = np.random.default_rng(4)
+            levels = rng.integers(0, sz.qptotal, 10)
+            freqs = np.concatenate([rng.uniform(-1.2, 1.2, 5), e[sz.qpmin + levels[5:]] + 0.05])
+            val = gwc.CalcCorrelationDiagElements(levels, freqs)
+            refv = np.array([gwo.sigma.CalcCorrelationDiagElement(int(l), float(x)) for l, x in zip(levels, freqs)])
+            np.testing.assert_allclose(val, refv, rtol=1e-8, atol=1e-10)
+            if name == "tiny":
+                gwc.CalculateGWPerturbation()
+                gwo.CalculateGWPerturbation()
+                np.testing.assert_allclose(gwc.getGWAResults(), gwo.getGWAResults(), rtol=0, atol=1e-6)
+            gwc.close()
         if rank == 0:
             print(f"mgpu ok: {name} world={world} S1={es[0]:.8f}", flush=True)
     torch.distributed.barrier()

@@ -53,3 +53,5 @@ def test_facade_full_step_matches_oracle(tmp_path):
     assert len(vals["btda"]) == nmax and len(vals["fosc"]) == nmax
     assert np.all(np.array(vals["btda"]) <= np.array(vals["singlet"]) + 1e-6)      # full BSE lies below TDA
     assert np.all(np.array(vals["fosc"]) >= 0.0)
+    assert vals["plot_rows"] == [11.0] and len(vals["dynamic"]) == nmax
+    assert np.abs(np.array(vals["dynamic"]) - np.array(vals["singlet"])).max() < 0.05

@@ -22,6 +22,10 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi& nccl_api() {
@@ -41,6 +45,10 @@ NcclApi& nccl_api() {
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
   api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+  api.Reduce = reinterpret_cast<decltype(api.Reduce)>(sym("ncclReduce"));
+  api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   loaded = true;
   return api;
@@ -98,6 +106,24 @@ void Context::allreduce_sum(double* buf, size_t count, cudaStream_t st) {
   XTPB_NCCL(nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(nccl), q));
   prof_end(slot, q);
 }
+
+// sum over ranks delivered to `root` only (in place there; the other ranks' buffers are left as they were)
+void Context::reduce_sum(double* buf, size_t count, int root, cudaStream_t st) {
+  if (world == 1 || count == 0) return;
+  cudaStream_t q = st ? st : stream;
+  const int slot = prof_begin(PROF_COMM, 8.0 * (double)count, q);
+  XTPB_NCCL(nccl_api().Reduce(buf, buf, count, ncclDouble, ncclSum, root, static_cast<ncclComm_t>(nccl), q));
+  prof_end(slot, q);
+}
+void Context::bcast(double* buf, size_t count, int root, cudaStream_t st) {
+  if (world == 1 || count == 0) return;
+  cudaStream_t q = st ? st : stream;
+  const int slot = prof_begin(PROF_COMM, 8.0 * (double)count, q);
+  XTPB_NCCL(nccl_api().Broadcast(buf, buf, count, ncclDouble, root, static_cast<ncclComm_t>(nccl), q));
+  prof_end(slot, q);
+}
+void Context::group_start() { if (world > 1) XTPB_NCCL(nccl_api().GroupStart()); }
+void Context::group_end() { if (world > 1) XTPB_NCCL(nccl_api().GroupEnd()); }
 
 void Context::allgather(const double* send, double* recv, size_t count_per_rank, cudaStream_t st) {
   if (world == 1) {

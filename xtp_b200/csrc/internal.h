@@ -65,6 +65,10 @@ struct Context {
   void comm_destroy();
   void allreduce_sum(double* buf, size_t count, cudaStream_t st = nullptr);
   void allgather(const double* send, double* recv, size_t count_per_rank, cudaStream_t st = nullptr);
+  void reduce_sum(double* buf, size_t count, int root, cudaStream_t st = nullptr);     // result on `root` only
+  void bcast(double* buf, size_t count, int root, cudaStream_t st = nullptr);
+  void group_start();           // NCCL group: the collectives in between are issued as one batch
+  void group_end();
 };
 void comm_unique_id(char* out_128);
 // hostlinalg.cu: symmetric eigenproblem on the host (A: n x n col-major, lower triangle read; A <- eigenvectors,
@@ -234,8 +238,11 @@ struct TCMatrix {
 };
 
 // eps(w) for n_omega frequencies on the device: out[w] (naux x naux, ld = naux).  energies_dev: rpatotal.
+// owner_shift < 0: every rank receives every matrix (all-reduce).  owner_shift >= 0 (frequency sharding, world > 1):
+// matrix w is summed onto rank (w + owner_shift) % world only -- the other ranks' copies hold partial sums and must not
+// be used; the caller inverts / consumes matrix w on its owner (Sigma_CDA's quadrature nodes and residue poles).
 void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
-                     int n_omega, bool imag, double gamma_extra, double* out_dev);
+                     int n_omega, bool imag, double gamma_extra, double* out_dev, int owner_shift = -1);
 
 // ---------------------------------------------------------------- GW
 struct GW {

@@ -170,21 +170,28 @@ __global__ void __launch_bounds__(256) cda_pairs_kernel(const double* __restrict
   if (threadIdx.x == 0) values[pair] = 0.5 / kPi * gq + tail;
 }
 // one CTA per residue item: v^T (Ainv - 1) v with v = slab[:, col]; Ainv symmetric column-major
+// Vb != nullptr (pole sharding over ranks): the vector of item `it` is Vb[it*naux ..] (gathered from the rank that owns
+// the column) and item_col[it] < 0 marks items whose inverse lives on another rank.
 __global__ void __launch_bounds__(256) cda_residue_kernel(const double* __restrict__ Ainv, int naux,
                                                           const double* __restrict__ M, long long ldn, long long slab,
                                                           const int* __restrict__ item_slab,
                                                           const int* __restrict__ item_col,
-                                                          const int* __restrict__ item_mat, double* __restrict__ out) {
+                                                          const int* __restrict__ item_mat,
+                                                          const double* __restrict__ Vb, double* __restrict__ out) {
   extern __shared__ double v[];
   __shared__ double sh[16];
   const int it = blockIdx.x;
   const int col = item_col[it];
-  if (col < 0) {                       // column owned by another rank
+  if (col < 0) {                       // column (or, sharded, the inverse) owned by another rank
     if (threadIdx.x == 0) out[it] = 0.0;
     return;
   }
-  const double* S = M + (long long)item_slab[it] * slab + col;
-  for (int P = threadIdx.x; P < naux; P += 256) v[P] = S[(long long)P * ldn];
+  if (Vb) {
+    for (int P = threadIdx.x; P < naux; P += 256) v[P] = Vb[(long long)it * naux + P];
+  } else {
+    const double* S = M + (long long)item_slab[it] * slab + col;
+    for (int P = threadIdx.x; P < naux; P += 256) v[P] = S[(long long)P * ldn];
+  }
   __syncthreads();
   const double* A = Ainv + (long long)item_mat[it] * naux * naux;
   double quad = 0.0, vv = 0.0;
@@ -198,6 +205,19 @@ __global__ void __launch_bounds__(256) cda_residue_kernel(const double* __restri
   for (int P = threadIdx.x; P < naux; P += 256) vv += v[P] * v[P];
   block_sum2(quad, vv, sh);
   if (threadIdx.x == 0) out[it] = quad - vv;
+}
+
+// Vb[it][P] = slab(item)[P][col] for the items whose column this rank owns, 0 otherwise (summed over ranks afterwards)
+__global__ void cda_gather_columns_kernel(double* __restrict__ Vb, int naux, const double* __restrict__ M, long long ldn,
+                                          long long slab, const int* __restrict__ item_slab,
+                                          const int* __restrict__ item_col, int n_items) {
+  const long long total = (long long)n_items * naux;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int it = (int)(idx / naux), P = (int)(idx % naux);
+    const int col = item_col[it];
+    Vb[idx] = col < 0 ? 0.0 : M[(long long)item_slab[it] * slab + (long long)P * ldn + col];
+  }
 }
 
 // ---------------------------------------------------------------- Gauss quadrature nodes (host)
@@ -390,13 +410,23 @@ void GW::prepare_cda() {
   gaussian_quadrature(opt.quadrature_scheme, opt.order, quad_points, quad_weights);
   const int order = (int)quad_points.size();
   cda_kernels.ensure((size_t)((order + 1) * nn));
-  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, quad_points.data(), order, true, 0.0, cda_kernels.p);
+  // Frequency sharding (BASELINE.json configs[2], north_star "frequency points for epsilon and Sigma"): with several
+  // ranks, eps(i w_j) is summed onto rank j % world only, which alone inverts it (the N_aux^3 work per node is done
+  // once, not world times); kappa(0) is owned by rank order % world.  The finished kernels are then broadcast, because
+  // every rank needs all of them for the quadratic forms over ITS share of the second tensor index.
+  const int world = ctx->world, rank = ctx->rank;
+  auto owner = [&](int j) { return j % world; };
+  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, quad_points.data(), order, true, 0.0, cda_kernels.p, 0);
   const double zero = 0.0;
   double* kappa0 = cda_kernels.p + (long long)order * nn;
-  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &zero, 1, false, 0.0, kappa0);
-  ctx->spd_inverse((int)na, kappa0, na);
-  k_add_diagonal(kappa0, (int)na, na, -1.0, ctx->stream);
+  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &zero, 1, false, 0.0, kappa0, order);
+  if (owner(order) == rank) {
+    ctx->spd_inverse((int)na, kappa0, na);
+    k_add_diagonal(kappa0, (int)na, na, -1.0, ctx->stream);
+  }
+  ctx->bcast(kappa0, (size_t)nn, owner(order));
   for (int j = 0; j < order; ++j) {
+    if (owner(j) != rank) continue;
     double* K = cda_kernels.p + (long long)j * nn;
     ctx->spd_inverse((int)na, K, na);
     // dielinv_j = -(eps^-1 - 1) + exp(-(alpha w_j)^2) kappa0
@@ -404,6 +434,9 @@ void GW::prepare_cda() {
     k_axpby(K, kappa0, nn, c, -1.0, ctx->stream);
     k_add_diagonal(K, (int)na, na, 1.0, ctx->stream);
   }
+  ctx->group_start();
+  for (int j = 0; j < order; ++j) ctx->bcast(cda_kernels.p + (long long)j * nn, (size_t)nn, owner(j));
+  ctx->group_end();
   cda_points_dev.ensure((size_t)(2 * order));
   ctx->h2d(cda_points_dev.p, quad_points.data(), (size_t)order);
   ctx->h2d(cda_points_dev.p + order, quad_weights.data(), (size_t)order);
@@ -482,11 +515,18 @@ void GW::cda_values(long long n, const long long* levels, const double* freqs, d
   if (items.empty()) return;
   const long long bmax = std::max<long long>(1, std::min<long long>((long long)items.size(), (1LL << 28) / nn));
   DBuf eps((size_t)(bmax * nn)), inv((size_t)(bmax * nn)), res((size_t)bmax + 1);
-  DBuf meta((size_t)(3 * ((bmax + 1) / 2 + 1)));
+  DBuf meta((size_t)(4 * ((bmax + 1) / 2 + 1)));
   int* slab_d = reinterpret_cast<int*>(meta.p);
   int* col_d = slab_d + bmax + 1;
   int* mat_d = col_d + bmax + 1;
-  std::vector<int> hs, hc, hm;
+  int* act_d = mat_d + bmax + 1;
+  // Pole sharding (world > 1): item k's eps(|e_i - w|) is summed onto rank k % world, which alone inverts it and
+  // evaluates the quadratic form; the vector it needs (one column of a slab, owned by the rank holding second-index
+  // column i) reaches it through a small all-reduced gather buffer.
+  const int world = ctx->world, rank = ctx->rank;
+  DBuf Vb;
+  if (world > 1) Vb.alloc((size_t)(bmax * na));
+  std::vector<int> hs, hc, hm, ha;
   std::vector<double> deltas, hres;
   const size_t smem = (size_t)na * sizeof(double);
   if (smem > 48 * 1024)
@@ -501,13 +541,26 @@ void GW::cda_values(long long n, const long long* levels, const double* freqs, d
       hc[k] = (it.i % tc->world == tc->rank) ? it.i / tc->world : -1;     // owner of second-index column i
       hm[k] = (int)k;
     }
-    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, deltas.data(), (int)cnt, false, 0.0, eps.p);
-    for (long long k = 0; k < cnt; ++k) ctx->general_inverse((int)na, eps.p + k * nn, na, inv.p + k * nn, na);
+    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, deltas.data(), (int)cnt, false, 0.0, eps.p, 0);
+    for (long long k = 0; k < cnt; ++k)
+      if (k % world == rank) ctx->general_inverse((int)na, eps.p + k * nn, na, inv.p + k * nn, na);
     XTPB_CUDA(cudaMemcpyAsync(slab_d, hs.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     XTPB_CUDA(cudaMemcpyAsync(col_d, hc.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     XTPB_CUDA(cudaMemcpyAsync(mat_d, hm.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    cda_residue_kernel<<<(unsigned)cnt, 256, smem, ctx->stream>>>(inv.p, (int)na, tc->M.p, tc->ldn, tc->slab, slab_d,
-                                                                 col_d, mat_d, res.p);
+    if (world > 1) {
+      cda_gather_columns_kernel<<<nblocks(cnt * na, 256), 256, 0, ctx->stream>>>(Vb.p, (int)na, tc->M.p, tc->ldn,
+                                                                               tc->slab, slab_d, col_d, (int)cnt);
+      LAUNCH_CHECK_SO();
+      ctx->allreduce_sum(Vb.p, (size_t)(cnt * na));
+      ha.resize((size_t)cnt);
+      for (long long k = 0; k < cnt; ++k) ha[k] = (k % world == rank) ? 0 : -1;      // >= 0: this rank evaluates item k
+      XTPB_CUDA(cudaMemcpyAsync(act_d, ha.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      cda_residue_kernel<<<(unsigned)cnt, 256, smem, ctx->stream>>>(inv.p, (int)na, tc->M.p, tc->ldn, tc->slab, slab_d,
+                                                                   act_d, mat_d, Vb.p, res.p);
+    } else {
+      cda_residue_kernel<<<(unsigned)cnt, 256, smem, ctx->stream>>>(inv.p, (int)na, tc->M.p, tc->ldn, tc->slab, slab_d,
+                                                                   col_d, mat_d, nullptr, res.p);
+    }
     LAUNCH_CHECK_SO();
     ctx->allreduce_sum(res.p, (size_t)cnt);
     hres.resize((size_t)cnt);

@@ -427,7 +427,7 @@ void TCMatrix::rotate(const double* R_dev, long long ldr) {
 // eps(w) = 1 + sum_{m occ} A_m^T diag(d_m(w)) A_m with A_m = M[m](unocc, :)   (upstream RPA::calculate_epsilon)
 // One lower-triangular SYRK-style launch per call; the frequency index is the batch dimension.
 void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
-                     int n_omega, bool imag, double, double* out_dev) {
+                     int n_omega, bool imag, double, double* out_dev, int owner_shift) {
   Context* ctx = tc.ctx;
   ProfScope prof(PROF_EPSILON);
   XTPB_REQUIRE(n_occ > 0 && n_occ < tc.ntotal_glob && n_occ <= tc.mtotal, "RPA needs occupied and unoccupied levels");
@@ -455,7 +455,18 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
   } else {
     XTPB_CUDA(cudaMemsetAsync(out_dev, 0, out_count * 8, ctx->stream));
   }
-  ctx->allreduce_sum(out_dev, out_count);           // partial sums over the local unoccupied levels
+  const bool sharded = owner_shift >= 0 && ctx->world > 1;
+  auto mine = [&](int w) { return !sharded || (w + owner_shift) % ctx->world == ctx->rank; };
+  if (sharded) {                                    // each frequency's matrix is summed onto its owner only
+    XTPB_REQUIRE(!tc.pending, "frequency-sharded epsilon needs a flushed tensor");
+    ctx->group_start();
+    for (int w = 0; w < n_omega; ++w)
+      ctx->reduce_sum(out_dev + (long long)w * tc.naux * tc.naux, (size_t)(tc.naux * tc.naux),
+                      (w + owner_shift) % ctx->world);
+    ctx->group_end();
+  } else {
+    ctx->allreduce_sum(out_dev, out_count);         // partial sums over the local unoccupied levels
+  }
   if (tc.pending) {
     // the tensor still lacks the deferred aux rotation Rp: eps = 1 + Rp^T E Rp with E from the un-rotated tensor
     const long long na = tc.naux;
@@ -479,7 +490,8 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
     ctx->sync();   // T is freed at scope exit
   }
   for (int w = 0; w < n_omega; ++w)
-    symmetrize_from_lower(out_dev + (long long)w * tc.naux * tc.naux, (int)tc.naux, tc.naux, 1.0, ctx->stream);
+    if (mine(w))
+      symmetrize_from_lower(out_dev + (long long)w * tc.naux * tc.naux, (int)tc.naux, tc.naux, 1.0, ctx->stream);
   ctx->sync();   // d is freed on return
 }
 

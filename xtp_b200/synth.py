@@ -66,6 +66,10 @@ WORKLOADS = {
     "ch4-svp-shape": Sizes(n_basis=34, n_aux=140, homo=4),
     "benzene-tzvp-shape": Sizes(n_basis=222, n_aux=1110, homo=20),
     "pentacene-tzvp-shape": Sizes(n_basis=766, n_aux=3830, homo=72),
+    # BASELINE.json configs[2]: pentacene evGW with the contour-deformation self-energy.  CDA needs one epsilon^-1 per
+    # enclosed pole and evaluation, so (as in production use of Sigma_CDA) the QP window is HOMO-4 .. LUMO+4; the RPA
+    # range is all levels and the BSE window the default one (it sticks out of the QP window on both sides)
+    "pentacene-tzvp-cda": Sizes(n_basis=766, n_aux=3830, homo=72, qpmin=68, qpmax=77, cmax=145),
     "c60-tzvp-shape": Sizes(n_basis=1860, n_aux=5500, homo=179),
     "synth-500": Sizes(n_basis=500, n_aux=1500, homo=49),
     "synth-1000": Sizes(n_basis=1000, n_aux=3000, homo=99),
