@@ -69,7 +69,7 @@ def test_main_arm_assembles_the_json_line_with_a_fake_device(monkeypatch, capsys
     calls = []
 
     class FakeJob:
-        def __init__(self, workload, device, rank=0, world=1, comm=None, e2e=True, seed=None):
+        def __init__(self, workload, device, rank=0, world=1, comm=None, e2e=True, seed=None, sigma="ppm", evgw=1):
             self.sz = synth.WORKLOADS[workload]
             self.pk = self.sz.n_basis * (self.sz.n_basis + 1) // 2
             self.last = {}
