@@ -90,6 +90,14 @@ int xtpb_tc_destroy(xtpb_tc* tc);
 int xtpb_tc_sizes(const xtpb_tc* tc, xtpb_index* auxsize, xtpb_index* msize, xtpb_index* nsize);
 /* whole tensor in the reference's host layout: mtotal slabs, each ntotal x auxsize column-major */
 int xtpb_tc_set_raw(xtpb_tc* tc, const double* M_host);
+/* the same from a device pointer (same layout, contiguous): synthetic tensors drawn on the GPU (BASELINE configs[4]) */
+int xtpb_tc_set_raw_dev(xtpb_tc* tc, const double* M_dev);
+/* Read-only view of the resident tensor for callers that keep working on the device (and for parity checks at sizes
+ * whose tensor does not fit host memory comfortably): element M[m](n, P) of the reference's matrix_[m] lives at
+ * M_dev[m*slab_stride + P*ld_n + n], n < n_local (this rank's share of the second index; all of it on one GPU).
+ * Pending aux rotations are applied first.  The pointer is invalidated by xtpb_tc_destroy only. */
+int xtpb_tc_device_view(xtpb_tc* tc, const double** M_dev, xtpb_index* ld_n, xtpb_index* slab_stride,
+                        xtpb_index* n_local);
 /* TCMatrix_gwbse::operator[](m): slab m (ntotal x auxsize, column-major, ld = ntotal) */
 int xtpb_tc_get_slab(xtpb_tc* tc, xtpb_index m, double* slab_host);
 /* TCMatrix_gwbse::Fill3cMO, split so the caller's integral loop can stream aux shells:

@@ -1,0 +1,160 @@
+"""-m gpu: parity AT THE BENCHMARKED SHAPES (pentacene/def2-TZVP and C60/def2-TZVP shape, BASELINE.json configs[2-3]).
+
+The numpy oracle needs hours at these sizes, so every stage is checked on SAMPLED outputs against an independent
+evaluation on the device's own operands:
+  * M after Fill3cMO + Coulomb metric: sampled (m, :, n) fibres against torch FP64 (cuBLAS / cuSOLVER -- none of this
+    library's kernels) evaluation of  sum_Q [C_n^T T_Q C_m] V^-1/2[Q, P]                 (north_star: 1e-10 relative)
+  * epsilon(i w): bilinear probes x^T eps y against the double sum over (occupied, empty) pairs
+  * Sigma_c (PPM): ~20 (level, frequency) points of the pair kernel AND of the compressed QP-grid scan against the
+    OpenMP C kernel of the oracle (oracle/cpu_kernels.c: sigma_ppm_diag) on the slabs read back from the device
+  * BSE_OPERATOR::matmul: H X for 3 random X, dense-H and factorised strategies, against the factorised product
+    written with torch einsum on the tensor windows
+The TMA instance of the contraction engine, the split-K heuristics, the dense-H scatter maps and the 28..100-bin grid
+plans only take their benchmarked code paths at these sizes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max()))
+
+
+@pytest.mark.parametrize("workload", ["pentacene-tzvp-shape", "c60-tzvp-shape"])
+def test_sampled_parity_at_benchmark_shape(workload, monkeypatch):
+    import torch
+
+    import bench
+    from oracle import cpu_reference as cr
+    from xtp_b200 import api
+
+    if torch.cuda.get_device_properties(0).total_memory < 150e9 and workload.startswith("c60"):
+        pytest.skip("needs a 180 GB device")
+    job = bench.GwbseJob(workload, 0)
+    sz, tc, dev = job.sz, job.tc, job.dev
+    nb, na, nocc = sz.n_basis, sz.n_aux, sz.n_occ
+    tma0 = api.tma_launch_count()
+
+    # ---------------------------------------------------------------- (1) Fill3cMO + Coulomb metric
+    tc.coulomb_metric_begin(job.V)
+    tc.fill_begin(job.C)
+    base = job.ao_dev.data_ptr()
+    for p in range(0, na, job.block):
+        cnt = min(job.block, na - p)
+        tc.fill_block_packed_dev(p, cnt, base + p * job.pk * 8)
+    job.ctx.sync()
+    assert tc.apply_coulomb_metric(job.V) == 0
+    M = tc.torch_view()                                          # [m, P, n]; applies the pending metric rotation
+    rng = np.random.default_rng(11)
+    ms = rng.integers(0, sz.mtotal, 5)
+    ns = rng.integers(0, sz.ntotal, 5)
+    Ct = torch.from_numpy(np.ascontiguousarray(job.C)).to(dev)
+    lam, U = torch.linalg.eigh(torch.from_numpy(np.ascontiguousarray(job.V)).to(dev))
+    R = (U / lam.sqrt()) @ U.T                                   # V^-1/2
+    il = torch.tril_indices(nb, nb, device=dev)
+    t = torch.empty((na, len(ms)), dtype=torch.float64, device=dev)
+    for q0 in range(0, na, 32):
+        q1 = min(na, q0 + 32)
+        T = torch.zeros((q1 - q0, nb, nb), dtype=torch.float64, device=dev)
+        T[:, il[0], il[1]] = job.ao_dev[q0:q1]
+        T[:, il[1], il[0]] = job.ao_dev[q0:q1]
+        W = T @ Ct[:, ms]                                        # (q, nb, samples)
+        t[q0:q1] = torch.einsum("qbs,bs->qs", W, Ct[:, ns])
+        del T, W
+    ref = (R.T @ t).T                                            # ref[s, P] = sum_Q t[Q, s] R[Q, P]
+    got = torch.stack([M[int(m), :, int(n)] for m, n in zip(ms, ns)])
+    assert rel(got.cpu().numpy(), ref.cpu().numpy()) < 1e-10
+    del R, U, lam, t
+
+    # ---------------------------------------------------------------- (2) epsilon(i w) probes
+    e = job.energies[sz.rpamin:sz.rpamax + 1]
+    rpa = api.RPA(tc)
+    rpa.configure(sz.homo, sz.rpamin, sz.rpamax)
+    rpa.setRPAInputEnergies(e)
+    w = 0.5
+    eps = rpa.calculate_epsilon_i(w)
+    assert rel(eps, eps.T) < 1e-13
+    et = torch.from_numpy(e).to(dev)
+    d = et[nocc:][None, :] - et[:nocc][:, None]
+    d = 4.0 * d / (d * d + w * w)                                # (occ, empty)
+    A = M[:nocc][:, :, nocc:]                                    # view (occ, P, empty)
+    for seed in (1, 2, 3):
+        r2 = np.random.default_rng(seed)
+        x, y = r2.standard_normal(na), r2.standard_normal(na)
+        xa = torch.matmul(torch.from_numpy(x).to(dev), A)        # (occ, empty)
+        ya = torch.matmul(torch.from_numpy(y).to(dev), A)
+        want = float(x @ y) + float((xa * ya * d).sum())
+        got = float(x @ eps @ y)
+        assert abs(got - want) < 1e-10 * max(1.0, abs(want)), (got, want)
+    del eps, A, xa, ya
+
+    # ---------------------------------------------------------------- (3) G0W0: Sigma_c (PPM) pair kernel and grid scan
+    gw = api.GW(job.ctx, tc, job.vxc, job.energies)
+    gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax))
+    gw.CalculateGWPerturbation()
+    qp = gw.getGWAResults()
+    assert gw.unconverged_levels() == 0 and np.all(np.isfinite(qp))
+    info = gw.grid_scan_info()
+    assert info["compressed"] and info["direct_evaluations"] < 0.5 * info["equivalent_evaluations"]
+    weight, freq = gw.getPpm()
+    fac = np.where(weight < 1e-9, 0.0, 0.5 * weight * freq)
+    M = tc.torch_view()                                          # now in the PPM eigenbasis
+    levels = np.array([0, sz.homo - sz.qpmin - 3, sz.homo - sz.qpmin, sz.homo + 1 - sz.qpmin, sz.qptotal - 1])
+    steps, spacing = 1001, 0.01
+    centers = job.energies[sz.qpmin:sz.qpmax + 1].copy()
+    grid = gw.CalcCorrelationGrid(centers)                       # the scan GW::SolveQP_Grid runs
+    pick = np.array([3, 250, 500, 777])                          # grid points checked per level
+    lv, fr, want, from_grid = [], [], [], []
+    for l in levels:
+        slab = np.ascontiguousarray(M[int(l) + sz.qpmin - sz.rpamin].cpu().numpy())     # [P, m]
+        om = centers[l] + (pick - (steps - 1) / 2) * spacing
+        want.extend(cr.sigma_ppm_diag(slab, nocc, e, freq, fac, om))
+        lv.extend([l] * len(pick)); fr.extend(om); from_grid.extend(grid[l][pick])
+    want = np.array(want)
+    got = gw.CalcCorrelationDiagElements(np.array(lv), np.array(fr))
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 1e-9 * scale, "pair kernel"
+    assert np.abs(np.array(from_grid) - want).max() < 1e-9 * scale, "compressed grid scan"
+
+    # ---------------------------------------------------------------- (4) BSE_OPERATOR::matmul
+    gw.CalculateHQP()
+    hqp, rpa_e = gw.getHQP(), gw.RPAInputEnergies()
+    gw.close()
+    bse = api.BSE(job.ctx, tc)
+    bse.configure(sz.homo, sz.rpamin, sz.rpamax, sz.qpmin, sz.qpmax, sz.vmin, sz.cmax, 3, rpa_e, hqp)
+    assert bse.eps0_reused()                                     # the windows are plain views of the tensor
+    einv = torch.from_numpy(bse.epsilon_0_inv()).to(dev)
+    vt, ct = sz.vtotal, sz.ctotal
+    v0, c0 = sz.vmin - sz.rpamin, sz.homo + 1 - sz.rpamin
+    Mvc, Mvv, Mcc = M[v0:v0 + vt][:, :, c0:c0 + ct], M[v0:v0 + vt][:, :, v0:v0 + vt], M[c0:c0 + ct][:, :, c0:c0 + ct]
+    k = 3
+    X = np.linalg.qr(np.random.default_rng(5).standard_normal((vt * ct, k)))[0]
+    X4 = torch.from_numpy(X).to(dev).reshape(vt, ct, k)
+    H = torch.from_numpy(hqp).to(dev)
+    q0 = sz.vmin - sz.qpmin                                       # default ranges: the BSE window is the QP window
+    assert q0 == 0 and vt + ct == hqp.shape[0]
+    Hv, Hc = H[:vt, :vt], H[vt:, vt:]
+    Y = torch.einsum("cd,vdk->vck", Hc, X4) - torch.einsum("vw,wck->vck", Hv, X4)
+    Tm = torch.einsum("vpc,vck->pk", Mvc, X4)
+    Y += 2.0 * torch.einsum("vpc,pk->vck", Mvc, Tm)
+    for kk in range(k):                                          # direct term one trial vector at a time (memory)
+        Uk = torch.einsum("cpd,wd->pcw", Mcc, X4[:, :, kk])
+        Y[:, :, kk] -= torch.einsum("vpw,p,pcw->vc", Mvv, einv, Uk)
+        del Uk
+    want = Y.reshape(vt * ct, k).cpu().numpy()
+    for mode in ("dense", "factorised"):
+        monkeypatch.setenv("XTPB_BSE_MODE", mode)
+        op = bse.make_operator("SingletOperator_TDA")
+        assert rel(op.matmul(X), want) < 1e-10, mode
+        op.close()
+    bse.close()
+    assert api.tma_launch_count() > tma0                          # the benchmarked (TMA-fed) contraction instance ran
+    job.close()

@@ -21,27 +21,68 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from xtp_b200 import api, synth  # noqa: E402
 
+DMMA_PEAK = 37.09      # TFLOP/s, profiles/r01_fp64_probe.json
+try:
+    HBM_PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                 "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:  # noqa: BLE001
+    HBM_PEAK = 6551.0
 
-def run(nb, ks, reps, out):
+
+def draw_window_on_device(sz, seed, chunk=100):
+    """M[m, P, n] for the BSE window only (m, n < v + c), drawn on the GPU with torch block by block, symmetric in
+    (m, n) as the real tensor is; same distribution as synth.make_M_direct.  (v+c)^2 N_aux doubles: 61 GB at N_b 4000,
+    where the full m x N_aux x N_b tensor would be 307 GB -- SURVEY.md section 7 hard part 4.)"""
+    import torch
+    mt, na = sz.mtotal, sz.n_aux
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    M = torch.empty((mt, na, mt), dtype=torch.float64, device="cuda")
+    scale = float(np.sqrt(synth.target_variance(sz)))
+    for i0 in range(0, mt, chunk):
+        i1 = min(mt, i0 + chunk)
+        for j0 in range(i0, mt, chunk):
+            j1 = min(mt, j0 + chunk)
+            R = torch.randn((i1 - i0, na, j1 - j0), dtype=torch.float64, device="cuda", generator=g) * scale
+            if i0 == j0:
+                R = (R + R.permute(2, 1, 0)) / np.sqrt(2.0)
+            M[i0:i1, :, j0:j1] = R
+            if i0 != j0:
+                M[j0:j1, :, i0:i1] = R.permute(2, 1, 0)
+    torch.cuda.synchronize()
+    return M
+
+
+def run(nb, ks, reps, out, strategies):
+    import torch
     homo = nb // 10 - 1
-    sz = synth.Sizes(n_basis=nb, n_aux=3 * nb, homo=homo)
+    # the operator needs the (v+c)^2 N_aux window of the tensor only: second index restricted to the BSE window
+    sz = synth.Sizes(n_basis=nb, n_aux=3 * nb, homo=homo, rpamax=2 * homo + 1)
     rng = np.random.default_rng(20260101 + nb)
     ctx = api.Context(0)
     tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
-    tc.set_raw(synth.make_M_direct(sz, rng))
+    Mdev = draw_window_on_device(sz, 20260101 + nb)
+    tc.set_raw_dev(Mdev.data_ptr())
+    del Mdev
+    torch.cuda.empty_cache()
     hs = sz.vtotal + sz.ctotal
     hq = np.diag(np.sort(rng.uniform(-1.0, 2.0, hs)))
     eps_inv = rng.uniform(0.2, 1.0, sz.n_aux)
     vc, v, c, na = sz.bse_size, sz.vtotal, sz.ctotal, sz.n_aux
-    for strategy in ("dense", "factorised"):
-        os.environ["XTPB_BSE_DENSE_MAX_GB"] = "0" if strategy == "factorised" else "64"
+    checks = {}
+    for strategy in strategies:
+        if strategy == "dense" and 8.0 * vc * vc > 64e9:
+            continue                                       # H does not fit: the factorised operator is mandatory
+        os.environ["XTPB_BSE_MODE"] = strategy
+        os.environ["XTPB_BSE_DENSE_MAX_GB"] = "64"
         t0 = time.perf_counter()
         op = api.BSE_OPERATOR(ctx, 1, 2, 1, 0, eps_inv, tc, hq, sz.homo, sz.rpamin, sz.vmin, sz.cmax)
         ctx.sync()
         build_s = time.perf_counter() - t0
         for k in ks:
-            X = np.linalg.qr(rng.standard_normal((vc, k)))[0]
-            op.matmul(X)                                   # warm-up (includes the host<->device copies of X, Y)
+            X = np.linalg.qr(np.random.default_rng(k).standard_normal((vc, k)))[0]
+            Y = op.matmul(X)                               # warm-up (includes the host<->device copies of X, Y)
+            checks.setdefault(k, {})[strategy] = Y
             api.profile_reset()
             api.profile_enable(True)
             for _ in range(reps):
@@ -50,12 +91,22 @@ def run(nb, ks, reps, out):
             p = api.profile_summary().get("bse_matmul", {"ms": 0.0, "work": 0.0, "launches": 0})
             ms = p["ms"] / reps
             flops = 4.0 * vc * na * k + 2.0 * na * k * vc * (v + c) + 2.0 * vc * k * (v + c)
+            # compulsory HBM bytes per call: dense = H once + the flat exchange operand twice; factorised = the three
+            # windows once -- plus X and Y
+            nbytes = (8.0 * vc * vc + 16.0 * vc * na if strategy == "dense" else 8.0 * na * (vc + v * v + c * c)) \
+                + 16.0 * vc * k
+            tf = flops / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0
+            gbs = nbytes / (ms * 1e-3) * 1e-9 if ms > 0 else 0.0
+            both = checks[k]
             rec = {"n_basis": nb, "n_aux": na, "bse_size": vc, "strategy": strategy, "k": k,
                    "operator_build_s": round(build_s, 4), "kernel_ms_per_matmul": round(ms, 4),
                    "launches_per_matmul": p["launches"] / reps,
-                   "algorithmic_tflops": round(flops / (ms * 1e-3) * 1e-12, 3) if ms > 0 else None,
-                   "dense_stream_gbs": round((8.0 * vc * vc + 16.0 * vc * na) / (ms * 1e-3) * 1e-9, 1)
-                   if ms > 0 and strategy == "dense" else None}
+                   "algorithmic_tflops": round(tf, 3), "dmma_frac": round(tf / DMMA_PEAK, 4),
+                   "compulsory_gbs": round(gbs, 1), "hbm_frac": round(gbs / HBM_PEAK, 4),
+                   "bound": "tensor" if tf / DMMA_PEAK > gbs / HBM_PEAK else "hbm",
+                   "dense_vs_factorised_rel_diff": (float(np.abs(both["dense"] - both["factorised"]).max()
+                                                          / np.abs(both["dense"]).max())
+                                                    if len(both) == 2 else None)}
             line = json.dumps(rec)
             print(line, flush=True)
             out.write(line + "\n")
@@ -70,11 +121,12 @@ def main():
     ap.add_argument("--k", default="1,10,20,40")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/bse_matvec.jsonl")
+    ap.add_argument("--strategies", default="dense,factorised")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         for nb in [int(x) for x in args.nb.split(",")]:
-            run(nb, [int(x) for x in args.k.split(",")], args.reps, f)
+            run(nb, [int(x) for x in args.k.split(",")], args.reps, f, args.strategies.split(","))
 
 
 if __name__ == "__main__":

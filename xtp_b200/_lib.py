@@ -87,6 +87,8 @@ PROTOTYPES = {
     "xtpb_tc_destroy": (C.c_int, [vp]),
     "xtpb_tc_sizes": (C.c_int, [vp, iptr, iptr, iptr]),
     "xtpb_tc_set_raw": (C.c_int, [vp, dptr]),
+    "xtpb_tc_set_raw_dev": (C.c_int, [vp, vp]),
+    "xtpb_tc_device_view": (C.c_int, [vp, C.POINTER(vp), iptr, iptr, iptr]),
     "xtpb_tc_get_slab": (C.c_int, [vp, idx, dptr]),
     "xtpb_tc_fill_begin": (C.c_int, [vp, idx, dptr, idx]),
     "xtpb_tc_fill_block": (C.c_int, [vp, idx, idx, dptr, idx]),

@@ -169,6 +169,28 @@ class TCMatrix_gwbse:
         assert M.shape == (self.msize(), self._aux, self.nsize())
         check(_lib.lib().xtpb_tc_set_raw(self._h, _d(M)))
 
+    def set_raw_dev(self, dev_ptr):
+        """Tensor from a contiguous device buffer [m][P][n] (e.g. a torch tensor's data_ptr())."""
+        check(_lib.lib().xtpb_tc_set_raw_dev(self._h, vp(int(dev_ptr))))
+
+    def device_view(self):
+        """(pointer, ld_n, slab_stride, n_local) of the resident tensor: M[m](n, P) at ptr + 8*(m*slab + P*ld_n + n)."""
+        p, ld, sl, nl = vp(), idx(0), idx(0), idx(0)
+        check(_lib.lib().xtpb_tc_device_view(self._h, C.byref(p), C.byref(ld), C.byref(sl), C.byref(nl)))
+        return int(p.value), int(ld.value), int(sl.value), int(nl.value)
+
+    def torch_view(self):
+        """The resident tensor as a torch tensor [m, P, ld_n] sharing the library's memory (read it, do not write it);
+        columns >= n_local of the last axis are padding."""
+        import torch
+        ptr, ld, sl, nl = self.device_view()
+        mt = self.mmax - self.mmin + 1
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (mt, self._aux, ld), "typestr": "<f8", "data": (ptr, False),
+                                        "version": 3, "strides": (sl * 8, ld * 8, 8)}
+        return torch.as_tensor(_Holder(), device="cuda")[:, :, :nl]
+
     def __getitem__(self, m):
         """operator[]: slab m as an (nsize x auxsize) matrix."""
         out = np.empty((self._aux, self.nsize()))

@@ -120,6 +120,30 @@ int xtpb_tc_set_raw(xtpb_tc* tc, const double* M_host) {
   tc->impl.set_raw(M_host);
   XTPB_API_END
 }
+int xtpb_tc_set_raw_dev(xtpb_tc* tc, const double* M_dev) {
+  XTPB_API_BEGIN
+  TCMatrix& t = tc->impl;
+  XTPB_REQUIRE(t.world == 1, "xtpb_tc_set_raw_dev: single rank only (use xtpb_tc_set_raw with several ranks)");
+  XTPB_REQUIRE(M_dev != nullptr, "null pointer");
+  t.pending = false;
+  t.eps0.valid = false;
+  XTPB_CUDA(cudaMemcpy2DAsync(t.M.p, t.ldn * 8, M_dev, t.ntotal * 8, t.ntotal * 8, t.mtotal * t.naux,
+                              cudaMemcpyDeviceToDevice, t.ctx->stream));
+  t.ctx->sync();
+  XTPB_API_END
+}
+int xtpb_tc_device_view(xtpb_tc* tc, const double** M_dev, xtpb_index* ld_n, xtpb_index* slab_stride,
+                        xtpb_index* n_local) {
+  XTPB_API_BEGIN
+  TCMatrix& t = tc->impl;
+  t.flush();
+  t.ctx->sync();
+  if (M_dev) *M_dev = t.M.p;
+  if (ld_n) *ld_n = t.ldn;
+  if (slab_stride) *slab_stride = t.slab;
+  if (n_local) *n_local = t.ntotal;
+  XTPB_API_END
+}
 int xtpb_tc_get_slab(xtpb_tc* tc, xtpb_index m, double* slab_host) {
   XTPB_API_BEGIN
   tc->impl.get_slab(m, slab_host);
