@@ -288,6 +288,35 @@ class GwbseJob:
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+CPU_VALIDATION_FILE = os.path.join(ROOT, "profiles", "r02_cpu_validation.json")
+
+
+def cpu_baseline_report(sz, davidson_calls, first=None):
+    """The CPU baseline object shared by both arms: reference-structure estimate (`value`), the same-algorithm
+    (factorised) estimate next to it, and the validation of the sampling against COMPLETE CPU steps -- benzene shape
+    run live (seconds), pentacene shape quoted from the committed run on a GPU box's host cores."""
+    from oracle import cpu_reference as cr
+    ref = first if first is not None else cr.sampled_step(sz, davidson_matmul_calls=davidson_calls)
+    same = cr.sampled_step(sz, davidson_matmul_calls=davidson_calls, algorithm="factorised")
+    validated = [cr.validate_against_full_step("benzene-tzvp-shape", "reference")]
+    try:
+        with open(CPU_VALIDATION_FILE) as f:
+            for rec in json.load(f)["runs"]:
+                rec = dict(rec)
+                rec["source"] = "profiles/r02_cpu_validation.json (complete step on a GPU box's host cores)"
+                validated.append(rec)
+    except Exception:  # noqa: BLE001
+        pass
+    sample = ("restated CPU baseline (reference-structure algorithms, NOT votca/xtp binaries), estimated from a bounded "
+              "sample per stage scaled by unit counts: " + "; ".join(f"{k}: {d}" for k, d in ref["describe"].items()))
+    return {"value": ref["seconds"], "unit": UNIT, "cores": ref["threads"], "kind": "port", "sample": sample,
+            "stage_seconds": ref["stage_seconds"],
+            "same_algorithm": {"value": same["seconds"], "unit": UNIT, "stage_seconds": same["stage_seconds"],
+                               "what": "the CUDA path's algorithm on the host cores (batched grid scan, weighted-slab "
+                                       "GEMM, factorised BSE matmul, eps(0) reuse), sampled the same way"},
+            "validated_against_full_step": validated}
+
+
 def run_reference(args):
     """Restated CPU baseline (reference-structure algorithms, all host threads), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -296,7 +325,7 @@ def run_reference(args):
     from oracle import cpu_reference as cr
     from xtp_b200 import synth
     sz = synth.WORKLOADS[args.workload]
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 2)):
         cr.sampled_step(sz, scale=0.25)
     vals, last = [], None
     t_wall = time.perf_counter()
@@ -304,18 +333,20 @@ def run_reference(args):
         last = cr.sampled_step(sz, davidson_matmul_calls=args.davidson_calls)
         vals.append(last["seconds"])
     wall = time.perf_counter() - t_wall
-    v = float(np.mean(vals))
-    sample = ("estimated from a bounded sample per stage, scaled by unit counts: " +
-              "; ".join(f"{k}: {d}" for k, d in last["describe"].items()))
+    v = float(np.median(vals))
+    cpu = cpu_baseline_report(sz, args.davidson_calls, first=last)
+    cpu["value"] = v
+    cpu["sample_wall_seconds_per_step"] = wall / args.steps
+    cpu["spread"] = {"min": float(np.min(vals)), "max": float(np.max(vals)), "steps": len(vals)}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n_basis": sz.n_basis, "n_aux": sz.n_aux, "homo": sz.homo,
                        "bse_size": sz.bse_size, "nmax": NMAX,
                        "note": "restated CPU baseline (reference-structure algorithms), NOT votca/xtp binaries: "
-                               "/root/reference is a one-line stub"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["threads"], "kind": "port", "sample": sample,
-                             "stage_seconds": last["stage_seconds"], "sample_wall_seconds_per_step": wall / args.steps},
+                               "/root/reference is a one-line stub; value = median over the steps of a sampled estimate, "
+                               "validated against complete CPU steps (cpu_baseline.validated_against_full_step)"},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -332,7 +363,9 @@ def main():
     ap.add_argument("--evgw", type=int, default=1, help="evGW iterations (1 = G0W0)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--davidson-calls", type=int, default=12, help="matmul calls assumed by the CPU sample")
+    ap.add_argument("--davidson-calls", type=int, default=40,
+                    help="BSE matmul calls per Davidson solve assumed by the CPU sample (the GPU arm's identical solver "
+                         "needs 40 on the C60-shape workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -487,14 +520,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1 and args.sigma == "ppm" and args.evgw <= 1:
-        from oracle import cpu_reference as cr
-        iters = int(job.last["davidson_iterations"])
-        s = cr.sampled_step(sz, davidson_matmul_calls=iters)
-        cpu = {"value": s["seconds"], "unit": UNIT, "cores": s["threads"], "kind": "port",
-               "sample": ("restated CPU baseline (reference-structure algorithms, NOT votca/xtp binaries), estimated "
-                          "from a bounded sample per stage scaled by unit counts: " +
-                          "; ".join(f"{k}: {d}" for k, d in s["describe"].items())),
-               "stage_seconds": s["stage_seconds"]}
+        cpu = cpu_baseline_report(sz, int(job.last["davidson_iterations"]))
 
     res = job.last
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

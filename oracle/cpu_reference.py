@@ -103,17 +103,32 @@ def unpack_symmetric(packed, n):
     return full
 
 
-def _timeit(fn, min_reps=1):
-    fn()                      # warm (page faults, BLAS thread spin-up)
-    t0 = time.perf_counter()
-    for _ in range(min_reps):
+def _timeit(fn, reps=2):
+    """Best of `reps` timed runs after one warm-up run (page faults, BLAS thread spin-up).  The short sleep lets the
+    worker threads of the OTHER runtime (OpenBLAS after a GEMM sample, OpenMP after a C-kernel sample) stop spinning:
+    without it a kernel sampled right after a GEMM was timed up to 2x too slow."""
+    time.sleep(0.15)
+    fn()
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
         fn()
-    return (time.perf_counter() - t0) / min_reps
+        best = min(best, time.perf_counter() - t0)
+    return best
 
 
-def sampled_step(sz, davidson_matmul_calls=12, grid_steps=1001, triplets=False, scale=1.0, seed=7):
-    """Estimated seconds per molecule for workload ``sz`` (xtp_b200.synth.Sizes), reference-structure CPU.
-    ``scale`` multiplies every sample size (1.0 ~ 15-25 s of CPU work on 16 cores at C60 size)."""
+def sampled_step(sz, davidson_matmul_calls=40, grid_steps=1001, triplets=False, scale=1.0, seed=7,
+                 algorithm="reference"):
+    """Estimated seconds per molecule for workload ``sz`` (xtp_b200.synth.Sizes) on the CPU, from a bounded sample of
+    the independent units of every stage, scaled by the unit counts.  The sample sizes are fixed numbers (they do not
+    depend on the core count); ``scale`` multiplies them (1.0 ~ 15-25 s of CPU work on 16 cores at C60 size).
+
+    algorithm="reference":  the reference's loop structure (see the module docstring and oracle/cpu_step.py).
+    algorithm="factorised": the CUDA path's algorithm on the CPU -- grid scan in one pass per slab, off-diagonal
+        Sigma_c as a weighted-slab GEMM, no second eps(0)/eigensolver/rotation for the BSE, factorised BSE matmul.
+    ``validate_against_full_step`` runs both this estimate and a complete step at a size where that is affordable."""
+    assert algorithm in ("reference", "factorised")
+    from xtp_b200 import synth
     use_all_host_threads()
     rng = np.random.default_rng(seed)
     nb, naux = sz.n_basis, sz.n_aux
@@ -147,21 +162,22 @@ def sampled_step(sz, davidson_matmul_calls=12, grid_steps=1001, triplets=False, 
     desc["solver"] = f"eigh/inverse/GEMM at n={ne}, scaled by (N_aux/n)^3"
     del S
 
-    # --- aux rotation: per slab M[m] (n x naux) @ A (naux x naux)
+    # --- aux rotation: per slab A^T (naux x naux) @ M[m] (naux x n)
     nr = cnt(2, m)
     A = rng.standard_normal((naux, naux))
-    slab = rng.standard_normal((n, naux))
-    t_rot_slab = _timeit(lambda: [slab @ A for _ in range(nr)]) / nr
+    slab = rng.standard_normal((naux, n))          # [P, level]
+    t_rot_slab = _timeit(lambda: [A.T @ slab for _ in range(nr)]) / nr
     desc["rotation"] = f"{nr} of {m} slabs"
     stage["metric"] = t_eigh + t_gemm + t_rot_slab * m      # one eigh + U s U^T + rotation
-    # --- epsilon: per occupied level A_m^T diag(d) A_m
+    # --- epsilon: per occupied level A_m diag(d) A_m^T
     nE = cnt(2, o)
-    Am = np.ascontiguousarray(slab[:u])
+    Am = np.ascontiguousarray(slab[:, :u])
     d = rng.random(u)
-    t_eps_level = _timeit(lambda: [(Am.T * d) @ Am for _ in range(nE)]) / nE
-    t_eps = t_eps_level * o
-    desc["epsilon"] = f"{nE} of {o} occupied levels per frequency; 3 frequencies per step (PPM 2, BSE 1)"
-    stage["epsilon"] = 3 * t_eps
+    t_eps_level = _timeit(lambda: [(Am * d) @ Am.T for _ in range(nE)]) / nE
+    n_eps = 3 if algorithm == "reference" else 2
+    desc["epsilon"] = (f"{nE} of {o} occupied levels per frequency; {n_eps} frequencies per step (PPM 2" +
+                       (", BSE 1)" if algorithm == "reference" else "; the BSE reads eps(0) from the PPM eigenbasis)"))
+    stage["epsilon"] = n_eps * t_eps_level * o
     stage["ppm"] = t_eigh + t_inv + 2 * t_gemm + t_rot_slab * m
     del A, Am
 
@@ -174,53 +190,134 @@ def sampled_step(sz, davidson_matmul_calls=12, grid_steps=1001, triplets=False, 
     desc["sigma_x"] = f"{nx}x{Mq.shape[0]} of {q}x{q} level pairs"
     del Mo, Mq
 
-    # --- Sigma_c grid: one level, nW frequencies through the OpenMP kernel
-    nW = cnt(2 * host_threads(), grid_steps)
-    slabP = np.ascontiguousarray(slab.T)            # [P, m]
-    e = np.sort(rng.uniform(-1, 3, n))
+    # --- Sigma_c QP grid.  Energies as the synthetic workloads have them, plasmon-pole frequencies 0.3 .. 2 Ha.
+    e = synth.make_energies(sz, np.random.default_rng(seed + 1))[sz.rpamin:sz.rpamax + 1]
     pf = rng.uniform(0.3, 2.0, naux)
     pw = rng.uniform(0.1, 1.0, naux)
-    om = np.linspace(-5, 5, nW)
-    t = _timeit(lambda: sigma_ppm_diag(slabP, o, e, pf, pw, om))
+    slab *= np.sqrt(synth.target_variance(sz))
     evals_per_level = grid_steps + 25               # grid + bisection / derivative evaluations
-    stage["sigma_c"] = t / nW * evals_per_level * q
-    desc["sigma_c"] = f"{nW} of {evals_per_level} frequency evaluations of 1 of {q} levels"
+    if algorithm == "reference":
+        nW = cnt(96, grid_steps)                    # frequencies of ONE level, one CalcCorrelationDiagElement each
+        om = e[o - 1] + 0.01 * (np.arange(nW) - nW / 2)
+        t = _timeit(lambda: sigma_ppm_diag(slab, o, e, pf, pw, om))
+        stage["sigma_c"] = t / nW * evals_per_level * q
+        desc["sigma_c"] = f"{nW} of {evals_per_level} frequency evaluations of 1 of {q} levels"
+    else:
+        from . import cpu_step
+        lib = cpu_step._lib()
+        nl = cnt(1, q)
+        blk = np.ascontiguousarray(np.broadcast_to(slab, (nl,) + slab.shape))
+        om0 = np.full(nl, e[o - 1] - 0.005 * (grid_steps - 1))
+        vals = np.empty((nl, grid_steps))
+        t = _timeit(lambda: lib.sigma_ppm_grid_batched(cpu_step._p(blk), naux * n, n, n, naux, o, cpu_step._p(e),
+                                                       cpu_step._p(pf), cpu_step._p(pw), nl, cpu_step._p(om0), 0.01,
+                                                       grid_steps, cpu_step._p(vals)), reps=1)
+        om = e[o - 1] + 0.01 * np.arange(8)
+        t1 = _timeit(lambda: sigma_ppm_diag(slab, o, e, pf, pw, om)) / 8
+        stage["sigma_c"] = t / nl * q + t1 * 25 * q
+        desc["sigma_c"] = (f"batched grid scan ({grid_steps} frequencies in one pass over the slab) of {nl} of {q} "
+                           f"levels + 25 point evaluations per level")
+        del blk
 
-    # --- Sigma_c off-diagonal: weighted slabs (one kernel-cost pass per level) + GEMM q x q over (P, m)
-    nl = cnt(4, q)
-    Wl = rng.standard_normal((nl, n * naux // 8))
-    t = _timeit(lambda: Wl @ Wl.T)
-    stage["offdiag"] = t * 8 * (q / nl) ** 2 + (stage["sigma_c"] / (evals_per_level * q)) * q
-    desc["offdiag"] = f"{nl}x{nl} of {q}x{q} pairs over 1/8 of the (P,m) range"
-    del Wl
+    # --- Sigma_c off-diagonal
+    # throughput cost of one pass over one slab with every thread busy (the level-pair loop is spread over the threads)
+    om_off = e[o - 1] + 0.05 * (np.arange(96) - 48)
+    t_pass = _timeit(lambda: sigma_ppm_diag(slab, o, e, pf, pw, om_off)) / 96       # all threads busy: throughput per pass
+    t_point = t_pass
+    if algorithm == "reference":
+        # CalcCorrelationOffDiagElement per level pair: two stabilised inverses per (P, m) = two point evaluations
+        stage["offdiag"] = t_point * 2 * q * (q - 1) / 2
+        desc["offdiag"] = f"2 slab passes per level pair, {q * (q - 1) // 2} pairs (pass cost from the Sigma_c sample)"
+    else:
+        nl = cnt(4, q)
+        Wl = rng.standard_normal((nl, n * naux // 8))
+        t = _timeit(lambda: Wl @ Wl.T)
+        stage["offdiag"] = t * 8 * (q / nl) ** 2 + t_point * q
+        desc["offdiag"] = f"weighted slabs + GEMM: {nl}x{nl} of {q}x{q} pairs over 1/8 of the (P,m) range"
+        del Wl
 
-    # --- BSE setup: epsilon counted above; eigh + rotation of the whole tensor (reference rotates every slab)
-    stage["bse_setup"] = t_eigh + t_rot_slab * m
+    # --- BSE setup
+    stage["bse_setup"] = (t_eigh + t_rot_slab * m) if algorithm == "reference" else 0.0
 
-    # --- Davidson: reference-structure matmul, H row block of one v1 = direct (vt x naux)(naux x ct^2)
-    #     + exchange (ct x naux)(naux x vt ct), then row block times X
+    # --- Davidson
     k = 15
-    nv = cnt(1, vt)
-    Mcc = rng.standard_normal((naux, ct * ct))
-    Mvc = rng.standard_normal((naux, vt * ct))
-    Mv1v = rng.standard_normal((vt, naux))
-    Mv1c = rng.standard_normal((ct, naux))
-    X = rng.standard_normal((vt * ct, k))
-
-    def row_block():
-        for _ in range(nv):
-            Hd = (Mv1v @ Mcc).reshape(vt, ct, ct)          # [v2, c1, c2]
-            Hx = Mv1c @ Mvc                                # [c1, (v2 c2)]
-            H = 2.0 * Hx - np.transpose(Hd, (1, 0, 2)).reshape(ct, vt * ct)
-            H @ X
-    t = _timeit(row_block) / nv
     n_solves = 2 if triplets else 1
-    stage["davidson"] = t * vt * davidson_matmul_calls * n_solves
-    desc["davidson"] = (f"{nv} of {vt} H row blocks of one matmul; {davidson_matmul_calls} matmul calls assumed per "
-                        f"solve, {n_solves} solve(s)")
+    X = rng.standard_normal((vt * ct, k))
+    if algorithm == "reference":
+        # matmul rebuilding H: row block of one v1 = direct (vt x naux)(naux x ct^2) + exchange (ct x naux)(naux x vt ct)
+        nv = cnt(1, vt)
+        Mcc = rng.standard_normal((naux, ct * ct))
+        Mvc = rng.standard_normal((naux, vt * ct))
+        Mv1v = rng.standard_normal((vt, naux))
+        Mv1c = rng.standard_normal((ct, naux))
+
+        def row_block():
+            for _ in range(nv):
+                Hd = (Mv1v @ Mcc).reshape(vt, ct, ct)          # [v2, c1, c2]
+                Hx = Mv1c @ Mvc                                # [c1, (v2 c2)]
+                H = 2.0 * Hx - np.transpose(Hd, (1, 0, 2)).reshape(ct, vt * ct)
+                H @ X
+        t = _timeit(row_block) / nv
+        stage["davidson"] = t * vt * davidson_matmul_calls * n_solves
+        desc["davidson"] = (f"{nv} of {vt} H row blocks of one matmul; {davidson_matmul_calls} matmul calls per solve, "
+                            f"{n_solves} solve(s)")
+    else:
+        # factorised matmul on a 1/16 slice of the aux range (every term is a sum over P)
+        pa = max(1, naux // 16)
+        Mvc = rng.standard_normal((vt * ct, pa))
+        Mcc = rng.standard_normal((pa * ct, ct))
+        Mvv = rng.standard_normal((pa, vt, vt))
+        Xt = rng.standard_normal((ct, vt * k))
+
+        def fact():
+            Mvc @ (Mvc.T @ X)
+            U = (Mcc @ Xt).reshape(pa, ct, vt, k)
+            np.einsum("pvw,pcwk->vck", Mvv, U, optimize=True)
+        t = _timeit(fact) * (naux / pa)
+        stage["davidson"] = t * davidson_matmul_calls * n_solves
+        desc["davidson"] = (f"factorised matmul over {pa} of {naux} aux functions; {davidson_matmul_calls} matmul calls "
+                            f"per solve, {n_solves} solve(s)")
     total = float(sum(stage.values()))
     return {"seconds": total, "stage_seconds": {k2: round(v, 3) for k2, v in stage.items()}, "describe": desc,
-            "threads": host_threads()}
+            "threads": host_threads(), "algorithm": algorithm}
+
+
+def lowmem_problem(workload, seed=None):
+    """synth.make_problem for shapes whose AO tensor is GBs (pentacene: 18 GB): slices generated chunk by chunk in
+    place (same distribution as synth.make_ao3c)."""
+    from xtp_b200 import synth
+    sz = synth.WORKLOADS[workload] if isinstance(workload, str) else workload
+    rng = np.random.default_rng(20260101 + sz.n_basis if seed is None else seed)
+    nb = sz.n_basis
+    prob = {"sizes": sz, "C": synth.make_mos(nb, rng), "energies": synth.make_energies(sz, rng)}
+    dd = np.abs(np.arange(nb)[:, None] - np.arange(nb)[None, :])
+    mask = np.exp(-dd / 32.0)
+    mask *= np.sqrt(synth.target_variance(sz) / np.mean(mask * mask))
+    ao = np.empty((sz.n_aux, nb, nb))
+    for p0 in range(0, sz.n_aux, 64):
+        p1 = min(sz.n_aux, p0 + 64)
+        G = rng.standard_normal((p1 - p0, nb, nb))
+        ao[p0:p1] = (G + np.transpose(G, (0, 2, 1))) * (mask / np.sqrt(2.0))
+    prob["ao3c"] = ao
+    prob["aux_coulomb"] = synth.make_aux_metric(sz, rng)
+    prob["vxc"] = synth.make_vxc(sz, rng)
+    return prob
+
+
+def validate_against_full_step(workload="benzene-tzvp-shape", algorithm="reference"):
+    """The sampled estimate next to a COMPLETE CPU step (oracle/cpu_step.py, nothing sampled or scaled) of the same
+    shape and algorithm, stage by stage -- the extrapolation error as a number."""
+    from . import cpu_step
+    prob = lowmem_problem(workload)
+    full = cpu_step.run_step(prob, algorithm=algorithm)
+    est = sampled_step(prob["sizes"], davidson_matmul_calls=full["matmul_calls"], algorithm=algorithm)
+    return {"shape": workload, "algorithm": algorithm, "cores": full["threads"],
+            "full_s": round(full["seconds"], 3), "sampled_s": round(est["seconds"], 3),
+            "sampled_over_full": round(est["seconds"] / full["seconds"], 3),
+            "full_stage_seconds": full["stage_seconds"], "sampled_stage_seconds": est["stage_seconds"],
+            "davidson_matmul_calls": full["matmul_calls"], "davidson_iterations": int(full["davidson_iterations"]),
+            "qp_homo_ha": float(full["qp"][prob["sizes"].homo - prob["sizes"].qpmin]),
+            "lowest_singlet_ha": float(full["singlets"][0])}
 
 
 def full_step(prob, nmax=10, grid_steps=1001, triplets=False):

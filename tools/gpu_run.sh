@@ -5,6 +5,12 @@ set -u
 TAG=$1; shift
 OUT=gpurun_out
 mkdir -p $OUT
+NGPU=${NGPU:-1}
+if [ "$NGPU" -gt 1 ]; then
+  RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29533"
+else
+  RUN="python"
+fi
 for step in "$@"; do
   case $step in
     tests)     timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "tests rc=$?"; tail -5 $OUT/pytest_$TAG.log ;;
@@ -16,6 +22,15 @@ for step in "$@"; do
     sweep)     timeout 1500 python tools/bench_bse_matvec.py --nb 500,1000,2000 --reps 5 --out $OUT/bse_matvec_$TAG.jsonl > $OUT/sweep_$TAG.log 2>&1; echo "sweep rc=$?"; tail -3 $OUT/sweep_$TAG.log ;;
     sweep4000) timeout 1500 python tools/bench_bse_matvec.py --nb 4000 --reps 2 --strategies factorised --out $OUT/bse_matvec4000_$TAG.jsonl > $OUT/sweep4000_$TAG.log 2>&1; echo "sweep4000 rc=$?"; tail -4 $OUT/sweep4000_$TAG.log ;;
     cda)       timeout 1500 python bench.py --workload pentacene-tzvp-cda --sigma cda --evgw 2 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/bench_cda_$TAG.json 2> $OUT/bench_cda_$TAG.err; echo "cda rc=$?"; cut -c1-300 $OUT/bench_cda_$TAG.json; tail -3 $OUT/bench_cda_$TAG.err ;;
+    c60n)      timeout 900 $RUN bench.py --gpus $NGPU --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_c60_n${NGPU}_$TAG.json 2> $OUT/bench_c60_n${NGPU}_$TAG.err; echo "c60 N=$NGPU rc=$?"; cut -c1-200 $OUT/bench_c60_n${NGPU}_$TAG.json ;;
+    cdan)      timeout 1500 $RUN bench.py --gpus $NGPU --workload pentacene-tzvp-cda --sigma cda --evgw 2 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/bench_cda_n${NGPU}_$TAG.json 2> $OUT/bench_cda_n${NGPU}_$TAG.err; echo "cda N=$NGPU rc=$?"; cut -c1-200 $OUT/bench_cda_n${NGPU}_$TAG.json; tail -3 $OUT/bench_cda_n${NGPU}_$TAG.err ;;
+    cpuval)    timeout 1700 python -c "
+import json
+from oracle import cpu_reference as cr
+runs = [cr.validate_against_full_step('pentacene-tzvp-shape', a) for a in ('reference', 'factorised')]
+json.dump({'runs': runs}, open('$OUT/cpu_validation_$TAG.json', 'w'), indent=1)
+print(json.dumps([(r['algorithm'], r['cores'], r['full_s'], r['sampled_s']) for r in runs]))
+" > $OUT/cpuval_$TAG.log 2>&1; echo "cpuval rc=$?"; tail -2 $OUT/cpuval_$TAG.log ;;
     smoke)     timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_$TAG.log ;;
     *)         echo "unknown step $step" ;;
   esac

@@ -58,6 +58,7 @@ struct Context {
   void eigh(int n, double* A, long long lda, double* w);            // A <- eigenvectors (ascending w)
   void spd_inverse(int n, double* A, long long lda);                // in place, full symmetric output
   void general_inverse(int n, double* A, long long lda, double* Ainv, long long ldi);   // A destroyed
+  void lu_solve_vector(int n, double* A, long long lda, double* x);                     // x <- A^-1 x, A destroyed
   void solver_begin();
   void solver_end();
   // collectives on `st` (default: the compute stream), FP64, in place; no-ops when world == 1

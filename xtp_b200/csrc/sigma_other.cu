@@ -170,43 +170,26 @@ __global__ void __launch_bounds__(256) cda_pairs_kernel(const double* __restrict
   if (threadIdx.x == 0) values[pair] = 0.5 / kPi * gq + tail;
 }
 // one CTA per residue item: v^T (Ainv - 1) v with v = slab[:, col]; Ainv symmetric column-major
-// Vb != nullptr (pole sharding over ranks): the vector of item `it` is Vb[it*naux ..] (gathered from the rank that owns
-// the column) and item_col[it] < 0 marks items whose inverse lives on another rank.
-__global__ void __launch_bounds__(256) cda_residue_kernel(const double* __restrict__ Ainv, int naux,
-                                                          const double* __restrict__ M, long long ldn, long long slab,
-                                                          const int* __restrict__ item_slab,
-                                                          const int* __restrict__ item_col,
-                                                          const int* __restrict__ item_mat,
-                                                          const double* __restrict__ Vb, double* __restrict__ out) {
-  extern __shared__ double v[];
+// out[it] = v_it . (x_it - v_it) = v^T (eps^-1 - 1) v for the items this rank evaluates (active[it] >= 0), 0 otherwise
+__global__ void __launch_bounds__(256) cda_residue_dot_kernel(const double* __restrict__ Vb,
+                                                              const double* __restrict__ Xb, int naux,
+                                                              const int* __restrict__ active, double* __restrict__ out) {
   __shared__ double sh[16];
   const int it = blockIdx.x;
-  const int col = item_col[it];
-  if (col < 0) {                       // column (or, sharded, the inverse) owned by another rank
+  if (active[it] < 0) {
     if (threadIdx.x == 0) out[it] = 0.0;
     return;
   }
-  if (Vb) {
-    for (int P = threadIdx.x; P < naux; P += 256) v[P] = Vb[(long long)it * naux + P];
-  } else {
-    const double* S = M + (long long)item_slab[it] * slab + col;
-    for (int P = threadIdx.x; P < naux; P += 256) v[P] = S[(long long)P * ldn];
-  }
-  __syncthreads();
-  const double* A = Ainv + (long long)item_mat[it] * naux * naux;
+  const double* v = Vb + (long long)it * naux;
+  const double* x = Xb + (long long)it * naux;
   double quad = 0.0, vv = 0.0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int P = warp; P < naux; P += 8) {
-    const double* colp = A + (long long)P * naux;
-    double d = 0.0;
-    for (int Qi = lane; Qi < naux; Qi += 32) d += colp[Qi] * v[Qi];
-    quad += d * v[P];      // lane-local partial of row P; the block sum below adds the lanes
+  for (int P = threadIdx.x; P < naux; P += 256) {
+    quad += v[P] * x[P];
+    vv += v[P] * v[P];
   }
-  for (int P = threadIdx.x; P < naux; P += 256) vv += v[P] * v[P];
   block_sum2(quad, vv, sh);
   if (threadIdx.x == 0) out[it] = quad - vv;
 }
-
 // Vb[it][P] = slab(item)[P][col] for the items whose column this rank owns, 0 otherwise (summed over ranks afterwards)
 __global__ void cda_gather_columns_kernel(double* __restrict__ Vb, int naux, const double* __restrict__ M, long long ldn,
                                           long long slab, const int* __restrict__ item_slab,
@@ -514,53 +497,41 @@ void GW::cda_values(long long n, const long long* levels, const double* freqs, d
     }
   if (items.empty()) return;
   const long long bmax = std::max<long long>(1, std::min<long long>((long long)items.size(), (1LL << 28) / nn));
-  DBuf eps((size_t)(bmax * nn)), inv((size_t)(bmax * nn)), res((size_t)bmax + 1);
-  DBuf meta((size_t)(4 * ((bmax + 1) / 2 + 1)));
+  DBuf eps((size_t)(bmax * nn)), res((size_t)bmax + 1);
+  DBuf meta((size_t)(3 * ((bmax + 1) / 2 + 1)));
   int* slab_d = reinterpret_cast<int*>(meta.p);
   int* col_d = slab_d + bmax + 1;
-  int* mat_d = col_d + bmax + 1;
-  int* act_d = mat_d + bmax + 1;
-  // Pole sharding (world > 1): item k's eps(|e_i - w|) is summed onto rank k % world, which alone inverts it and
-  // evaluates the quadratic form; the vector it needs (one column of a slab, owned by the rank holding second-index
-  // column i) reaches it through a small all-reduced gather buffer.
+  int* act_d = col_d + bmax + 1;
+  // Pole sharding (world > 1): item k's eps(|e_i - w|) is summed onto rank k % world, which alone factorises it and
+  // solves eps x = v; the vector v (one column of a slab, owned by the rank holding second-index column i) reaches it
+  // through a small all-reduced gather buffer.  One LU factorisation + one triangular solve per item (the residue
+  // needs v^T eps^-1 v for a single vector), not a full inverse.
   const int world = ctx->world, rank = ctx->rank;
-  DBuf Vb;
-  if (world > 1) Vb.alloc((size_t)(bmax * na));
-  std::vector<int> hs, hc, hm, ha;
+  DBuf Vb((size_t)(bmax * na)), Xb((size_t)(bmax * na));
+  std::vector<int> hs, hc, ha;
   std::vector<double> deltas, hres;
-  const size_t smem = (size_t)na * sizeof(double);
-  if (smem > 48 * 1024)
-    XTPB_CUDA(cudaFuncSetAttribute(cda_residue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (size_t b0 = 0; b0 < items.size(); b0 += (size_t)bmax) {
     const long long cnt = (long long)std::min<size_t>((size_t)bmax, items.size() - b0);
-    deltas.resize((size_t)cnt); hs.resize((size_t)cnt); hc.resize((size_t)cnt); hm.resize((size_t)cnt);
+    deltas.resize((size_t)cnt); hs.resize((size_t)cnt); hc.resize((size_t)cnt); ha.resize((size_t)cnt);
     for (long long k = 0; k < cnt; ++k) {
       const Item& it = items[b0 + k];
       deltas[k] = it.delta;
       hs[k] = (int)(q0 + it.level);
       hc[k] = (it.i % tc->world == tc->rank) ? it.i / tc->world : -1;     // owner of second-index column i
-      hm[k] = (int)k;
+      ha[k] = (k % world == rank) ? 0 : -1;                               // >= 0: this rank evaluates item k
     }
     rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, deltas.data(), (int)cnt, false, 0.0, eps.p, 0);
-    for (long long k = 0; k < cnt; ++k)
-      if (k % world == rank) ctx->general_inverse((int)na, eps.p + k * nn, na, inv.p + k * nn, na);
     XTPB_CUDA(cudaMemcpyAsync(slab_d, hs.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     XTPB_CUDA(cudaMemcpyAsync(col_d, hc.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    XTPB_CUDA(cudaMemcpyAsync(mat_d, hm.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if (world > 1) {
-      cda_gather_columns_kernel<<<nblocks(cnt * na, 256), 256, 0, ctx->stream>>>(Vb.p, (int)na, tc->M.p, tc->ldn,
-                                                                               tc->slab, slab_d, col_d, (int)cnt);
-      LAUNCH_CHECK_SO();
-      ctx->allreduce_sum(Vb.p, (size_t)(cnt * na));
-      ha.resize((size_t)cnt);
-      for (long long k = 0; k < cnt; ++k) ha[k] = (k % world == rank) ? 0 : -1;      // >= 0: this rank evaluates item k
-      XTPB_CUDA(cudaMemcpyAsync(act_d, ha.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-      cda_residue_kernel<<<(unsigned)cnt, 256, smem, ctx->stream>>>(inv.p, (int)na, tc->M.p, tc->ldn, tc->slab, slab_d,
-                                                                   act_d, mat_d, Vb.p, res.p);
-    } else {
-      cda_residue_kernel<<<(unsigned)cnt, 256, smem, ctx->stream>>>(inv.p, (int)na, tc->M.p, tc->ldn, tc->slab, slab_d,
-                                                                   col_d, mat_d, nullptr, res.p);
-    }
+    XTPB_CUDA(cudaMemcpyAsync(act_d, ha.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    cda_gather_columns_kernel<<<nblocks(cnt * na, 256), 256, 0, ctx->stream>>>(Vb.p, (int)na, tc->M.p, tc->ldn, tc->slab,
+                                                                             slab_d, col_d, (int)cnt);
+    LAUNCH_CHECK_SO();
+    ctx->allreduce_sum(Vb.p, (size_t)(cnt * na));
+    XTPB_CUDA(cudaMemcpyAsync(Xb.p, Vb.p, (size_t)(cnt * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (long long k = 0; k < cnt; ++k)
+      if (k % world == rank) ctx->lu_solve_vector((int)na, eps.p + k * nn, na, Xb.p + k * na);
+    cda_residue_dot_kernel<<<(unsigned)cnt, 256, 0, ctx->stream>>>(Vb.p, Xb.p, (int)na, act_d, res.p);
     LAUNCH_CHECK_SO();
     ctx->allreduce_sum(res.p, (size_t)cnt);
     hres.resize((size_t)cnt);
