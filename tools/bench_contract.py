@@ -95,8 +95,75 @@ def shapes(nb, naux, homo):
     return out
 
 
+def cublas_reference(nb, naux, homo, reps):
+    """What the reference's GPU path runs for the same stages: cuBLAS through torch's FP64 matmul (cublasDgemm /
+    cublasDgemmStridedBatched) on the same shapes, same box.  epsilon follows OpenMP_CUDA::A_TDA (upstream
+    openmp_cuda.cc / cudapipeline.cc): per occupied level a row scaling (Ddgmm) and a full Dgemm accumulated into the
+    N_aux^2 result -- 2 o u N_aux^2 flops where the SYRK-shaped launch of this library needs half."""
+    import torch
+    dev = torch.device("cuda", 0)
+    o = homo + 1
+    n, m, u = nb, 2 * o, nb - o
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+
+    def rnd(*shape):
+        return torch.randn(shape, dtype=torch.float64, device=dev, generator=g) * 1e-2
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    nbat = 32
+    # aux rotation: out[m] = R^T M[m], M[m] is (N_aux x n) row-major = the library's [P][n] slab
+    R, Mb = rnd(naux, naux), rnd(nbat, naux, n)
+    Ob = torch.empty_like(Mb)
+    ms = timed(lambda: torch.matmul(R.T, Mb, out=Ob))
+    out["aux_rotation"] = (ms, 2.0 * n * naux * naux * nbat)
+    del R, Mb, Ob
+    # Fill3cMO: W_P = T_P C_m, then C_n^T W_P, batched over 32 aux functions
+    Tb, Cm, Cn = rnd(nbat, nb, nb), rnd(nb, m), rnd(nb, n)
+    W = torch.empty((nbat, nb, m), dtype=torch.float64, device=dev)
+    ms = timed(lambda: torch.matmul(Tb, Cm, out=W))
+    out["fill_T_times_Cm"] = (ms, 2.0 * nb * m * nb * nbat)
+    O2 = torch.empty((nbat, n, m), dtype=torch.float64, device=dev)
+    ms = timed(lambda: torch.matmul(Cn.T, W, out=O2))
+    out["fill_CnT_times_W"] = (ms, 2.0 * n * m * nb * nbat)
+    del Tb, W, O2
+    # epsilon: per occupied level A (N_aux x u): acc += (A * d) A^T   (Ddgmm + Dgemm), a sample of 8 levels scaled to o
+    A, d = rnd(8, naux, u), torch.rand((8, u), dtype=torch.float64, device=dev, generator=g)
+    acc = torch.zeros((naux, naux), dtype=torch.float64, device=dev)
+
+    def eps():
+        for i in range(8):
+            acc.addmm_(A[i] * d[i], A[i].T)
+    ms = timed(eps) * o / 8.0
+    K = u
+    out["epsilon_syrk"] = (ms, float(naux) * naux * K * o)           # algorithmic (SYRK-minimal) flops, like the library line
+    out["epsilon_gemm_equivalent_tflops"] = 2.0 * naux * naux * K * o / ms * 1e-9
+    del A, acc
+    for s_ in (4096, 8192):
+        X, Y = rnd(s_, s_), rnd(s_, s_)
+        Z = torch.empty_like(X)
+        ms = timed(lambda: torch.matmul(X, Y, out=Z))
+        out[f"square_{s_}_kc_kc"] = (ms, 2.0 * s_ ** 3)
+        del X, Y, Z
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--cublas", action="store_true", help="add cuBLAS (torch FP64 matmul) timings of the same shapes")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--nb", type=int, default=1860)
     ap.add_argument("--naux", type=int, default=5500)
@@ -106,6 +173,7 @@ def main():
     args = ap.parse_args()
     ctx = api.Context(0)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    cublas = cublas_reference(args.nb, args.naux, args.homo, args.reps) if args.cublas else {}
     with open(args.out, "w") as f:
         only = set(x for x in args.only.split(",") if x)
         for name, d, flops in shapes(args.nb, args.naux, args.homo):
@@ -115,6 +183,14 @@ def main():
                 ms = api.contract_bench(ctx, d, args.reps)
                 rec = {"shape": name, "M": d.M, "N": d.N, "K": d.K, "n_outer": d.n_outer, "n_batch": d.n_batch,
                        "lower": d.lower, "ms": round(ms, 4), "algorithmic_tflops": round(flops / ms * 1e-9, 3)}
+                if name in cublas:
+                    cms, cfl = cublas[name]
+                    rec["cublas_ms"] = round(cms, 4)
+                    rec["cublas_algorithmic_tflops"] = round(cfl / cms * 1e-9, 3)
+                    rec["speedup_vs_cublas"] = round(cms / ms, 3)
+                    if name == "epsilon_syrk":
+                        rec["cublas_gemm_equivalent_tflops"] = round(cublas["epsilon_gemm_equivalent_tflops"], 3)
+                        rec["cublas_what"] = "Ddgmm + Dgemm per occupied level (upstream OpenMP_CUDA::A_TDA), 8 levels timed"
             except Exception as e:  # noqa: BLE001
                 rec = {"shape": name, "error": str(e)}
             print(json.dumps(rec), flush=True)

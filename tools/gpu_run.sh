@@ -31,6 +31,10 @@ runs = [cr.validate_against_full_step('pentacene-tzvp-shape', a) for a in ('refe
 json.dump({'runs': runs}, open('$OUT/cpu_validation_$TAG.json', 'w'), indent=1)
 print(json.dumps([(r['algorithm'], r['cores'], r['full_s'], r['sampled_s']) for r in runs]))
 " > $OUT/cpuval_$TAG.log 2>&1; echo "cpuval rc=$?"; tail -2 $OUT/cpuval_$TAG.log ;;
+    cublas)    timeout 900 python tools/bench_contract.py --cublas --reps 5 --out $OUT/contract_vs_cublas_$TAG.jsonl > $OUT/cublas_$TAG.log 2>&1; echo "cublas rc=$?"; tail -14 $OUT/cublas_$TAG.log | cut -c1-260 ;;
+    ncu_eps)   timeout 900 ncu --set full --clock-control none --import-source on -k regex:contract -c 2 -f -o $OUT/r02_eps_c60 python tools/bench_contract.py --only epsilon_syrk --reps 1 --out $OUT/ncu_eps_$TAG.jsonl > $OUT/ncu_eps_$TAG.log 2>&1; echo "ncu_eps rc=$?"; tail -3 $OUT/ncu_eps_$TAG.log | cut -c1-200 ;;
+    ncu_rot)   timeout 900 ncu --set full --clock-control none --import-source on -k regex:contract -c 2 -f -o $OUT/r02_rot_c60 python tools/bench_contract.py --only aux_rotation --reps 1 --out $OUT/ncu_rot_$TAG.jsonl > $OUT/ncu_rot_$TAG.log 2>&1; echo "ncu_rot rc=$?"; tail -3 $OUT/ncu_rot_$TAG.log | cut -c1-200 ;;
+    launches)  XTPB_BENCH_MIN_WARMUP=1 timeout 1700 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:xtpb --csv --log-file $OUT/r02_launches_c60.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/launches_$TAG.json 2> $OUT/launches_$TAG.err; echo "launches rc=$?"; wc -l $OUT/r02_launches_c60.csv ;;
     smoke)     timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_$TAG.log ;;
     *)         echo "unknown step $step" ;;
   esac

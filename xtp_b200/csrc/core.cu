@@ -218,16 +218,33 @@ void Context::general_inverse(int n, double* A, long long lda, double* Ainv, lon
 }  // namespace xtpb
 
 namespace xtpb {
-// x <- A^-1 x for one right-hand side (A destroyed: LU factors).  The CDA residues need v^T eps^-1 v for ONE vector per
-// matrix: factorisation + a single triangular solve (2/3 n^3) instead of a full inverse (8/3 n^3).
+// x <- A^-1 x for one right-hand side, A symmetric (destroyed).  The CDA residues need v^T eps^-1 v for ONE vector per
+// matrix: a factorisation + one pair of triangular solves instead of a full inverse (8/3 n^3).  eps(w) on the real
+// axis is positive definite below the first transition energy, so Cholesky (n^3/3, and cuSOLVER's potrf runs several
+// times faster than its getrf) is tried first on a copy; an indefinite matrix (devInfo > 0) falls back to LU.
 void Context::lu_solve_vector(int n, double* A, long long lda, double* x) {
-  int lwork = 0;
+  int lwork = 0, lwork_c = 0;
   XTPB_SOLVER(cusolverDnDgetrf_bufferSize(solver, n, n, A, (int)lda, &lwork));
+  XTPB_SOLVER(cusolverDnDpotrf_bufferSize(solver, CUBLAS_FILL_MODE_LOWER, n, A, (int)lda, &lwork_c));
+  lwork = std::max(lwork, lwork_c);
   solver_work.ensure((size_t)lwork + (size_t)(n + 1) / 2 + 1);
+  scratch_a.ensure((size_t)n * n);
   int* ipiv = reinterpret_cast<int*>(solver_work.p + lwork);
-  solver_begin();
-  XTPB_SOLVER(cusolverDnDgetrf(solver, n, n, A, (int)lda, solver_work.p, ipiv, dev_info));
-  XTPB_SOLVER(cusolverDnDgetrs(solver, CUBLAS_OP_N, n, 1, A, (int)lda, ipiv, x, n, dev_info));
+  XTPB_CUDA(cudaMemcpy2DAsync(scratch_a.p, (size_t)n * 8, A, (size_t)lda * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice,
+                              stream));
+  XTPB_CUDA(cudaEventRecord(ev0, stream));
+  solver_prof_slot = prof_begin(PROF_SOLVER, 0.0, stream);
+  XTPB_SOLVER(cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n, scratch_a.p, n, solver_work.p, lwork, dev_info));
+  int info = 0;
+  XTPB_CUDA(cudaMemcpyAsync(&info, dev_info, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  XTPB_CUDA(cudaStreamSynchronize(stream));
+  if (info == 0) {
+    XTPB_SOLVER(cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n, 1, scratch_a.p, n, x, n, dev_info));
+  } else {
+    XTPB_REQUIRE(info > 0, "cuSOLVER potrf: illegal argument");
+    XTPB_SOLVER(cusolverDnDgetrf(solver, n, n, A, (int)lda, solver_work.p, ipiv, dev_info));
+    XTPB_SOLVER(cusolverDnDgetrs(solver, CUBLAS_OP_N, n, 1, A, (int)lda, ipiv, x, n, dev_info));
+  }
   solver_end();
 }
 }  // namespace xtpb
