@@ -132,6 +132,8 @@ Context::Context(int dev) : device(dev) {
 
 Context::~Context() {
   comm_destroy();
+  if (async_eigh.th.joinable()) async_eigh.th.join();
+  if (side_ready) cudaEventDestroy(side_ready);
   if (side_solver) cusolverDnDestroy(side_solver);
   if (side_info) cudaFree(side_info);
   if (side_stream) cudaStreamDestroy(side_stream);
@@ -246,5 +248,52 @@ void Context::lu_solve_vector(int n, double* A, long long lda, double* x) {
     XTPB_SOLVER(cusolverDnDgetrs(solver, CUBLAS_OP_N, n, 1, A, (int)lda, ipiv, x, n, dev_info));
   }
   solver_end();
+}
+}  // namespace xtpb
+
+namespace xtpb {
+void Context::side_init() {
+  if (side_stream) return;
+  int lo = 0, hi = 0;
+  XTPB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  XTPB_CUDA(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, hi));
+  XTPB_SOLVER(cusolverDnCreate(&side_solver));
+  XTPB_SOLVER(cusolverDnSetStream(side_solver, side_stream));
+  XTPB_CUDA(cudaMalloc(&side_info, sizeof(int)));
+  XTPB_CUDA(cudaEventCreateWithFlags(&side_ready, cudaEventDisableTiming));
+}
+
+void Context::eigh_async_begin(int n, double* A, long long lda, double* w, double* lam_host) {
+  side_init();
+  if (async_eigh.th.joinable()) async_eigh.th.join();
+  async_eigh.err = nullptr;
+  async_eigh.active = true;
+  int lwork = 0;
+  XTPB_SOLVER(cusolverDnDsyevd_bufferSize(side_solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, (int)lda,
+                                          w, &lwork));
+  side_work.ensure((size_t)lwork);
+  XTPB_CUDA(cudaEventRecord(side_ready, stream));            // A is complete once the main stream reaches this point
+  XTPB_CUDA(cudaStreamWaitEvent(side_stream, side_ready, 0));
+  async_eigh.th = std::thread([this, n, A, lda, w, lam_host, lwork] {
+    try {
+      XTPB_CUDA(cudaSetDevice(device));
+      XTPB_SOLVER(cusolverDnDsyevd(side_solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, (int)lda, w,
+                                   side_work.p, lwork, side_info));
+      int info = 0;
+      XTPB_CUDA(cudaMemcpyAsync(lam_host, w, (size_t)n * 8, cudaMemcpyDeviceToHost, side_stream));
+      XTPB_CUDA(cudaMemcpyAsync(&info, side_info, sizeof(int), cudaMemcpyDeviceToHost, side_stream));
+      XTPB_CUDA(cudaStreamSynchronize(side_stream));
+      XTPB_REQUIRE(info == 0, "cuSOLVER devInfo " + std::to_string(info) + " in the overlapped eigensolver");
+    } catch (...) {
+      async_eigh.err = std::current_exception();
+    }
+  });
+}
+
+void Context::eigh_async_join() {
+  if (!async_eigh.active) return;
+  if (async_eigh.th.joinable()) async_eigh.th.join();
+  async_eigh.active = false;
+  if (async_eigh.err) std::rethrow_exception(async_eigh.err);
 }
 }  // namespace xtpb

@@ -73,11 +73,21 @@ void GW::prepare_ppm() {
   DBuf eps((size_t)(2 * na * na)), T1((size_t)(na * na)), lam((size_t)na);
   const double w_r = 0.0, w_i = 0.5;    // screening_r, screening_i [Ha]
   rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_r, 1, false, 0.0, eps.p);
-  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
   double* phi = eps.p;                  // eigh overwrites eps(0) with its eigenvectors
-  ctx->eigh((int)na, phi, na, lam.p);
   std::vector<double> lambda((size_t)na);
-  ctx->d2h(lambda.data(), lam.p, (size_t)na);
+  // the eigensolver of eps(0) (latency-bound, replicated on every rank) runs on the helper stream underneath the
+  // contraction for eps(i 0.5), which does not depend on it; XTPB_PPM_OVERLAP=0 runs them one after the other
+  static const bool overlap = [] { const char* e = getenv("XTPB_PPM_OVERLAP"); return !(e && e[0] == '0'); }();
+  if (overlap) {
+    tc->metric_prefetch_join();         // (a prefetch nobody consumed would still own the helper stream)
+    ctx->eigh_async_begin((int)na, phi, na, lam.p, lambda.data());
+    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
+    ctx->eigh_async_join();
+  } else {
+    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
+    ctx->eigh((int)na, phi, na, lam.p);
+    ctx->d2h(lambda.data(), lam.p, (size_t)na);
+  }
   // ortho = phi^T eps(i 0.5) phi
   GemmParams g{};
   g.A = op_k_contig(eps.p + na * na, na);          // eps symmetric

@@ -32,11 +32,24 @@ struct Context {
   cudaStream_t comm_stream = nullptr;
   double comm_seconds = 0.0;    // not timed per call; collectives are stream-ordered
 
-  // helper-thread resources of TCMatrix::metric_prefetch_begin (created on first use)
+  // helper-thread resources (created on first use): a second, high-priority stream with its own cuSOLVER handle, on
+  // which a dense eigensolver runs underneath independent work of the main stream
+  // (TCMatrix::metric_prefetch_begin under Fill3cMO; eigh_async under the second epsilon of the plasmon-pole model)
   cudaStream_t side_stream = nullptr;
   cusolverDnHandle_t side_solver = nullptr;
   DBuf side_work;
   int* side_info = nullptr;
+  cudaEvent_t side_ready = nullptr;
+  void side_init();
+  struct AsyncEigh {
+    std::thread th;
+    std::exception_ptr err;
+    bool active = false;
+  } async_eigh;
+  // A (n x n, ld = lda, on the device, produced by work already enqueued on `stream`) <- eigenvectors, w <- eigenvalues
+  // (device), lam_host <- eigenvalues; returns at once, eigh_async_join() waits and rethrows
+  void eigh_async_begin(int n, double* A, long long lda, double* w, double* lam_host);
+  void eigh_async_join();
   explicit Context(int dev);
   ~Context();
   void sync() { XTPB_CUDA(cudaStreamSynchronize(stream)); }
@@ -160,6 +173,10 @@ void k_cols_full_to_local(double* loc, long long ld_loc, const double* full, lon
                           long long ncols_loc, int rank, int world, cudaStream_t s);
 void k_cols_local_to_full(double* full, long long ld_full, const double* loc, long long ld_loc, long long rows,
                           long long ncols_loc, int rank, int world, cudaStream_t s);
+// collective Fill3cMO, second half: M[m][P(slot)][n] = stage[m][slot][n] for slot = s*B + idx < world*B with
+// P = naux*s/world + round*B + idx inside rank s's aux range (other slots are padding of the last round)
+void k_scatter_fill_slots(double* M, long long ldn, long long slab, const double* stage, int mtotal, int ntotal,
+                          int naux, int world, int B, int round, cudaStream_t s);
 // BSE window re-shard: dst[i][Ql][j] = G[s(j)][i][P0+Ql][jl(j)], gathered blocks of [mcnt][naux][ldl]
 void k_window_from_gathered(double* dst, long long dst_ld, long long dst_slab, const double* G, long long ldl,
                             int mcnt, int naux, int P0, int pcnt, int n0, int ncnt, int world, cudaStream_t s);

@@ -1039,6 +1039,30 @@ void k_col_norms(const double* A, long long ld, long long rows, int cols, double
   col_norms_kernel<<<cols, 256, 0, s>>>(A, ld, rows, out);
   LAUNCH_CHECK();
 }
+__global__ void scatter_fill_slots_kernel(double* __restrict__ M, long long ldn, long long slab,
+                                          const double* __restrict__ stage, int mtotal, int ntotal, int naux, int world,
+                                          int B, int round) {
+  const long long slots = (long long)world * B;
+  const long long total = (long long)mtotal * slots * ldn;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % ldn);
+    const long long t = (idx / ldn) % slots;
+    const long long m = idx / (ldn * slots);
+    if (n >= ntotal) continue;
+    const int s = (int)(t / B), k = (int)(t % B);
+    const long long a = (long long)naux * s / world, e = (long long)naux * (s + 1) / world;
+    const long long P = a + (long long)round * B + k;
+    if (P < e) M[m * slab + P * ldn + n] = stage[idx];
+  }
+}
+void k_scatter_fill_slots(double* M, long long ldn, long long slab, const double* stage, int mtotal, int ntotal,
+                          int naux, int world, int B, int round, cudaStream_t s) {
+  const long long total = (long long)mtotal * world * B * ldn;
+  scatter_fill_slots_kernel<<<blocks_for(total, 256, 16384), 256, 0, s>>>(M, ldn, slab, stage, mtotal, ntotal, naux,
+                                                                        world, B, round);
+  LAUNCH_CHECK();
+}
 void k_column_dots(double* out, const double* A, long long lda, const double* B, long long ldb, long long rows, int cols,
                    cudaStream_t s) {
   if (cols == 0) return;

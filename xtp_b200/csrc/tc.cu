@@ -220,6 +220,11 @@ void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
     wall[b].alloc((size_t)(world * B * wslice));
   }
   unpacked.ensure((size_t)(B * full_slice));
+  // second half: ONE batched launch per round over all world*B gathered slices (a launch per source rank has only
+  // ~1.3 waves of tiles at 8 ranks) into a staging tensor [m][slot][n_loc]; the slots are then scattered to their aux
+  // index (the canonical aux ranges of the ranks differ in length by one, so the slot -> P map is not one stride)
+  ctx->scratch_b.ensure((size_t)(mtotal * world * B * ldn));
+  double* stage_out = ctx->scratch_b.p;
   if (!on_device) for (int b = 0; b < 2; ++b) stage2[b].ensure((size_t)(B * pk_slice));
   if (!copy_stream) {
     XTPB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -241,21 +246,17 @@ void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
     const int b = (int)(i & 1);
     XTPB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_g[b], 0));
     ProfScope prof(PROF_FILL);
-    for (int s = 0; s < world; ++s) {
-      long long a, e;
-      aux_range(s, a, e);
-      const long long p0 = a + i * B;
-      const long long cnt = std::min(B, e - p0);
-      if (cnt <= 0) continue;
-      GemmParams h{};
-      h.A = GemmOperand{Cn.p, ldc, 1, 0, 0};
-      h.B = GemmOperand{wall[b].p + (long long)s * B * wslice, ldw, 1, 0, wslice};
-      h.C = M.p + p0 * ldn; h.c_sm = 1; h.c_sn = slab; h.c_batch = ldn;
-      h.M = (int)ntotal; h.N = (int)mtotal; h.K = (int)n_basis; h.n_outer = 1; h.n_batch = (int)cnt;
-      h.alpha = 1.0; h.beta = 0.0;
-      contract(h, ctx->ws, ctx->stream);
-    }
-    XTPB_CUDA(cudaEventRecord(ev_free[b], ctx->stream));
+    const long long slots = (long long)world * B;
+    GemmParams h{};
+    h.A = GemmOperand{Cn.p, ldc, 1, 0, 0};
+    h.B = GemmOperand{wall[b].p, ldw, 1, 0, wslice};
+    h.C = stage_out; h.c_sm = 1; h.c_sn = slots * ldn; h.c_batch = ldn;
+    h.M = (int)ntotal; h.N = (int)mtotal; h.K = (int)n_basis; h.n_outer = 1; h.n_batch = (int)slots;
+    h.alpha = 1.0; h.beta = 0.0;
+    contract(h, ctx->ws, ctx->stream);
+    XTPB_CUDA(cudaEventRecord(ev_free[b], ctx->stream));      // the gathered blocks are consumed
+    k_scatter_fill_slots(M.p, ldn, slab, stage_out, (int)mtotal, (int)ntotal, (int)naux, world, (int)B, (int)i,
+                         ctx->stream);
   };
   for (long long i = 0; i < rounds; ++i) {
     const int b = (int)(i & 1);
@@ -332,14 +333,8 @@ void TCMatrix::metric_prefetch_begin(const double* X_host, long long ldx, bool o
   prefetch.w.ensure((size_t)naux);
   prefetch.lam.assign((size_t)naux, 0.0);
   Context* c = ctx;
-  if (!c->side_stream) {
-    int lo = 0, hi = 0;
-    XTPB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    XTPB_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));
-    if (cusolverDnCreate(&c->side_solver) != CUSOLVER_STATUS_SUCCESS) throw Error("xtpb: cusolverDnCreate failed");
-    cusolverDnSetStream(c->side_solver, c->side_stream);
-    XTPB_CUDA(cudaMalloc(&c->side_info, sizeof(int)));
-  }
+  c->side_init();
+  c->eigh_async_join();       // the helper stream / handle / workspace are shared with Context::eigh_async
   int lwork = 0;
   if (cusolverDnDsyevd_bufferSize(c->side_solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)naux,
                                   prefetch.U.p, (int)naux, prefetch.w.p, &lwork) != CUSOLVER_STATUS_SUCCESS)
