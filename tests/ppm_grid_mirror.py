@@ -10,7 +10,7 @@ from oracle import gwbse_oracle as orc
 from xtp_b200 import _lib
 
 ORDER = 16       # kCmpOrder
-CHUNK = 32       # kCmpChunk
+CHUNK = _lib.lib().xtpb_ppm_grid_chunk()       # kCmpChunk
 
 
 def plan(grid_start, spacing, steps, zmin, zmax):

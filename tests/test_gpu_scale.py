@@ -158,3 +158,48 @@ def test_sampled_parity_at_benchmark_shape(workload, monkeypatch):
     bse.close()
     assert api.tma_launch_count() > tma0                          # the benchmarked (TMA-fed) contraction instance ran
     job.close()
+
+
+@pytest.mark.parametrize("nb,k", [(1000, 40), (2000, 10)])
+def test_bse_matmul_on_window_tensor_many_trial_vectors(nb, k, monkeypatch):
+    """BASELINE.json configs[4] shapes (synthetic sweep: N_aux = 3 N_b, v = c = N_b/10, tensor restricted to the BSE
+    window): dense-H and factorised strategies with enough trial vectors that the factorised direct term runs in
+    several chunks of its U intermediate, against the factorised product written with torch on the same tensor."""
+    import torch
+
+    from xtp_b200 import api, synth
+    homo = nb // 10 - 1
+    sz = synth.Sizes(n_basis=nb, n_aux=3 * nb, homo=homo, rpamax=2 * homo + 1)
+    ctx = api.Context(0)
+    tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+    Md = synth.draw_window_on_device(sz, 20260101 + nb)
+    assert float((Md - Md.permute(2, 1, 0)).abs().max()) == 0.0
+    tc.set_raw_dev(Md.data_ptr())
+    del Md
+    M = tc.torch_view()
+    dev = M.device
+    rng = np.random.default_rng(1)
+    vt, ct, na = sz.vtotal, sz.ctotal, sz.n_aux
+    hq = rng.standard_normal((vt + ct, vt + ct)) * 0.05
+    hq = 0.5 * (hq + hq.T) + np.diag(np.sort(rng.uniform(-1.0, 2.0, vt + ct)))
+    eps_inv = rng.uniform(0.2, 1.0, na)
+    X = np.linalg.qr(rng.standard_normal((vt * ct, k)))[0]
+    X4 = torch.from_numpy(X).to(dev).reshape(vt, ct, k)
+    H = torch.from_numpy(hq).to(dev)
+    einv = torch.from_numpy(eps_inv).to(dev)
+    Mvc, Mvv, Mcc = M[:vt][:, :, vt:vt + ct], M[:vt][:, :, :vt], M[vt:vt + ct][:, :, vt:vt + ct]
+    Y = torch.einsum("cd,vdk->vck", H[vt:, vt:], X4) - torch.einsum("vw,wck->vck", H[:vt, :vt], X4)
+    Y += 2.0 * torch.einsum("vpc,pk->vck", Mvc, torch.einsum("vpc,vck->pk", Mvc, X4))
+    for kk in range(k):
+        Uk = torch.einsum("cpd,wd->pcw", Mcc, X4[:, :, kk])
+        Y[:, :, kk] -= torch.einsum("vpw,p,pcw->vc", Mvv, einv, Uk)
+        del Uk
+    want = Y.reshape(vt * ct, k).cpu().numpy()
+    for mode in ("dense", "factorised"):
+        monkeypatch.setenv("XTPB_BSE_MODE", mode)
+        op = api.BSE_OPERATOR(ctx, 1, 2, 1, 0, eps_inv, tc, hq, sz.homo, sz.rpamin, sz.vmin, sz.cmax)
+        assert rel(op.matmul(X), want) < 1e-10, mode
+        op.close()
+    tc.close()
+    ctx.close()
+

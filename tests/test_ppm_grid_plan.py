@@ -16,11 +16,12 @@ def _check_plan(edges, near, grid_start, spacing, steps, zmin, zmax):
     assert edges[-1] >= zmax - 1e-12 or edges[-2] <= zmax
     c, h = 0.5 * (edges[:-1] + edges[1:]), 0.5 * np.diff(edges)
     assert h.min() >= 0.5 * W - 1e-12                        # no bin is narrower than the damping window
-    n_chunks = (steps + 31) // 32
+    ck = mir.CHUNK
+    n_chunks = (steps + ck - 1) // ck
     assert near.shape == (len(grid_start), n_chunks, 2)
     for l, g0 in enumerate(grid_start):
         for ch in range(n_chunks):
-            wa, wb = g0 + spacing * 32 * ch, g0 + spacing * (32 * (ch + 1) - 1)
+            wa, wb = g0 + spacing * ck * ch, g0 + spacing * (ck * (ch + 1) - 1)
             lo, hi = near[l, ch]
             assert 0 <= lo <= nb and -1 <= hi < nb
             for b in list(range(0, lo)) + list(range(hi + 1, nb)):

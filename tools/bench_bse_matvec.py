@@ -29,30 +29,6 @@ except Exception:  # noqa: BLE001
     HBM_PEAK = 6551.0
 
 
-def draw_window_on_device(sz, seed, chunk=100):
-    """M[m, P, n] for the BSE window only (m, n < v + c), drawn on the GPU with torch block by block, symmetric in
-    (m, n) as the real tensor is; same distribution as synth.make_M_direct.  (v+c)^2 N_aux doubles: 61 GB at N_b 4000,
-    where the full m x N_aux x N_b tensor would be 307 GB -- SURVEY.md section 7 hard part 4.)"""
-    import torch
-    mt, na = sz.mtotal, sz.n_aux
-    g = torch.Generator(device="cuda")
-    g.manual_seed(seed)
-    M = torch.empty((mt, na, mt), dtype=torch.float64, device="cuda")
-    scale = float(np.sqrt(synth.target_variance(sz)))
-    for i0 in range(0, mt, chunk):
-        i1 = min(mt, i0 + chunk)
-        for j0 in range(i0, mt, chunk):
-            j1 = min(mt, j0 + chunk)
-            R = torch.randn((i1 - i0, na, j1 - j0), dtype=torch.float64, device="cuda", generator=g) * scale
-            if i0 == j0:
-                R = (R + R.permute(2, 1, 0)) / np.sqrt(2.0)
-            M[i0:i1, :, j0:j1] = R
-            if i0 != j0:
-                M[j0:j1, :, i0:i1] = R.permute(2, 1, 0)
-    torch.cuda.synchronize()
-    return M
-
-
 def run(nb, ks, reps, out, strategies):
     import torch
     homo = nb // 10 - 1
@@ -61,7 +37,7 @@ def run(nb, ks, reps, out, strategies):
     rng = np.random.default_rng(20260101 + nb)
     ctx = api.Context(0)
     tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
-    Mdev = draw_window_on_device(sz, 20260101 + nb)
+    Mdev = synth.draw_window_on_device(sz, 20260101 + nb)
     tc.set_raw_dev(Mdev.data_ptr())
     del Mdev
     torch.cuda.empty_cache()

@@ -52,17 +52,22 @@ def main():
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         # the two ways the scan can run: pole by pole and compressed (the latter for several register/occupancy caps)
-        for mode, occ in (("direct", ""), ("compressed", "3"), ("compressed", "4"), ("compressed", "5"), ("compressed", "6")):
+        # and, for the compressed scan, narrower core bins of the pole axis (XTPB_GRID_BIN_WIDTH, default 0.25 Ha)
+        for mode, occ, bw in (("direct", "", ""), ("compressed", "3", ""), ("compressed", "4", ""), ("compressed", "5", ""),
+                              ("compressed", "6", ""), ("compressed", "5", "0.125"), ("compressed", "6", "0.125"),
+                              ("compressed", "5", "0.0625")):
             env = dict(os.environ, XTPB_SIGMA_GRID=mode)
             if occ:
                 env["XTPB_GRID_OCC"] = occ
+            if bw:
+                env["XTPB_GRID_BIN_WIDTH"] = bw
             r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
                                 str(args.reps)], env=env, capture_output=True, text=True)
             if r.stdout.strip():
                 rec = json.loads(r.stdout.strip().splitlines()[-1])
             else:
                 rec = {"error": r.stderr[-400:]}
-            rec.update({"mode": mode, "min_blocks_per_sm": occ})
+            rec.update({"mode": mode, "min_blocks_per_sm": occ, "bin_width": bw or "0.25"})
             line = json.dumps(rec)
             print(line, flush=True)
             f.write(line + "\n")

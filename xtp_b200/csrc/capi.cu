@@ -327,6 +327,7 @@ int xtpb_gw_grid_scan_info(xtpb_gw* gw, int* compressed, xtpb_index* n_bins, dou
   if (equivalent_evaluations) *equivalent_evaluations = gw->impl.grid_equiv_evals;
   XTPB_API_END
 }
+int xtpb_ppm_grid_chunk(void) { return kPpmGridChunk; }
 int xtpb_ppm_grid_plan(xtpb_index n_levels, const double* grid_start, double spacing, xtpb_index steps, double zmin,
                        double zmax, xtpb_index edges_capacity, double* edges, xtpb_index* n_bins, int* near_ranges,
                        xtpb_index* n_chunks, int* usable) {

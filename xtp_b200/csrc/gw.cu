@@ -188,20 +188,27 @@ bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing,
                    double zmax, PpmGridPlan& plan) {
   if (n_levels <= 0 || steps <= 0 || !(zmax >= zmin) || !std::isfinite(zmin) || !std::isfinite(zmax)) return false;
   const double W = kPpmDampingWindow;
+  // width of the core bins: the damping half-window unless XTPB_GRID_BIN_WIDTH says otherwise (experiments: narrower
+  // bins shrink the near window by their own width on each side and double the far-field work per halving)
+  double Bw = W;
+  if (const char* env = std::getenv("XTPB_GRID_BIN_WIDTH")) {
+    const double v = std::atof(env);
+    if (v >= 0.01 && v <= 1.0) Bw = v;
+  }
   double t_lo = grid_start[0], t_hi = grid_start[0];
   for (long long l = 0; l < n_levels; ++l) {
     t_lo = std::min(t_lo, grid_start[l]);
     t_hi = std::max(t_hi, grid_start[l] + spacing * double(steps - 1));
   }
   const long long kMaxBins = 2048;
-  if (!std::isfinite(t_lo) || !std::isfinite(t_hi) || (t_hi - t_lo) / W > double(kMaxBins - 128)) return false;
+  if (!std::isfinite(t_lo) || !std::isfinite(t_hi) || (t_hi - t_lo) / Bw > double(kMaxBins - 128)) return false;
   std::vector<double> down;                       // edges below the first core edge, descending
   const double core_lo = t_lo - W, core_hi = t_hi + W;
-  const long long ncore = (long long)std::ceil((core_hi - core_lo) / W);
+  const long long ncore = (long long)std::ceil((core_hi - core_lo) / Bw);
   std::vector<double> edges;
-  for (long long i = 0; i <= ncore; ++i) edges.push_back(core_lo + W * double(i));
-  for (double w = W; edges.back() < zmax && edges.size() < (size_t)kMaxBins; w *= 2.0) edges.push_back(edges.back() + w);
-  for (double w = W, e = edges.front(); e > zmin && down.size() < (size_t)kMaxBins; w *= 2.0) {
+  for (long long i = 0; i <= ncore; ++i) edges.push_back(core_lo + Bw * double(i));
+  for (double w = Bw; edges.back() < zmax && edges.size() < (size_t)kMaxBins; w *= 2.0) edges.push_back(edges.back() + w);
+  for (double w = Bw, e = edges.front(); e > zmin && down.size() < (size_t)kMaxBins; w *= 2.0) {
     e -= w;
     down.push_back(e);
   }

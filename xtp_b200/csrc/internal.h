@@ -134,7 +134,7 @@ struct PpmGridPlan {
   int nb = 0, n_chunks = 0;
 };
 constexpr double kPpmDampingWindow = 0.25;   // |x| below which Sigma_PPM::Stabilize damps 1/x (sigma_ppm.cc)
-constexpr int kPpmGridChunk = 32;            // grid points per warp of the compressed scan
+constexpr int kPpmGridChunk = 8;             // grid points per warp of the compressed scan (see kernels.cu (1b))
 bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing, long long steps, double zmin,
                    double zmax, PpmGridPlan& plan);
 void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,

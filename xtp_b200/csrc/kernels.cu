@@ -346,7 +346,15 @@ __global__ void sigma_ppm_grid_reduce(double* __restrict__ values, const double*
 //     evaluated one by one, with the Rohlfing damping, exactly as in (1).  With sorted energies the poles of a bin are
 //     a contiguous m-range per aux function and occupied/unoccupied segment (ppm_bin_table_kernel), so both kernels
 //     stream contiguous pieces of the slab rows.  All sums run in a fixed order (deterministic).
-constexpr int kCmpOrder = 16, kCmpChunk = 32, kCmpWarps = 4, kCmpG = 8, kCmpMomentWarps = 8, kCmpMinBlocks = 3;
+// A warp owns a chunk of kCmpChunk = 8 consecutive grid points and walks the near poles four at a time: lane =
+// (slot, point) with slot = lane / 8 the pole a lane takes out of each group of four and point = lane % 8 its grid
+// point; the four slots are summed by two shuffles at the end (fixed order).  Short chunks (0.07 Ha at the default
+// 0.01 Ha spacing, against the 0.5 Ha wide damping window) keep the near window small and, above all, make almost
+// every group of poles warp-uniform: nobody damped (reciprocal path) or everybody damped (polynomial path); the round-1
+// kernel with 32-point chunks spent most of its time in the mixed case that evaluates both.
+constexpr int kCmpOrder = 16, kCmpChunk = kPpmGridChunk, kCmpSlots = 32 / kCmpChunk, kCmpWarps = 4, kCmpG = 4,
+              kCmpMomentWarps = 8, kCmpMinBlocks = 3;
+static_assert(kCmpChunk * kCmpSlots == 32 && 32 % (kCmpSlots * kCmpG) == 0, "lane = (slot, point) mapping");
 
 // binstart[(seg*naux + P)*(nb+1) + b] = first m of segment seg (0 occupied, 1 unoccupied) whose pole lies at or above
 // edges[b]; b = 0 -> segment start, b = nb -> segment end (the outermost bins take whatever lies beyond the edges).
@@ -450,11 +458,11 @@ __global__ void __launch_bounds__(kCmpMomentWarps * 32) ppm_moments_kernel(
   }
 }
 
-// One warp per (level, chunk of 32 consecutive grid points); blockIdx.z splits the aux range of the near field when few
-// warps would leave SMs idle (split 0 also adds the far field).  near_range[(level*n_chunks + chunk)*2 + {0,1}] is the
-// inclusive range of bins whose poles are evaluated one by one (lo > hi: none).
+// One warp per (level, chunk of kCmpChunk consecutive grid points); blockIdx.z splits the aux range of the near field
+// when few warps would leave SMs idle (split 0 also adds the far field).  near_range[(level*n_chunks + chunk)*2 + {0,1}]
+// is the inclusive range of bins whose poles are evaluated one by one (lo > hi: none).
 // MINB = resident CTAs per SM the register allocation is capped for (occupancy against unrolling depth; the launcher
-// picks kCmpMinBlocks unless XTPB_GRID_OCC says otherwise -- measured in profiles/r01_sigma_grid_variants_*.jsonl).
+// picks kCmpMinBlocks unless XTPB_GRID_OCC says otherwise).
 template <int MINB>
 __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compressed_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int naux, const double* __restrict__ energies,
@@ -468,18 +476,21 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
   const int chunk = blockIdx.x * kCmpWarps + warp, level = blockIdx.y;
   if (chunk >= n_chunks) return;              // warps are independent: no block-wide barrier below
   const double* S = M + (long long)level_slab[level] * slab;
-  const int j = chunk * kCmpChunk + lane;
+  const int point = lane & (kCmpChunk - 1), slot = lane / kCmpChunk;
+  const int j = chunk * kCmpChunk + point;
   const double om = omega0[level] + domega * (double)j;
   const int b_lo = near_range[((long long)level * n_chunks + chunk) * 2 + 0];
   const int b_hi = near_range[((long long)level * n_chunks + chunk) * 2 + 1];
   const int p_per = (naux + gridDim.z - 1) / gridDim.z;
   const int p_begin = blockIdx.z * p_per, p_end = min(naux, p_begin + p_per);
-  double acc4[4] = {0.0, 0.0, 0.0, 0.0};     // four independent accumulation chains, summed in a fixed order
+  double acc4[kCmpG];                         // independent accumulation chains, summed in a fixed order
+#pragma unroll
+  for (int g = 0; g < kCmpG; ++g) acc4[g] = 0.0;
   long long n_near = 0;                       // poles this warp evaluates one by one (bookkeeping for the reports)
-  // ---- near field: the damped kernel, pole by pole (lanes = grid points, poles broadcast from shared memory)
+  // ---- near field: the damped kernel, pole by pole (poles broadcast from shared memory, four per step)
   if (b_lo <= b_hi) {
     // m-ranges of the near bins for aux function P: {occupied lo, hi, unoccupied lo, hi}; the look-up of P + 1 is in
-    // flight while P is evaluated (the ranges of small systems are short: table latency would otherwise be exposed)
+    // flight while P is evaluated
     int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
     auto ranges_of = [&](int P) {
       const int* bs0 = binstart + (long long)P * (nb + 1);
@@ -517,22 +528,24 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
           __syncwarp();
           tile[warp][lane] = el;
           __syncwarp();
-          const int cnt = (min(32, hi - m0) + kCmpG - 1) / kCmpG * kCmpG;
-          for (int t = 0; t < cnt; t += kCmpG) {
+          constexpr int kStep = kCmpSlots * kCmpG;          // poles consumed per step by the warp
+          const int cnt = (min(32, hi - m0) + kStep - 1) / kStep * kStep;
+          for (int t = 0; t < cnt; t += kStep) {
             double2 e[kCmpG];
             double x[kCmpG], r[kCmpG];
             bool in[kCmpG], any = false, all = true;
 #pragma unroll
             for (int g = 0; g < kCmpG; ++g) {
-              e[g] = tile[warp][t + g];
+              e[g] = tile[warp][t + g * kCmpSlots + slot];
               x[g] = om - e[g].y;
               in[g] = ppm_in_window(x[g]);
               any |= in[g];
               all &= in[g];
             }
-            // the poles of a segment ascend, so a group of kCmpG is almost always of one kind for the whole warp:
-            // nobody damped (plain reciprocal), everybody damped (polynomial, no reciprocal), or -- at the two edges
-            // of the window -- mixed (both, selected per element).  Warp-uniform branches: no divergence.
+            // the poles of a segment ascend and the chunk is much shorter than the damping window, so a step is almost
+            // always of one kind for the whole warp: nobody damped (plain reciprocal), everybody damped (polynomial,
+            // no reciprocal), or -- in two narrow zones at the edges of the window -- mixed (both, selected per
+            // element).  Warp-uniform branches: no divergence.
             if (!__any_sync(0xffffffffu, any)) {
 #pragma unroll
               for (int g = 0; g < kCmpG; ++g) r[g] = rcp_fast(x[g]);
@@ -547,17 +560,19 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
               }
             }
 #pragma unroll
-            for (int g = 0; g < kCmpG; ++g) acc4[g & 3] = fma(e[g].x, r[g], acc4[g & 3]);
+            for (int g = 0; g < kCmpG; ++g) acc4[g] = fma(e[g].x, r[g], acc4[g]);
           }
         }
       }
     }
   }
-  double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-  // ---- far field: Chebyshev series of the Cauchy kernel over the condensed bins
+  double acc = 0.0;
+#pragma unroll
+  for (int g = 0; g < kCmpG; g += 2) acc += acc4[g] + acc4[g + 1];
+  // ---- far field: Chebyshev series of the Cauchy kernel over the condensed bins, the bins dealt out to the slots
   if (blockIdx.z == 0) {
     const double* mom = moments + ((long long)level * nb) * kCmpOrder;
-    for (int b = 0; b < nb; ++b) {
+    for (int b = slot; b < nb; b += kCmpSlots) {
       if (b >= b_lo && b <= b_hi) continue;
       const double e0 = edges[b], e1 = edges[b + 1];
       const double h = 0.5 * (e1 - e0);
@@ -573,7 +588,10 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
       acc = fma(f, 2.0 * sg / (sq * h), acc);
     }
   }
-  if (j < n_omega) out[(long long)blockIdx.z * out_split_stride + (long long)level * n_omega + j] = acc;
+  // sum of the slots: lanes point, point + 8, point + 16, point + 24 (fixed order)
+#pragma unroll
+  for (int o = kCmpChunk; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (slot == 0 && j < n_omega) out[(long long)blockIdx.z * out_split_stride + (long long)level * n_omega + j] = acc;
   if (lane == 0 && n_near > 0) atomicAdd(near_poles, (unsigned long long)n_near);   // integer: order-independent
 }
 

@@ -142,3 +142,29 @@ def make_problem(name_or_sizes, seed=None, identity_metric=False):
         "aux_coulomb": make_aux_metric(sz, rng, identity_metric),
         "vxc": make_vxc(sz, rng),
     }
+
+
+def draw_window_on_device(sz: Sizes, seed, chunk=100):
+    """M[m, P, n] for a tensor whose second index is restricted to the m-window (mtotal == ntotal: what the BSE operator
+    needs), drawn on the GPU with torch block by block, symmetric in (m, n) as the real tensor is; same distribution as
+    make_M_direct.  (v+c)^2 N_aux doubles: 61 GB at N_b 4000, where the full m x N_aux x N_b tensor would be 307 GB --
+    SURVEY.md section 7 hard part 4.  Returns a torch tensor (hand its data_ptr() to TCMatrix_gwbse.set_raw_dev)."""
+    import torch
+    mt, na = sz.mtotal, sz.n_aux
+    assert sz.ntotal == mt, "window tensor: second index range must equal the first"
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    M = torch.empty((mt, na, mt), dtype=torch.float64, device="cuda")
+    scale = float(np.sqrt(target_variance(sz)))
+    for i0 in range(0, mt, chunk):
+        i1 = min(mt, i0 + chunk)
+        for j0 in range(i0, mt, chunk):
+            j1 = min(mt, j0 + chunk)
+            R = torch.randn((i1 - i0, na, j1 - j0), dtype=torch.float64, device="cuda", generator=g) * scale
+            if i0 == j0:
+                R = (R + R.permute(2, 1, 0)) / np.sqrt(2.0)
+            M[i0:i1, :, j0:j1] = R
+            if i0 != j0:
+                M[j0:j1, :, i0:i1] = R.permute(2, 1, 0)
+    torch.cuda.synchronize()
+    return M
