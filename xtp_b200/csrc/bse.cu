@@ -471,7 +471,19 @@ void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, l
     const long long n2 = cd ? vt : ct;                 // output index delivered by the screened factor
     const long long ldu = round_up(vt, 2);
     const long long per_k = r1 * naux * ldu;
-    const long long budget = 1LL << 29;                // doubles (4 GiB) for U
+    // U[kl][r][P][v2] holds one trial-vector chunk of the half-contracted direct term.  The more vectors per chunk, the
+    // wider the two contractions below (their N resp. M dimension is kc * v) and the less tile padding they carry, so
+    // U may take up to a third of the free device memory, at most 24 GiB (XTPB_BSE_U_MAX_GB), at least 4 GiB.
+    long long budget = 1LL << 29;                      // doubles (4 GiB)
+    {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const char* env = getenv("XTPB_BSE_U_MAX_GB");
+        const double cap_gb = env ? atof(env) : 24.0;
+        const double want = std::min((double)free_b / 3.0 + (double)U.n * 8.0, cap_gb * 1073741824.0);
+        budget = std::max<long long>(budget, (long long)(want / 8.0));
+      }
+    }
     const int kchunk = (int)std::max<long long>(1, std::min<long long>(k, budget / per_k));
     U.ensure((size_t)(per_k * kchunk));
     const double coef = cd ? (double)cd : (double)cd2;
