@@ -144,6 +144,101 @@ def _worker(rank, world, port, results):
         part = mir.grid_values(np.ascontiguousarray(Ml[level]), el, n_occ_loc, Om, fac, g0[0], spacing, steps, pl[0], pl[1][0])
         full = mir.direct_values(tc.M[level], e, n_occ, Om, fac, g0[0], spacing, steps)
         np.testing.assert_allclose(_allreduce(part), full, rtol=1e-10, atol=1e-12)
+        # ---- collective Fill3cMO, second half in ONE batched product per round: the gathered half-transformed blocks
+        # sit in slots (source rank, index in the round); slot -> aux index as k_scatter_fill_slots maps it
+        B = 5
+        rounds = (maxcnt + B - 1) // B
+        M_slots = np.zeros((sz.mtotal, sz.n_aux, len(cols)))
+        for i in range(rounds):
+            for s_ in range(world):
+                a, b = dist.aux_range(sz.n_aux, s_, world)
+                for k_ in range(B):
+                    P_ = a + i * B + k_
+                    if P_ < b:                                      # other slots are padding of the last round
+                        M_slots[:, P_, :] = np.einsum('an,am->mn', Cn, gathered[s_].numpy()[i * B + k_])
+        np.testing.assert_allclose(M_slots, M[:, :, cols], rtol=0, atol=1e-13)
+
+        # ---- Sigma_CDA with the quadrature nodes and the residue poles sharded over the ranks (sigma_other.cu):
+        # eps(i w_j) is summed onto rank j % world only (reduce), inverted there, and broadcast; every rank forms the
+        # quadratic forms over ITS columns; a residue's eps(|e_i - w|) is summed onto rank k % world, which solves
+        # eps x = v with the vector v gathered from the rank that owns second-index column i
+        tc2 = orc.TCMatrix_gwbse().Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+        tc2.Fill(prob["ao3c"], prob["C"], prob["aux_coulomb"])
+        rpa2 = orc.RPA(tc2)
+        rpa2.configure(sz.homo, sz.rpamin, sz.rpamax)
+        rpa2.setRPAInputEnergies(e)
+        cda = orc.Sigma_CDA(tc2, rpa2)
+        cda.configure(orc.SigmaOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax, order=8))
+        cda.PrepareScreening()
+        M2l = tc2.M[:, :, cols]
+
+        def eps_partial(omega, imag):
+            dE = el[n_occ_loc:][None, :] - e[:n_occ][:, None]
+            if imag:
+                d = 4.0 * dE / (dE * dE + omega * omega)
+            else:
+                d = 2.0 * ((dE - omega) / ((dE - omega) ** 2 + rpa2.eta ** 2) + (dE + omega) / ((dE + omega) ** 2 + rpa2.eta ** 2))
+            part = np.zeros((sz.n_aux, sz.n_aux))
+            for m in range(n_occ):
+                A = M2l[m][:, n_occ_loc:]
+                part += (A * d[m][None, :]) @ A.T
+            return part
+
+        def reduce_to(part, root):
+            t = torch.from_numpy(part.copy())
+            tdist.reduce(t, dst=root)
+            return t.numpy()
+
+        def bcast(a, root):
+            t = torch.from_numpy(np.ascontiguousarray(a).copy())
+            tdist.broadcast(t, src=root)
+            return t.numpy()
+
+        order = cda.gq.Order()
+        eye = np.eye(sz.n_aux)
+        k0 = reduce_to(eps_partial(0.0, False), order % world)
+        kappa0 = bcast(np.linalg.inv(k0 + eye) - eye if rank == order % world else np.zeros_like(k0), order % world)
+        np.testing.assert_allclose(kappa0, cda.kappa0, rtol=0, atol=1e-10)
+        kernels = []
+        for j in range(order):
+            wj = cda.gq.ScaledPoint(j)
+            full = reduce_to(eps_partial(wj, True), j % world)
+            mine = -(np.linalg.inv(full + eye) - eye) + np.exp(-(cda.opt.alpha * wj) ** 2) * kappa0 \
+                if rank == j % world else np.zeros_like(full)
+            kernels.append(bcast(mine, j % world))
+            np.testing.assert_allclose(kernels[j], cda.dielinv[j], rtol=0, atol=1e-10)
+        level, freq = 2, e[q0 + 2] + 0.07
+        slab_l = M2l[q0 + level]                                      # [P, local m]
+        dEc = (freq - el).astype(np.complex128)
+        dEc[:n_occ_loc] += 1j * rpa2.getEta()
+        dEc[n_occ_loc:] -= 1j * rpa2.getEta()
+        gq = 0.0
+        for j in range(order):
+            wj = cda.gq.ScaledPoint(j)
+            den = (1.0 / (dEc + 1j * wj) + 1.0 / (dEc - 1j * wj)).real
+            gq += cda.gq.ScaledWeight(j) * float((den * np.einsum('pm,pm->m', slab_l, kernels[j] @ slab_l)).sum())
+        gq = _allreduce(np.array([0.5 / np.pi * gq]))[0]
+        np.testing.assert_allclose(gq, cda.SigmaGQDiag(freq, level), rtol=0, atol=1e-11)
+        # residues: items = enclosed poles (identical list on every rank), item k evaluated by rank k % world
+        fermi = 0.5 * (e[n_occ - 1] + e[n_occ])
+        items = [(i, cda.CalcResiduePrefactor(fermi, e[i], freq)) for i in range(len(e))]
+        items = [(i, f_) for i, f_ in items if abs(f_) > 1e-10]
+        assert items, "pick a frequency that encloses at least one pole"
+        res = 0.0
+        for k_, (i, f_) in enumerate(items):
+            full = reduce_to(eps_partial(abs(e[i] - freq), False), k_ % world)
+            v = np.zeros(sz.n_aux)
+            if i % world == rank:                                     # owner of second-index column i
+                v = tc2.M[q0 + level][:, i].copy()
+            v = _allreduce(v)
+            if k_ % world == rank:
+                x = np.linalg.solve(full + eye, v)
+                res += f_ * float(v @ x - v @ v)
+        res = _allreduce(np.array([res]))[0]
+        tail_free = orc.Sigma_CDA(tc2, rpa2)
+        tail_free.configure(orc.SigmaOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax, order=8, alpha=0.0))
+        tail_free.kappa0, tail_free.dielinv, tail_free.gq = cda.kappa0, cda.dielinv, cda.gq
+        np.testing.assert_allclose(res, tail_free.CalcResidueContribution(freq, level), rtol=0, atol=1e-10)
         results[rank] = "ok"
     except Exception as exc:  # noqa: BLE001
         import traceback
