@@ -6,7 +6,8 @@ import pytest
 
 import ppm_grid_mirror as mir
 
-W = 0.25
+W = 0.25          # damping half-window of Sigma_PPM::Stabilize
+BIN = 0.125       # kPpmGridBinWidth
 
 
 def _check_plan(edges, near, grid_start, spacing, steps, zmin, zmax):
@@ -15,7 +16,7 @@ def _check_plan(edges, near, grid_start, spacing, steps, zmin, zmax):
     assert edges[0] <= zmin + 1e-12 or edges[1] > zmin      # the first kept bin reaches down to the lowest pole
     assert edges[-1] >= zmax - 1e-12 or edges[-2] <= zmax
     c, h = 0.5 * (edges[:-1] + edges[1:]), 0.5 * np.diff(edges)
-    assert h.min() >= 0.5 * W - 1e-12                        # no bin is narrower than the damping window
+    assert h.min() >= 0.5 * BIN - 1e-12                      # no bin is narrower than the core bin width
     ck = mir.CHUNK
     n_chunks = (steps + ck - 1) // ck
     assert near.shape == (len(grid_start), n_chunks, 2)

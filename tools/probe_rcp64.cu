@@ -21,6 +21,16 @@ __device__ __forceinline__ double rcp_fast(double x) {
   const double t = fma(e, e, e);
   return fma(r, t, r);
 }
+// alternative seed: FP32 MUFU.RCP on the rounded argument, two Newton steps in FP64 (4 DFMA + 2 conversions)
+__device__ __forceinline__ double rcp_f32seed(double x) {
+  float rf;
+  asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
+  double r = (double)rf;
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 __device__ __forceinline__ double damped_poly(double x) {
   const double u = x * x;
   double h = 4.7076855031461505630e+01;
@@ -42,7 +52,11 @@ __global__ void __launch_bounds__(1024) unary_loop(double* out, int iters, doubl
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < ILP; ++i) {
-      const double v = MODE == 0 ? rcp_seed(x[i]) : (MODE == 1 ? rcp_fast(x[i]) : damped_poly(x[i] * 0.01));
+      const double v = MODE == 0 ? rcp_seed(x[i])
+                     : MODE == 1 ? rcp_fast(x[i])
+                     : MODE == 2 ? damped_poly(x[i] * 0.01)
+                     : MODE == 3 ? rcp_f32seed(x[i])
+                                 : fma(fma(fma(fma(x[i], 0.99, 0.1), 0.98, 0.2), 0.97, 0.3), 0.96, 0.4);   // 4 DFMA
       x[i] = v + c;              // one DADD per evaluation, like the subtraction w - z of the kernel
     }
   }
@@ -93,6 +107,8 @@ int main() {
     report("mufu_rcp64h+dadd", warps, 8, time_ms([&] { unary_loop<0, 8><<<sms, warps * 32>>>(out, iters, 0.25); }));
     report("rcp_fast+dadd", warps, 8, time_ms([&] { unary_loop<1, 8><<<sms, warps * 32>>>(out, iters, 0.25); }));
     report("damped_poly+dadd", warps, 8, time_ms([&] { unary_loop<2, 8><<<sms, warps * 32>>>(out, iters, 0.25); }));
+    report("rcp_f32seed+dadd", warps, 8, time_ms([&] { unary_loop<3, 8><<<sms, warps * 32>>>(out, iters, 0.25); }));
+    report("4dfma+dadd", warps, 8, time_ms([&] { unary_loop<4, 8><<<sms, warps * 32>>>(out, iters, 0.25); }));
   }
   report("rcp_fast+dadd", 16, 2, time_ms([&] { unary_loop<1, 2><<<sms, 16 * 32>>>(out, iters, 0.25); }));
   report("rcp_fast+dadd", 16, 4, time_ms([&] { unary_loop<1, 4><<<sms, 16 * 32>>>(out, iters, 0.25); }));

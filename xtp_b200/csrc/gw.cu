@@ -188,9 +188,10 @@ bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing,
                    double zmax, PpmGridPlan& plan) {
   if (n_levels <= 0 || steps <= 0 || !(zmax >= zmin) || !std::isfinite(zmin) || !std::isfinite(zmax)) return false;
   const double W = kPpmDampingWindow;
-  // width of the core bins: the damping half-window unless XTPB_GRID_BIN_WIDTH says otherwise (experiments: narrower
-  // bins shrink the near window by their own width on each side and double the far-field work per halving)
-  double Bw = W;
+  // width of the core bins (0.125 Ha: half the damping half-window; measured best of 0.25 / 0.125 / 0.0625 on B200,
+  // profiles/r02_sigma_grid_variants.jsonl) unless XTPB_GRID_BIN_WIDTH says otherwise: narrower bins shrink the near
+  // window by their own width on each side and double the far-field work per halving
+  double Bw = kPpmGridBinWidth;
   if (const char* env = std::getenv("XTPB_GRID_BIN_WIDTH")) {
     const double v = std::atof(env);
     if (v >= 0.01 && v <= 1.0) Bw = v;

@@ -134,6 +134,7 @@ struct PpmGridPlan {
   int nb = 0, n_chunks = 0;
 };
 constexpr double kPpmDampingWindow = 0.25;   // |x| below which Sigma_PPM::Stabilize damps 1/x (sigma_ppm.cc)
+constexpr double kPpmGridBinWidth = 0.125;   // width of the core bins of the pole axis [Ha]
 constexpr int kPpmGridChunk = 8;             // grid points per warp of the compressed scan (see kernels.cu (1b))
 bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing, long long steps, double zmin,
                    double zmax, PpmGridPlan& plan);

@@ -353,7 +353,7 @@ __global__ void sigma_ppm_grid_reduce(double* __restrict__ values, const double*
 // every group of poles warp-uniform: nobody damped (reciprocal path) or everybody damped (polynomial path); the round-1
 // kernel with 32-point chunks spent most of its time in the mixed case that evaluates both.
 constexpr int kCmpOrder = 16, kCmpChunk = kPpmGridChunk, kCmpSlots = 32 / kCmpChunk, kCmpWarps = 4, kCmpG = 4,
-              kCmpMomentWarps = 8, kCmpMinBlocks = 3;
+              kCmpMomentWarps = 8, kCmpMinBlocks = 5;
 static_assert(kCmpChunk * kCmpSlots == 32 && 32 % (kCmpSlots * kCmpG) == 0, "lane = (slot, point) mapping");
 
 // binstart[(seg*naux + P)*(nb+1) + b] = first m of segment seg (0 occupied, 1 unoccupied) whose pole lies at or above
