@@ -16,6 +16,33 @@ et al. JCP 152, 114103).  What can be pinned is pinned by ``tests/test_oracle_*`
 dense-vs-factorised BSE, Davidson-vs-eigh, PPM/CDA/exact mutual agreement,
 RI four-index invariants, aux-rotation invariance.
 
+PINS.  With no reference vectors to check against, each quantity below is pinned to something that does not depend
+on the missing source (tests named in brackets; the same checks run on the CUDA path in tests/test_gpu_closed_forms.py):
+  quantity                                   pinned to
+  -----------------------------------------  ---------------------------------------------------------------------
+  Pseudo_InvSqrt_GWBSE (metric factor R)     [MATH] R R^T = V^-1 for any aux overlap; RI four-index identity
+                                             sum_P M_mn^P M_kl^P = (mn|V^-1|kl)        [test_oracle_selfconsistency]
+  RPA epsilon(i w), epsilon_r(w)             element-wise double sum over (occ, empty) pairs; SPD, monotone, -> 1
+  PPM weight / frequency                     closed form of the two-level system (single plasmon pole: weight
+                                             4 D |m|^2 / W^2, frequency W = sqrt(D^2 + 4 D |m|^2))  [test_closed_forms]
+  Sigma_PPM / Sigma_Exact / Sigma_CDA        closed form of the two-level system, Sigma_c = (2D/W) sum_l (M_nl.m)^2 /
+  (prefactors, signs, pole positions)        (w - e_l +- W); Sigma_Exact also against an adaptive imaginary-axis
+                                             quadrature of -(1/pi) int G W_c on a generic problem (no eigenmodes, no
+                                             plasmon poles: scipy.integrate.quad + dense inverses); CDA error falls
+                                             with the quadrature order                                [test_closed_forms]
+  Sigma_x                                    -sum_occ (nm|n'm) from the un-factorised RI integrals
+  BSE_OPERATOR (Hqp, Hx, Hd, Hd2, all 8      element-wise dense assembly from the definitions; two-level closed forms
+  typedefs), BSE::configure                  for TDA and full BSE, singlet and triplet; LITERATURE: H2 / STO-3G CIS
+                                             energies from Szabo & Ostlund's integrals (e1, e2, J12, K12)  [test_closed_forms]
+  Perturbative_DynamicalScreening            scalar fixed-point iteration of the two-level exciton     [test_closed_forms]
+  DavidsonSolver                             numpy eigh on random diagonally dominant matrices (upstream's own test pattern)
+  Anderson mixing                            exact solution of a linear fixed-point map once the history spans the space
+  GaussianQuadrature                         numpy's Gauss-Legendre / Laguerre / Hermite rules
+  molecule inputs (tests only)               LITERATURE: RHF/STO-3G energies of H2 (-1.1167 Ha) and H2O (-74.942079928 Ha)
+What stays unpinned is everything that is a CONVENTION of upstream rather than physics or mathematics: option
+defaults, the damping window of Sigma_PPM::Stabilize (0.25 Ha), the 1e-5 / 1e-9 weight cut-offs of the PPM, the QP
+root selection rule, Davidson's search-space bookkeeping, the AdjustHqpSize window logic, the `ranges` arithmetic.
+
 Layout conventions (identical to the reference's host layout so the same
 buffers feed the C ABI):
   * ``M[m, P, n]`` C-contiguous  ==  ``std::vector<Eigen::MatrixXd>`` of length

@@ -82,11 +82,15 @@ def test_main_arm_assembles_the_json_line_with_a_fake_device(monkeypatch, capsys
             sz = self.sz
             self.last = {"qp": np.linspace(-1, 1, sz.qptotal), "singlets": np.array([0.3, 0.4]), "vectors": None,
                          "davidson_info": "Success", "davidson_iterations": 7, "qp_unconverged": 0,
-                         "stage_seconds": {"fill3c": 0.01, "total": 0.02},
+                         "stage_seconds": {"fill3c": 0.01, "bse_davidson": 0.005, "total": 0.02},
                          "grid_scan": {"compressed": True, "bins": 30, "direct_evaluations": 10.0,
                                        "equivalent_evaluations": 100.0}}
             time.sleep(0.002)
             return self.last
+
+        def solve_bse_again(self):
+            calls.append("bse-factorised")
+            return {"singlets": np.array([0.3, 0.4]), "iterations": 9}
 
         def pin_host_copy(self):
             calls.append("pin")
@@ -144,4 +148,5 @@ def test_main_arm_assembles_the_json_line_with_a_fake_device(monkeypatch, capsys
     assert d["e2e"]["h2d_bytes_per_step"] == 5000 and d["e2e"]["d2h_bytes_per_step"] == 300 and d["e2e"]["value"] > 0
     assert d["host_alloc"]["block_cache"] is True
     # 3 warm-up + 2 timed resident steps, then pin -> (1 warm-up + 2 timed) e2e steps -> unpin
-    assert calls == ["resident"] * 5 + ["pin"] + ["e2e"] * 3 + ["unpin"]
+    assert calls == ["resident"] * 5 + ["bse-factorised", "pin"] + ["e2e"] * 3 + ["unpin"]
+    assert d["bse_modes"]["factorised_iterations"] == 9 and d["bse_modes"]["default"] == "dense"
