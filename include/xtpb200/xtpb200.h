@@ -199,11 +199,14 @@ int xtpb_gw_grid_scan_info(xtpb_gw* gw, int* compressed, xtpb_index* n_bins, dou
                            double* equivalent_evaluations);
 /* Host-side plan of the compressed grid scan behind xtpb_gw_sigma_c_grid / GW::SolveQP_Grid (needs no device; exposed
  * so that the bin/near-range logic can be tested on a CPU box).  The pole axis [zmin, zmax] is cut into n_bins bins
- * (edges: n_bins + 1 ascending values); near_ranges[(level*n_chunks + chunk)*2 + {0,1}] is the inclusive range of bins
+ * (edges: n_bins + 1 ascending values); near_ranges[(level*n_chunks + chunk)*4 + {0,1}] is the inclusive range of bins
  * whose poles are summed one by one for the chunk of C = xtpb_ppm_grid_chunk() consecutive grid points starting at
  * grid_start[level] + C*chunk*spacing (lo > hi: none); every other bin enters through its Chebyshev moments.
+ * Entries {2,3} are the inclusive sub-range of INNER bins, all of whose poles lie inside the damping window of every
+ * grid point of the chunk: there the damped kernel is smooth in the pole position and the bin is replaced by 16
+ * equivalent poles at its Chebyshev nodes (none: entry 2 = entry 1 + 1, entry 3 = entry 1).
  * usable = 0: the scan falls back to the pole-by-pole kernel.  edges / near_ranges may be NULL to query the sizes
- * (near_ranges needs 2*n_levels*n_chunks ints, n_chunks = ceil(steps/C)). */
+ * (near_ranges needs 4*n_levels*n_chunks ints, n_chunks = ceil(steps/C)). */
 int xtpb_ppm_grid_chunk(void);      /* consecutive grid points per chunk of the plan below */
 int xtpb_ppm_grid_plan(xtpb_index n_levels, const double* grid_start, double spacing, xtpb_index steps, double zmin,
                        double zmax, xtpb_index edges_capacity, double* edges, xtpb_index* n_bins, int* near_ranges,

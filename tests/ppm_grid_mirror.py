@@ -24,7 +24,7 @@ def plan(grid_start, spacing, steps, zmin, zmax):
     if not usable.value:
         return None
     edges = np.empty(nb.value + 1)
-    near = np.empty((nl, nch.value, 2), dtype=np.int32)
+    near = np.empty((nl, nch.value, 4), dtype=np.int32)
     _lib.check(lib.xtpb_ppm_grid_plan(nl, dp(grid_start), float(spacing), int(steps), float(zmin), float(zmax),
                                       len(edges), dp(edges), C.byref(nb), near.ctypes.data_as(C.POINTER(C.c_int)),
                                       C.byref(nch), C.byref(usable)))
@@ -76,28 +76,47 @@ def moments(slab, e, freq, fac, edges, table):
     return mu
 
 
+def equivalent_poles(mu, edges):
+    """ppm_equivalent_poles_kernel: per bin, ORDER poles at the Chebyshev-Gauss nodes with weights
+    w_n = (2/K) [mu_0/2 + sum_k mu_k T_k(t_n)] that reproduce sum_i A_i f(z_i) for every f smooth on the bin."""
+    nb = len(edges) - 1
+    n = np.arange(ORDER)
+    t = np.cos(np.pi * (n + 0.5) / ORDER)
+    Tk = np.cos(np.outer(np.arange(ORDER), np.arccos(t)))          # T_k(t_n)
+    w = (2.0 / ORDER) * (0.5 * mu[:, :1] + mu[:, 1:] @ Tk[1:])        # (nb, ORDER)
+    c, h = 0.5 * (edges[:-1] + edges[1:]), 0.5 * np.diff(edges)
+    return w, c[:, None] + h[:, None] * t[None, :]
+
+
 def grid_values(slab, e, n_occ, freq, fac, om0, spacing, steps, edges, near_level, counters=None):
-    """sigma_ppm_grid_compressed_kernel for one level: near bins pole by pole (damped kernel), far bins by the series."""
+    """sigma_ppm_grid_compressed_kernel for one level: poles of the near bins one by one (damped kernel) except the
+    INNER bins (inside every target's damping window), which enter through their equivalent poles; far bins by the
+    Cauchy series of their moments."""
     table = bin_table(edges, e, n_occ, freq)
     mu = moments(slab, e, freq, fac, edges, table)
+    eq_w, eq_z = equivalent_poles(mu, edges)
     nb = len(edges) - 1
     out = np.zeros(steps)
     for ch in range(near_level.shape[0]):
         js = np.arange(ch * CHUNK, min(steps, (ch + 1) * CHUNK))
         om = om0 + spacing * js
-        b_lo, b_hi = near_level[ch]
+        b_lo, b_hi, i_lo, i_hi = near_level[ch]
         acc = np.zeros(len(js))
         if b_lo <= b_hi:
             for P in np.nonzero(fac)[0]:
                 for seg in range(2):
-                    lo, hi = table[seg, P, b_lo], table[seg, P, b_hi + 1]
-                    if hi <= lo:
-                        continue
-                    z = e[lo:hi] + (freq[P] if seg else -freq[P])
-                    a = fac[P] * slab[P, lo:hi] ** 2
-                    acc += (a[None, :] * orc.ppm_stabilized_inverse(om[:, None] - z[None, :])).sum(axis=1)
-                    if counters is not None:
-                        counters["near"] += (hi - lo) * len(js)
+                    for lo, hi in ((table[seg, P, b_lo], table[seg, P, i_lo]), (table[seg, P, i_hi + 1], table[seg, P, b_hi + 1])):
+                        if hi <= lo:
+                            continue
+                        z = e[lo:hi] + (freq[P] if seg else -freq[P])
+                        a = fac[P] * slab[P, lo:hi] ** 2
+                        acc += (a[None, :] * orc.ppm_stabilized_inverse(om[:, None] - z[None, :])).sum(axis=1)
+                        if counters is not None:
+                            counters["near"] += (hi - lo) * len(js)
+            for b in range(i_lo, i_hi + 1):
+                x = om[:, None] - eq_z[b][None, :]
+                assert np.all(np.abs(x) < 0.25), "an inner bin must lie inside every target's damping window"
+                acc += (eq_w[b][None, :] * orc.ppm_stabilized_inverse(x)).sum(axis=1)
         for b in range(nb):
             if b_lo <= b <= b_hi:
                 continue

@@ -19,12 +19,22 @@ def _check_plan(edges, near, grid_start, spacing, steps, zmin, zmax):
     assert h.min() >= 0.5 * BIN - 1e-12                      # no bin is narrower than the core bin width
     ck = mir.CHUNK
     n_chunks = (steps + ck - 1) // ck
-    assert near.shape == (len(grid_start), n_chunks, 2)
+    assert near.shape == (len(grid_start), n_chunks, 4)
     for l, g0 in enumerate(grid_start):
         for ch in range(n_chunks):
             wa, wb = g0 + spacing * ck * ch, g0 + spacing * (ck * (ch + 1) - 1)
-            lo, hi = near[l, ch]
+            lo, hi, ilo, ihi = near[l, ch]
             assert 0 <= lo <= nb and -1 <= hi < nb
+            # inner bins: a sub-range of the near bins (or the empty range hi+1 .. hi) whose poles are damped for every
+            # target of the chunk; the near bins next to it are not
+            if ilo <= ihi:
+                assert lo <= ilo and ihi <= hi
+                assert edges[ilo] > wb - W and edges[ihi + 1] < wa + W
+                for b in (ilo - 1, ihi + 1):
+                    if lo <= b <= hi:
+                        assert not (edges[b] >= wb - W + 1e-6 and edges[b + 1] <= wa + W - 1e-6)
+            else:
+                assert (ilo, ihi) == (hi + 1, hi)
             for b in list(range(0, lo)) + list(range(hi + 1, nb)):
                 dist = max(wa - c[b], c[b] - wb, 0.0)
                 assert dist >= 3.0 * h[b] and dist >= h[b] + W, (l, ch, b)

@@ -40,6 +40,7 @@ print(json.dumps([(r['algorithm'], r['cores'], r['full_s'], r['sampled_s']) for 
     ncu_grid)  XTPB_SIGMA_GRID=compressed timeout 900 ncu --set full --clock-control none -k regex:sigma_ppm_grid_compressed -c 1 -f -o /tmp/r02_grid python tools/bench_sigma_grid.py --child --workload synth-1000 --reps 1 > $OUT/ncu_grid_$TAG.log 2>&1; echo "ncu_grid rc=$?"; ncu -i /tmp/r02_grid.ncu-rep --page raw --csv > $OUT/r02_grid_raw.csv 2>/dev/null; ncu -i /tmp/r02_grid.ncu-rep --page details --csv > $OUT/r02_grid_details.csv 2>/dev/null; ls -la $OUT/r02_grid_*.csv ;;
     scaletests) timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q > $OUT/pytest_scale_$TAG.log 2>&1; echo "scaletests rc=$?"; tail -15 $OUT/pytest_scale_$TAG.log | cut -c1-300 ;;
     probe)     tools/probe_rcp64 > $OUT/probe_rcp64_$TAG.json 2> $OUT/probe_rcp64_$TAG.err; echo "probe rc=$?"; cat $OUT/probe_rcp64_$TAG.json | cut -c1-200 ;;
+    benzene)   timeout 600 python bench.py --workload benzene-tzvp-shape --steps 3 --warmup 3 > $OUT/bench_benzene_$TAG.json 2> $OUT/bench_benzene_$TAG.err; echo "benzene rc=$?"; cut -c1-300 $OUT/bench_benzene_$TAG.json ;;
     smoke)     timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_$TAG.log ;;
     *)         echo "unknown step $step" ;;
   esac

@@ -222,7 +222,7 @@ bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing,
   plan.nb = (int)plan.edges.size() - 1;
   if (plan.nb < 1 || plan.nb > kMaxBins) return false;
   plan.n_chunks = (int)((steps + kPpmGridChunk - 1) / kPpmGridChunk);
-  plan.near.assign((size_t)(2 * n_levels * plan.n_chunks), 0);
+  plan.near.assign((size_t)(4 * n_levels * plan.n_chunks), 0);
   for (long long l = 0; l < n_levels; ++l)
     for (int ch = 0; ch < plan.n_chunks; ++ch) {
       const double wa = grid_start[l] + spacing * double((long long)ch * kPpmGridChunk);
@@ -235,8 +235,26 @@ bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing,
       int lo = 0, hi = plan.nb - 1;
       while (lo <= hi && is_far(lo)) ++lo;
       while (hi >= lo && is_far(hi)) --hi;
-      plan.near[(size_t)(2 * (l * plan.n_chunks + ch))] = lo;          // lo > hi: every bin is far
-      plan.near[(size_t)(2 * (l * plan.n_chunks + ch) + 1)] = hi;
+      // INNER bins: every pole of the bin is inside the damping window of EVERY target of the chunk
+      // (wb - W < z < wa + W with a safety margin), where the damped kernel sin^2(2 pi x)/x is an entire function of the
+      // pole position: the bin's poles are replaced by kCmpOrder equivalent poles at its Chebyshev nodes (weights from
+      // the moments; kernels.cu: ppm_equivalent_poles_kernel).  Contiguous by geometry; none: i_lo = hi + 1, i_hi = hi.
+      const double margin = 1e-6;
+      int ilo = hi + 1, ihi = hi;
+      for (int b = lo; b <= hi; ++b) {
+        const bool inner = plan.edges[b] >= wb - W + margin && plan.edges[b + 1] <= wa + W - margin;
+        if (inner) {
+          if (ilo > ihi) ilo = b;
+          ihi = b;
+        } else if (ilo <= ihi) {
+          break;
+        }
+      }
+      const size_t at = (size_t)(4 * (l * plan.n_chunks + ch));
+      plan.near[at] = lo;          // lo > hi: every bin is far
+      plan.near[at + 1] = hi;
+      plan.near[at + 2] = ilo;
+      plan.near[at + 3] = ihi;
     }
   return true;
 }

@@ -119,7 +119,7 @@ void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal
                       const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
                       const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s);
 // compressed grid scan (kernels.cu (1b)): far bins of the pole axis through Chebyshev moments, near bins pole by pole;
-// edges_host: nb+1 bin edges, near_host: [level][chunk][2] inclusive near-bin ranges (ppm_grid_plan)
+// edges_host: nb+1 bin edges, near_host: [level][chunk][4] inclusive near-bin and inner-bin ranges (ppm_grid_plan)
 void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                                  const double* energies, const double* ppm_freq, const double* ppm_fac,
                                  const int* level_slab, const double* omega0, double domega, int n_omega, int n_levels,
@@ -130,7 +130,7 @@ void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab,
 // Returns false when the scan should use the direct kernel (no poles, too many bins).
 struct PpmGridPlan {
   std::vector<double> edges;    // nb + 1, ascending
-  std::vector<int> near;        // [level][chunk][2]
+  std::vector<int> near;        // [level][chunk][4]: near bins lo..hi (inclusive), of which inner bins ilo..ihi
   int nb = 0, n_chunks = 0;
 };
 constexpr double kPpmDampingWindow = 0.25;   // |x| below which Sigma_PPM::Stabilize damps 1/x (sigma_ppm.cc)

@@ -458,9 +458,41 @@ __global__ void __launch_bounds__(kCmpMomentWarps * 32) ppm_moments_kernel(
   }
 }
 
+// Equivalent poles of a bin: for any function f that is smooth on the bin (here: the DAMPED kernel as a function of the
+// pole position, for grid points whose whole damping window covers the bin), sum_i A_i f(z_i) = sum_n w_n f(z_n) with
+// z_n the kCmpOrder Chebyshev-Gauss nodes of the bin and w_n = (2/K) [mu_0/2 + sum_{k>=1} mu_k T_k(t_n)]
+// (Chebyshev interpolation through the nodes, integrated against the poles = the bin's moments).  The interpolation
+// error of sin^2(2 pi x)/x over a bin of half-width h <= 1/16 Ha is below (2 pi h)^16 / 16! ~ 1e-20 of its maximum.
+// eq[((level*nb + b)*K + n)] = (w_n, z_n): fed to the near-field loop like real poles.
+__global__ void ppm_equivalent_poles_kernel(double2* __restrict__ eq, const double* __restrict__ moments,
+                                            const double* __restrict__ edges, int nb, long long n_level_bins) {
+  const long long total = n_level_bins * kCmpOrder;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % kCmpOrder);
+    const long long lb = idx / kCmpOrder;
+    const int b = (int)(lb % nb);
+    const double* mu = moments + lb * kCmpOrder;
+    const double t = cospi((n + 0.5) / kCmpOrder);
+    // Clenshaw for sum'_k mu_k T_k(t)
+    double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int k = kCmpOrder - 1; k >= 1; --k) {
+      const double b0 = fma(2.0 * t, b1, mu[k] - b2);
+      b2 = b1;
+      b1 = b0;
+    }
+    const double sum = fma(t, b1, 0.5 * mu[0] - b2);
+    const double c = 0.5 * (edges[b] + edges[b + 1]), h = 0.5 * (edges[b + 1] - edges[b]);
+    eq[idx] = make_double2(sum * (2.0 / kCmpOrder), fma(h, t, c));
+  }
+}
+
 // One warp per (level, chunk of kCmpChunk consecutive grid points); blockIdx.z splits the aux range of the near field
-// when few warps would leave SMs idle (split 0 also adds the far field).  near_range[(level*n_chunks + chunk)*2 + {0,1}]
-// is the inclusive range of bins whose poles are evaluated one by one (lo > hi: none).
+// when few warps would leave SMs idle (split 0 also adds the far field and the equivalent poles of the inner bins).
+// near_range[(level*n_chunks + chunk)*4 + {0..3}]: near bins b_lo..b_hi (inclusive; lo > hi: none), of which the
+// inner bins i_lo..i_hi are represented by their equivalent poles; the poles of the remaining near bins are evaluated
+// one by one.
 // MINB = resident CTAs per SM the register allocation is capped for (occupancy against unrolling depth; the launcher
 // picks kCmpMinBlocks unless XTPB_GRID_OCC says otherwise).
 template <int MINB>
@@ -469,8 +501,8 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
     const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac, const int* __restrict__ level_slab,
     const double* __restrict__ omega0, double domega, int n_omega, const int* __restrict__ binstart,
     const double* __restrict__ edges, int nb, const int* __restrict__ near_range, int n_chunks,
-    const double* __restrict__ moments, double* __restrict__ out, long long out_split_stride,
-    unsigned long long* __restrict__ near_poles) {
+    const double* __restrict__ moments, const double2* __restrict__ eq_poles, double* __restrict__ out,
+    long long out_split_stride, unsigned long long* __restrict__ near_poles) {
   __shared__ double2 tile[kCmpWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x * kCmpWarps + warp, level = blockIdx.y;
@@ -479,91 +511,116 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
   const int point = lane & (kCmpChunk - 1), slot = lane / kCmpChunk;
   const int j = chunk * kCmpChunk + point;
   const double om = omega0[level] + domega * (double)j;
-  const int b_lo = near_range[((long long)level * n_chunks + chunk) * 2 + 0];
-  const int b_hi = near_range[((long long)level * n_chunks + chunk) * 2 + 1];
+  const int4 nr = reinterpret_cast<const int4*>(near_range)[(long long)level * n_chunks + chunk];
+  const int b_lo = nr.x, b_hi = nr.y, i_lo = nr.z, i_hi = nr.w;
   const int p_per = (naux + gridDim.z - 1) / gridDim.z;
   const int p_begin = blockIdx.z * p_per, p_end = min(naux, p_begin + p_per);
   double acc4[kCmpG];                         // independent accumulation chains, summed in a fixed order
 #pragma unroll
   for (int g = 0; g < kCmpG; ++g) acc4[g] = 0.0;
   long long n_near = 0;                       // poles this warp evaluates one by one (bookkeeping for the reports)
+
+  // evaluates the 32 poles in tile[warp] (weight, position z: x = w - z; padding: weight 0, far away) against this
+  // lane's grid point, kCmpSlots * kCmpG poles per step
+  auto eval_tile = [&](int count) {
+    constexpr int kStep = kCmpSlots * kCmpG;
+    const int cnt = (count + kStep - 1) / kStep * kStep;
+    for (int t = 0; t < cnt; t += kStep) {
+      double2 e[kCmpG];
+      double x[kCmpG], r[kCmpG];
+      unsigned hmin = 0xffffffffu, hmax = 0u;
+#pragma unroll
+      for (int g = 0; g < kCmpG; ++g) {
+        e[g] = tile[warp][t + g * kCmpSlots + slot];
+        x[g] = om - e[g].y;
+        const unsigned hw = static_cast<unsigned>(__double2hiint(x[g])) & 0x7fffffffu;      // |x| by its high word
+        hmin = min(hmin, hw);
+        hmax = max(hmax, hw);
+      }
+      // the poles of a range ascend and the chunk is much shorter than the damping window, so a step is almost always
+      // of one kind for the whole warp: nobody damped (plain reciprocal), everybody damped (polynomial, no
+      // reciprocal), or -- in two narrow zones at the edges of the window -- mixed (both, selected per element).
+      // Warp-uniform branches (one warp-wide min / max of the exponent words): no divergence.
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, hmin), wmax = __reduce_max_sync(0xffffffffu, hmax);
+      if (wmin >= 0x3fd00000u) {
+#pragma unroll
+        for (int g = 0; g < kCmpG; ++g) r[g] = rcp_fast(x[g]);
+      } else if (wmax < 0x3fd00000u) {
+#pragma unroll
+        for (int g = 0; g < kCmpG; ++g) r[g] = ppm_ginv_poly(x[g]);
+      } else {
+#pragma unroll
+        for (int g = 0; g < kCmpG; ++g) {
+          const double plain = rcp_fast(x[g]), damped = ppm_ginv_poly(x[g]);
+          r[g] = ppm_in_window(x[g]) ? damped : plain;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < kCmpG; ++g) acc4[g] = fma(e[g].x, r[g], acc4[g]);
+    }
+  };
+
   // ---- near field: the damped kernel, pole by pole (poles broadcast from shared memory, four per step)
   if (b_lo <= b_hi) {
-    // m-ranges of the near bins for aux function P: {occupied lo, hi, unoccupied lo, hi}; the look-up of P + 1 is in
-    // flight while P is evaluated
-    int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    // m-ranges of aux function P that are evaluated pole by pole: per segment (occupied / unoccupied) the poles of the
+    // near bins below and above the inner bins.  The table look-up of P + 1 is in flight while P is evaluated.
+    int t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
     auto ranges_of = [&](int P) {
       const int* bs0 = binstart + (long long)P * (nb + 1);
       const int* bs1 = binstart + ((long long)naux + P) * (nb + 1);
-      n0 = bs0[b_lo]; n1 = bs0[b_hi + 1]; n2 = bs1[b_lo]; n3 = bs1[b_hi + 1];
+      t0 = bs0[b_lo]; t1 = bs0[i_lo]; t2 = bs0[i_hi + 1]; t3 = bs0[b_hi + 1];
+      t4 = bs1[b_lo]; t5 = bs1[i_lo]; t6 = bs1[i_hi + 1]; t7 = bs1[b_hi + 1];
     };
     if (p_begin < p_end) ranges_of(p_begin);
     for (int P = p_begin; P < p_end; ++P) {
-      const int c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+      const int c0 = t0, c1 = t1, c2 = t2, c3 = t3, c4 = t4, c5 = t5, c6 = t6, c7 = t7;
       if (P + 1 < p_end) ranges_of(P + 1);
       const double fac = ppm_fac[P];
       if (fac == 0.0) continue;
       const double Om = ppm_freq[P];
       const double* row = S + (long long)P * ldn;
 #pragma unroll 1
-      for (int seg = 0; seg < 2; ++seg) {
-        const int lo = seg ? c2 : c0, hi = seg ? c3 : c1;
-        const double shift = seg ? Om : -Om;
+      for (int rg = 0; rg < 4; ++rg) {
+        const int lo = rg == 0 ? c0 : (rg == 1 ? c2 : (rg == 2 ? c4 : c6));
+        const int hi = rg == 0 ? c1 : (rg == 1 ? c3 : (rg == 2 ? c5 : c7));
+        if (lo >= hi) continue;
+        const double shift = rg >= 2 ? Om : -Om;
         n_near += hi - lo;
-        // lane's pole of the tile that starts at m0 (weight, position z: x = w - z); padding: weight 0, far away
-        auto load_pole = [&](int m0) {
+        // raw tensor element / energy of this lane's pole in the tile that starts at m0: the arithmetic on them happens
+        // when the tile is stored, so that the loads of the NEXT tile stay in flight while this one is evaluated
+        double nv = 0.0, ne = 0.0;
+        auto fetch = [&](int m0) {
           const int m = m0 + lane;
-          double2 el = make_double2(0.0, -1.0e30);
+          nv = 0.0;
+          ne = -1.0e30;
           if (m < hi) {
-            const double v = row[m];
-            el.x = fac * v * v;
-            el.y = energies[m] + shift;
+            nv = row[m];
+            ne = energies[m];
           }
-          return el;
         };
-        double2 next = load_pole(lo);
+        fetch(lo);
         for (int m0 = lo; m0 < hi; m0 += 32) {
-          const double2 el = next;
-          if (m0 + 32 < hi) next = load_pole(m0 + 32);      // in flight while this tile is evaluated
+          const double2 el = make_double2(fac * nv * nv, ne + shift);
+          if (m0 + 32 < hi) fetch(m0 + 32);
           __syncwarp();
           tile[warp][lane] = el;
           __syncwarp();
-          constexpr int kStep = kCmpSlots * kCmpG;          // poles consumed per step by the warp
-          const int cnt = (min(32, hi - m0) + kStep - 1) / kStep * kStep;
-          for (int t = 0; t < cnt; t += kStep) {
-            double2 e[kCmpG];
-            double x[kCmpG], r[kCmpG];
-            bool in[kCmpG], any = false, all = true;
-#pragma unroll
-            for (int g = 0; g < kCmpG; ++g) {
-              e[g] = tile[warp][t + g * kCmpSlots + slot];
-              x[g] = om - e[g].y;
-              in[g] = ppm_in_window(x[g]);
-              any |= in[g];
-              all &= in[g];
-            }
-            // the poles of a segment ascend and the chunk is much shorter than the damping window, so a step is almost
-            // always of one kind for the whole warp: nobody damped (plain reciprocal), everybody damped (polynomial,
-            // no reciprocal), or -- in two narrow zones at the edges of the window -- mixed (both, selected per
-            // element).  Warp-uniform branches: no divergence.
-            if (!__any_sync(0xffffffffu, any)) {
-#pragma unroll
-              for (int g = 0; g < kCmpG; ++g) r[g] = rcp_fast(x[g]);
-            } else if (__all_sync(0xffffffffu, all)) {
-#pragma unroll
-              for (int g = 0; g < kCmpG; ++g) r[g] = ppm_ginv_poly(x[g]);
-            } else {
-#pragma unroll
-              for (int g = 0; g < kCmpG; ++g) {
-                const double plain = rcp_fast(x[g]), damped = ppm_ginv_poly(x[g]);
-                r[g] = in[g] ? damped : plain;
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < kCmpG; ++g) acc4[g] = fma(e[g].x, r[g], acc4[g]);
-          }
+          eval_tile(min(32, hi - m0));
         }
       }
+    }
+  }
+  // ---- inner bins: their equivalent poles (all of them inside every grid point's damping window), split 0 only
+  if (blockIdx.z == 0 && i_lo <= i_hi) {
+    const double2* eq = eq_poles + ((long long)level * nb + i_lo) * kCmpOrder;
+    const int total = (i_hi - i_lo + 1) * kCmpOrder;
+    for (int m0 = 0; m0 < total; m0 += 32) {
+      const int m = m0 + lane;
+      const double2 el = m < total ? eq[m] : make_double2(0.0, -1.0e30);
+      __syncwarp();
+      tile[warp][lane] = el;
+      __syncwarp();
+      eval_tile(min(32, total - m0));
     }
   }
   double acc = 0.0;
@@ -963,8 +1020,9 @@ void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab,
   slices = std::max(1, std::min(slices, std::min(16, std::max(1, naux / 64))));
   const long long n = (long long)n_levels * n_omega;
   const long long n_mom = (long long)n_levels * nb * kCmpOrder;
-  const long long n_table = 2LL * naux * (nb + 1), n_near = 2LL * n_levels * n_chunks;
+  const long long n_table = 2LL * naux * (nb + 1), n_near = 4LL * n_levels * n_chunks;
   DBuf edges((size_t)(nb + 1)), table((size_t)((n_table + 1) / 2)), near_buf((size_t)((n_near + 1) / 2));
+  DBuf eq_buf((size_t)(2 * n_mom));           // equivalent poles: (weight, position) per (level, bin, node)
   DBuf mom_part((size_t)(n_mom * slices)), mom_sum, partial, counter(1);
   counter.zero(s);
   if (slices > 1) mom_sum.alloc((size_t)n_mom);
@@ -986,6 +1044,9 @@ void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab,
     sigma_ppm_grid_reduce<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(mom_sum.p, mom_part.p, n_mom, slices);
     LAUNCH_CHECK();
   }
+  ppm_equivalent_poles_kernel<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(
+      reinterpret_cast<double2*>(eq_buf.p), slices > 1 ? mom_sum.p : mom_part.p, edges.p, nb, (long long)n_levels * nb);
+  LAUNCH_CHECK();
   const char* occ_env = std::getenv("XTPB_GRID_OCC");
   const int occ = occ_env ? std::atoi(occ_env) : kCmpMinBlocks;
   auto kernel = occ <= 3 ? sigma_ppm_grid_compressed_kernel<3>
@@ -994,7 +1055,8 @@ void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab,
                          : sigma_ppm_grid_compressed_kernel<6>;
   kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
       M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab, omega0, domega, n_omega, table_i, edges.p, nb,
-      near_i, n_chunks, slices > 1 ? mom_sum.p : mom_part.p, splits > 1 ? partial.p : values, n,
+      near_i, n_chunks, slices > 1 ? mom_sum.p : mom_part.p, reinterpret_cast<const double2*>(eq_buf.p),
+      splits > 1 ? partial.p : values, n,
       reinterpret_cast<unsigned long long*>(counter.p));
   LAUNCH_CHECK();
   if (splits > 1) {
