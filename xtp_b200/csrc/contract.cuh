@@ -292,6 +292,21 @@ __device__ __forceinline__ void store_tile(const GemmParams& p, const double (&a
 }
 
 // ============================================================ cp.async instance (any alignment, any strides)
+// Output tile of a CTA.  CTAs are launched in blockIdx order, so the ~148 that run together should share operand
+// panels: tiles are walked in groups of kTileGroup tile columns, row by row inside a group (a wave then touches about
+// 8 + 18 panels of a large product instead of all tile rows + 3 columns; ncu of the eps SYRK at C60 size showed 13x the
+// compulsory DRAM reads with the plain column-major walk, profiles/r02_contract_tma_ncu_c60.md).
+constexpr int kTileGroup = 8;
+__device__ __forceinline__ void tile_of_block(int block, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int per_group = kTileGroup * tiles_m;
+  const int grp = block / per_group;
+  const int n_first = grp * kTileGroup;
+  const int gsz = min(tiles_n - n_first, kTileGroup);
+  const int r = block - grp * per_group;
+  tn = n_first + r % gsz;
+  tm = r / gsz;
+}
+
 template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D, bool VEC>
 __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -302,7 +317,8 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_kernel(const GemmParams
   const int li = lane >> 2, lt = lane & 3;
 
   const int tiles_m = (p.M + BM - 1) / BM;
-  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  int tm, tn;
+  tile_of_block(blockIdx.x, tiles_m, gridDim.x / tiles_m, tm, tn);
   if (p.lower && tn * BN > tm * BM + BM - 1) return;
   const int split = blockIdx.z % p.splits, batch = blockIdx.z / p.splits;
 
@@ -465,7 +481,8 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_tma_kernel(const GemmPa
   const int li = lane >> 2, lt = lane & 3;
 
   const int tiles_m = (p.M + BM - 1) / BM;
-  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  int tm, tn;
+  tile_of_block(blockIdx.x, tiles_m, gridDim.x / tiles_m, tm, tn);
   if (p.lower && tn * BN > tm * BM + BM - 1) return;
   const int split = blockIdx.z % p.splits, batch = blockIdx.z / p.splits;
 
