@@ -460,7 +460,7 @@ def main():
     # timed region mixes shapes, so `achieved` is the flop-weighted mean over all launches and `traffic` is per launch
     # of the captured one, with its algorithmic bytes next to it)
     traffic, traffic_detail = None, None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_contract_traffic.json")
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_contract_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic_detail = json.load(f)
