@@ -581,6 +581,9 @@ def main():
             # host/driver time between kernels: cudaMalloc + cudaFree of the library's scratch buffers, per step
             "host_alloc": {"seconds_per_step": round(alloc["seconds"] / args.steps, 4),
                            "calls_per_step": alloc["calls"] / args.steps,
+                           # waiting for outstanding GPU work (e.g. the overlapped eigensolver) before a released block
+                           # is recycled: device time spent inside free(), not allocator time
+                           "free_wait_seconds_per_step": round(alloc.get("free_wait_seconds", 0.0) / args.steps, 4),
                            "block_cache": os.environ.get("XTPB_ALLOC_CACHE", "1") != "0",
                            "cache_hits_per_step": alloc["cache_hits"] / args.steps,
                            "cached_gb": round(alloc["cached_gb"], 3)},

@@ -64,6 +64,9 @@ int xtpb_ctx_comm_info(xtpb_ctx* ctx, int* rank, int* world);
  * in an exact-size cache instead of being returned to the driver -- cache hits and bytes currently cached.
  * Any pointer may be NULL; reset != 0 zeroes the counters. */
 int xtpb_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, int reset);
+/* Host seconds spent, since the last reset of xtpb_alloc_stats, waiting for outstanding GPU work before a released block
+ * went into the cache (the device-wide synchronisation cudaFree would have implied): GPU time, not allocator time. */
+int xtpb_alloc_free_wait_seconds(double* seconds);
 
 /* pinned (page-locked) host memory for the caller's AO-integral and result buffers: H2D/D2H copies from it run
  * asynchronously at PCIe rate and overlap the contractions (xtpb_tc_fill_block*). */

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "xtpb_ctx_comm_init": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int]),
     "xtpb_ctx_comm_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "xtpb_alloc_stats": (C.c_int, [dptr, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dptr, C.c_int]),
+    "xtpb_alloc_free_wait_seconds": (C.c_int, [dptr]),
     "xtpb_host_alloc": (C.c_int, [C.c_ulonglong, C.POINTER(vp)]),
     "xtpb_host_free": (C.c_int, [vp]),
     "xtpb_profile_enable": (C.c_int, [C.c_int]),

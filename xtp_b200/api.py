@@ -716,8 +716,11 @@ def alloc_stats(reset=False):
     """Host seconds inside cudaMalloc/cudaFree, allocation count, block-cache hits and cached GB (xtpb_alloc_stats)."""
     sec, cached = C.c_double(0.0), C.c_double(0.0)
     calls, hits = C.c_longlong(0), C.c_longlong(0)
+    wait = C.c_double(0.0)
+    check(_lib.lib().xtpb_alloc_free_wait_seconds(C.byref(wait)))        # before a reset zeroes it
     check(_lib.lib().xtpb_alloc_stats(C.byref(sec), C.byref(calls), C.byref(hits), C.byref(cached), int(reset)))
-    return {"seconds": sec.value, "calls": calls.value, "cache_hits": hits.value, "cached_gb": cached.value * 1e-9}
+    return {"seconds": sec.value, "calls": calls.value, "cache_hits": hits.value, "cached_gb": cached.value * 1e-9,
+            "free_wait_seconds": wait.value}
 
 
 RANGES = {"default": 0, "factor": 1, "explicit": 2, "full": 3}

@@ -89,6 +89,12 @@ int xtpb_ctx_solver_seconds(xtpb_ctx* ctx, double* seconds, int reset) {
   XTPB_API_END
 }
 
+int xtpb_alloc_free_wait_seconds(double* seconds) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(seconds != nullptr, "null pointer");
+  *seconds = device_free_wait_seconds();
+  XTPB_API_END
+}
 int xtpb_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, int reset) {
   XTPB_API_BEGIN
   device_alloc_stats(seconds, calls, cache_hits, cached_bytes, reset != 0);

@@ -53,6 +53,8 @@ struct Error : std::runtime_error {
 void* device_alloc(size_t bytes);
 void device_free(void* p, size_t bytes);
 void device_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, bool reset);
+// host seconds device_free spent waiting for outstanding GPU work before recycling a block (not allocator time)
+double device_free_wait_seconds();
 
 // Owning device allocation of doubles (or bytes via count*8).
 struct DBuf {

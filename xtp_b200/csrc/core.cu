@@ -23,7 +23,7 @@ std::pair<int, size_t> cache_key(size_t bytes) {
   cudaGetDevice(&dev);
   return {dev, bytes};
 }
-double g_cached_bytes = 0.0, g_alloc_seconds = 0.0;
+double g_cached_bytes = 0.0, g_alloc_seconds = 0.0, g_free_wait_seconds = 0.0;
 long long g_alloc_calls = 0, g_cache_hits = 0;
 // on unless XTPB_ALLOC_CACHE=0; at most XTPB_ALLOC_CACHE_MAX_GB (default 64) are kept
 bool alloc_cache_on() {
@@ -82,15 +82,24 @@ void device_free(void* p, size_t bytes) {
   const auto t0 = std::chrono::steady_clock::now();
   std::lock_guard<std::mutex> lock(g_alloc_mu);
   if (alloc_cache_on() && g_cached_bytes + (double)bytes <= alloc_cache_cap_bytes()) {
-    cudaDeviceSynchronize();                    // what cudaFree implies: nothing in flight may still use the block
+    // what cudaFree implies: nothing in flight may still use the block.  The wait is for outstanding GPU work (e.g. an
+    // eigensolver running on the helper stream), not allocator time: it is accounted separately.
+    cudaDeviceSynchronize();
+    g_free_wait_seconds += seconds_since(t0);
+    const auto t1 = std::chrono::steady_clock::now();
     g_block_cache.emplace(cache_key(bytes), p);
     g_cached_bytes += (double)bytes;
-  } else {
-    cudaFree(p);
+    g_alloc_seconds += seconds_since(t1);
+    return;
   }
+  cudaFree(p);
   g_alloc_seconds += seconds_since(t0);
 }
 
+double device_free_wait_seconds() {
+  std::lock_guard<std::mutex> lock(g_alloc_mu);
+  return g_free_wait_seconds;
+}
 void device_alloc_stats(double* seconds, long long* calls, long long* cache_hits, double* cached_bytes, bool reset) {
   std::lock_guard<std::mutex> lock(g_alloc_mu);
   if (seconds) *seconds = g_alloc_seconds;
@@ -98,6 +107,7 @@ void device_alloc_stats(double* seconds, long long* calls, long long* cache_hits
   if (cache_hits) *cache_hits = g_cache_hits;
   if (cached_bytes) *cached_bytes = g_cached_bytes;
   if (reset) {
+    g_free_wait_seconds = 0.0;
     g_alloc_seconds = 0.0;
     g_alloc_calls = 0;
     g_cache_hits = 0;

@@ -579,34 +579,36 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
       if (fac == 0.0) continue;
       const double Om = ppm_freq[P];
       const double* row = S + (long long)P * ldn;
-#pragma unroll 1
-      for (int rg = 0; rg < 4; ++rg) {
-        const int lo = rg == 0 ? c0 : (rg == 1 ? c2 : (rg == 2 ? c4 : c6));
-        const int hi = rg == 0 ? c1 : (rg == 1 ? c3 : (rg == 2 ? c5 : c7));
-        if (lo >= hi) continue;
-        const double shift = rg >= 2 ? Om : -Om;
-        n_near += hi - lo;
-        // raw tensor element / energy of this lane's pole in the tile that starts at m0: the arithmetic on them happens
-        // when the tile is stored, so that the loads of the NEXT tile stay in flight while this one is evaluated
-        double nv = 0.0, ne = 0.0;
-        auto fetch = [&](int m0) {
-          const int m = m0 + lane;
-          nv = 0.0;
-          ne = -1.0e30;
-          if (m < hi) {
-            nv = row[m];
-            ne = energies[m];
-          }
-        };
-        fetch(lo);
-        for (int m0 = lo; m0 < hi; m0 += 32) {
-          const double2 el = make_double2(fac * nv * nv, ne + shift);
-          if (m0 + 32 < hi) fetch(m0 + 32);
-          __syncwarp();
-          tile[warp][lane] = el;
-          __syncwarp();
-          eval_tile(min(32, hi - m0));
+      // The four m-ranges of this aux function (occupied / unoccupied segment, below / above the inner bins) are
+      // walked as ONE virtual index space, so that short ranges (a rank of eight holds 1/8 of the levels) share tiles:
+      // virtual index t -> range rg = #{offsets <= t}, m = lo_rg + (t - offset_rg); ranges 2, 3 are unoccupied (+Omega)
+      const int o1 = max(c1 - c0, 0), o2 = o1 + max(c3 - c2, 0), o3 = o2 + max(c5 - c4, 0);
+      const int total = o3 + max(c7 - c6, 0);
+      if (total == 0) continue;
+      n_near += total;
+      // raw tensor element / energy of this lane's pole in the tile that starts at t0: the arithmetic on them happens
+      // when the tile is stored, so that the loads of the NEXT tile stay in flight while this one is evaluated
+      double nv = 0.0, ne = 0.0, nsh = 0.0;
+      auto fetch = [&](int first) {
+        const int t = first + lane;
+        nv = 0.0;
+        ne = -1.0e30;
+        nsh = 0.0;
+        if (t < total) {
+          const int m = t < o1 ? c0 + t : (t < o2 ? c2 + (t - o1) : (t < o3 ? c4 + (t - o2) : c6 + (t - o3)));
+          nv = row[m];
+          ne = energies[m];
+          nsh = t < o2 ? -Om : Om;
         }
+      };
+      fetch(0);
+      for (int v0 = 0; v0 < total; v0 += 32) {
+        const double2 el = make_double2(fac * nv * nv, ne + nsh);
+        if (v0 + 32 < total) fetch(v0 + 32);
+        __syncwarp();
+        tile[warp][lane] = el;
+        __syncwarp();
+        eval_tile(min(32, total - v0));
       }
     }
   }
