@@ -34,7 +34,7 @@ print(json.dumps([(r['algorithm'], r['cores'], r['full_s'], r['sampled_s']) for 
     cublas)    timeout 900 python tools/bench_contract.py --cublas --reps 5 --out $OUT/contract_vs_cublas_$TAG.jsonl > $OUT/cublas_$TAG.log 2>&1; echo "cublas rc=$?"; tail -14 $OUT/cublas_$TAG.log | cut -c1-260 ;;
     ncu_eps)   timeout 900 ncu --set full --clock-control none -k regex:contract -c 1 -f -o /tmp/r02_eps_c60 python tools/bench_contract.py --only epsilon_syrk --reps 1 --out $OUT/ncu_eps_$TAG.jsonl > $OUT/ncu_eps_$TAG.log 2>&1; echo "ncu_eps rc=$?"; ncu -i /tmp/r02_eps_c60.ncu-rep --page raw --csv > $OUT/r02_eps_c60_raw.csv 2>/dev/null; ncu -i /tmp/r02_eps_c60.ncu-rep --page details --csv > $OUT/r02_eps_c60_details.csv 2>/dev/null; ls -la $OUT/r02_eps_c60_*.csv ;;
     ncu_rot)   timeout 900 ncu --set full --clock-control none -k regex:contract -c 1 -f -o /tmp/r02_rot_c60 python tools/bench_contract.py --only aux_rotation --reps 1 --out $OUT/ncu_rot_$TAG.jsonl > $OUT/ncu_rot_$TAG.log 2>&1; echo "ncu_rot rc=$?"; ncu -i /tmp/r02_rot_c60.ncu-rep --page raw --csv > $OUT/r02_rot_c60_raw.csv 2>/dev/null; ncu -i /tmp/r02_rot_c60.ncu-rep --page details --csv > $OUT/r02_rot_c60_details.csv 2>/dev/null; ls -la $OUT/r02_rot_c60_*.csv ;;
-    launches)  XTPB_BENCH_MIN_WARMUP=1 timeout 1700 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:xtpb --csv --log-file $OUT/r02_launches_c60.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/launches_$TAG.json 2> $OUT/launches_$TAG.err; echo "launches rc=$?"; wc -l $OUT/r02_launches_c60.csv ;;
+    launches)  XTPB_BENCH_MIN_WARMUP=1 timeout 1700 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(contract|sigma_ppm|ppm_|chi0_|unpack_|splitk_|symmetrize_|bse_|col_norms|column_dots|residuals_|correction_|olsen_|copy_2d|extract_|scale_|axpby_|scatter_fill|cda_|exact_|set_identity|add_|unit_vectors|gather_strided|cyclic_cols|window_from)' --csv --log-file $OUT/r02_launches_c60.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/launches_$TAG.json 2> $OUT/launches_$TAG.err; echo "launches rc=$?"; wc -l $OUT/r02_launches_c60.csv ;;
     grid)      timeout 900 python tools/bench_sigma_grid.py --workload synth-1000 --out $OUT/sigma_grid_$TAG.jsonl > $OUT/grid_$TAG.log 2>&1; echo "grid rc=$?"; cut -c1-330 $OUT/grid_$TAG.log ;;
     gridtests) timeout 600 python -m pytest tests/test_gpu_gwbse.py -m gpu -x -q -k "grid or ppm or full_gwbse or g0w0" > $OUT/pytest_grid_$TAG.log 2>&1; echo "gridtests rc=$?"; tail -4 $OUT/pytest_grid_$TAG.log ;;
     ncu_grid)  XTPB_SIGMA_GRID=compressed timeout 900 ncu --set full --clock-control none -k regex:sigma_ppm_grid_compressed -c 1 -f -o /tmp/r02_grid python tools/bench_sigma_grid.py --child --workload synth-1000 --reps 1 > $OUT/ncu_grid_$TAG.log 2>&1; echo "ncu_grid rc=$?"; ncu -i /tmp/r02_grid.ncu-rep --page raw --csv > $OUT/r02_grid_raw.csv 2>/dev/null; ncu -i /tmp/r02_grid.ncu-rep --page details --csv > $OUT/r02_grid_details.csv 2>/dev/null; ls -la $OUT/r02_grid_*.csv ;;
