@@ -141,6 +141,14 @@ class TCMatrix_gwbse {
   void Fill3cMO_block_packed(Index P0, Index nP, const double* ao3c_packed) {
     check(xtpb_tc_fill_block_packed(h_, P0, nP, ao3c_packed));
   }
+  // Optional, BEFORE the Fill3cMO calls: start the first eigendecomposition of the metric step on the library's helper
+  // thread so that it runs underneath the MO transform; ApplyCoulombMetric with the SAME matrices (which must stay
+  // alive and unmoved until then) joins it.
+  void CoulombMetricBegin(const Matrix& aux_coulomb, const Matrix* aux_overlap = nullptr) {
+    check(xtpb_tc_coulomb_metric_begin(h_, aux_coulomb.data(), aux_coulomb.rows(),
+                                       aux_overlap ? aux_overlap->data() : nullptr,
+                                       aux_overlap ? aux_overlap->rows() : 0));
+  }
   // second half of Fill: Pseudo_InvSqrt_GWBSE(auxoverlap, 5e-7) + MultiplyRightWithAuxMatrix
   Index ApplyCoulombMetric(const Matrix& aux_coulomb, const Matrix* aux_overlap = nullptr, double etol = 5e-7) {
     Index removed = 0;

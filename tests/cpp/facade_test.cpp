@@ -69,6 +69,7 @@ int main(int argc, char** argv) {
     Context ctx(0);
     TCMatrix_gwbse<> Mmn(ctx);
     Mmn.Initialize(naux, 0, mmax, 0, rpamax);
+    Mmn.CoulombMetricBegin(V);          // the metric's eigensolver runs underneath the MO transform
     Mmn.Fill3cMO_begin(C);
     Mmn.Fill3cMO_block(0, naux, ao, nb);
     Mmn.ApplyCoulombMetric(V);
