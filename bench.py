@@ -343,7 +343,9 @@ def run_reference(args):
     vals, last = [], None
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        last = cr.sampled_step(sz, davidson_matmul_calls=args.davidson_calls)
+        # the median over the steps absorbs the noise of single samples, so one timed run per sample is enough
+        # when many steps are asked for (keeps `--steps 20` within a few minutes)
+        last = cr.sampled_step(sz, davidson_matmul_calls=args.davidson_calls, reps=1 if args.steps > 5 else 2)
         vals.append(last["seconds"])
     wall = time.perf_counter() - t_wall
     v = float(np.median(vals))

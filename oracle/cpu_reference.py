@@ -118,7 +118,7 @@ def _timeit(fn, reps=2):
 
 
 def sampled_step(sz, davidson_matmul_calls=40, grid_steps=1001, triplets=False, scale=1.0, seed=7,
-                 algorithm="reference"):
+                 algorithm="reference", reps=2):
     """Estimated seconds per molecule for workload ``sz`` (xtp_b200.synth.Sizes) on the CPU, from a bounded sample of
     the independent units of every stage, scaled by the unit counts.  The sample sizes are fixed numbers (they do not
     depend on the core count); ``scale`` multiplies them (1.0 ~ 15-25 s of CPU work on 16 cores at C60 size).
@@ -130,6 +130,10 @@ def sampled_step(sz, davidson_matmul_calls=40, grid_steps=1001, triplets=False, 
     assert algorithm in ("reference", "factorised")
     from xtp_b200 import synth
     use_all_host_threads()
+    _base_timeit = globals()["_timeit"]
+
+    def _timeit(fn, reps=reps):          # `reps` timed runs per sample (bench.py uses 1 when it takes the median of many steps)
+        return _base_timeit(fn, reps)
     rng = np.random.default_rng(seed)
     nb, naux = sz.n_basis, sz.n_aux
     m, n, o = sz.mtotal, sz.ntotal, sz.n_occ
