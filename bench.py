@@ -501,6 +501,14 @@ def main():
         other["sigma_ppm_pairs"] = {"bound": "hbm", "achieved_gbs": round(gbs, 1), "peak_gbs": hbm,
                                     "frac": round(gbs / hbm, 4), "peak_source": hbm_src,
                                     "ms_per_step": round(g["ms"] / args.steps, 3)}
+    if "sigma_ppm_points" in prof:
+        # single (level, frequency) points -- bisection rounds, final Sigma_c -- evaluated through the moments the grid
+        # scan left behind instead of streaming the slabs (sigma_ppm_pairs); work = pairs of the equivalent direct sums
+        g = prof["sigma_ppm_points"]
+        other["sigma_ppm_points"] = {"bound": "latency (near poles of <= 8 targets per warp)",
+                                     "equivalent_gevals_per_s": round(g["work"] / (g["ms"] * 1e-3) * 1e-9, 2),
+                                     "launches_per_step": g["launches"] / args.steps,
+                                     "ms_per_step": round(g["ms"] / args.steps, 3)}
     if "unpack" in prof:
         g = prof["unpack"]
         gbs = g["work"] / (g["ms"] * 1e-3) * 1e-9

@@ -200,6 +200,12 @@ int xtpb_gw_sigma_c_grid(xtpb_gw* gw, const double* center_frequencies_host, dou
  * performed one by one and the number the plain double sum needs.  Any pointer may be NULL. */
 int xtpb_gw_grid_scan_info(xtpb_gw* gw, int* compressed, xtpb_index* n_bins, double* direct_evaluations,
                            double* equivalent_evaluations);
+/* How single (level, frequency) values of the plasmon-pole Sigma_c without derivatives (the bisection rounds and the
+ * final Sigma_c of GW::SolveQP, xtpb_gw_sigma_c_diag_elements with derivatives == NULL) have been evaluated since the
+ * handle was created: calls served from the moments of the last compressed grid scan (no slab traffic; valid while
+ * the tensor, the RPA energies and the PPM parameters are unchanged) and calls that streamed the slabs
+ * (XTPB_SIGMA_POINTS=direct forces the latter).  Either pointer may be NULL. */
+int xtpb_gw_point_eval_info(xtpb_gw* gw, xtpb_index* compressed_calls, xtpb_index* direct_calls);
 /* Host-side plan of the compressed grid scan behind xtpb_gw_sigma_c_grid / GW::SolveQP_Grid (needs no device; exposed
  * so that the bin/near-range logic can be tested on a CPU box).  The pole axis [zmin, zmax] is cut into n_bins bins
  * (edges: n_bins + 1 ascending values); near_ranges[(level*n_chunks + chunk)*4 + {0,1}] is the inclusive range of bins

@@ -211,6 +211,72 @@ def test_sigma_c_qp_grid(ctx, prob, mode, steps, spacing, monkeypatch):
                                atol=1e-12)
 
 
+def test_sigma_c_points_through_scan_state(ctx, prob, monkeypatch):
+    """Single (level, frequency) values after a compressed grid scan come from its moments (no slab traffic) and agree
+    with the slab-streaming pair kernel and the oracle -- inside the grid, between grid points, far outside the binned
+    core; anything that changes the tensor, the energies or the PPM parameters sends them back to the pair kernel."""
+    sz = prob["sizes"]
+    monkeypatch.setenv("XTPB_SIGMA_GRID", "compressed")
+    gw, gwo, tc, _ = _gw_pair(ctx, prob)
+    gwo.rpa.setRPAInputEnergies(prob["energies"][sz.rpamin:sz.rpamax + 1])
+    gw.PrepareScreening()
+    gwo.sigma.PrepareScreening()
+    centers = prob["energies"][sz.qpmin:sz.qpmax + 1].copy()
+    rng = np.random.default_rng(21)
+    lv = rng.integers(0, sz.qptotal, 40)
+    fr = centers[lv] + rng.uniform(-5.0, 5.0, 40) * rng.choice([1.0, 0.1, 3.0], 40)
+    before = gw.point_eval_info()
+    v_pairs = gw.CalcCorrelationDiagElements(lv, fr)                    # no scan yet: pair kernel
+    assert gw.point_eval_info()["direct_calls"] == before["direct_calls"] + 1
+    gw.CalcCorrelationGrid(centers)
+    assert gw.grid_scan_info()["compressed"]
+    mid = gw.point_eval_info()
+    v_scan = gw.CalcCorrelationDiagElements(lv, fr)
+    after = gw.point_eval_info()
+    assert after["compressed_calls"] == mid["compressed_calls"] + 1 and after["direct_calls"] == mid["direct_calls"]
+    scale = max(np.abs(v_pairs).max(), 1e-3)
+    assert np.abs(v_scan - v_pairs).max() < 1e-10 * scale
+    ref = np.array([gwo.sigma.CalcCorrelationDiagElement(int(l), float(f)) for l, f in zip(lv[:12], fr[:12])])
+    np.testing.assert_allclose(v_scan[:12], ref, rtol=1e-9, atol=1e-11)
+    # derivatives always take the pair kernel
+    gw.CalcCorrelationDiagElements(lv, fr, True)
+    assert gw.point_eval_info()["compressed_calls"] == after["compressed_calls"]
+    # XTPB_SIGMA_POINTS=direct
+    monkeypatch.setenv("XTPB_SIGMA_POINTS", "direct")
+    np.testing.assert_array_equal(gw.CalcCorrelationDiagElements(lv, fr), v_pairs)
+    assert gw.point_eval_info()["compressed_calls"] == after["compressed_calls"]
+    monkeypatch.delenv("XTPB_SIGMA_POINTS")
+    # new energies invalidate the state
+    e2 = prob["energies"][sz.rpamin:sz.rpamax + 1].copy()
+    e2[sz.n_occ:] += 0.01
+    gw.setRPAInputEnergies(e2)
+    n0 = gw.point_eval_info()["compressed_calls"]
+    gw.CalcCorrelationDiagElements(lv, fr)
+    assert gw.point_eval_info()["compressed_calls"] == n0
+    # ... and so does a rotation of the tensor behind the GW object's back
+    gw.CalcCorrelationGrid(centers)
+    tc.MultiplyRightWithAuxMatrix(np.eye(sz.n_aux))
+    gw.CalcCorrelationDiagElements(lv, fr)
+    assert gw.point_eval_info()["compressed_calls"] == n0
+
+
+@pytest.mark.parametrize("solver", ["grid", "fixedpoint"])
+def test_g0w0_qp_energies_same_through_scan_state_and_pair_kernel(ctx, prob, solver, monkeypatch):
+    """G0W0 quasiparticle energies with the bisection rounds served three levels at a time from the grid scan's moments
+    (default) and one midpoint at a time by the pair kernel (XTPB_SIGMA_POINTS=direct): same roots."""
+    out = {}
+    for mode in ("scan", "direct"):
+        if mode == "direct":
+            monkeypatch.setenv("XTPB_SIGMA_POINTS", "direct")
+        gw, _, _, _ = _gw_pair(ctx, prob, qp_solver=solver)
+        gw.CalculateGWPerturbation()
+        out[mode] = (gw.getGWAResults(), gw.point_eval_info())
+    if solver == "grid":
+        assert out["scan"][1]["compressed_calls"] > 0
+    assert out["direct"][1]["compressed_calls"] == 0
+    np.testing.assert_allclose(out["scan"][0], out["direct"][0], rtol=0, atol=1e-8)
+
+
 def test_sigma_c_qp_grid_compressed_vs_direct_large(ctx, monkeypatch):
     """synth-500 shape (500 levels x 1500 aux functions, 100 QP levels, the default 1001-point grid): the compressed
     scan against the pole-by-pole kernel on every grid point, against a numpy pole sum over the device's own rotated

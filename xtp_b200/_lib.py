@@ -117,6 +117,7 @@ PROTOTYPES = {
     "xtpb_gw_plot_sigma": (C.c_int, [vp, idx, C.c_double, idx, iptr, dptr]),
     "xtpb_gw_sigma_c_offdiag": (C.c_int, [vp, dptr, dptr]),
     "xtpb_gw_grid_scan_info": (C.c_int, [vp, C.POINTER(C.c_int), iptr, dptr, dptr]),
+    "xtpb_gw_point_eval_info": (C.c_int, [vp, iptr, iptr]),
     "xtpb_ppm_grid_chunk": (C.c_int, []),
     "xtpb_ppm_grid_plan": (C.c_int, [idx, dptr, C.c_double, idx, C.c_double, C.c_double, idx, dptr, iptr,
                                      C.POINTER(C.c_int), iptr, C.POINTER(C.c_int)]),

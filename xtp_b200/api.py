@@ -100,7 +100,7 @@ class PinnedBuffer:
 
 PROFILE_TAGS = {"other": 0, "fill": 1, "rotate": 2, "epsilon": 3, "sigma_x": 4, "sigma_offdiag": 5, "bse_matmul": 6,
                 "davidson": 7, "dense_aux": 8, "sigma_ppm_grid": 9, "sigma_ppm_pairs": 10, "solver": 11,
-                "unpack": 12, "cda": 13, "exact": 14, "comm": 15}
+                "unpack": 12, "cda": 13, "exact": 14, "comm": 15, "sigma_ppm_points": 16}
 CONTRACTION_TAGS = ("other", "fill", "rotate", "epsilon", "sigma_x", "sigma_offdiag", "bse_matmul", "davidson",
                     "dense_aux", "cda", "exact")
 
@@ -436,6 +436,13 @@ class GW:
         check(_lib.lib().xtpb_gw_grid_scan_info(self._h, C.byref(comp), C.byref(nb), C.byref(direct), C.byref(equiv)))
         return {"compressed": bool(comp.value), "bins": nb.value, "direct_evaluations": direct.value,
                 "equivalent_evaluations": equiv.value}
+
+    def point_eval_info(self):
+        """Calls that evaluated single (level, frequency) Sigma_c values through the moments of the last compressed
+        grid scan / by streaming the slabs (xtpb_gw_point_eval_info)."""
+        comp, direct = idx(0), idx(0)
+        check(_lib.lib().xtpb_gw_point_eval_info(self._h, C.byref(comp), C.byref(direct)))
+        return {"compressed_calls": int(comp.value), "direct_calls": int(direct.value)}
 
     def PlotSigma(self, steps, spacing, states, filename=None):
         """GW::PlotSigma: (steps, 2*len(states)) table, columns (frequency, Sigma_c + e_KS + Sigma_x - Vxc) per state;

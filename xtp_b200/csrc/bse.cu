@@ -9,7 +9,9 @@
 //   Hqp X : two small products with the QP Hamiltonian blocks.
 // Two strategies (BseOperator): "factorised" applies the products above on every call and never holds H;
 // "dense" (XTPB_BSE_MODE=dense, or auto when it fits XTPB_BSE_DENSE_MAX_GB) builds the screened direct term + Hqp
-// once as a (vc)^2 matrix in HBM and streams it per call, the exchange term staying factorised.
+// once as a (vc)^2 matrix in HBM and streams it per call, the exchange term staying factorised.  On a single rank the
+// direct term is contracted for the occupied pairs v1 <= v2 only (Hd is symmetric under (v1,c1) <-> (v2,c2)) and
+// mirrored by a scatter kernel: v (v+1) c^2 N_aux flops instead of 2 v^2 c^2 N_aux.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -295,10 +297,47 @@ BseOperator::BseOperator(Context* c, TCMatrix* tc, long long homo, long long rpa
     // NOTE (multi-GPU): every flat() is a collective re-shard, so all ranks must ask for the SAME window; the
     // column range a rank owns is then a contiguous row range of the flat operand (first index = v2), which is why
     // the symmetric partners M[v2][P][v1] = M[v1][P][v2] and M[v2][P][c1] = M[c1][P][v2] are used below.
-    if (cd && ncols > 0) {
-      // Hd[(v1,c1),(v2,c2)] = sum_P Mcc[c2][P][c1] * (eps_inv_P Mvv[v2][P][v1])
+    // single rank: Hd is symmetric under (v1,c1) <-> (v2,c2), so only the pairs v1 <= v2 are contracted (half of the
+    // 2 (vc)^2 N_aux flops) into a scratch [(c2,c1)][pair] and scattered into H and its mirror image
+    // (XTPB_BSE_SYM=0: contract every (v1, v2)); with several ranks every rank owns a v2 range and contracts all v1
+    bool sym_done = false;
+    if (cd && ncols > 0 && world == 1 && vt > 1) {
+      const char* sym_env = getenv("XTPB_BSE_SYM");
+      const long long npairs = vt * (vt + 1) / 2;
+      size_t free_b = 0, total_b = 0;
+      long long budget = 1LL << 28;                                        // doubles (2 GiB) when the query fails
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)                // else half of what is free, <= 8 GiB
+        budget = std::min<long long>((long long)(free_b / 16), 1LL << 30);
       flat(Fa, ldA, c0, (int)ct, c0, (int)ct, false);                      // rows (i = c2, j = c1)
-      flat(Fb, ldB, v0, (int)vt, v0, (int)vt, true);                       // rows (i = v2, j = v1), all v2
+      flat(Fb, ldB, v0, (int)vt, v0, (int)vt, true);                       // rows (i = v2, j = v1)
+      long long tchunk = std::min<long long>(npairs, budget / (ct * ct));
+      if (tchunk < npairs) tchunk = tchunk / 128 * 128;                    // whole tile columns, 16-byte aligned chunks
+      if (!(sym_env && sym_env[0] == '0') && tchunk >= std::min<long long>(npairs, 128)) {
+        const long long ldT = round_up(npairs, 2);
+        DBuf Ftri((size_t)(ldT * naux_glob)), Tmp((size_t)(tchunk * ct * ct));
+        Ftri.zero(ctx->stream);
+        k_bse_pack_pairs(Ftri.p, ldT, Fb.p, ldB, (int)vt, (int)naux_glob, ctx->stream);
+        for (long long t0 = 0; t0 < npairs; t0 += tchunk) {
+          const long long tc_ = std::min(tchunk, npairs - t0);
+          GemmParams g{};
+          g.A = GemmOperand{Fa.p, 1, ldA, 0, 0};
+          g.B = GemmOperand{Ftri.p + t0, 1, ldT, 0, 0};
+          g.C = Tmp.p; g.c_sm = 1; g.c_sn = ct * ct;
+          g.M = (int)(ct * ct); g.N = (int)tc_; g.K = (int)naux_glob; g.n_outer = 1; g.n_batch = 1;
+          g.alpha = -(double)cd; g.beta = 0.0;
+          contract(g, ctx->ws, ctx->stream);
+          k_bse_scatter_pairs(H.p, h_ld, (int)ct, Tmp.p, t0, tc_, ctx->stream);
+        }
+        ctx->sync();
+        sym_done = true;
+        Fa.release();
+        Fb.release();
+      }
+    }
+    if (cd && ncols > 0 && !sym_done) {
+      // Hd[(v1,c1),(v2,c2)] = sum_P Mcc[c2][P][c1] * (eps_inv_P Mvv[v2][P][v1])
+      if (!Fa.p) flat(Fa, ldA, c0, (int)ct, c0, (int)ct, false);           // rows (i = c2, j = c1)
+      if (!Fb.p) flat(Fb, ldB, v0, (int)vt, v0, (int)vt, true);            // rows (i = v2, j = v1), all v2
       GemmParams g{};
       g.A = GemmOperand{Fa.p, 1, ldA, 0, 0};
       g.B = GemmOperand{Fb.p + v2lo * vt, 1, ldB, 0, 0};                   // this rank's v2 range

@@ -133,6 +133,7 @@ int xtpb_tc_set_raw_dev(xtpb_tc* tc, const double* M_dev) {
   XTPB_REQUIRE(M_dev != nullptr, "null pointer");
   t.pending = false;
   t.eps0.valid = false;
+  ++t.generation;
   XTPB_CUDA(cudaMemcpy2DAsync(t.M.p, t.ldn * 8, M_dev, t.ntotal * 8, t.ntotal * 8, t.mtotal * t.naux,
                               cudaMemcpyDeviceToDevice, t.ctx->stream));
   t.ctx->sync();
@@ -331,6 +332,13 @@ int xtpb_gw_grid_scan_info(xtpb_gw* gw, int* compressed, xtpb_index* n_bins, dou
   if (n_bins) *n_bins = gw->impl.grid_bins;
   if (direct_evaluations) *direct_evaluations = gw->impl.grid_direct_evals;
   if (equivalent_evaluations) *equivalent_evaluations = gw->impl.grid_equiv_evals;
+  XTPB_API_END
+}
+int xtpb_gw_point_eval_info(xtpb_gw* gw, xtpb_index* compressed_calls, xtpb_index* direct_calls) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(gw, "null pointer");
+  if (compressed_calls) *compressed_calls = gw->impl.points_compressed_calls;
+  if (direct_calls) *direct_calls = gw->impl.points_direct_calls;
   XTPB_API_END
 }
 int xtpb_ppm_grid_chunk(void) { return kPpmGridChunk; }

@@ -33,7 +33,8 @@ extern std::atomic<long long> g_tma_launch_count;   // of which contraction laun
 enum ProfTag {
   PROF_OTHER = 0, PROF_FILL = 1, PROF_ROTATE = 2, PROF_EPSILON = 3, PROF_SIGMA_X = 4, PROF_SIGMA_OFFDIAG = 5,
   PROF_BSE_MATMUL = 6, PROF_DAVIDSON = 7, PROF_DENSE_AUX = 8, PROF_SIGMA_GRID = 9, PROF_SIGMA_PAIRS = 10,
-  PROF_SOLVER = 11, PROF_UNPACK = 12, PROF_CDA = 13, PROF_EXACT = 14, PROF_COMM = 15, PROF_NTAGS = 16
+  PROF_SOLVER = 11, PROF_UNPACK = 12, PROF_CDA = 13, PROF_EXACT = 14, PROF_COMM = 15,
+  PROF_SIGMA_POINTS = 16, PROF_NTAGS = 17
 };
 void prof_enable(bool on);
 void prof_reset();

@@ -42,6 +42,7 @@ GW::GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host
 }
 
 void GW::set_rpa_energies(const double* e) {
+  scan.valid = false;
   rpa_energies.assign(e, e + rpatotal);
   ctx->h2d(energies_dev.p, rpa_energies.data(), (size_t)rpatotal);
   e_loc = tc->local_energies(energies_dev.p, energies_loc_dev);
@@ -68,6 +69,7 @@ void GW::exchange(double* out_host) {
 
 // PPM::PPM_construct_parameters (ppm.cc) followed by the aux rotation of Sigma_PPM::PrepareScreening.
 void GW::prepare_ppm() {
+  scan.valid = false;
   ProfScope prof(PROF_DENSE_AUX);
   const long long na = tc->naux;
   DBuf eps((size_t)(2 * na * na)), T1((size_t)(na * na)), lam((size_t)na);
@@ -160,6 +162,8 @@ void GW::sigma_c_diag_elements(long long n, const long long* levels, const doubl
       XTPB_REQUIRE(levels[i] >= 0 && levels[i] < qptotal, "gw level out of range");
       slabs[i] = (int)(q0 + levels[i]);
     }
+    if (!derivs && points_compressed(n, levels, freqs, 0.0, 1, values)) return;
+    ++points_direct_calls;
     DBuf buf((size_t)(3 * n + (n + 1) / 2 + 1 + sigma_ppm_pair_partial_doubles((int)n)));
     double* om = buf.p;
     double* val = om + n;
@@ -227,35 +231,77 @@ bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing,
     for (int ch = 0; ch < plan.n_chunks; ++ch) {
       const double wa = grid_start[l] + spacing * double((long long)ch * kPpmGridChunk);
       const double wb = grid_start[l] + spacing * double((long long)(ch + 1) * kPpmGridChunk - 1);
-      auto is_far = [&](int b) {
-        const double c = 0.5 * (plan.edges[b] + plan.edges[b + 1]), h = 0.5 * (plan.edges[b + 1] - plan.edges[b]);
-        const double dist = std::max(std::max(wa - c, c - wb), 0.0);
-        return dist >= 3.0 * h && dist >= h + W;
-      };
-      int lo = 0, hi = plan.nb - 1;
-      while (lo <= hi && is_far(lo)) ++lo;
-      while (hi >= lo && is_far(hi)) --hi;
-      // INNER bins: every pole of the bin is inside the damping window of EVERY target of the chunk
-      // (wb - W < z < wa + W with a safety margin), where the damped kernel sin^2(2 pi x)/x is an entire function of the
-      // pole position: the bin's poles are replaced by kCmpOrder equivalent poles at its Chebyshev nodes (weights from
-      // the moments; kernels.cu: ppm_equivalent_poles_kernel).  Contiguous by geometry; none: i_lo = hi + 1, i_hi = hi.
-      const double margin = 1e-6;
-      int ilo = hi + 1, ihi = hi;
-      for (int b = lo; b <= hi; ++b) {
-        const bool inner = plan.edges[b] >= wb - W + margin && plan.edges[b + 1] <= wa + W - margin;
-        if (inner) {
-          if (ilo > ihi) ilo = b;
-          ihi = b;
-        } else if (ilo <= ihi) {
-          break;
-        }
-      }
-      const size_t at = (size_t)(4 * (l * plan.n_chunks + ch));
-      plan.near[at] = lo;          // lo > hi: every bin is far
-      plan.near[at + 1] = hi;
-      plan.near[at + 2] = ilo;
-      plan.near[at + 3] = ihi;
+      ppm_grid_near(plan.edges.data(), plan.nb, wa, wb, &plan.near[(size_t)(4 * (l * plan.n_chunks + ch))]);
     }
+  return true;
+}
+
+void ppm_grid_near(const double* edges, int nb, double wa, double wb, int* out) {
+  const double W = kPpmDampingWindow;
+  if (wb < wa) std::swap(wa, wb);
+  auto is_far = [&](int b) {
+    const double c = 0.5 * (edges[b] + edges[b + 1]), h = 0.5 * (edges[b + 1] - edges[b]);
+    const double dist = std::max(std::max(wa - c, c - wb), 0.0);
+    return dist >= 3.0 * h && dist >= h + W;
+  };
+  int lo = 0, hi = nb - 1;
+  while (lo <= hi && is_far(lo)) ++lo;
+  while (hi >= lo && is_far(hi)) --hi;
+  // INNER bins: every pole of the bin is inside the damping window of EVERY target of the chunk
+  // (wb - W < z < wa + W with a safety margin), where the damped kernel sin^2(2 pi x)/x is an entire function of the
+  // pole position: the bin's poles are replaced by kCmpOrder equivalent poles at its Chebyshev nodes (weights from
+  // the moments; kernels.cu: ppm_equivalent_poles_kernel).  Contiguous by geometry; none: i_lo = hi + 1, i_hi = hi.
+  const double margin = 1e-6;
+  int ilo = hi + 1, ihi = hi;
+  for (int b = lo; b <= hi; ++b) {
+    const bool inner = edges[b] >= wb - W + margin && edges[b + 1] <= wa + W - margin;
+    if (inner) {
+      if (ilo > ihi) ilo = b;
+      ihi = b;
+    } else if (ilo <= ihi) {
+      break;
+    }
+  }
+  out[0] = lo;          // lo > hi: every bin is far
+  out[1] = hi;
+  out[2] = ilo;
+  out[3] = ihi;
+}
+
+// values[i*n_omega + j] = Sigma_c(levels[i], om0[i] + j*domega) through the state the last compressed grid scan left
+// behind: far bins by their moments, inner bins by their equivalent poles, the rest of the near poles one by one --
+// the slabs are not streamed again (the pair kernel reads 8 ntotal N_aux bytes per point).  False: no usable state
+// (no compressed scan yet, the tensor / energies / PPM parameters changed since, a target outside the binned range is
+// fine -- the outermost bins are open-ended -- but more than kPpmGridChunk targets per row are not supported).
+bool GW::points_compressed(long long n, const long long* levels, const double* om0, double domega, int n_omega,
+                           double* values) {
+  const char* env = std::getenv("XTPB_SIGMA_POINTS");        // read per call: tests toggle it
+  const bool off = env && std::strcmp(env, "direct") == 0;
+  if (off || !scan.valid || scan.generation != tc->generation || scan.n_levels != (int)qptotal) return false;
+  if (n <= 0 || n_omega < 1 || n_omega > kPpmGridChunk || n > (1LL << 24)) return false;
+  std::vector<int> slabs((size_t)n), rows((size_t)n), near((size_t)(4 * n));
+  for (long long i = 0; i < n; ++i) {
+    slabs[i] = (int)(q0 + levels[i]);
+    rows[i] = (int)levels[i];
+    ppm_grid_near(scan.edges.data(), scan.nb, om0[i], om0[i] + domega * double(n_omega - 1), &near[(size_t)(4 * i)]);
+  }
+  DBuf buf((size_t)(n * n_omega + n + n + 2));
+  double* val = buf.p;
+  double* om = val + n * n_omega;
+  int* sl = reinterpret_cast<int*>(om + n);
+  int* rw = sl + n + (n & 1);
+  ctx->h2d(om, om0, (size_t)n);
+  XTPB_CUDA(cudaMemcpyAsync(sl, slabs.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  XTPB_CUDA(cudaMemcpyAsync(rw, rows.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  // work = pole evaluations of the equivalent direct sums, as for the grid scan
+  const int slot = prof_begin(PROF_SIGMA_POINTS, (double)tc->ntotal * (double)tc->naux * (double)n_omega * (double)n,
+                              ctx->stream);
+  k_ppm_scan_evaluate(tc->M.p, tc->ldn, tc->slab, (int)tc->naux, e_loc, ppm_freq_dev.p, ppm_fac_dev.p, sl, rw, om,
+                      domega, n_omega, (int)n, near.data(), 1, scan, val, nullptr, ctx->stream);
+  prof_end(slot, ctx->stream);
+  ctx->allreduce_sum(val, (size_t)(n * n_omega));
+  ctx->d2h(values, val, (size_t)(n * n_omega));
+  ++points_compressed_calls;
   return true;
 }
 
@@ -302,21 +348,35 @@ void GW::grid_scan(const std::vector<double>& f0, std::vector<double>& values) {
     }
     grid_compressed = compressed ? 1 : 0;
     grid_bins = compressed ? plan.nb : 0;
+    scan.valid = false;
     grid_equiv_evals = double(tc->ntotal) * double(tc->naux) * double(steps) * double(qptotal);
     grid_direct_evals = grid_equiv_evals;
     if (compressed)
       k_sigma_ppm_grid_compressed(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ_loc, e_loc,
                                   ppm_freq_dev.p, ppm_fac_dev.p, sl, om, opt.qp_grid_spacing, (int)steps, (int)qptotal,
                                   plan.edges.data(), plan.nb, plan.near.data(), plan.n_chunks, val, &grid_direct_evals,
-                                  ctx->stream);
+                                  scan, ctx->stream);
     else
       k_sigma_ppm_grid(tc->M.p, tc->ldn, tc->slab, (int)tc->ntotal, (int)tc->naux, (int)n_occ_loc, e_loc,
                        ppm_freq_dev.p, ppm_fac_dev.p, sl, om, opt.qp_grid_spacing, (int)steps, (int)qptotal, val,
                        ctx->stream);
     ctx->allreduce_sum(val, (size_t)(qptotal * steps));
     ctx->d2h(values.data(), val, (size_t)(qptotal * steps));
+    // the moments of every QP level stay valid until the tensor, the energies or the PPM parameters change; the
+    // decision to keep them must be the same on every rank (the point evaluations end in a collective)
+    double keep = (compressed && scan.valid) ? 1.0 : 0.0;
+    if (ctx->world > 1) {
+      DBuf flag(1);
+      ctx->h2d(flag.p, &keep, 1);
+      ctx->allreduce_sum(flag.p, 1);
+      ctx->d2h(&keep, flag.p, 1);
+      keep = keep > ctx->world - 0.5 ? 1.0 : 0.0;
+    }
+    scan.valid = keep > 0.5;
+    scan.generation = tc->generation;
     return;
   }
+  scan.valid = false;
   std::vector<long long> lv((size_t)(qptotal * steps));
   std::vector<double> fr((size_t)(qptotal * steps));
   for (long long l = 0; l < qptotal; ++l)
@@ -383,7 +443,10 @@ std::vector<double> GW::solve_qp(const std::vector<double>& frequencies) {
         tprev = tv;
       }
     }
-    // GW::SolveQP_Bisection, all brackets advanced together
+    // GW::SolveQP_Bisection, all brackets advanced together.  While the state of the compressed grid scan is usable,
+    // three bisection levels are taken per round: the seven interior points lo + w j/8 of every bracket are evaluated
+    // in one launch (a chunk of the compressed scan) and the three halvings are replayed on the host with exactly the
+    // decisions of the one-midpoint-at-a-time loop (which remains the fallback).
     while (true) {
       std::vector<long long> lv;
       std::vector<double> fr;
@@ -401,6 +464,47 @@ std::vector<double> GW::solve_qp(const std::vector<double>& frequencies) {
         who.push_back(b);
       }
       if (who.empty()) break;
+      // multi-level round: needs one common bracket width (true by construction: every bracket starts one grid
+      // spacing wide and is halved once per round) -- checked, not assumed
+      bool multi = opt.sigma_integration == XTPB_SIGMA_PPM && scan.valid;
+      const double w = br[who[0]].hi - br[who[0]].lo;
+      for (size_t i = 0; i < who.size() && multi; ++i)
+        if (std::fabs((br[who[i]].hi - br[who[i]].lo) - w) > 1e-9 * std::fabs(w)) multi = false;
+      if (multi) {
+        const int np = 7;
+        const double dw = w / 8.0;
+        std::vector<double> first(who.size()), val7(who.size() * np);
+        for (size_t i = 0; i < who.size(); ++i) first[i] = br[who[i]].lo + dw;
+        if (points_compressed((long long)who.size(), lv.data(), first.data(), dw, np, val7.data())) {
+          for (size_t i = 0; i < who.size(); ++i) {
+            Bracket& B = br[who[i]];
+            int a = 0, e = 8;                      // the bracket in units of dw, relative to first[i] - dw
+            for (int level = 0; level < 3 && !B.done; ++level) {
+              if (level > 0 && std::fabs(B.hi - B.lo) < opt.g_sc_limit) {
+                B.root = 0.5 * (B.lo + B.hi);
+                B.done = true;
+                break;
+              }
+              const int mid = (a + e) / 2;
+              const double cmid = first[i] + dw * double(mid - 1);
+              const double yc = val7[i * np + (size_t)(mid - 1)] + intercept[B.level] - cmid;
+              if (std::fabs(yc) < opt.g_sc_limit) {
+                B.root = cmid;
+                B.done = true;
+              } else if (yc * B.flo > 0) {
+                B.lo = cmid;
+                B.flo = yc;
+                a = mid;
+              } else {
+                B.hi = cmid;
+                B.fhi = yc;
+                e = mid;
+              }
+            }
+          }
+          continue;
+        }
+      }
       std::vector<double> val(who.size());
       sigma_c_diag_elements((long long)who.size(), lv.data(), fr.data(), val.data(), nullptr);
       for (size_t i = 0; i < who.size(); ++i) {
@@ -500,6 +604,7 @@ void GW::calculate_gw_perturbation() {
     if (i_gw % opt.reset_3c == 0 && i_gw != 0) {
       XTPB_CUDA(cudaMemcpyAsync(tc->M.p, backup.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       tc->eps0.valid = false;
+      ++tc->generation;
     }
     if (!(screening_done && i_gw == 0)) prepare_screening();
     if (evgw && opt.gw_mixing_order > 0) mixing.update_input(freqs);

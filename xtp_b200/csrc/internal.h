@@ -119,12 +119,29 @@ void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal
                       const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
                       const double* omega0, double domega, int n_omega, int n_levels, double* values, cudaStream_t s);
 // compressed grid scan (kernels.cu (1b)): far bins of the pole axis through Chebyshev moments, near bins pole by pole;
-// edges_host: nb+1 bin edges, near_host: [level][chunk][4] inclusive near-bin and inner-bin ranges (ppm_grid_plan)
+// edges_host: nb+1 bin edges, near_host: [level][chunk][4] inclusive near-bin and inner-bin ranges (ppm_grid_plan).
+// The target-independent part (bin table, moments, equivalent poles) is kept in a PpmScanState so that further points
+// of the same levels (bisection rounds, final Sigma_c) are evaluated without streaming the slabs again.
+struct PpmScanState {
+  bool valid = false;
+  unsigned long long generation = 0;   // TCMatrix::generation the moments were built from
+  int nb = 0, n_levels = 0;
+  std::vector<double> edges;           // host copy of the bin edges (nb + 1)
+  DBuf edges_dev, table, mom, eq;
+};
+void k_ppm_scan_prepare(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                        const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
+                        int n_levels, const double* edges_host, int nb, PpmScanState& st, cudaStream_t s);
+void k_ppm_scan_evaluate(const double* M, long long ldn, long long slab, int naux, const double* energies,
+                         const double* ppm_freq, const double* ppm_fac, const int* level_slab, const int* level_mom,
+                         const double* omega0, double domega, int n_omega, int n_items, const int* near_host,
+                         int n_chunks, const PpmScanState& st, double* values, double* direct_evaluations,
+                         cudaStream_t s);
 void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                                  const double* energies, const double* ppm_freq, const double* ppm_fac,
                                  const int* level_slab, const double* omega0, double domega, int n_omega, int n_levels,
                                  const double* edges_host, int nb, const int* near_host, int n_chunks, double* values,
-                                 double* direct_evaluations, cudaStream_t s);
+                                 double* direct_evaluations, PpmScanState& st, cudaStream_t s);
 // host plan of the compressed scan: bins of the pole axis and, per level and chunk of 32 grid points, the bins that
 // are too close for the series.  grid_start[level] = first grid frequency; [zmin, zmax] = range of the live poles.
 // Returns false when the scan should use the direct kernel (no poles, too many bins).
@@ -138,6 +155,8 @@ constexpr double kPpmGridBinWidth = 0.125;   // width of the core bins of the po
 constexpr int kPpmGridChunk = 8;             // grid points per warp of the compressed scan (see kernels.cu (1b))
 bool ppm_grid_plan(const double* grid_start, long long n_levels, double spacing, long long steps, double zmin,
                    double zmax, PpmGridPlan& plan);
+// near / inner bin ranges (out[0..3], as in PpmGridPlan::near) of the targets [wa, wb] for the bins `edges` (nb + 1)
+void ppm_grid_near(const double* edges, int nb, double wa, double wb, int* out);
 void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                        const double* energies, const double* ppm_freq, const double* ppm_fac, const int* pair_slab,
                        const double* pair_omega, int n_pairs, double* values, double* derivs, double* partial,
@@ -164,6 +183,10 @@ void k_unit_vectors(double* V, long long ld, long long n, const long long* idx, 
 // dense BSE Hamiltonian: H[(v1,c1),(v2l,c2)] += cqp (Hqp[vt+c1,vt+c2] d(v1,v2) - Hqp[v1,v2] d(c1,c2)) for the local columns
 void k_bse_add_hqp(double* H, long long ld, int vt, int ct, int v2lo, int ns, const double* hqp, long long hs,
                    double cqp, cudaStream_t s);
+// dense BSE direct term over the occupied pairs v1 <= v2 only (t = v2(v2+1)/2 + v1): packed pair columns of the flat
+// operand [P][v2][v1], and the scatter of the contracted pair blocks T[(c1,c2)][t] into H and its mirror image
+void k_bse_pack_pairs(double* Ftri, long long ldt, const double* F, long long ldf, int vt, int naux, cudaStream_t s);
+void k_bse_scatter_pairs(double* H, long long ld, int ct, const double* T, long long t0, long long tcnt, cudaStream_t s);
 // full[b](mu,nu) = full[b](nu,mu) = packed[b][mu(mu+1)/2 + nu] (nu <= mu), b < count
 void k_unpack_symmetric(double* full, long long ld, long long full_slice, const double* packed, long long pk_slice,
                         int n, int count, cudaStream_t s);
@@ -187,6 +210,7 @@ struct TCMatrix {
   Context* ctx;
   long long naux, mmin, mmax, nmin, nmax, mtotal, ntotal;
   long long ldn, slab;          // device layout [m][P][ldn], ldn = ntotal rounded up to even
+  unsigned long long generation = 0;   // bumped by everything that writes the tensor (caches keyed on its contents)
   // Multi-GPU: the second index is distributed cyclically, rank r holds the columns n = r, r + world, ... of
   // nmin..nmax.  `ntotal` is the LOCAL column count (== ntotal_glob when world == 1); every stage that sums over
   // the second index produces a partial result that is all-reduced.
@@ -284,6 +308,13 @@ struct GW {
   long long grid_bins = 0;
   double grid_direct_evals = 0.0, grid_equiv_evals = 0.0;
   DBuf ppm_freq_dev, ppm_fac_dev;
+  // target-independent state of the last compressed grid scan (bin table, moments, equivalent poles of every QP
+  // level): single (level, frequency) evaluations without derivatives go through it while it matches the tensor,
+  // the energies and the PPM parameters (XTPB_SIGMA_POINTS=direct forces the slab-streaming pair kernel)
+  PpmScanState scan;
+  bool points_compressed(long long n, const long long* levels, const double* om0, double domega, int n_omega,
+                         double* values);
+  long long points_compressed_calls = 0, points_direct_calls = 0;
   // exact
   std::vector<double> rpa_omegas;
   DBuf residues;                // [level][s][m]  (m fastest, ld = tc->ldn)

@@ -499,7 +499,8 @@ template <int MINB>
 __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compressed_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int naux, const double* __restrict__ energies,
     const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac, const int* __restrict__ level_slab,
-    const double* __restrict__ omega0, double domega, int n_omega, const int* __restrict__ binstart,
+    const int* __restrict__ level_mom, const double* __restrict__ omega0, double domega, int n_omega,
+    const int* __restrict__ binstart,
     const double* __restrict__ edges, int nb, const int* __restrict__ near_range, int n_chunks,
     const double* __restrict__ moments, const double2* __restrict__ eq_poles, double* __restrict__ out,
     long long out_split_stride, unsigned long long* __restrict__ near_poles) {
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
   const int chunk = blockIdx.x * kCmpWarps + warp, level = blockIdx.y;
   if (chunk >= n_chunks) return;              // warps are independent: no block-wide barrier below
   const double* S = M + (long long)level_slab[level] * slab;
+  const int mrow = level_mom ? level_mom[level] : level;      // row of the moment / equivalent-pole tables
   const int point = lane & (kCmpChunk - 1), slot = lane / kCmpChunk;
   const int j = chunk * kCmpChunk + point;
   const double om = omega0[level] + domega * (double)j;
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
   }
   // ---- inner bins: their equivalent poles (all of them inside every grid point's damping window), split 0 only
   if (blockIdx.z == 0 && i_lo <= i_hi) {
-    const double2* eq = eq_poles + ((long long)level * nb + i_lo) * kCmpOrder;
+    const double2* eq = eq_poles + ((long long)mrow * nb + i_lo) * kCmpOrder;
     const int total = (i_hi - i_lo + 1) * kCmpOrder;
     for (int m0 = 0; m0 < total; m0 += 32) {
       const int m = m0 + lane;
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
   for (int g = 0; g < kCmpG; g += 2) acc += acc4[g] + acc4[g + 1];
   // ---- far field: Chebyshev series of the Cauchy kernel over the condensed bins, the bins dealt out to the slots
   if (blockIdx.z == 0) {
-    const double* mom = moments + ((long long)level * nb) * kCmpOrder;
+    const double* mom = moments + ((long long)mrow * nb) * kCmpOrder;
     for (int b = slot; b < nb; b += kCmpSlots) {
       if (b >= b_lo && b <= b_hi) continue;
       const double e0 = edges[b], e1 = edges[b + 1];
@@ -925,6 +927,60 @@ __global__ void bse_add_hqp_kernel(double* __restrict__ H, long long ld, int vt,
     else H[(long long)t * ct + c2 + col * ld] -= cqp * hqp[t + (long long)v2 * hs];
   }
 }
+
+// ------------------------------------------------------------------ dense BSE Hamiltonian: (v1,c1) <-> (v2,c2) symmetry
+// The screened direct term Hd[(v1,c1),(v2,c2)] = sum_P Mcc[c2][P][c1] w_P Mvv[v2][P][v1] is symmetric under the
+// simultaneous swap v1 <-> v2, c1 <-> c2, so only the occupied pairs v1 <= v2 are contracted (half the flops).
+// t = v2 (v2 + 1) / 2 + v1 enumerates them.
+__device__ __forceinline__ void pair_of_index(long long t, int& v2, int& v1) {
+  int a = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long long)(a + 1) * (a + 2) / 2 <= t) ++a;
+  while ((long long)a * (a + 1) / 2 > t) --a;
+  v2 = a;
+  v1 = (int)(t - (long long)a * (a + 1) / 2);
+}
+// Ftri[P*ldt + t] = F[P*ldf + v2*vt + v1]: the pair columns of the flat operand [P][v2][v1], packed
+__global__ void bse_pack_pairs_kernel(double* __restrict__ Ftri, long long ldt, const double* __restrict__ F,
+                                      long long ldf, int vt, long long npairs, int naux) {
+  const long long total = npairs * naux;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx % npairs;
+    const int P = (int)(idx / npairs);
+    int v2, v1;
+    pair_of_index(t, v2, v1);
+    Ftri[(long long)P * ldt + t] = F[(long long)P * ldf + (long long)v2 * vt + v1];
+  }
+}
+// T[(c1 + c2*ct) + tl*ct*ct], tl < tcnt (pairs t0 + tl), holds alpha * Hd for the pair's ct x ct block:
+//   H[(v1*ct + c1) + (v2*ct + c2)*ld] += T   and, for v1 != v2, the mirrored H[(v2*ct + c2) + (v1*ct + c1)*ld] += T
+// (a 32 x 32 tile per block; the mirror goes through a shared-memory transpose so that both writes are coalesced).
+__global__ void __launch_bounds__(256) bse_scatter_pairs_kernel(double* __restrict__ H, long long ld, int ct,
+                                                                const double* __restrict__ T, long long t0) {
+  __shared__ double tile[32][33];
+  const int tiles = (ct + 31) / 32;
+  const int tc1 = blockIdx.x % tiles, tc2 = blockIdx.x / tiles;
+  const long long tl = blockIdx.y;
+  int v2, v1;
+  pair_of_index(t0 + tl, v2, v1);
+  const double* src = T + tl * (long long)ct * ct;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c1 = tc1 * 32 + tx, c2 = tc2 * 32 + r;
+    double v = 0.0;
+    if (c1 < ct && c2 < ct) {
+      v = src[c1 + (long long)c2 * ct];
+      H[((long long)v1 * ct + c1) + ((long long)v2 * ct + c2) * ld] += v;
+    }
+    tile[r][tx] = v;
+  }
+  if (v1 == v2) return;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c2 = tc2 * 32 + tx, c1 = tc1 * 32 + r;
+    if (c1 < ct && c2 < ct) H[((long long)v2 * ct + c2) + ((long long)v1 * ct + c1) * ld] += tile[tx][r];
+  }
+}
 }  // namespace
 
 // ------------------------------------------------------------------ host wrappers
@@ -1007,69 +1063,109 @@ void k_sigma_ppm_grid(const double* M, long long ldn, long long slab, int ntotal
   prof_end(slot, s);
   if (splits > 1) XTPB_CUDA(cudaStreamSynchronize(s));   // partial is freed on return
 }
-void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
-                                 const double* energies, const double* ppm_freq, const double* ppm_fac,
-                                 const int* level_slab, const double* omega0, double domega, int n_omega, int n_levels,
-                                 const double* edges_host, int nb, const int* near_host, int n_chunks, double* values,
-                                 double* direct_evaluations, cudaStream_t s) {
+// Compressed scan, part 1: everything that depends on the tensor, the energies and the plasmon-pole parameters but not
+// on the target frequencies -- the bin table, the Chebyshev moments per (level, bin) (one stream over the slabs) and
+// the equivalent poles.  The state outlives the call: GW::grid_scan builds it, the bisection rounds and the final
+// Sigma_c of GW::SolveQP evaluate further points through it (k_ppm_scan_evaluate) without touching the slabs again.
+void k_ppm_scan_prepare(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                        const double* energies, const double* ppm_freq, const double* ppm_fac, const int* level_slab,
+                        int n_levels, const double* edges_host, int nb, PpmScanState& st, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int slices = (4 * sms + n_levels - 1) / n_levels;
+  slices = std::max(1, std::min(slices, std::min(16, std::max(1, naux / 64))));
+  const long long n_mom = (long long)n_levels * nb * kCmpOrder;
+  const long long n_table = 2LL * naux * (nb + 1);
+  st.valid = false;
+  st.nb = nb;
+  st.n_levels = n_levels;
+  st.edges.assign(edges_host, edges_host + nb + 1);
+  st.edges_dev.ensure((size_t)(nb + 1));
+  st.table.ensure((size_t)((n_table + 1) / 2));
+  st.eq.ensure((size_t)(2 * n_mom));            // equivalent poles: (weight, position) per (level, bin, node)
+  st.mom.ensure((size_t)n_mom);
+  DBuf mom_part;
+  if (slices > 1) mom_part.alloc((size_t)(n_mom * slices));
+  int* table_i = reinterpret_cast<int*>(st.table.p);
+  XTPB_CUDA(cudaMemcpyAsync(st.edges_dev.p, st.edges.data(), (size_t)(nb + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+  ppm_bin_table_kernel<<<blocks_for(n_table, 256, 4096), 256, 0, s>>>(table_i, st.edges_dev.p, nb, energies, ntotal,
+                                                                     n_occ, ppm_freq, naux);
+  LAUNCH_CHECK();
+  ppm_moments_kernel<<<dim3(slices, n_levels), kCmpMomentWarps * 32, 0, s>>>(
+      M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab, table_i, st.edges_dev.p, nb,
+      slices > 1 ? mom_part.p : st.mom.p);
+  LAUNCH_CHECK();
+  if (slices > 1) {
+    sigma_ppm_grid_reduce<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(st.mom.p, mom_part.p, n_mom, slices);
+    LAUNCH_CHECK();
+  }
+  ppm_equivalent_poles_kernel<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(
+      reinterpret_cast<double2*>(st.eq.p), st.mom.p, st.edges_dev.p, nb, (long long)n_levels * nb);
+  LAUNCH_CHECK();
+  if (slices > 1) XTPB_CUDA(cudaStreamSynchronize(s));   // mom_part is freed on return
+  st.valid = true;
+}
+
+// Compressed scan, part 2: n_items rows of n_omega uniformly spaced targets each (row i: slab level_slab[i], moment
+// row level_mom[i] (nullptr: i), first target omega0[i]); near_host: [item][chunk][4] near / inner bin ranges.
+void k_ppm_scan_evaluate(const double* M, long long ldn, long long slab, int naux, const double* energies,
+                         const double* ppm_freq, const double* ppm_fac, const int* level_slab, const int* level_mom,
+                         const double* omega0, double domega, int n_omega, int n_items, const int* near_host,
+                         int n_chunks, const PpmScanState& st, double* values, double* direct_evaluations,
+                         cudaStream_t s) {
+  XTPB_REQUIRE(st.valid, "compressed scan evaluated without its prepared state");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int bx = (n_chunks + kCmpWarps - 1) / kCmpWarps;
-  int splits = (8 * sms + bx * n_levels - 1) / (bx * n_levels);
+  int splits = (int)((8LL * sms + (long long)bx * n_items - 1) / ((long long)bx * n_items));
   splits = std::max(1, std::min(splits, std::min(16, std::max(1, naux / 64))));
-  int slices = (4 * sms + n_levels - 1) / n_levels;
-  slices = std::max(1, std::min(slices, std::min(16, std::max(1, naux / 64))));
-  const long long n = (long long)n_levels * n_omega;
-  const long long n_mom = (long long)n_levels * nb * kCmpOrder;
-  const long long n_table = 2LL * naux * (nb + 1), n_near = 4LL * n_levels * n_chunks;
-  DBuf edges((size_t)(nb + 1)), table((size_t)((n_table + 1) / 2)), near_buf((size_t)((n_near + 1) / 2));
-  DBuf eq_buf((size_t)(2 * n_mom));           // equivalent poles: (weight, position) per (level, bin, node)
-  DBuf mom_part((size_t)(n_mom * slices)), mom_sum, partial, counter(1);
+  const long long n = (long long)n_items * n_omega;
+  const long long n_near = 4LL * n_items * n_chunks;
+  DBuf near_buf((size_t)((n_near + 1) / 2)), partial, counter(1);
   counter.zero(s);
-  if (slices > 1) mom_sum.alloc((size_t)n_mom);
   if (splits > 1) partial.alloc((size_t)(n * splits));
-  int* table_i = reinterpret_cast<int*>(table.p);
   int* near_i = reinterpret_cast<int*>(near_buf.p);
-  XTPB_CUDA(cudaMemcpyAsync(edges.p, edges_host, (size_t)(nb + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
   XTPB_CUDA(cudaMemcpyAsync(near_i, near_host, (size_t)n_near * sizeof(int), cudaMemcpyHostToDevice, s));
-  // work = pole evaluations of the equivalent direct sum (what (1) would do), so that rates stay comparable
-  const int slot = prof_begin(PROF_SIGMA_GRID, (double)ntotal * naux * (double)n_omega * n_levels, s);
-  ppm_bin_table_kernel<<<blocks_for(n_table, 256, 4096), 256, 0, s>>>(table_i, edges.p, nb, energies, ntotal, n_occ,
-                                                                     ppm_freq, naux);
-  LAUNCH_CHECK();
-  ppm_moments_kernel<<<dim3(slices, n_levels), kCmpMomentWarps * 32, 0, s>>>(M, ldn, slab, naux, energies, ppm_freq,
-                                                                            ppm_fac, level_slab, table_i, edges.p, nb,
-                                                                            mom_part.p);
-  LAUNCH_CHECK();
-  if (slices > 1) {
-    sigma_ppm_grid_reduce<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(mom_sum.p, mom_part.p, n_mom, slices);
-    LAUNCH_CHECK();
-  }
-  ppm_equivalent_poles_kernel<<<blocks_for(n_mom, 256, 2048), 256, 0, s>>>(
-      reinterpret_cast<double2*>(eq_buf.p), slices > 1 ? mom_sum.p : mom_part.p, edges.p, nb, (long long)n_levels * nb);
-  LAUNCH_CHECK();
   const char* occ_env = std::getenv("XTPB_GRID_OCC");
   const int occ = occ_env ? std::atoi(occ_env) : kCmpMinBlocks;
   auto kernel = occ <= 3 ? sigma_ppm_grid_compressed_kernel<3>
               : occ == 4 ? sigma_ppm_grid_compressed_kernel<4>
               : occ == 5 ? sigma_ppm_grid_compressed_kernel<5>
                          : sigma_ppm_grid_compressed_kernel<6>;
-  kernel<<<dim3(bx, n_levels, splits), kCmpWarps * 32, 0, s>>>(
-      M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab, omega0, domega, n_omega, table_i, edges.p, nb,
-      near_i, n_chunks, slices > 1 ? mom_sum.p : mom_part.p, reinterpret_cast<const double2*>(eq_buf.p),
-      splits > 1 ? partial.p : values, n,
-      reinterpret_cast<unsigned long long*>(counter.p));
-  LAUNCH_CHECK();
+  for (int off = 0; off < n_items; off += 32768) {         // gridDim.y limit
+    const int cnt = std::min(32768, n_items - off);
+    kernel<<<dim3(bx, cnt, splits), kCmpWarps * 32, 0, s>>>(
+        M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab + off, level_mom ? level_mom + off : nullptr,
+        omega0 + off, domega, n_omega, reinterpret_cast<const int*>(st.table.p), st.edges_dev.p, st.nb,
+        near_i + 4LL * off * n_chunks, n_chunks, st.mom.p, reinterpret_cast<const double2*>(st.eq.p),
+        (splits > 1 ? partial.p : values) + (long long)off * n_omega, n,
+        reinterpret_cast<unsigned long long*>(counter.p));
+    LAUNCH_CHECK();
+  }
   if (splits > 1) {
     sigma_ppm_grid_reduce<<<blocks_for(n, 256, 2048), 256, 0, s>>>(values, partial.p, n, splits);
     LAUNCH_CHECK();
   }
-  prof_end(slot, s);
   unsigned long long near_poles = 0;
   XTPB_CUDA(cudaMemcpyAsync(&near_poles, counter.p, sizeof(near_poles), cudaMemcpyDeviceToHost, s));
   XTPB_CUDA(cudaStreamSynchronize(s));   // the scratch buffers are freed on return
   if (direct_evaluations) *direct_evaluations = (double)near_poles * kCmpChunk;
+}
+
+void k_sigma_ppm_grid_compressed(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
+                                 const double* energies, const double* ppm_freq, const double* ppm_fac,
+                                 const int* level_slab, const double* omega0, double domega, int n_omega, int n_levels,
+                                 const double* edges_host, int nb, const int* near_host, int n_chunks, double* values,
+                                 double* direct_evaluations, PpmScanState& st, cudaStream_t s) {
+  // work = pole evaluations of the equivalent direct sum (what (1) would do), so that rates stay comparable
+  const int slot = prof_begin(PROF_SIGMA_GRID, (double)ntotal * naux * (double)n_omega * n_levels, s);
+  k_ppm_scan_prepare(M, ldn, slab, ntotal, naux, n_occ, energies, ppm_freq, ppm_fac, level_slab, n_levels, edges_host,
+                     nb, st, s);
+  k_ppm_scan_evaluate(M, ldn, slab, naux, energies, ppm_freq, ppm_fac, level_slab, nullptr, omega0, domega, n_omega,
+                      n_levels, near_host, n_chunks, st, values, direct_evaluations, s);
+  prof_end(slot, s);
 }
 void k_sigma_ppm_pairs(const double* M, long long ldn, long long slab, int ntotal, int naux, int n_occ,
                        const double* energies, const double* ppm_freq, const double* ppm_fac, const int* pair_slab,
@@ -1219,6 +1315,21 @@ void k_bse_add_hqp(double* H, long long ld, int vt, int ct, int v2lo, int ns, co
     const long long total = (long long)ns * ct * (part == 0 ? ct : vt);
     if (total == 0) continue;
     bse_add_hqp_kernel<<<blocks_for(total, 256, 8192), 256, 0, s>>>(H, ld, vt, ct, v2lo, ns, hqp, hs, cqp, part);
+    LAUNCH_CHECK();
+  }
+}
+
+void k_bse_pack_pairs(double* Ftri, long long ldt, const double* F, long long ldf, int vt, int naux, cudaStream_t s) {
+  const long long npairs = (long long)vt * (vt + 1) / 2;
+  bse_pack_pairs_kernel<<<blocks_for(npairs * naux, 256, 16384), 256, 0, s>>>(Ftri, ldt, F, ldf, vt, npairs, naux);
+  LAUNCH_CHECK();
+}
+void k_bse_scatter_pairs(double* H, long long ld, int ct, const double* T, long long t0, long long tcnt, cudaStream_t s) {
+  const int tiles = (ct + 31) / 32;
+  for (long long off = 0; off < tcnt; off += 32768) {
+    const long long cnt = std::min<long long>(32768, tcnt - off);
+    bse_scatter_pairs_kernel<<<dim3(tiles * tiles, (unsigned)cnt), 256, 0, s>>>(H, ld, ct, T + off * (long long)ct * ct,
+                                                                              t0 + off);
     LAUNCH_CHECK();
   }
 }

@@ -33,6 +33,7 @@ TCMatrix::~TCMatrix() {
 void TCMatrix::set_raw(const double* host) {
   pending = false;
   eps0.valid = false;
+  ++generation;
   if (world == 1) {
     ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
     ctx->sync();
@@ -73,6 +74,7 @@ void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host
   XTPB_REQUIRE(nb > 0 && ldc_host >= nb, "bad MO coefficient matrix");
   pending = false;            // a new fill starts from the un-rotated tensor
   eps0.valid = false;
+  ++generation;
   n_basis = nb;
   ldc = round_up(nb, 2);
   Cm.alloc((size_t)(ldc * mtotal));
@@ -92,6 +94,7 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
   XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill_block");
   XTPB_REQUIRE(world == 1, "with more than one rank use the collective fill (xtpb_tc_fill_sharded_packed)");
   XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux && ld_ao >= n_basis, "bad aux block");
+  ++generation;
   ProfScope prof(PROF_FILL);
   const long long ldw = round_up(n_basis, 2);
   const long long wslice = ldw * mtotal;
@@ -193,6 +196,7 @@ void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
   XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before fill");
   long long lo, hi;
   aux_range(rank, lo, hi);
+  ++generation;
   if (world == 1) {
     if (on_device) fill_block_packed_dev(lo, hi - lo, packed);
     else fill_block_host(lo, hi - lo, packed, 0, true);
@@ -375,6 +379,7 @@ bool TCMatrix::metric_prefetch_join() {
 void TCMatrix::set_pending(const double* R_dev, long long ldr) {
   flush();
   eps0.valid = false;
+  ++generation;
   static const bool lazy = [] { const char* e = getenv("XTPB_LAZY_METRIC"); return !(e && e[0] == '0'); }();
   if (!lazy) {
     rotate(R_dev, ldr);
@@ -392,6 +397,7 @@ void TCMatrix::flush() {
 }
 
 void TCMatrix::rotate(const double* R_dev, long long ldr) {
+  ++generation;
   eps0.valid = false;         // the caller re-validates when R is an eps(0) eigenbasis (GW::prepare_ppm)
   DBuf folded;
   if (pending) {      // M <- M (Rp R): fold the deferred factor into this rotation
