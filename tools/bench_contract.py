@@ -86,11 +86,22 @@ def shapes(nb, naux, homo):
                                 a_row=naux * ld, a_k=1, a_outer=ld, a_len=q * naux * ld,
                                 b_row=naux * ld, b_k=1, b_outer=ld, b_len=q * naux * ld,
                                 c_row=1, c_col=q, c_len=q * q), float(q) * q * o * naux))
+    # dense BSE direct term over the occupied pairs (bse.cu): rows (c2,c1), a slice of the pair columns, K = naux;
+    # both operands row-contiguous with long k strides
+    npair = v * (v + 1) // 2
+    ncol = min(npair, 8192)
+    lda, ldb = c * c + (c * c & 1), npair + (npair & 1)
+    out.append(("bse_dense_direct_pairs", desc(M=c * c, N=ncol, K=naux,
+                                               a_row=1, a_k=lda, a_len=naux * lda,
+                                               b_row=1, b_k=ldb, b_len=naux * ldb,
+                                               c_row=1, c_col=c * c, c_len=c * c * ncol), 2.0 * c * c * ncol * naux))
     # plain square DGEMM for reference
     for s in (4096, 8192):
         out.append((f"square_{s}_kc_kc", desc(M=s, N=s, K=s, a_row=s, a_k=1, a_len=s * s, b_row=s, b_k=1,
                                               b_len=s * s, c_row=1, c_col=s, c_len=s * s), 2.0 * s ** 3))
         out.append((f"square_{s}_mc_kc", desc(M=s, N=s, K=s, a_row=1, a_k=s, a_len=s * s, b_row=s, b_k=1,
+                                              b_len=s * s, c_row=1, c_col=s, c_len=s * s), 2.0 * s ** 3))
+        out.append((f"square_{s}_mc_mc", desc(M=s, N=s, K=s, a_row=1, a_k=s, a_len=s * s, b_row=1, b_k=s,
                                               b_len=s * s, c_row=1, c_col=s, c_len=s * s), 2.0 * s ** 3))
     return out
 

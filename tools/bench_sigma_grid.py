@@ -45,29 +45,34 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="gpurun_out/sigma_grid.jsonl")
     ap.add_argument("--child", action="store_true")
+    ap.add_argument("--walk-only", action="store_true", help="only the three near-range walks (XTPB_GRID_WALK)")
     args = ap.parse_args()
     if args.child:
         child(args.workload, args.reps)
         return
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
-        # the two ways the scan can run: pole by pole and compressed (the latter for several register/occupancy caps)
-        # and, for the compressed scan, narrower core bins of the pole axis (XTPB_GRID_BIN_WIDTH, default 0.25 Ha)
-        for mode, occ, bw in (("direct", "", ""), ("compressed", "3", ""), ("compressed", "4", ""), ("compressed", "5", ""),
-                              ("compressed", "6", ""), ("compressed", "5", "0.125"), ("compressed", "6", "0.125"),
-                              ("compressed", "5", "0.0625")):
+        # the two ways the scan can run: pole by pole and compressed; for the compressed scan the three walks of the
+        # near m-ranges (XTPB_GRID_WALK) and register/occupancy caps around the default
+        variants = [("direct", "", "", ""), ("compressed", "5", "", "0"), ("compressed", "5", "", "1"),
+                    ("compressed", "5", "", "2"), ("compressed", "4", "", "2"), ("compressed", "6", "", "2")]
+        if args.walk_only:
+            variants = [v for v in variants if v[0] == "compressed" and v[1] == "5"]
+        for mode, occ, bw, walk in variants:
             env = dict(os.environ, XTPB_SIGMA_GRID=mode)
             if occ:
                 env["XTPB_GRID_OCC"] = occ
             if bw:
                 env["XTPB_GRID_BIN_WIDTH"] = bw
+            if walk:
+                env["XTPB_GRID_WALK"] = walk
             r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
                                 str(args.reps)], env=env, capture_output=True, text=True)
             if r.stdout.strip():
                 rec = json.loads(r.stdout.strip().splitlines()[-1])
             else:
                 rec = {"error": r.stderr[-400:]}
-            rec.update({"mode": mode, "min_blocks_per_sm": occ, "bin_width": bw or "0.25"})
+            rec.update({"mode": mode, "min_blocks_per_sm": occ, "bin_width": bw or "0.125", "walk": walk})
             line = json.dumps(rec)
             print(line, flush=True)
             f.write(line + "\n")

@@ -41,6 +41,10 @@ print(json.dumps([(r['algorithm'], r['cores'], r['full_s'], r['sampled_s']) for 
     scaletests) timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q > $OUT/pytest_scale_$TAG.log 2>&1; echo "scaletests rc=$?"; tail -15 $OUT/pytest_scale_$TAG.log | cut -c1-300 ;;
     probe)     tools/probe_rcp64 > $OUT/probe_rcp64_$TAG.json 2> $OUT/probe_rcp64_$TAG.err; echo "probe rc=$?"; cat $OUT/probe_rcp64_$TAG.json | cut -c1-200 ;;
     benzene)   timeout 600 python bench.py --workload benzene-tzvp-shape --steps 3 --warmup 3 > $OUT/bench_benzene_$TAG.json 2> $OUT/bench_benzene_$TAG.err; echo "benzene rc=$?"; cut -c1-300 $OUT/bench_benzene_$TAG.json ;;
+    walk)      timeout 600 python tools/bench_sigma_grid.py --workload synth-1000 --walk-only --out $OUT/sigma_grid_walk_$TAG.jsonl > $OUT/walk_$TAG.log 2>&1; echo "walk rc=$?"; cut -c1-260 $OUT/walk_$TAG.log ;;
+    diag)      timeout 600 python tools/bench_contract.py --only epsilon_syrk,bse_dense_direct_pairs,square_4096_kc_kc,square_4096_mc_kc,square_4096_mc_mc,fill_T_times_Cm --reps 3 --out $OUT/contract_diag_$TAG.jsonl > $OUT/diag_$TAG.log 2>&1; echo "diag rc=$?"; cut -c1-220 $OUT/diag_$TAG.log ;;
+    diag0)     XTPB_TAIL_SPLIT=0 timeout 600 python tools/bench_contract.py --only epsilon_syrk --reps 3 --out $OUT/contract_diag0_$TAG.jsonl > $OUT/diag0_$TAG.log 2>&1; echo "diag0 rc=$?"; cut -c1-220 $OUT/diag0_$TAG.log ;;
+    ncu_pairs) timeout 900 ncu --set full --clock-control none -k regex:contract -c 1 -f -o /tmp/r02_pairs python tools/bench_contract.py --only bse_dense_direct_pairs --reps 1 --out $OUT/ncu_pairs_$TAG.jsonl > $OUT/ncu_pairs_$TAG.log 2>&1; echo "ncu_pairs rc=$?"; ncu -i /tmp/r02_pairs.ncu-rep --page raw --csv > $OUT/r02_pairs_raw.csv 2>/dev/null; ncu -i /tmp/r02_pairs.ncu-rep --page details --csv > $OUT/r02_pairs_details.csv 2>/dev/null; ls -la $OUT/r02_pairs_*.csv ;;
     smoke)     timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_$TAG.log ;;
     *)         echo "unknown step $step" ;;
   esac

@@ -305,6 +305,33 @@ int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, in
     if (tiles < 2LL * sms && nkt >= 16) {
       splits = (int)std::min<long long>({(3LL * sms + tiles - 1) / tiles, nkt / 8, 64LL});
       if (splits < 1) splits = 1;
+    } else if (nkt >= 512) {
+      // Long contractions with a handful of waves (the eps(w) SYRK at C60 size: 946 lower-triangle tiles = 6.4 waves of
+      // 40 ms tiles, of which the seventh runs 0.4 full): splitting the contraction index s ways turns the tail into
+      // ceil(s * tiles / slots) / s waves.  Taken when the saved tile time clearly exceeds the extra pass over the
+      // partial results (and the workspace stays below 2 GiB); deterministic like every split-K launch.
+      long long real_tiles = tiles;
+      if (p.lower) {        // tiles on or below the diagonal (BM = BN = 128 for lower-triangular outputs)
+        const long long tm = (p.M + 127) / 128, tn = (p.N + 127) / 128;
+        real_tiles = 0;
+        for (long long j = 0; j < tn; ++j) real_tiles += std::max<long long>(0, tm - j);
+        real_tiles *= p.n_batch;
+      }
+      const long long slots = (long long)sms * (cfg == 0 ? 1 : 2);
+      auto waves = [&](int s_) { return double((real_tiles * s_ + slots - 1) / slots) / s_; };
+      const double tile_us = 2.1 * double(nkt) * (bn / 128.0);             // one CTA, whole contraction index
+      const double mn_bytes = 8.0 * double(p.M) * double(p.N) * p.n_batch * (p.lower ? 0.5 : 1.0);
+      int best = 1;
+      double best_gain = 0.0;
+      for (int s_ = 2; s_ <= 8; ++s_) {
+        if (nkt / s_ < 256 || mn_bytes * (p.lower ? 2.0 : 1.0) * s_ > 2147483648.0) break;
+        const double saved_us = (waves(1) - waves(s_)) * tile_us;
+        const double reduce_us = (s_ + 1) * mn_bytes / 4.0e6 + 10.0;       // ~4 TB/s over partials + output
+        const double gain = saved_us - 3.0 * reduce_us;
+        if (gain > best_gain + 1e-9) { best_gain = gain; best = s_; }
+      }
+      static const bool tail_split = [] { const char* e = getenv("XTPB_TAIL_SPLIT"); return !(e && e[0] == '0'); }();
+      if (tail_split) splits = best;
     }
   }
   XTPB_REQUIRE((long long)p.n_batch * splits <= 65535, "batch*splits exceeds gridDim.z");

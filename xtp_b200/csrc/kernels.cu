@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -353,7 +354,7 @@ __global__ void sigma_ppm_grid_reduce(double* __restrict__ values, const double*
 // every group of poles warp-uniform: nobody damped (reciprocal path) or everybody damped (polynomial path); the round-1
 // kernel with 32-point chunks spent most of its time in the mixed case that evaluates both.
 constexpr int kCmpOrder = 16, kCmpChunk = kPpmGridChunk, kCmpSlots = 32 / kCmpChunk, kCmpWarps = 4, kCmpG = 4,
-              kCmpMomentWarps = 8, kCmpMinBlocks = 5;
+              kCmpMomentWarps = 8, kCmpMinBlocks = 5, kCmpWalk = 2;
 static_assert(kCmpChunk * kCmpSlots == 32 && 32 % (kCmpSlots * kCmpG) == 0, "lane = (slot, point) mapping");
 
 // binstart[(seg*naux + P)*(nb+1) + b] = first m of segment seg (0 occupied, 1 unoccupied) whose pole lies at or above
@@ -495,7 +496,11 @@ __global__ void ppm_equivalent_poles_kernel(double2* __restrict__ eq, const doub
 // one by one.
 // MINB = resident CTAs per SM the register allocation is capped for (occupancy against unrolling depth; the launcher
 // picks kCmpMinBlocks unless XTPB_GRID_OCC says otherwise).
-template <int MINB>
+// WALK = how the (up to four) near m-ranges of an aux function are turned into 32-pole tiles: 0 range by range,
+// 1 as one virtual index space (short ranges share tiles), 2 like 1 with the padding lanes of the last tile carrying
+// the last real pole's position at weight zero, so that a partly filled step keeps the kind (plain / damped) of its
+// real poles instead of falling into the mixed branch (XTPB_GRID_WALK; measured in profiles/r02_sigma_grid_walk.jsonl).
+template <int MINB, int WALK>
 __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compressed_kernel(
     const double* __restrict__ M, long long ldn, long long slab, int naux, const double* __restrict__ energies,
     const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac, const int* __restrict__ level_slab,
@@ -581,6 +586,38 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
       if (fac == 0.0) continue;
       const double Om = ppm_freq[P];
       const double* row = S + (long long)P * ldn;
+      if (WALK == 0) {
+#pragma unroll 1
+        for (int rg = 0; rg < 4; ++rg) {
+          const int lo = rg == 0 ? c0 : (rg == 1 ? c2 : (rg == 2 ? c4 : c6));
+          const int hi = rg == 0 ? c1 : (rg == 1 ? c3 : (rg == 2 ? c5 : c7));
+          if (lo >= hi) continue;
+          const double shift = rg >= 2 ? Om : -Om;
+          n_near += hi - lo;
+          // raw tensor element / energy of this lane's pole in the tile that starts at m0: the arithmetic on them
+          // happens when the tile is stored, so that the loads of the NEXT tile stay in flight while this one is evaluated
+          double nv = 0.0, ne = 0.0;
+          auto fetch = [&](int m0) {
+            const int m = m0 + lane;
+            nv = 0.0;
+            ne = -1.0e30;
+            if (m < hi) {
+              nv = row[m];
+              ne = energies[m];
+            }
+          };
+          fetch(lo);
+          for (int m0 = lo; m0 < hi; m0 += 32) {
+            const double2 el = make_double2(fac * nv * nv, ne + shift);
+            if (m0 + 32 < hi) fetch(m0 + 32);
+            __syncwarp();
+            tile[warp][lane] = el;
+            __syncwarp();
+            eval_tile(min(32, hi - m0));
+          }
+        }
+        continue;
+      }
       // The four m-ranges of this aux function (occupied / unoccupied segment, below / above the inner bins) are
       // walked as ONE virtual index space, so that short ranges (a rank of eight holds 1/8 of the levels) share tiles:
       // virtual index t -> range rg = #{offsets <= t}, m = lo_rg + (t - offset_rg); ranges 2, 3 are unoccupied (+Omega)
@@ -592,13 +629,15 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
       // when the tile is stored, so that the loads of the NEXT tile stay in flight while this one is evaluated
       double nv = 0.0, ne = 0.0, nsh = 0.0;
       auto fetch = [&](int first) {
-        const int t = first + lane;
+        int t = first + lane;
         nv = 0.0;
         ne = -1.0e30;
         nsh = 0.0;
+        const bool real = t < total;
+        if (WALK == 2) t = min(t, total - 1);      // padding lanes: position of the last real pole, weight zero
         if (t < total) {
           const int m = t < o1 ? c0 + t : (t < o2 ? c2 + (t - o1) : (t < o3 ? c4 + (t - o2) : c6 + (t - o3)));
-          nv = row[m];
+          nv = real ? row[m] : 0.0;
           ne = energies[m];
           nsh = t < o2 ? -Om : Om;
         }
@@ -1130,10 +1169,19 @@ void k_ppm_scan_evaluate(const double* M, long long ldn, long long slab, int nau
   XTPB_CUDA(cudaMemcpyAsync(near_i, near_host, (size_t)n_near * sizeof(int), cudaMemcpyHostToDevice, s));
   const char* occ_env = std::getenv("XTPB_GRID_OCC");
   const int occ = occ_env ? std::atoi(occ_env) : kCmpMinBlocks;
-  auto kernel = occ <= 3 ? sigma_ppm_grid_compressed_kernel<3>
-              : occ == 4 ? sigma_ppm_grid_compressed_kernel<4>
-              : occ == 5 ? sigma_ppm_grid_compressed_kernel<5>
-                         : sigma_ppm_grid_compressed_kernel<6>;
+  const char* walk_env = std::getenv("XTPB_GRID_WALK");
+  const int walk = walk_env ? std::atoi(walk_env) : kCmpWalk;
+  using KernelFn = decltype(&sigma_ppm_grid_compressed_kernel<5, 1>);
+  auto pick = [&](auto walk_tag) -> KernelFn {
+    constexpr int W = decltype(walk_tag)::value;
+    return occ <= 3 ? sigma_ppm_grid_compressed_kernel<3, W>
+         : occ == 4 ? sigma_ppm_grid_compressed_kernel<4, W>
+         : occ == 5 ? sigma_ppm_grid_compressed_kernel<5, W>
+                    : sigma_ppm_grid_compressed_kernel<6, W>;
+  };
+  KernelFn kernel = walk <= 0 ? pick(std::integral_constant<int, 0>{})
+                  : walk == 1 ? pick(std::integral_constant<int, 1>{})
+                              : pick(std::integral_constant<int, 2>{});
   for (int off = 0; off < n_items; off += 32768) {         // gridDim.y limit
     const int cnt = std::min(32768, n_items - off);
     kernel<<<dim3(bx, cnt, splits), kCmpWarps * 32, 0, s>>>(

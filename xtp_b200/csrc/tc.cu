@@ -87,6 +87,11 @@ void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host
   ctx->sync();
 }
 
+static bool fill_merge_batches() {
+  static const bool on = [] { const char* e = getenv("XTPB_FILL_MERGE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // Fill3cMO for aux functions P0..P0+nP-1 (upstream: per aux function dftn^T * T_P * dftm; here batched over P):
 //   W_P  = T_P * C_m            (n_basis x mtotal)      2 n_basis^2 mtotal flops per P
 //   M[m][P][:] = C_n^T * W_P    (ntotal x mtotal)       2 ntotal n_basis mtotal flops per P
@@ -98,7 +103,7 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
   ProfScope prof(PROF_FILL);
   const long long ldw = round_up(n_basis, 2);
   const long long wslice = ldw * mtotal;
-  const long long sub_max = std::max<long long>(1, std::min<long long>(64, (1LL << 27) / std::max<long long>(1, wslice)));
+  const long long sub_max = std::max<long long>(1, std::min<long long>(128, (1LL << 27) / std::max<long long>(1, wslice)));
   ctx->scratch_a.ensure((size_t)(sub_max * wslice));
   double* W = ctx->scratch_a.p;
   for (long long p = 0; p < nP; p += sub_max) {
@@ -110,7 +115,6 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
     g.C = W; g.c_sm = 1; g.c_sn = ldw; g.c_batch = wslice;
     g.M = (int)n_basis; g.N = (int)mtotal; g.K = (int)n_basis; g.n_outer = 1; g.n_batch = (int)cnt;
     g.alpha = 1.0; g.beta = 0.0;
-    contract(g, ctx->ws, ctx->stream);
     GemmParams h{};
     // out(n, m) = sum_mu Cn(mu,n) W(mu,m) -> M[m][P0+p+b][n]
     h.A = GemmOperand{Cn.p, ldc, 1, 0, 0};
@@ -118,6 +122,14 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
     h.C = M.p + (P0 + p) * ldn; h.c_sm = 1; h.c_sn = slab; h.c_batch = ldn;
     h.M = (int)ntotal; h.N = (int)mtotal; h.K = (int)n_basis; h.n_outer = 1; h.n_batch = (int)cnt;
     h.alpha = 1.0; h.beta = 0.0;
+    if (fill_merge_batches() && cnt * n_basis < (1LL << 31) && cnt * mtotal < (1LL << 31)) {
+      // The slices of a group are equally spaced, so the batch index folds into an operand row index: rows (b, mu) of
+      // the first product, columns (b, m) of the second (two-level output maps) -- one tile grid without the padding
+      // of n_basis and mtotal to whole tiles in every batch (C60 size: 1860 -> 1920 rows, 360 -> 384 columns).
+      g.M = (int)(cnt * n_basis); g.n_batch = 1; g.c_m_inner = (int)n_basis; g.c_sm_outer = wslice;
+      h.N = (int)(cnt * mtotal); h.n_batch = 1; h.c_n_inner = (int)mtotal; h.c_sn_outer = ldn;
+    }
+    contract(g, ctx->ws, ctx->stream);
     contract(h, ctx->ws, ctx->stream);
   }
 }
@@ -177,7 +189,11 @@ void TCMatrix::fill_block_packed_dev(long long P0, long long nP, const double* p
   XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux, "bad aux block");
   const long long ldt = round_up(n_basis, 2);
   const long long full_slice = ldt * n_basis, pk_slice = n_basis * (n_basis + 1) / 2;
-  const long long sub_max = std::max<long long>(1, std::min<long long>(nP, (1LL << 26) / full_slice));
+  // up to 2 GiB of unpacked slices per group: the two contractions of a group are one launch each, and the longer the
+  // launch the smaller the share of its last, partly filled wave of tiles (C60 size: 64 slices = 19.5 waves)
+  const long long cap = std::max<long long>(1, std::min<long long>(nP, (1LL << 28) / full_slice));
+  const long long groups = (nP + cap - 1) / std::max<long long>(cap, 1);
+  const long long sub_max = groups > 0 ? (nP + groups - 1) / groups : 1;     // equal groups, none of them short
   unpacked.ensure((size_t)(sub_max * full_slice));
   for (long long p = 0; p < nP; p += sub_max) {
     const long long cnt = std::min(sub_max, nP - p);
@@ -257,6 +273,9 @@ void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
     h.C = stage_out; h.c_sm = 1; h.c_sn = slots * ldn; h.c_batch = ldn;
     h.M = (int)ntotal; h.N = (int)mtotal; h.K = (int)n_basis; h.n_outer = 1; h.n_batch = (int)slots;
     h.alpha = 1.0; h.beta = 0.0;
+    if (fill_merge_batches() && slots * mtotal < (1LL << 31)) {     // columns (slot, m): see fill_block_dev
+      h.N = (int)(slots * mtotal); h.n_batch = 1; h.c_n_inner = (int)mtotal; h.c_sn_outer = ldn;
+    }
     contract(h, ctx->ws, ctx->stream);
     XTPB_CUDA(cudaEventRecord(ev_free[b], ctx->stream));      // the gathered blocks are consumed
     k_scatter_fill_slots(M.p, ldn, slab, stage_out, (int)mtotal, (int)ntotal, (int)naux, world, (int)B, (int)i,
@@ -284,6 +303,9 @@ void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
       g.C = wsend[b].p; g.c_sm = 1; g.c_sn = ldw; g.c_batch = wslice;
       g.M = (int)n_basis; g.N = (int)mtotal; g.K = (int)n_basis; g.n_outer = 1; g.n_batch = (int)cnt;
       g.alpha = 1.0; g.beta = 0.0;
+      if (fill_merge_batches() && cnt * n_basis < (1LL << 31)) {     // rows (b, mu): see fill_block_dev
+        g.M = (int)(cnt * n_basis); g.n_batch = 1; g.c_m_inner = (int)n_basis; g.c_sm_outer = wslice;
+      }
       contract(g, ctx->ws, ctx->stream);
     }
     XTPB_CUDA(cudaEventRecord(ev_w[b], ctx->stream));
