@@ -40,6 +40,8 @@ int xtpb_version(void);
 long long xtpb_launch_count(void);
 /* of which launches of the contraction engine's TMA-fed instance (cp.async.bulk.tensor + mbarrier pipeline) */
 long long xtpb_tma_launch_count(void);
+/* ... of which launches that fetch a row-contiguous operand tile with ONE 5-D tensor-map box (contract.cu) */
+long long xtpb_tma_single_box_launch_count(void);
 
 /* ---- context: one CUDA device + stream + scratch.  Replaces OpenMP_CUDA / CudaPipeline
  *      (upstream xtp/src/libxtp/openmp_cuda.cc, cudapipeline.cc). ---- */

@@ -149,6 +149,21 @@ def test_tma_weights_outer_batch_lower(ctx, a_kc, b_kc):
     _tma_case(ctx, 90, 60, 20, a_kc, b_kc, col_inner=12, cfg=10, seed=26)
 
 
+def test_tma_row_contiguous_operands_use_one_box(ctx, monkeypatch):
+    """Row-contiguous operands reach the TMA instance through the 5-D tensor map (one box per tile instead of one per
+    16 rows) unless the driver refuses the map; row counts that are not multiples of 16 over-read into the next k-row,
+    which must not leak into stored results."""
+    from xtp_b200 import api
+    before = api.tma_single_box_launch_count()
+    _tma_case(ctx, 1000, 330, 200, False, False, cfg=8, seed=40)
+    _tma_case(ctx, 517 * 2, 130, 64, False, True, n_outer=3, n_batch=2, use_d=True, cfg=9, seed=41)
+    _tma_case(ctx, 250, 122, 96, True, False, lower=False, splits=2, cfg=10, seed=42)
+    used = api.tma_single_box_launch_count() - before
+    assert used in (0, 3)
+    if used == 0:
+        pytest.skip("the driver refused the 5-D map: the per-16-row boxes were used")
+
+
 def test_tma_long_pipeline(ctx):
     """many k-tiles per CTA: every stage and both mbarrier parities are reused many times"""
     _tma_case(ctx, 128, 128, 4096, True, True, cfg=8, seed=27)

@@ -14,7 +14,11 @@ fi
 for step in "$@"; do
   case $step in
     tests)     timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "tests rc=$?"; tail -5 $OUT/pytest_$TAG.log ;;
-    trace)     XTPB_TRACE=1 timeout 600 python bench.py --workload c60-tzvp-shape --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/trace_$TAG.json 2> $OUT/trace_$TAG.err; echo "trace rc=$?"; grep "xtpb trace" $OUT/trace_$TAG.err | tail -4 ;;
+    trace)     XTPB_TRACE=1 XTPB_BENCH_MIN_WARMUP=1 timeout 600 python bench.py --workload c60-tzvp-shape --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/trace_$TAG.json 2> $OUT/trace_$TAG.err; echo "trace rc=$?"; grep "xtpb trace \[" $OUT/trace_$TAG.err | tail -9 ;;
+    trace_nosplit) XTPB_TAIL_SPLIT=0 XTPB_TRACE=1 XTPB_BENCH_MIN_WARMUP=1 timeout 600 python bench.py --workload c60-tzvp-shape --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/trace_nosplit_$TAG.json 2> $OUT/trace_nosplit_$TAG.err; echo "trace_nosplit rc=$?"; grep "xtpb trace \[" $OUT/trace_nosplit_$TAG.err | tail -9 ;;
+    trace_noovl) XTPB_PPM_OVERLAP=0 XTPB_TRACE=1 XTPB_BENCH_MIN_WARMUP=1 timeout 600 python bench.py --workload c60-tzvp-shape --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/trace_noovl_$TAG.json 2> $OUT/trace_noovl_$TAG.err; echo "trace_noovl rc=$?"; grep "xtpb trace \[" $OUT/trace_noovl_$TAG.err | tail -9 ;;
+    diag5)     timeout 600 python tools/bench_contract.py --only aux_rotation,bse_dense_direct_pairs,square_4096_mc_kc,square_4096_mc_mc,bse_direct_step1 --reps 3 --out $OUT/contract_diag5_$TAG.jsonl > $OUT/diag5_$TAG.log 2>&1; echo "diag5 rc=$?"; cut -c1-200 $OUT/diag5_$TAG.log ;;
+    contracttests) timeout 600 python -m pytest tests/test_gpu_contract.py -m gpu -x -q > $OUT/pytest_contract_$TAG.log 2>&1; echo "contracttests rc=$?"; tail -4 $OUT/pytest_contract_$TAG.log ;;
     c60)       timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/bench_c60_$TAG.json 2> $OUT/bench_c60_$TAG.err; echo "c60 rc=$?"; cut -c1-600 $OUT/bench_c60_$TAG.json ;;
     c60fast)   timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_c60_$TAG.json 2> $OUT/bench_c60_$TAG.err; echo "c60 rc=$?"; cut -c1-600 $OUT/bench_c60_$TAG.json ;;
     pentacene) timeout 600 python bench.py --workload pentacene-tzvp-shape --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_pentacene_$TAG.json 2> $OUT/bench_pentacene_$TAG.err; echo "pentacene rc=$?"; cut -c1-400 $OUT/bench_pentacene_$TAG.json ;;

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "xtpb_version": (C.c_int, []),
     "xtpb_launch_count": (C.c_longlong, []),
     "xtpb_tma_launch_count": (C.c_longlong, []),
+    "xtpb_tma_single_box_launch_count": (C.c_longlong, []),
     "xtpb_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "xtpb_ctx_destroy": (C.c_int, [vp]),
     "xtpb_ctx_sync": (C.c_int, [vp]),

@@ -69,6 +69,10 @@ def tma_launch_count():
     return int(_lib.lib().xtpb_tma_launch_count())
 
 
+def tma_single_box_launch_count():
+    return int(_lib.lib().xtpb_tma_single_box_launch_count())
+
+
 def comm_unique_id() -> bytes:
     """128-byte NCCL unique id (call on rank 0, distribute to every rank, then Context.comm_init)."""
     buf = C.create_string_buffer(128)

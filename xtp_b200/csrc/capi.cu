@@ -19,6 +19,7 @@ const char* xtpb_last_error(void) { return last_error_cstr(); }
 int xtpb_version(void) { return 100; }
 long long xtpb_launch_count(void) { return g_launch_count; }
 long long xtpb_tma_launch_count(void) { return g_tma_launch_count; }
+long long xtpb_tma_single_box_launch_count(void) { return g_tma5d_launch_count; }
 
 int xtpb_ctx_create(int device, xtpb_ctx** out) {
   XTPB_API_BEGIN

@@ -11,6 +11,7 @@ namespace xtpb {
 
 std::atomic<long long> g_launch_count{0};
 std::atomic<long long> g_tma_launch_count{0};
+std::atomic<long long> g_tma5d_launch_count{0};
 
 // ------------------------------------------------------------------ event-pair profiler
 namespace {
@@ -155,14 +156,50 @@ bool make_tensor_map(CUtensorMap* map, const GemmOperand& o, bool kc, int rows, 
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+// Row-contiguous operand as ONE box per tile: dims (row % 16, k, row / 16, outer, batch) with strides (8 B,) s_k, 128 B,
+// ... and box (16, 16, rows_box / 16, 1, 1) land in shared memory as [row / 16][k][16 rows] -- exactly the mc tile
+// layout the per-16-row boxes of the 4-D map produce, with one cp.async.bulk.tensor instead of rows_box / 16 of them
+// (each costs the issuing warp ~200 cycles; with both operands row-contiguous the 16 issues per k-tile made warp 0 the
+// straggler of its CTA: 29.6 TFLOP/s against 35.0 for two K-contiguous operands, profiles/r02_contract_diag.jsonl).
+// The last row group of an operand whose row count is not a multiple of 16 reads up to 15 elements past the end of a
+// k-row (the next k-row, or the slack every library allocation carries: core.cu device_alloc); those values only reach
+// accumulators of rows >= M resp. columns >= N, which are never stored.  False: fall back to the 4-D map.
+bool make_tensor_map_mc5(CUtensorMap* map, const GemmOperand& o, int rows, int rows_box, int K, int n_outer,
+                         int n_batch, int* use_outer, int* use_batch) {
+  static const bool on = [] { const char* e = getenv("XTPB_TMA5D"); return !(e && e[0] == '0'); }();
+  if (!on || !o.library_owned) return false;
+  *use_outer = (n_outer > 1 && o.s_outer != 0) ? 1 : 0;
+  *use_batch = (n_batch > 1 && o.s_batch != 0) ? 1 : 0;
+  if (reinterpret_cast<uintptr_t>(o.p) % 16) return false;
+  if (o.s_k <= 0 || o.s_k % 2 || (*use_outer && (o.s_outer <= 0 || o.s_outer % 2)) ||
+      (*use_batch && (o.s_batch <= 0 || o.s_batch % 2)))
+    return false;
+  cuuint64_t dims[5] = {16u, (cuuint64_t)K, (cuuint64_t)((rows + 15) / 16), (cuuint64_t)(*use_outer ? n_outer : 1),
+                        (cuuint64_t)(*use_batch ? n_batch : 1)};
+  cuuint64_t strides[4] = {(cuuint64_t)o.s_k * 8, 128u, (cuuint64_t)(*use_outer ? o.s_outer * 8 : 16),
+                           (cuuint64_t)(*use_batch ? o.s_batch * 8 : 16)};
+  cuuint32_t box[5] = {16u, 16u, (cuuint32_t)(rows_box / 16), 1u, 1u};
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  for (int i = 0; i < 4; ++i)
+    if (strides[i] >= (1ULL << 40)) return false;
+  const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double*>(o.p), dims, strides,
+                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 
 template <int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, bool HAS_D>
 bool launch_tma(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BM, BN, WM, WN, A_KC, B_KC, kStages>;
   alignas(64) CUtensorMap mapA, mapB;
   TmaCoords tc{};
-  if (!make_tensor_map(&mapA, p.A, A_KC, p.M, BM, p.K, p.n_outer, p.n_batch, &tc.a_outer, &tc.a_batch)) return false;
-  if (!make_tensor_map(&mapB, p.B, B_KC, p.N, BN, p.K, p.n_outer, p.n_batch, &tc.b_outer, &tc.b_batch)) return false;
+  tc.a_mc5 = !A_KC && make_tensor_map_mc5(&mapA, p.A, p.M, BM, p.K, p.n_outer, p.n_batch, &tc.a_outer, &tc.a_batch);
+  tc.b_mc5 = !B_KC && make_tensor_map_mc5(&mapB, p.B, p.N, BN, p.K, p.n_outer, p.n_batch, &tc.b_outer, &tc.b_batch);
+  if (!tc.a_mc5 && !make_tensor_map(&mapA, p.A, A_KC, p.M, BM, p.K, p.n_outer, p.n_batch, &tc.a_outer, &tc.a_batch))
+    return false;
+  if (!tc.b_mc5 && !make_tensor_map(&mapB, p.B, B_KC, p.N, BN, p.K, p.n_outer, p.n_batch, &tc.b_outer, &tc.b_batch))
+    return false;
+  if (tc.a_mc5 || tc.b_mc5) ++g_tma5d_launch_count;
   auto kern = contract_tma_kernel<Cfg, BM, BN, WM, WN, A_KC, B_KC, kStages, HAS_D>;
   constexpr int smem_bytes = kStages * (Cfg::A_BYTES + Cfg::B_BYTES + 1024) + 2 * kStages * 8;
   static unsigned long long optin_mask = 0;

@@ -23,6 +23,9 @@ namespace xtpb {
 struct GemmOperand {
   const double* p;
   long long s_row, s_k, s_outer, s_batch;
+  // 1: the operand lies in a library allocation (which carries >= 256 bytes of slack behind its last element), so a
+  // tile load may read up to 15 elements past the end of a k-row (single-box TMA loads of row-contiguous operands)
+  int library_owned = 1;
 };
 
 struct GemmParams {
@@ -462,8 +465,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint3
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 struct TmaCoords {        // per-operand multipliers: 0 when the tensor map has no outer / batch dimension
   int a_outer, a_batch, b_outer, b_batch;
+  int a_mc5, b_mc5;       // row-contiguous operand described by the 5-D map (one box per tile)
 };
 
 template <typename Cfg, int BM, int BN, int WM, int WN, bool A_KC, bool B_KC, int STAGES, bool HAS_D>
@@ -523,6 +535,8 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_tma_kernel(const GemmPa
       mbar_arrive_expect_tx(full, Cfg::A_BYTES + Cfg::B_BYTES);
       if (A_KC) {
         tma_load_4d(sA, &mapA, full, l_k0, m0, l_outer * tc.a_outer, batch * tc.a_batch);
+      } else if (tc.a_mc5) {
+        tma_load_5d(sA, &mapA, full, 0, l_k0, m0 >> 4, l_outer * tc.a_outer, batch * tc.a_batch);
       } else {
 #pragma unroll
         for (int g = 0; g < BM / 16; ++g)
@@ -530,6 +544,8 @@ __global__ void __launch_bounds__(Cfg::THREADS) contract_tma_kernel(const GemmPa
       }
       if (B_KC) {
         tma_load_4d(sB, &mapB, full, l_k0, n0, l_outer * tc.b_outer, batch * tc.b_batch);
+      } else if (tc.b_mc5) {
+        tma_load_5d(sB, &mapB, full, 0, l_k0, n0 >> 4, l_outer * tc.b_outer, batch * tc.b_batch);
       } else {
 #pragma unroll
         for (int g = 0; g < BN / 16; ++g)

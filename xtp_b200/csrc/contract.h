@@ -27,6 +27,7 @@ inline GemmOperand op_k_contig(const double* p, long long ld) { return GemmOpera
 
 extern std::atomic<long long> g_launch_count;       // kernels launched by this library (bench.py's gpu_launches)
 extern std::atomic<long long> g_tma_launch_count;   // of which contraction launches on the TMA instance
+extern std::atomic<long long> g_tma5d_launch_count; // of which with a single-box (5-D map) row-contiguous operand
 
 // ---- in-library kernel timing (bench.py's roofline object): CUDA-event pairs on the launching stream around
 // every launch of a tagged kernel family; summed per tag.  Off by default (no events recorded).

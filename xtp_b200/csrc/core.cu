@@ -47,6 +47,8 @@ void flush_block_cache_locked() {
 }
 }  // namespace
 
+constexpr size_t kAllocSlack = 256;
+
 void* device_alloc(size_t bytes) {
   const auto t0 = std::chrono::steady_clock::now();
   void* p = nullptr;
@@ -61,12 +63,14 @@ void* device_alloc(size_t bytes) {
     }
   }
   if (!p) {
-    cudaError_t err = cudaMalloc(&p, bytes);
+    // kAllocSlack bytes behind every block: single-box TMA loads of row-contiguous operands may read up to 15 doubles
+    // past the last element of an operand (contract.cu: make_tensor_map_mc5)
+    cudaError_t err = cudaMalloc(&p, bytes + kAllocSlack);
     if (err == cudaErrorMemoryAllocation && !g_block_cache.empty()) {
       cudaGetLastError();                       // clear the sticky error, give the cached blocks back, try again
       cudaDeviceSynchronize();
       flush_block_cache_locked();
-      err = cudaMalloc(&p, bytes);
+      err = cudaMalloc(&p, bytes + kAllocSlack);
     }
     if (err != cudaSuccess)
       throw Error(std::string("CUDA error ") + cudaGetErrorString(err) + " in cudaMalloc of " + std::to_string(bytes) +

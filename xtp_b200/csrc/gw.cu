@@ -1,7 +1,9 @@
 // RPA screening, plasmon-pole model, Sigma_x / Sigma_c and the GW driver (host control, device math).
 // Upstream: xtp/src/libxtp/gwbse/{rpa,ppm,sigma_base,sigma_ppm,gw}.cc.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -11,6 +13,28 @@
 namespace xtpb {
 
 int sigma_ppm_pair_partial_doubles(int n_pairs);
+
+namespace {
+// XTPB_TRACE=1: host seconds per phase (with a stream synchronisation at every mark, so only for diagnosis)
+struct PhaseTrace {
+  Context* ctx;
+  const char* what;
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  PhaseTrace(Context* c, const char* w) : ctx(c), what(w) {
+    const char* e = std::getenv("XTPB_TRACE");
+    on = e && e[0] == '1';
+    if (on) { ctx->sync(); t = std::chrono::steady_clock::now(); }
+  }
+  void mark(const char* label) {
+    if (!on) return;
+    ctx->sync();
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "xtpb trace [%s] %-28s %.4f s\n", what, label, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
+}  // namespace
 
 GW::GW(Context* c, TCMatrix* t, const xtpb_gw_options& o, const double* vxc_host, long long ldv, const double* e,
        long long ne)
@@ -74,7 +98,9 @@ void GW::prepare_ppm() {
   const long long na = tc->naux;
   DBuf eps((size_t)(2 * na * na)), T1((size_t)(na * na)), lam((size_t)na);
   const double w_r = 0.0, w_i = 0.5;    // screening_r, screening_i [Ha]
+  PhaseTrace trace(ctx, "ppm");
   rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_r, 1, false, 0.0, eps.p);
+  trace.mark("eps(0)");
   double* phi = eps.p;                  // eigh overwrites eps(0) with its eigenvectors
   std::vector<double> lambda((size_t)na);
   // the eigensolver of eps(0) (latency-bound, replicated on every rank) runs on the helper stream underneath the
@@ -84,7 +110,9 @@ void GW::prepare_ppm() {
     tc->metric_prefetch_join();         // (a prefetch nobody consumed would still own the helper stream)
     ctx->eigh_async_begin((int)na, phi, na, lam.p, lambda.data());
     rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
+    trace.mark("eps(0.5i) under eigh");
     ctx->eigh_async_join();
+    trace.mark("eigh join (exposed)");
   } else {
     rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
     ctx->eigh((int)na, phi, na, lam.p);
@@ -104,7 +132,9 @@ void GW::prepare_ppm() {
   h.C = ortho; h.c_sm = 1; h.c_sn = na;
   h.M = h.N = h.K = (int)na; h.n_outer = 1; h.n_batch = 1; h.alpha = 1.0; h.lower = 1;
   contract(h, ctx->ws, ctx->stream);
+  trace.mark("phi^T eps phi");
   ctx->spd_inverse((int)na, ortho, na);
+  trace.mark("spd inverse");
   k_extract_diagonal(ortho, (int)na, na, lam.p, ctx->stream);
   std::vector<double> inv_diag((size_t)na);
   ctx->d2h(inv_diag.data(), lam.p, (size_t)na);
@@ -132,6 +162,7 @@ void GW::prepare_ppm() {
   ctx->h2d(ppm_freq_dev.p, ppm_freq.data(), (size_t)na);
   ctx->h2d(ppm_fac_dev.p, fac.data(), (size_t)na);
   tc->rotate(phi, na);
+  trace.mark("tensor rotation");
   // the tensor now lives in the eigenbasis of eps(0) at these energies (see TCMatrix::Eps0Basis)
   tc->eps0.valid = true;
   tc->eps0.energies = rpa_energies;
@@ -428,7 +459,9 @@ std::vector<double> GW::solve_qp(const std::vector<double>& frequencies) {
     const long long steps = opt.qp_grid_steps;
     const double range = opt.qp_grid_spacing * double(steps - 1) / 2.0;
     std::vector<double> sig;
+    PhaseTrace trace(ctx, "qp");
     grid_scan(frequencies, sig);
+    trace.mark("grid scan");
     struct Bracket { long long level; double lo, flo, hi, fhi, root; bool done; };
     std::vector<Bracket> br;
     for (long long l = 0; l < q; ++l) {
@@ -523,6 +556,7 @@ std::vector<double> GW::solve_qp(const std::vector<double>& frequencies) {
         }
       }
     }
+    trace.mark("bisection");
     if (!br.empty()) {   // choose the root with the smallest |dSigma/dw - 1| (largest pole weight)
       std::vector<long long> lv(br.size());
       std::vector<double> fr(br.size()), val(br.size()), der(br.size());

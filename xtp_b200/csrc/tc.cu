@@ -111,6 +111,7 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
     GemmParams g{};
     // W(mu, m) = sum_nu T(mu,nu) Cm(nu,m):   A(row mu, k nu) = T[nu + mu*ld]  (T symmetric)
     g.A = GemmOperand{ao + p * ld_ao * n_basis, ld_ao, 1, 0, ld_ao * n_basis};
+    g.A.library_owned = 0;        // may be the caller's device memory (xtpb_tc_fill_block_dev)
     g.B = GemmOperand{Cm.p, ldc, 1, 0, 0};
     g.C = W; g.c_sm = 1; g.c_sn = ldw; g.c_batch = wslice;
     g.M = (int)n_basis; g.N = (int)mtotal; g.K = (int)n_basis; g.n_outer = 1; g.n_batch = (int)cnt;
