@@ -129,12 +129,20 @@ int xtpb_tc_multiply_right_with_aux_matrix(xtpb_tc* tc, const double* A_host, xt
  * MultiplyRightWithAuxMatrix.  S_host may be NULL (orthonormal aux basis). */
 int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
                                  xtpb_index lds, double etol, xtpb_index* removed_functions);
-/* Optional: start the first eigendecomposition of that step (of S when given, else of V) on a helper thread, stream
- * and cuSOLVER handle NOW, so that it runs underneath the xtpb_tc_fill_* calls that follow (the two halves of
- * TCMatrix_gwbse::Fill have independent inputs).  The same pointers must then be passed to
- * xtpb_tc_apply_coulomb_metric, which joins the helper; the host matrices must stay valid until it returns. */
+/* Optional hint, given BEFORE the xtpb_tc_fill_* calls: the matrices xtpb_tc_apply_coulomb_metric will receive (the two
+ * halves of TCMatrix_gwbse::Fill have independent inputs).  The same pointers must then be passed to
+ * xtpb_tc_apply_coulomb_metric; the host matrices must stay valid until it returns.  With XTPB_METRIC_CHOLESKY=0 (or
+ * XTPB_LAZY_METRIC=0) the first eigendecomposition of the metric step is started on a helper thread / stream at once,
+ * underneath the fill; otherwise nothing is started (see xtpb_tc_metric_path_info). */
 int xtpb_tc_coulomb_metric_begin(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
                                  xtpb_index lds);
+/* How xtpb_tc_apply_coulomb_metric obtained its factor R (R R^T = V^-1) so far on this tensor.  eigensolver: the
+ * reference's construction, S^-1/2 (S^-1/2 V S^-1/2)^-1/2 with eigenvalues below etol dropped.  cholesky: when two
+ * Cholesky factorisations prove that S - etol and V - etol S are positive definite (no function would be removed),
+ * R = U^-1 from V = U^T U: epsilon, the plasmon-pole-rotated tensor, Sigma and the BSE are the same for every such R,
+ * and if the metric-rotated tensor itself is read before the next rotation the symmetric factor is built then (counted
+ * as an eigensolver call).  Either pointer may be NULL. */
+int xtpb_tc_metric_path_info(xtpb_tc* tc, xtpb_index* cholesky_calls, xtpb_index* eigensolver_calls);
 
 /* ---- RPA (upstream xtp/src/libxtp/gwbse/rpa.cc) ---- */
 /* RPA::calculate_epsilon_i / calculate_epsilon_r for n_omega frequencies in one call.

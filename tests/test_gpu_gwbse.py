@@ -105,6 +105,65 @@ def test_coulomb_metric_with_overlap_and_removed_functions(ctx, prob):
     assert rel(tc.get_raw(), ref.M) < 1e-8
 
 
+def test_coulomb_metric_cholesky_path(ctx, prob, monkeypatch):
+    """When no function would be removed the metric factor comes from a Cholesky factorisation (R = U^-1, R R^T = V^-1)
+    and stays pending: epsilon and the G0W0 energies do not depend on which factor is used, and reading the tensor
+    builds the reference's symmetric factor after all.  A matrix with eigenvalues below etol takes the eigensolver."""
+    from xtp_b200 import api
+    sz = prob["sizes"]
+    rng = np.random.default_rng(15)
+    B = rng.standard_normal((sz.n_aux, sz.n_aux))
+    S = B @ B.T / sz.n_aux + 0.5 * np.eye(sz.n_aux)
+    for overlap in (None, S):
+        tc = gpu_tc(ctx, prob)
+        assert tc.apply_coulomb_metric(prob["aux_coulomb"], overlap) == 0
+        info = tc.metric_path_info()
+        assert info == {"cholesky_calls": 1, "eigensolver_calls": 0}
+        # epsilon from the pending (triangular) factor: same spectrum, and the same matrix up to the orthogonal factor
+        e = prob["energies"][sz.rpamin:sz.rpamax + 1]
+        rpa_c = api.RPA(tc)
+        rpa_c.configure(sz.homo, sz.rpamin, sz.rpamax)
+        rpa_c.setRPAInputEnergies(e)
+        eps_c = rpa_c.calculate_epsilon_i(0.5)
+        assert tc.metric_path_info()["eigensolver_calls"] == 0          # epsilon does not need the symmetric factor
+        ref = copy.deepcopy(prob["tc_o"])
+        R, _ = orc.Pseudo_InvSqrt_GWBSE(prob["aux_coulomb"], overlap)
+        ref.MultiplyRightWithAuxMatrix(R)
+        rpa_o = orc.RPA(ref)
+        rpa_o.configure(sz.homo, sz.rpamin, sz.rpamax)
+        rpa_o.setRPAInputEnergies(e)
+        eps_o = rpa_o.calculate_epsilon_i(0.5)
+        np.testing.assert_allclose(np.linalg.eigvalsh(eps_c), np.linalg.eigvalsh(eps_o), rtol=1e-9, atol=1e-11)
+        # reading the tensor flushes: the symmetric factor is built now and the observable tensor is the reference's
+        assert rel(tc.get_raw(), ref.M) < 1e-9
+        assert tc.metric_path_info() == {"cholesky_calls": 1, "eigensolver_calls": 1}
+    # G0W0 + BSE through both factors
+    out = {}
+    for mode in ("1", "0"):
+        tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+        tc.Fill3cMO(prob["ao3c"], prob["C"])
+        if mode == "1":
+            tc.apply_coulomb_metric(prob["aux_coulomb"])
+            assert tc.metric_path_info()["cholesky_calls"] == 1
+        else:
+            tc.apply_coulomb_metric(prob["aux_coulomb"])
+            tc.get_raw()                                   # forces the symmetric factor onto the tensor
+            assert tc.metric_path_info()["eigensolver_calls"] == 1
+        gw = api.GW(ctx, tc, prob["vxc"], prob["energies"])
+        gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax))
+        gw.CalculateGWPerturbation()
+        out[mode] = gw.getGWAResults()
+        if mode == "1":
+            assert tc.metric_path_info()["eigensolver_calls"] == 0      # folded into the PPM rotation, never built
+    np.testing.assert_allclose(out["1"], out["0"], rtol=0, atol=1e-8)
+    # eigenvalues below etol: the Cholesky test must fail and the eigensolver path must remove them
+    w, U = np.linalg.eigh(prob["aux_coulomb"])
+    w[:2] = 1e-9
+    tc = gpu_tc(ctx, prob)
+    assert tc.apply_coulomb_metric((U * w) @ U.T) == 2
+    assert tc.metric_path_info() == {"cholesky_calls": 0, "eigensolver_calls": 1}
+
+
 def test_multiply_right_with_aux_matrix(ctx, prob):
     sz = prob["sizes"]
     R = np.random.default_rng(2).standard_normal((sz.n_aux, sz.n_aux))

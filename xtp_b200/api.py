@@ -257,9 +257,16 @@ class TCMatrix_gwbse:
         self.Fill3cMO(ao3c, C_mo)
         self.removedfunctions = self.apply_coulomb_metric(aux_coulomb, aux_overlap, etol)
 
+    def metric_path_info(self):
+        """How apply_coulomb_metric obtained its factor so far (xtpb_tc_metric_path_info)."""
+        ch, ei = idx(0), idx(0)
+        check(_lib.lib().xtpb_tc_metric_path_info(self._h, C.byref(ch), C.byref(ei)))
+        return {"cholesky_calls": int(ch.value), "eigensolver_calls": int(ei.value)}
+
     def coulomb_metric_begin(self, V, S=None):
-        """Start the metric's first eigendecomposition on the library's helper thread (xtpb_tc_coulomb_metric_begin);
-        the matching apply_coulomb_metric(V, S) call joins it.  The column-major copies are kept alive here."""
+        """Announce the metric matrices before the fill (xtpb_tc_coulomb_metric_begin: on the eigensolver path the first
+        decomposition starts underneath the fill); the matching apply_coulomb_metric(V, S) call consumes the hint.  The
+        column-major copies are kept alive here."""
         Vf = _f(V)
         Sf = _f(S) if S is not None else None
         self._metric_inputs = (V, S, Vf, Sf)

@@ -133,6 +133,7 @@ int xtpb_tc_set_raw_dev(xtpb_tc* tc, const double* M_dev) {
   XTPB_REQUIRE(t.world == 1, "xtpb_tc_set_raw_dev: single rank only (use xtpb_tc_set_raw with several ranks)");
   XTPB_REQUIRE(M_dev != nullptr, "null pointer");
   t.pending = false;
+  t.metric_src = TCMatrix::MetricSources{};
   t.eps0.valid = false;
   ++t.generation;
   XTPB_CUDA(cudaMemcpy2DAsync(t.M.p, t.ldn * 8, M_dev, t.ntotal * 8, t.ntotal * 8, t.mtotal * t.naux,
@@ -210,84 +211,21 @@ int xtpb_tc_coulomb_metric_begin(xtpb_tc* tc, const double* V_host, xtpb_index l
                                  xtpb_index lds) {
   XTPB_API_BEGIN
   XTPB_REQUIRE(tc && V_host, "null pointer");
-  if (S_host) tc->impl.metric_prefetch_begin(S_host, lds, true);
-  else tc->impl.metric_prefetch_begin(V_host, ldv, false);
+  tc->impl.metric_hint(V_host, ldv, S_host, lds);
+  XTPB_API_END
+}
+int xtpb_tc_metric_path_info(xtpb_tc* tc, xtpb_index* cholesky_calls, xtpb_index* eigensolver_calls) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(tc, "null pointer");
+  if (cholesky_calls) *cholesky_calls = tc->impl.metric_cholesky_count;
+  if (eigensolver_calls) *eigensolver_calls = tc->impl.metric_eig_count;
   XTPB_API_END
 }
 int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
                                  xtpb_index lds, double etol, xtpb_index* removed_functions) {
   XTPB_API_BEGIN
-  TCMatrix& t = tc->impl;
-  Context* ctx = t.ctx;
-  const long long na = t.naux;
-  long long removed = 0;
-  DBuf A((size_t)(na * na)), B((size_t)(na * na)), Cc((size_t)(na * na)), w((size_t)na), Ssqrt;
-  std::vector<double> lam((size_t)na), sc((size_t)na);
-  auto mm = [&](const double* X, bool, const double* Yp, double* Z) {
-    // Z = X * Y for symmetric X (read through its K-contiguous view), Y column-major
-    GemmParams g{};
-    g.A = op_k_contig(X, na);
-    g.B = op_k_contig(Yp, na);
-    g.C = Z; g.c_sm = 1; g.c_sn = na;
-    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
-    contract(g, ctx->ws, ctx->stream);
-  };
-  // the first decomposition may have been started before Fill3cMO (xtpb_tc_coulomb_metric_begin)
-  bool prefetched = t.metric_prefetch_join();
-  if (prefetched) {
-    XTPB_REQUIRE(t.prefetch.of_overlap == (S_host != nullptr) && t.prefetch.src == (S_host ? S_host : V_host),
-                 "xtpb_tc_coulomb_metric_begin was given different matrices than xtpb_tc_apply_coulomb_metric");
-  }
-  // f(X) = U diag(1/sqrt(lambda) | 0) U^T for symmetric X (eigenvalues < etol dropped)
-  auto inv_sqrt = [&](double* X, double* out) {
-    if (prefetched) {                            // eigenvectors / eigenvalues are already there
-      prefetched = false;
-      XTPB_CUDA(cudaMemcpyAsync(X, t.prefetch.U.p, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-      lam = t.prefetch.lam;
-    } else {
-      ctx->eigh((int)na, X, na, w.p);            // X <- U
-      ctx->d2h(lam.data(), w.p, (size_t)na);
-    }
-    for (long long i = 0; i < na; ++i) {
-      if (lam[i] < etol) { ++removed; sc[i] = 0.0; } else sc[i] = 1.0 / std::sqrt(lam[i]);
-    }
-    ctx->h2d(w.p, sc.data(), (size_t)na);
-    XTPB_CUDA(cudaMemcpyAsync(B.p, X, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_scale_columns(B.p, (int)na, (int)na, na, w.p, ctx->stream);   // B = U diag(s)
-    // out = B U^T : out(i,j) = sum_k B(i,k) U(j,k)  -> A rows-contig (B), B-operand rows-contig (U)
-    GemmParams g{};
-    g.A = op_rows_contig(B.p, na);
-    g.B = op_rows_contig(X, na);
-    g.C = out; g.c_sm = 1; g.c_sn = na;
-    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
-    contract(g, ctx->ws, ctx->stream);
-  };
-  if (S_host || !prefetched) ctx->h2d_2d(A.p, na, V_host, ldv, na, na);
-  if (S_host) {
-    Ssqrt.alloc((size_t)(na * na));
-    DBuf S((size_t)(na * na));
-    if (!prefetched) ctx->h2d_2d(S.p, na, S_host, lds, na, na);
-    inv_sqrt(S.p, Ssqrt.p);
-    // ortho = Ssqrt V Ssqrt  (all symmetric)
-    mm(Ssqrt.p, true, A.p, Cc.p);
-    // Cc is not symmetric: (Cc * Ssqrt)(i,j) = sum_k Cc(i,k) Ssqrt(k,j) -> rows-contiguous view of Cc
-    GemmParams g{};
-    g.A = op_rows_contig(Cc.p, na);
-    g.B = op_k_contig(Ssqrt.p, na);
-    g.C = A.p; g.c_sm = 1; g.c_sn = na;
-    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
-    contract(g, ctx->ws, ctx->stream);
-  }
-  DBuf Vm1((size_t)(na * na));
-  inv_sqrt(A.p, Vm1.p);
-  double* R = Vm1.p;
-  if (S_host) {
-    // R = S^-1/2 (S^-1/2 V S^-1/2)^-1/2  ("((S-1/2 V S-1/2)-1/2 S-1/2)T" in upstream's words): R R^T = V^-1
-    mm(Ssqrt.p, true, Vm1.p, Cc.p);      // Cc = Ssqrt * Vm1
-    R = Cc.p;
-  }
-  t.set_pending(R, na);       // deferred: folded into the next full rotation (see TCMatrix::set_pending)
-  ctx->sync();
+  XTPB_REQUIRE(tc && V_host, "null pointer");
+  const long long removed = tc->impl.apply_coulomb_metric(V_host, ldv, S_host, lds, etol);
   if (removed_functions) *removed_functions = removed;
   XTPB_API_END
 }

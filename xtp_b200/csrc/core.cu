@@ -4,6 +4,7 @@
 #include <mutex>
 #include <map>
 #include <utility>
+#include <vector>
 
 #include "internal.h"
 
@@ -215,6 +216,39 @@ void Context::spd_inverse(int n, double* A, long long lda) {
   XTPB_SOLVER(cusolverDnDpotri(solver, CUBLAS_FILL_MODE_LOWER, n, A, (int)lda, solver_work.p, lwork2, dev_info));
   solver_end();
   symmetrize_from_lower(A, n, lda, 0.0, stream);
+}
+
+bool Context::cholesky(int n, double* A, long long lda, bool upper) {
+  const cublasFillMode_t uplo = upper ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
+  int lwork = 0;
+  XTPB_SOLVER(cusolverDnDpotrf_bufferSize(solver, uplo, n, A, (int)lda, &lwork));
+  solver_work.ensure((size_t)lwork);
+  XTPB_CUDA(cudaEventRecord(ev0, stream));
+  solver_prof_slot = prof_begin(PROF_SOLVER, 0.0, stream);
+  XTPB_SOLVER(cusolverDnDpotrf(solver, uplo, n, A, (int)lda, solver_work.p, lwork, dev_info));
+  prof_end(solver_prof_slot, stream);
+  XTPB_CUDA(cudaEventRecord(ev1, stream));
+  XTPB_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0;
+  XTPB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  solver_seconds += ms * 1e-3;
+  int info = 0;
+  XTPB_CUDA(cudaMemcpy(&info, dev_info, sizeof(int), cudaMemcpyDeviceToHost));
+  XTPB_REQUIRE(info >= 0, "cuSOLVER potrf: illegal argument");
+  return info == 0;
+}
+
+void Context::tri_inverse(int n, double* L, long long lda, bool upper) {
+  const cublasFillMode_t uplo = upper ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
+  size_t dev_bytes = 0, host_bytes = 0;
+  XTPB_SOLVER(cusolverDnXtrtri_bufferSize(solver, uplo, CUBLAS_DIAG_NON_UNIT, n, CUDA_R_64F, L, lda,
+                                          &dev_bytes, &host_bytes));
+  solver_work.ensure((dev_bytes + 7) / 8 + 1);
+  std::vector<char> host_work(host_bytes + 1);
+  solver_begin();
+  XTPB_SOLVER(cusolverDnXtrtri(solver, uplo, CUBLAS_DIAG_NON_UNIT, n, CUDA_R_64F, L, lda,
+                               solver_work.p, dev_bytes, host_work.data(), host_bytes, dev_info));
+  solver_end();
 }
 
 void Context::general_inverse(int n, double* A, long long lda, double* Ainv, long long ldi) {

@@ -118,20 +118,9 @@ void GW::prepare_ppm() {
     ctx->eigh((int)na, phi, na, lam.p);
     ctx->d2h(lambda.data(), lam.p, (size_t)na);
   }
-  // ortho = phi^T eps(i 0.5) phi
-  GemmParams g{};
-  g.A = op_k_contig(eps.p + na * na, na);          // eps symmetric
-  g.B = op_k_contig(phi, na);
-  g.C = T1.p; g.c_sm = 1; g.c_sn = na;
-  g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
-  contract(g, ctx->ws, ctx->stream);
+  // ortho = phi^T eps(i 0.5) phi (in place; split over the ranks when there are several)
   double* ortho = eps.p + na * na;
-  GemmParams h{};
-  h.A = op_k_contig(phi, na);
-  h.B = op_k_contig(T1.p, na);
-  h.C = ortho; h.c_sm = 1; h.c_sn = na;
-  h.M = h.N = h.K = (int)na; h.n_outer = 1; h.n_batch = 1; h.alpha = 1.0; h.lower = 1;
-  contract(h, ctx->ws, ctx->stream);
+  congruence_sym(ctx, ortho, phi, T1.p, na);
   trace.mark("phi^T eps phi");
   ctx->spd_inverse((int)na, ortho, na);
   trace.mark("spd inverse");

@@ -70,6 +70,8 @@ struct Context {
   // dense solver calls (cuSOLVER; timed separately from the contraction kernels)
   void eigh(int n, double* A, long long lda, double* w);            // A <- eigenvectors (ascending w)
   void spd_inverse(int n, double* A, long long lda);                // in place, full symmetric output
+  bool cholesky(int n, double* A, long long lda, bool upper);       // A <- factor in that triangle; false: not pos. def.
+  void tri_inverse(int n, double* T, long long lda, bool upper);    // that triangle <- its inverse (rest untouched)
   void general_inverse(int n, double* A, long long lda, double* Ainv, long long ldi);   // A destroyed
   void lu_solve_vector(int n, double* A, long long lda, double* x);                     // x <- A^-1 x, A destroyed
   void solver_begin();
@@ -108,6 +110,7 @@ void k_set_identity(double* A, int n, long long ld, cudaStream_t s);
 void k_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s);
 void k_scale_columns(double* A, int rows, int cols, long long ld, const double* scale, cudaStream_t s);  // A(:,j)*=scale[j]
 void k_extract_diagonal(const double* A, int n, long long ld, double* out, cudaStream_t s);
+void k_zero_strict_lower(double* A, int n, long long ld, cudaStream_t s);   // A(i,j) = 0 for i > j
 void k_copy_2d(double* dst, long long ldd, const double* src, long long lds, int rows, long long cols, cudaStream_t s);
 void k_scale(double* x, long long n, double a, cudaStream_t s);
 void k_axpby(double* y, const double* x, long long n, double a, double b, cudaStream_t s);   // y = a*x + b*y
@@ -275,6 +278,27 @@ struct TCMatrix {
   } prefetch;
   void metric_prefetch_begin(const double* X_host, long long ldx, bool of_overlap);
   bool metric_prefetch_join();      // true when a prefetched decomposition is available in prefetch.U / lam
+  // AOCoulomb::Pseudo_InvSqrt_GWBSE + MultiplyRightWithAuxMatrix (second half of TCMatrix_gwbse::Fill).  Returns the
+  // number of removed functions.  The factor R (R R^T = V^-1 on the kept space) becomes the pending right factor.
+  //  * eigen path: R = [S^-1/2] (S^-1/2 V S^-1/2)^-1/2 from one or two N_aux eigendecompositions, eigenvalues below
+  //    etol dropped -- the reference's construction;
+  //  * Cholesky path (default whenever it is exact): when S - etol and V - etol S (V - etol without an overlap) are
+  //    positive definite -- two Cholesky factorisations decide that rigorously -- no function is removed by either
+  //    decomposition and ANY R with R R^T = V^-1 gives the same epsilon spectrum, the same PPM-rotated tensor
+  //    M R Phi (Phi absorbs the orthogonal factor between two choices of R) and the same Sigma_x; R = L^-T from
+  //    V = L L^T replaces ~0.2 s of latency-bound eigensolver per decomposition by ~0.04 s of Cholesky work.  What the
+  //    host can observe is unchanged: if anything needs the metric-rotated tensor itself (flush()), the symmetric
+  //    factor is computed then, from retained copies of V and S.  XTPB_METRIC_CHOLESKY=0 disables the path.
+  long long apply_coulomb_metric(const double* V_host, long long ldv, const double* S_host, long long lds, double etol);
+  void metric_hint(const double* V_host, long long ldv, const double* S_host, long long lds);
+  long long metric_factor_eig(double* V_dev, double* S_dev, double etol, bool prefetched, DBuf& R_out);
+  struct MetricSources {            // Cholesky path: what flush() needs to build the symmetric factor after all
+    bool cholesky = false, has_S = false;
+    DBuf V, S;
+    double etol = 0.0;
+  } metric_src;
+  struct MetricHint { bool given = false; const double* V = nullptr; const double* S = nullptr; } hint;
+  long long metric_cholesky_count = 0, metric_eig_count = 0;   // which path apply_coulomb_metric took (tests, reports)
   // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]   (window rotation into a caller-owned buffer)
   void rotate_window(double* dst, long long dst_ld, long long dst_slab, int m0, int mcnt, int n0, int ncnt,
                      const double* R_dev, long long ldr);
@@ -286,6 +310,10 @@ struct TCMatrix {
 // be used; the caller inverts / consumes matrix w on its owner (Sigma_CDA's quadrature nodes and residue poles).
 void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
                      int n_omega, bool imag, double gamma_extra, double* out_dev, int owner_shift = -1);
+
+// E <- R^T E R (E symmetric, full storage in; lower triangle out on one rank, full matrix out when the product is
+// split over the ranks); T: n x n scratch.  tc.cu.
+void congruence_sym(Context* ctx, double* E, const double* R, double* T, long long n);
 
 // ---------------------------------------------------------------- GW
 struct GW {

@@ -166,6 +166,14 @@ __global__ void scale_columns_kernel(double* A, int rows, int cols, long long ld
     A[r + c * ld] *= scale[c];
   }
 }
+__global__ void zero_strict_lower_kernel(double* A, int n, long long ld) {
+  const long long total = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % n), j = (int)(idx / n);
+    if (i > j) A[i + (long long)j * ld] = 0.0;
+  }
+}
 __global__ void extract_diagonal_kernel(const double* A, int n, long long ld, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = A[i + i * ld];
@@ -1040,6 +1048,10 @@ void k_add_diagonal(double* A, int n, long long ld, double v, cudaStream_t s) {
 }
 void k_scale_columns(double* A, int rows, int cols, long long ld, const double* scale, cudaStream_t s) {
   scale_columns_kernel<<<blocks_for((long long)rows * cols, 256, 4096), 256, 0, s>>>(A, rows, cols, ld, scale);
+  LAUNCH_CHECK();
+}
+void k_zero_strict_lower(double* A, int n, long long ld, cudaStream_t s) {
+  zero_strict_lower_kernel<<<blocks_for((long long)n * n, 256, 8192), 256, 0, s>>>(A, n, ld);
   LAUNCH_CHECK();
 }
 void k_extract_diagonal(const double* A, int n, long long ld, double* out, cudaStream_t s) {

@@ -32,6 +32,7 @@ TCMatrix::~TCMatrix() {
 
 void TCMatrix::set_raw(const double* host) {
   pending = false;
+  metric_src = MetricSources{};
   eps0.valid = false;
   ++generation;
   if (world == 1) {
@@ -73,6 +74,7 @@ const double* TCMatrix::local_energies(const double* e_glob_dev, DBuf& tmp) {
 void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host) {
   XTPB_REQUIRE(nb > 0 && ldc_host >= nb, "bad MO coefficient matrix");
   pending = false;            // a new fill starts from the un-rotated tensor
+  metric_src = MetricSources{};
   eps0.valid = false;
   ++generation;
   n_basis = nb;
@@ -85,6 +87,12 @@ void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host
   // local second-index columns: host columns nmin + rank, nmin + rank + world, ... (pitch world*ldc_host)
   ctx->h2d_2d(Cn.p, ldc, C_host + (nmin + rank) * ldc_host, ldc_host * world, nb, ntotal);
   ctx->sync();
+}
+
+// XTPB_SHARD_DENSE=0: every rank forms the replicated N_aux^3 products (metric / PPM sandwiches, folded rotation) whole
+static bool shard_dense_products() {
+  static const bool on = [] { const char* e = getenv("XTPB_SHARD_DENSE"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 static bool fill_merge_batches() {
@@ -415,8 +423,159 @@ void TCMatrix::set_pending(const double* R_dev, long long ldr) {
 
 void TCMatrix::flush() {
   if (!pending) return;
+  if (metric_src.cholesky) {
+    // somebody needs the metric-rotated tensor itself: build the reference's symmetric factor after all, from the
+    // retained matrices (the Cholesky tests have shown that it removes no function)
+    DBuf R;
+    metric_factor_eig(metric_src.V.p, metric_src.has_S ? metric_src.S.p : nullptr, metric_src.etol, false, R);
+    XTPB_CUDA(cudaMemcpyAsync(pendR.p, R.p, (size_t)(naux * naux) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->sync();
+    metric_src = MetricSources{};
+  }
   pending = false;
   rotate(pendR.p, naux);
+}
+
+void TCMatrix::metric_hint(const double* V_host, long long ldv, const double* S_host, long long lds) {
+  static const bool chol = [] { const char* e = getenv("XTPB_METRIC_CHOLESKY"); return !(e && e[0] == '0'); }();
+  static const bool lazy = [] { const char* e = getenv("XTPB_LAZY_METRIC"); return !(e && e[0] == '0'); }();
+  hint.given = true;
+  hint.V = V_host;
+  hint.S = S_host;
+  // eigen path only: start its first eigendecomposition underneath the fill.  With the Cholesky path the decision
+  // needs etol (known at apply time) and ~0.04 s of factorisations, so nothing is started here.
+  if (!(chol && lazy)) {
+    if (S_host) metric_prefetch_begin(S_host, lds, true);
+    else metric_prefetch_begin(V_host, ldv, false);
+  }
+}
+
+// f(X) = U diag(1/sqrt(lambda) | 0) U^T for symmetric X, eigenvalues < etol dropped; the reference's construction
+long long TCMatrix::metric_factor_eig(double* A, double* S, double etol, bool prefetched, DBuf& R_out) {
+  const long long na = naux;
+  long long removed = 0;
+  DBuf B((size_t)(na * na)), Cc((size_t)(na * na)), w((size_t)na), Ssqrt, Vm1((size_t)(na * na));
+  std::vector<double> lam((size_t)na), sc((size_t)na);
+  auto mm = [&](const double* X, const double* Yp, double* Z) {
+    // Z = X * Y for symmetric X (read through its K-contiguous view), Y column-major
+    GemmParams g{};
+    g.A = op_k_contig(X, na);
+    g.B = op_k_contig(Yp, na);
+    g.C = Z; g.c_sm = 1; g.c_sn = na;
+    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+  };
+  auto inv_sqrt = [&](double* X, double* out) {
+    if (prefetched) {                            // eigenvectors / eigenvalues are already there
+      prefetched = false;
+      XTPB_CUDA(cudaMemcpyAsync(X, prefetch.U.p, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      lam = prefetch.lam;
+    } else {
+      ctx->eigh((int)na, X, na, w.p);            // X <- U
+      ctx->d2h(lam.data(), w.p, (size_t)na);
+    }
+    for (long long i = 0; i < na; ++i) {
+      if (lam[i] < etol) { ++removed; sc[i] = 0.0; } else sc[i] = 1.0 / std::sqrt(lam[i]);
+    }
+    ctx->h2d(w.p, sc.data(), (size_t)na);
+    XTPB_CUDA(cudaMemcpyAsync(B.p, X, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_scale_columns(B.p, (int)na, (int)na, na, w.p, ctx->stream);   // B = U diag(s)
+    // out = B U^T : out(i,j) = sum_k B(i,k) U(j,k)  -> A rows-contig (B), B-operand rows-contig (U)
+    GemmParams g{};
+    g.A = op_rows_contig(B.p, na);
+    g.B = op_rows_contig(X, na);
+    g.C = out; g.c_sm = 1; g.c_sn = na;
+    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+  };
+  if (S) {
+    Ssqrt.alloc((size_t)(na * na));
+    inv_sqrt(S, Ssqrt.p);
+    // ortho = Ssqrt V Ssqrt  (all symmetric)
+    mm(Ssqrt.p, A, Cc.p);
+    // Cc is not symmetric: (Cc * Ssqrt)(i,j) = sum_k Cc(i,k) Ssqrt(k,j) -> rows-contiguous view of Cc
+    GemmParams g{};
+    g.A = op_rows_contig(Cc.p, na);
+    g.B = op_k_contig(Ssqrt.p, na);
+    g.C = A; g.c_sm = 1; g.c_sn = na;
+    g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    contract(g, ctx->ws, ctx->stream);
+  }
+  inv_sqrt(A, Vm1.p);
+  if (S) {
+    // R = S^-1/2 (S^-1/2 V S^-1/2)^-1/2  ("((S-1/2 V S-1/2)-1/2 S-1/2)T" in upstream's words): R R^T = V^-1
+    mm(Ssqrt.p, Vm1.p, Cc.p);      // Cc = Ssqrt * Vm1
+    R_out = std::move(Cc);
+  } else {
+    R_out = std::move(Vm1);
+  }
+  ctx->sync();
+  ++metric_eig_count;
+  return removed;
+}
+
+long long TCMatrix::apply_coulomb_metric(const double* V_host, long long ldv, const double* S_host, long long lds,
+                                         double etol) {
+  static const bool chol = [] { const char* e = getenv("XTPB_METRIC_CHOLESKY"); return !(e && e[0] == '0'); }();
+  static const bool lazy = [] { const char* e = getenv("XTPB_LAZY_METRIC"); return !(e && e[0] == '0'); }();
+  const long long na = naux;
+  if (hint.given) {
+    const bool same = hint.V == V_host && hint.S == S_host;
+    hint = MetricHint{};
+    if (!same) {
+      metric_prefetch_join();
+      throw Error("xtpb: xtpb_tc_coulomb_metric_begin was given different matrices than xtpb_tc_apply_coulomb_metric");
+    }
+  }
+  const bool prefetched = metric_prefetch_join();
+  flush();                      // an earlier pending factor reaches the tensor in its reference (symmetric) form
+  metric_src = MetricSources{};
+  DBuf A((size_t)(na * na)), S;
+  // a prefetched decomposition already holds the eigenvectors of its matrix on the device
+  if (S_host || !prefetched) ctx->h2d_2d(A.p, na, V_host, ldv, na, na);
+  if (S_host) {
+    S.alloc((size_t)(na * na));
+    if (!prefetched) ctx->h2d_2d(S.p, na, S_host, lds, na, na);
+  }
+  if (chol && lazy && !prefetched && etol > 0.0) {
+    // would the reference remove a function?  S - etol > 0 and V - etol S > 0 (V - etol without an overlap), decided
+    // by Cholesky factorisations of copies
+    DBuf T((size_t)(na * na));
+    bool none_removed = true;
+    if (S_host) {
+      XTPB_CUDA(cudaMemcpyAsync(T.p, S.p, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      k_add_diagonal(T.p, (int)na, na, -etol, ctx->stream);
+      none_removed = ctx->cholesky((int)na, T.p, na, false);
+    }
+    if (none_removed) {
+      XTPB_CUDA(cudaMemcpyAsync(T.p, A.p, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (S_host) k_axpby(T.p, S.p, na * na, -etol, 1.0, ctx->stream);
+      else k_add_diagonal(T.p, (int)na, na, -etol, ctx->stream);
+      none_removed = ctx->cholesky((int)na, T.p, na, false);
+    }
+    if (none_removed) {
+      // V = U^T U (upper factor), R = U^-1: R R^T = (U^T U)^-1 = V^-1
+      XTPB_CUDA(cudaMemcpyAsync(T.p, A.p, (size_t)(na * na) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (ctx->cholesky((int)na, T.p, na, true)) {
+        ctx->tri_inverse((int)na, T.p, na, true);
+        k_zero_strict_lower(T.p, (int)na, na, ctx->stream);
+        set_pending(T.p, na);
+        metric_src.cholesky = true;
+        metric_src.has_S = S_host != nullptr;
+        metric_src.etol = etol;
+        metric_src.V = std::move(A);
+        if (S_host) metric_src.S = std::move(S);
+        ctx->sync();
+        ++metric_cholesky_count;
+        return 0;
+      }
+    }
+  }
+  DBuf R;
+  const long long removed = metric_factor_eig(A.p, S_host ? S.p : nullptr, etol, prefetched, R);
+  set_pending(R.p, na);       // deferred: folded into the next full rotation (see TCMatrix::set_pending)
+  ctx->sync();
+  return removed;
 }
 
 void TCMatrix::rotate(const double* R_dev, long long ldr) {
@@ -425,14 +584,27 @@ void TCMatrix::rotate(const double* R_dev, long long ldr) {
   DBuf folded;
   if (pending) {      // M <- M (Rp R): fold the deferred factor into this rotation
     pending = false;
+    metric_src = MetricSources{};   // the folded product is the same for every Rp with Rp Rp^T = V^-1 (see internal.h)
     folded.alloc((size_t)(naux * naux));
     ProfScope prof(PROF_DENSE_AUX);
+    // every rank holds Rp and R: with several ranks each forms a column block of the product, exchanged by one
+    // grouped broadcast (see congruence_sym)
+    const bool split = world > 1 && shard_dense_products() && naux >= 64LL * world;
+    const long long j0 = split ? naux * rank / world : 0, j1 = split ? naux * (rank + 1) / world : naux;
     GemmParams g{};
     g.A = op_rows_contig(pendR.p, naux);
-    g.B = op_k_contig(R_dev, ldr);
-    g.C = folded.p; g.c_sm = 1; g.c_sn = naux;
-    g.M = g.N = g.K = (int)naux; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+    g.B = op_k_contig(R_dev + j0 * ldr, ldr);
+    g.C = folded.p + j0 * naux; g.c_sm = 1; g.c_sn = naux;
+    g.M = g.K = (int)naux; g.N = (int)(j1 - j0); g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
     contract(g, ctx->ws, ctx->stream);
+    if (split) {
+      ctx->group_start();
+      for (int r = 0; r < world; ++r) {
+        const long long a = naux * r / world, b = naux * (r + 1) / world;
+        ctx->bcast(folded.p + a * naux, (size_t)((b - a) * naux), r);
+      }
+      ctx->group_end();
+    }
     R_dev = folded.p;
     ldr = naux;
   }
@@ -446,6 +618,38 @@ void TCMatrix::rotate(const double* R_dev, long long ldr) {
     k_copy_2d(slab_ptr(m), ldn, ctx->scratch_b.p, ldn, (int)ntotal, cnt * naux, ctx->stream);
   }
   if (folded.p) ctx->sync();      // folded is freed on return
+}
+
+// E <- R^T E R for a symmetric E (full storage on entry) and a general R, both n x n with ld = n; T: n x n scratch.
+// One rank: T = E R, then the lower triangle of R^T T (3 n^3 flops; the upper triangle of the result is NOT written).
+// Several ranks hold the same E and R: rank r forms the column block [n r / world, n (r+1) / world) of T and of the
+// full result (4 n^3 / world flops instead of 3 n^3 on every rank) and the blocks are exchanged by one grouped
+// broadcast (n^2 doubles in total); the result is then complete (both triangles) and identical on every rank.
+void congruence_sym(Context* ctx, double* E, const double* R, double* T, long long n) {
+  const int world = ctx->world;
+  const bool split = world > 1 && shard_dense_products() && n >= 64LL * world;
+  const long long j0 = split ? n * ctx->rank / world : 0, j1 = split ? n * (ctx->rank + 1) / world : n;
+  GemmParams g{};
+  g.A = op_k_contig(E, n);                              // E symmetric: E(i,k) = E[k + i n]
+  g.B = op_k_contig(R + j0 * n, n);                     // columns j0..j1 of R
+  g.C = T + j0 * n; g.c_sm = 1; g.c_sn = n;
+  g.M = (int)n; g.N = (int)(j1 - j0); g.K = (int)n; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
+  contract(g, ctx->ws, ctx->stream);
+  GemmParams h{};
+  h.A = op_k_contig(R, n);                              // (R^T)(i,k) = R[k + i n]
+  h.B = op_k_contig(T + j0 * n, n);
+  h.C = E + j0 * n; h.c_sm = 1; h.c_sn = n;
+  h.M = (int)n; h.N = (int)(j1 - j0); h.K = (int)n; h.n_outer = 1; h.n_batch = 1; h.alpha = 1.0;
+  h.lower = split ? 0 : 1;
+  contract(h, ctx->ws, ctx->stream);
+  if (split) {
+    ctx->group_start();
+    for (int r = 0; r < world; ++r) {
+      const long long a = n * r / world, b = n * (r + 1) / world;
+      ctx->bcast(E + a * n, (size_t)((b - a) * n), r);
+    }
+    ctx->group_end();
+  }
 }
 
 // eps(w) = 1 + sum_{m occ} A_m^T diag(d_m(w)) A_m with A_m = M[m](unocc, :)   (upstream RPA::calculate_epsilon)
@@ -498,18 +702,7 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
     for (int w = 0; w < n_omega; ++w) {
       double* E = out_dev + (long long)w * na * na;
       symmetrize_from_lower(E, (int)na, na, 0.0, ctx->stream);
-      GemmParams g{};
-      g.A = op_k_contig(E, na);                      // E symmetric
-      g.B = op_k_contig(tc.pendR.p, na);
-      g.C = T.p; g.c_sm = 1; g.c_sn = na;
-      g.M = g.N = g.K = (int)na; g.n_outer = 1; g.n_batch = 1; g.alpha = 1.0;
-      contract(g, ctx->ws, ctx->stream);
-      GemmParams h{};
-      h.A = op_k_contig(tc.pendR.p, na);
-      h.B = op_k_contig(T.p, na);
-      h.C = E; h.c_sm = 1; h.c_sn = na;
-      h.M = h.N = h.K = (int)na; h.n_outer = 1; h.n_batch = 1; h.alpha = 1.0; h.lower = 1;
-      contract(h, ctx->ws, ctx->stream);
+      congruence_sym(ctx, E, tc.pendR.p, T.p, na);
     }
     ctx->sync();   // T is freed at scope exit
   }
