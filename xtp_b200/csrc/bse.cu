@@ -100,6 +100,9 @@ std::unique_ptr<DBuf> bse_setup_screening(BSE& b, const double* rpa_e, double om
       return nullptr;
     }
   }
+  // the eigenvectors below are tied to the aux basis epsilon is formed in, and the windows are cut from the flushed
+  // tensor: flush first, so that both see the same (reference, symmetric) metric factor
+  tc->flush();
   DBuf e_dev((size_t)rpatotal), lam((size_t)na);
   ctx->h2d(e_dev.p, rpa_e, (size_t)rpatotal);
   auto U = std::make_unique<DBuf>((size_t)(na * na));

@@ -238,6 +238,9 @@ int xtpb_rpa_epsilon(xtpb_tc* tc, const double* energies_host, xtpb_index homo, 
   XTPB_REQUIRE(rpamin == t.nmin && rpamax == t.nmax && rpamin == t.mmin, "TCMatrix ranges do not match rpamin/rpamax");
   XTPB_REQUIRE(n_omega >= 1, "need at least one frequency");
   const long long na = t.naux, rpatotal = rpamax - rpamin + 1;
+  // the matrix handed back is basis dependent: a pending Cholesky factor of the metric (any R with R R^T = V^-1 serves
+  // the library's own consumers) is replaced by the reference's symmetric factor first
+  if (t.metric_src.cholesky) t.flush();
   DBuf e((size_t)rpatotal), eps((size_t)(na * na * n_omega));
   t.ctx->h2d(e.p, energies_host, (size_t)rpatotal);
   rpa_epsilon_dev(t, e.p, homo - rpamin + 1, eta, omegas_host, n_omega, imaginary_axis != 0, 0.0, eps.p);
