@@ -54,25 +54,24 @@ def main():
     with open(args.out, "w") as f:
         # the two ways the scan can run: pole by pole and compressed; for the compressed scan the three walks of the
         # near m-ranges (XTPB_GRID_WALK) and register/occupancy caps around the default
-        variants = [("direct", "", "", ""), ("compressed", "5", "", "0"), ("compressed", "5", "", "1"),
-                    ("compressed", "5", "", "2"), ("compressed", "4", "", "2"), ("compressed", "6", "", "2")]
+        variants = [("direct", {}), ("compressed", {"XTPB_GRID_KERNEL": "warp", "XTPB_GRID_WALK": "0"}),
+                    ("compressed", {"XTPB_GRID_KERNEL": "warp", "XTPB_GRID_WALK": "1"}),
+                    ("compressed", {"XTPB_GRID_KERNEL": "warp", "XTPB_GRID_WALK": "2"}),
+                    ("compressed", {"XTPB_GRID_KERNEL": "cta", "XTPB_GRID_OCC": "3"}),
+                    ("compressed", {"XTPB_GRID_KERNEL": "cta", "XTPB_GRID_OCC": "4"}),
+                    ("compressed", {"XTPB_GRID_KERNEL": "cta", "XTPB_GRID_OCC": "5"})]
         if args.walk_only:
-            variants = [v for v in variants if v[0] == "compressed" and v[1] == "5"]
-        for mode, occ, bw, walk in variants:
+            variants = [v for v in variants if v[1].get("XTPB_GRID_WALK") == "2" or v[1].get("XTPB_GRID_KERNEL") == "cta"]
+        for mode, extra in variants:
             env = dict(os.environ, XTPB_SIGMA_GRID=mode)
-            if occ:
-                env["XTPB_GRID_OCC"] = occ
-            if bw:
-                env["XTPB_GRID_BIN_WIDTH"] = bw
-            if walk:
-                env["XTPB_GRID_WALK"] = walk
+            env.update(extra)
             r = subprocess.run([sys.executable, __file__, "--child", "--workload", args.workload, "--reps",
                                 str(args.reps)], env=env, capture_output=True, text=True)
             if r.stdout.strip():
                 rec = json.loads(r.stdout.strip().splitlines()[-1])
             else:
                 rec = {"error": r.stderr[-400:]}
-            rec.update({"mode": mode, "min_blocks_per_sm": occ, "bin_width": bw or "0.125", "walk": walk})
+            rec.update({"mode": mode, "env": extra})
             line = json.dumps(rec)
             print(line, flush=True)
             f.write(line + "\n")

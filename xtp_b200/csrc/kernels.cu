@@ -703,6 +703,239 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_compresse
   if (lane == 0 && n_near > 0) atomicAdd(near_poles, (unsigned long long)n_near);   // integer: order-independent
 }
 
+// (1c) CTA-cooperative near field.  The four warps of a CTA own four consecutive chunks of ONE level, so their near
+//     ranges overlap almost completely; in (1b) every warp nevertheless looks up its own eight table entries per aux
+//     function (latency-bound global loads) and stages its own 32-pole tiles -- at C60 size about as many instructions
+//     as the evaluations themselves (ncu: 59 thread instructions per evaluated pair against ~19 of arithmetic).  Here
+//     the CTA works through the aux functions together:
+//       * the table entries of bins B_lo .. B_hi + 1 (union of the warps' near bins) of aux function P + 1 and the
+//         poles of the union range of P + 1 (raw tensor elements and energies, up to kCtaCap of them) are loaded by all
+//         128 threads, coalesced, into registers while P is being evaluated, and stored to shared memory (double-
+//         buffered) at the top of the next round: ONE barrier per aux function;
+//       * every warp reads its eight range bounds from shared memory and evaluates its own sub-ranges of the staged
+//         poles straight from the shared pole array (same step structure as (1b), padding lanes carry the last real
+//         pole at weight zero);
+//       * union ranges longer than kCtaCap are finished in further pieces, loaded synchronously (rare).
+//     Inner bins (equivalent poles), far field, reduction and output are those of (1b).
+constexpr int kCtaCap = 1024, kCtaPre = kCtaCap / (kCmpWarps * 32), kCtaMaxTab = 64, kCtaMinBlocks = 4;
+
+template <int MINB>
+__global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_cta_kernel(
+    const double* __restrict__ M, long long ldn, long long slab, int naux, const double* __restrict__ energies,
+    const double* __restrict__ ppm_freq, const double* __restrict__ ppm_fac, const int* __restrict__ level_slab,
+    const int* __restrict__ level_mom, const double* __restrict__ omega0, double domega, int n_omega,
+    const int* __restrict__ binstart,
+    const double* __restrict__ edges, int nb, const int* __restrict__ near_range, int n_chunks,
+    const double* __restrict__ moments, const double2* __restrict__ eq_poles, double* __restrict__ out,
+    long long out_split_stride, unsigned long long* __restrict__ near_poles) {
+  constexpr int kThreads = kCmpWarps * 32;
+  __shared__ double2 poles[2][kCtaCap];
+  __shared__ double2 tile[kCmpWarps][32];
+  __shared__ int tab[2][2][kCtaMaxTab];
+  __shared__ int cta_lo, cta_hi;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x * kCmpWarps + warp, level = blockIdx.y;
+  const bool active = chunk < n_chunks;       // idle warps of the last CTA of a level still load and synchronise
+  const double* S = M + (long long)level_slab[level] * slab;
+  const int mrow = level_mom ? level_mom[level] : level;
+  const int point = lane & (kCmpChunk - 1), slot = lane / kCmpChunk;
+  const int j = chunk * kCmpChunk + point;
+  const double om = omega0[level] + domega * (double)j;
+  int b_lo = 1, b_hi = 0, i_lo = 1, i_hi = 0;
+  if (active) {
+    const int4 nr = reinterpret_cast<const int4*>(near_range)[(long long)level * n_chunks + chunk];
+    b_lo = nr.x; b_hi = nr.y; i_lo = nr.z; i_hi = nr.w;
+  }
+  const bool has_near = b_lo <= b_hi;
+  if (tid == 0) { cta_lo = 0x7fffffff; cta_hi = -1; }
+  __syncthreads();
+  if (lane == 0 && has_near) { atomicMin(&cta_lo, b_lo); atomicMax(&cta_hi, b_hi); }
+  __syncthreads();
+  const int B_lo = cta_lo, B_hi = cta_hi;
+  const int ntab = B_hi - B_lo + 2;           // table entries b = B_lo .. B_hi + 1 (<= kCtaMaxTab, checked by the host)
+  const int p_per = (naux + gridDim.z - 1) / gridDim.z;
+  const int p_begin = blockIdx.z * p_per, p_end = min(naux, p_begin + p_per);
+  double acc4[kCmpG];
+#pragma unroll
+  for (int g = 0; g < kCmpG; ++g) acc4[g] = 0.0;
+  long long n_near = 0;
+
+  // evaluates src[a .. b) (weight, position) against this lane's grid point, kCmpSlots * kCmpG poles per step; the
+  // lanes past the end of the range read its last pole at weight zero (keeps the step's kind)
+  auto eval_range = [&](const double2* src, int a, int b) {
+    constexpr int kStep = kCmpSlots * kCmpG;
+    const int last = b - 1;
+    for (int t = a; t < b; t += kStep) {
+      double2 e[kCmpG];
+      double x[kCmpG], r[kCmpG];
+      unsigned hmin = 0xffffffffu, hmax = 0u;
+#pragma unroll
+      for (int g = 0; g < kCmpG; ++g) {
+        const int idx = t + g * kCmpSlots + slot;
+        e[g] = src[min(idx, last)];
+        if (idx > last) e[g].x = 0.0;
+        x[g] = om - e[g].y;
+        const unsigned hw = static_cast<unsigned>(__double2hiint(x[g])) & 0x7fffffffu;
+        hmin = min(hmin, hw);
+        hmax = max(hmax, hw);
+      }
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, hmin), wmax = __reduce_max_sync(0xffffffffu, hmax);
+      if (wmin >= 0x3fd00000u) {
+#pragma unroll
+        for (int g = 0; g < kCmpG; ++g) r[g] = rcp_fast(x[g]);
+      } else if (wmax < 0x3fd00000u) {
+#pragma unroll
+        for (int g = 0; g < kCmpG; ++g) r[g] = ppm_ginv_poly(x[g]);
+      } else {
+#pragma unroll
+        for (int g = 0; g < kCmpG; ++g) {
+          const double plain = rcp_fast(x[g]), damped = ppm_ginv_poly(x[g]);
+          r[g] = ppm_in_window(x[g]) ? damped : plain;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < kCmpG; ++g) acc4[g] = fma(e[g].x, r[g], acc4[g]);
+    }
+  };
+
+  if (B_lo <= B_hi && p_begin < p_end) {
+    // state of an aux function: union range [u0, u0 + nA) of the occupied segment (poles e - Omega) followed by
+    // [u2, u2 + nB) of the unoccupied one (e + Omega) as one index space t; this warp's four sub-ranges in m
+    struct PState { int u0, u2, nA, total; double fac, Om; int c[8]; };
+    auto read_state = [&](int tb, int P, PState& st) {
+      const int* t0 = tab[tb][0];
+      const int* t1 = tab[tb][1];
+      st.fac = ppm_fac[P];
+      st.Om = ppm_freq[P];
+      st.u0 = t0[0];
+      st.u2 = t1[0];
+      st.nA = max(t0[ntab - 1] - st.u0, 0);
+      st.total = st.fac != 0.0 ? st.nA + max(t1[ntab - 1] - st.u2, 0) : 0;
+      if (has_near) {
+        st.c[0] = t0[b_lo - B_lo]; st.c[1] = t0[i_lo - B_lo]; st.c[2] = t0[i_hi + 1 - B_lo]; st.c[3] = t0[b_hi + 1 - B_lo];
+        st.c[4] = t1[b_lo - B_lo]; st.c[5] = t1[i_lo - B_lo]; st.c[6] = t1[i_hi + 1 - B_lo]; st.c[7] = t1[b_hi + 1 - B_lo];
+      }
+    };
+    auto tab_entry = [&](int P) -> int {        // this thread's entry of the table rows of P (tid < 2 * ntab)
+      const int seg = tid / ntab, b = B_lo + tid % ntab;
+      return binstart[((long long)seg * naux + P) * (nb + 1) + b];
+    };
+    double pv[kCtaPre], pe[kCtaPre];
+    // raw loads of piece [ps, ps + kCtaCap) of the aux function with state st, element q * kThreads + tid per thread
+    auto load_piece = [&](const PState& st, int P, int ps) {
+      const double* row = S + (long long)P * ldn;
+#pragma unroll
+      for (int q = 0; q < kCtaPre; ++q) {
+        const int t = ps + q * kThreads + tid;
+        pv[q] = 0.0;
+        pe[q] = 0.0;
+        if (t < st.total) {
+          const int m = t < st.nA ? st.u0 + t : st.u2 + (t - st.nA);
+          pv[q] = row[m];
+          pe[q] = energies[m];
+        }
+      }
+    };
+    auto store_piece = [&](const PState& st, int buf, int ps) {
+#pragma unroll
+      for (int q = 0; q < kCtaPre; ++q) {
+        const int t = ps + q * kThreads + tid;
+        if (t < st.total)
+          poles[buf][t - ps] = make_double2(st.fac * pv[q] * pv[q], pe[q] + (t < st.nA ? -st.Om : st.Om));
+      }
+    };
+    // this warp's sub-ranges of piece [ps, pe) of the staged poles
+    auto eval_piece = [&](const PState& st, int buf, int ps, int pend) {
+      if (!has_near) return;
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) {
+        const int lo = st.c[2 * rg], hi = st.c[2 * rg + 1];
+        if (lo >= hi) continue;
+        const int off = rg < 2 ? -st.u0 : st.nA - st.u2;      // m -> t
+        const int ta = max(lo + off, ps), tb = min(hi + off, pend);
+        if (ta < tb) eval_range(poles[buf], ta - ps, tb - ps);
+      }
+    };
+
+    PState cur, nxt;
+    int tab_reg = 0;
+    if (tid < 2 * ntab) tab[0][tid / ntab][tid % ntab] = tab_entry(p_begin);
+    __syncthreads();
+    read_state(0, p_begin, nxt);
+    load_piece(nxt, p_begin, 0);
+    if (p_begin + 1 < p_end && tid < 2 * ntab) tab_reg = tab_entry(p_begin + 1);
+    for (int P = p_begin; P < p_end; ++P) {
+      const int buf = (P - p_begin) & 1;
+      cur = nxt;
+      store_piece(cur, buf, 0);
+      if (P + 1 < p_end && tid < 2 * ntab) tab[buf ^ 1][tid / ntab][tid % ntab] = tab_reg;
+      __syncthreads();
+      if (P + 1 < p_end) {
+        read_state(buf ^ 1, P + 1, nxt);
+        load_piece(nxt, P + 1, 0);
+        if (P + 2 < p_end && tid < 2 * ntab) tab_reg = tab_entry(P + 2);
+      }
+      if (cur.total == 0) continue;
+      if (has_near)
+        n_near += max(cur.c[1] - cur.c[0], 0) + max(cur.c[3] - cur.c[2], 0) + max(cur.c[5] - cur.c[4], 0) +
+                  max(cur.c[7] - cur.c[6], 0);
+      eval_piece(cur, buf, 0, min(cur.total, kCtaCap));
+      if (cur.total > kCtaCap) {
+        // the rest of a long union range, piece by piece through the same buffer; the prefetched registers of P + 1
+        // are parked in shared memory-free fashion: they are simply reloaded afterwards
+        for (int ps = kCtaCap; ps < cur.total; ps += kCtaCap) {
+          __syncthreads();                     // everybody is done with the previous piece
+          load_piece(cur, P, ps);
+          store_piece(cur, buf, ps);
+          __syncthreads();
+          eval_piece(cur, buf, ps, min(cur.total, ps + kCtaCap));
+        }
+        if (P + 1 < p_end) load_piece(nxt, P + 1, 0);
+      }
+    }
+  }
+  // ---- inner bins: their equivalent poles, split 0 only
+  if (active && blockIdx.z == 0 && i_lo <= i_hi) {
+    const double2* eq = eq_poles + ((long long)mrow * nb + i_lo) * kCmpOrder;
+    const int total = (i_hi - i_lo + 1) * kCmpOrder;
+    for (int m0 = 0; m0 < total; m0 += 32) {
+      const int m = m0 + lane;
+      const double2 el = m < total ? eq[m] : make_double2(0.0, -1.0e30);
+      __syncwarp();
+      tile[warp][lane] = el;
+      __syncwarp();
+      eval_range(tile[warp], 0, min(32, total - m0));
+    }
+  }
+  if (!active) return;
+  double acc = 0.0;
+#pragma unroll
+  for (int g = 0; g < kCmpG; g += 2) acc += acc4[g] + acc4[g + 1];
+  // ---- far field: Chebyshev series of the Cauchy kernel over the condensed bins, the bins dealt out to the slots
+  if (blockIdx.z == 0) {
+    const double* mom = moments + ((long long)mrow * nb) * kCmpOrder;
+    for (int b = slot; b < nb; b += kCmpSlots) {
+      if (b >= b_lo && b <= b_hi) continue;
+      const double e0 = edges[b], e1 = edges[b + 1];
+      const double h = 0.5 * (e1 - e0);
+      const double d = (om - 0.5 * (e0 + e1)) / h;
+      const double ad = fabs(d), sg = d < 0.0 ? -1.0 : 1.0;
+      const double sq = sqrt(fma(ad, ad, -1.0));
+      const double r = sg / (ad + sq);
+      const double* mu = mom + (long long)b * kCmpOrder;
+      double f = 0.0;
+#pragma unroll
+      for (int jj = kCmpOrder - 1; jj >= 1; --jj) f = (f + mu[jj]) * r;
+      f = fma(0.5, mu[0], f);
+      acc = fma(f, 2.0 * sg / (sq * h), acc);
+    }
+  }
+#pragma unroll
+  for (int o = kCmpChunk; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (slot == 0 && j < n_omega) out[(long long)blockIdx.z * out_split_stride + (long long)level * n_omega + j] = acc;
+  if (lane == 0 && n_near > 0) atomicAdd(near_poles, (unsigned long long)n_near);
+}
+
 // (2) pair kernel: arbitrary (level, frequency) pairs (bisection steps, final Sigma_c, derivatives).
 //     One CTA column per pair, kPairChunks CTAs split the aux range; deterministic two-stage reduction.
 //     Bound: HBM/L2 (each pair streams its slab once).
@@ -1194,6 +1427,24 @@ void k_ppm_scan_evaluate(const double* M, long long ldn, long long slab, int nau
   KernelFn kernel = walk <= 0 ? pick(std::integral_constant<int, 0>{})
                   : walk == 1 ? pick(std::integral_constant<int, 1>{})
                               : pick(std::integral_constant<int, 2>{});
+  // CTA-cooperative near field (1c) whenever the union of the near bins of every CTA fits its shared table
+  // (XTPB_GRID_KERNEL=warp: the warp-private kernel (1b))
+  const char* kern_env = std::getenv("XTPB_GRID_KERNEL");
+  bool use_cta = !(kern_env && std::strcmp(kern_env, "warp") == 0);
+  for (long long it = 0; it < n_items && use_cta; ++it)
+    for (int c0 = 0; c0 < n_chunks && use_cta; c0 += kCmpWarps) {
+      int lo = 0x7fffffff, hi = -1;
+      for (int c = c0; c < std::min(n_chunks, c0 + kCmpWarps); ++c) {
+        const int* nr = near_host + 4 * (it * n_chunks + c);
+        if (nr[0] <= nr[1]) { lo = std::min(lo, nr[0]); hi = std::max(hi, nr[1]); }
+      }
+      if (hi >= lo && hi - lo + 2 > kCtaMaxTab) use_cta = false;
+    }
+  if (use_cta) {
+    const int cocc = occ_env ? occ : kCtaMinBlocks;
+    kernel = cocc <= 3 ? sigma_ppm_grid_cta_kernel<3> : cocc == 4 ? sigma_ppm_grid_cta_kernel<4>
+                                                                  : sigma_ppm_grid_cta_kernel<5>;
+  }
   for (int off = 0; off < n_items; off += 32768) {         // gridDim.y limit
     const int cnt = std::min(32768, n_items - off);
     kernel<<<dim3(bx, cnt, splits), kCmpWarps * 32, 0, s>>>(
