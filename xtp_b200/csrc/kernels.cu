@@ -826,6 +826,7 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_cta_kerne
       const double* row = S + (long long)P * ldn;
 #pragma unroll
       for (int q = 0; q < kCtaPre; ++q) {
+        if (ps + q * kThreads >= st.total) break;          // CTA-uniform: the slots past the end cost nothing
         const int t = ps + q * kThreads + tid;
         pv[q] = 0.0;
         pe[q] = 0.0;
@@ -839,6 +840,7 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_cta_kerne
     auto store_piece = [&](const PState& st, int buf, int ps) {
 #pragma unroll
       for (int q = 0; q < kCtaPre; ++q) {
+        if (ps + q * kThreads >= st.total) break;
         const int t = ps + q * kThreads + tid;
         if (t < st.total)
           poles[buf][t - ps] = make_double2(st.fac * pv[q] * pv[q], pe[q] + (t < st.nA ? -st.Om : st.Om));
