@@ -826,7 +826,6 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_cta_kerne
       const double* row = S + (long long)P * ldn;
 #pragma unroll
       for (int q = 0; q < kCtaPre; ++q) {
-        if (ps + q * kThreads >= st.total) break;          // CTA-uniform: the slots past the end cost nothing
         const int t = ps + q * kThreads + tid;
         pv[q] = 0.0;
         pe[q] = 0.0;
@@ -840,7 +839,6 @@ __global__ void __launch_bounds__(kCmpWarps * 32, MINB) sigma_ppm_grid_cta_kerne
     auto store_piece = [&](const PState& st, int buf, int ps) {
 #pragma unroll
       for (int q = 0; q < kCtaPre; ++q) {
-        if (ps + q * kThreads >= st.total) break;
         const int t = ps + q * kThreads + tid;
         if (t < st.total)
           poles[buf][t - ps] = make_double2(st.fac * pv[q] * pv[q], pe[q] + (t < st.nA ? -st.Om : st.Om));
@@ -1429,10 +1427,12 @@ void k_ppm_scan_evaluate(const double* M, long long ldn, long long slab, int nau
   KernelFn kernel = walk <= 0 ? pick(std::integral_constant<int, 0>{})
                   : walk == 1 ? pick(std::integral_constant<int, 1>{})
                               : pick(std::integral_constant<int, 2>{});
-  // CTA-cooperative near field (1c) whenever the union of the near bins of every CTA fits its shared table
-  // (XTPB_GRID_KERNEL=warp: the warp-private kernel (1b))
+  // XTPB_GRID_KERNEL=cta: the CTA-cooperative near field (1c), possible whenever the union of the near bins of every
+  // CTA fits its shared table.  Measured (profiles/r02_sigma_grid_walk.jsonl): 72.2 ms against 76.7 ms for the
+  // warp-private kernel (1b) at synth-1000 size, no difference at C60 size (361 ms both) -- the staging it shares is a
+  // minor part of the per-aux-function overhead -- so (1b) stays the default.
   const char* kern_env = std::getenv("XTPB_GRID_KERNEL");
-  bool use_cta = !(kern_env && std::strcmp(kern_env, "warp") == 0);
+  bool use_cta = kern_env && std::strcmp(kern_env, "cta") == 0;
   for (long long it = 0; it < n_items && use_cta; ++it)
     for (int c0 = 0; c0 < n_chunks && use_cta; c0 += kCmpWarps) {
       int lo = 0x7fffffff, hi = -1;
