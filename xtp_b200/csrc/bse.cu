@@ -526,7 +526,9 @@ void BseOperator::matmul_dev(const double* X, long long ldx, int k, double* Y, l
         budget = std::max<long long>(budget, (long long)(want / 8.0));
       }
     }
-    const int kchunk = (int)std::max<long long>(1, std::min<long long>(k, budget / per_k));
+    const int kmax = (int)std::max<long long>(1, std::min<long long>(k, budget / per_k));
+    const int kchunks = (k + kmax - 1) / kmax;
+    const int kchunk = (k + kchunks - 1) / kchunks;        // equal chunks: no short (badly padded) last one
     U.ensure((size_t)(per_k * kchunk));
     const double coef = cd ? (double)cd : (double)cd2;
     const double b0 = beta();
