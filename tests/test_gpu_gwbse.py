@@ -135,6 +135,17 @@ def test_coulomb_metric_cholesky_path(ctx, prob, monkeypatch):
         assert rel(eps_c, rpa_o.calculate_epsilon_i(0.5)) < 1e-9
         assert rel(tc.get_raw(), ref.M) < 1e-9
         assert tc.metric_path_info() == {"cholesky_calls": 1, "eigensolver_calls": 1}
+    # a caller's own rotation right after the metric step meets the reference's symmetric factor, not the Cholesky one
+    tc = gpu_tc(ctx, prob)
+    tc.apply_coulomb_metric(prob["aux_coulomb"])
+    Ruser = np.random.default_rng(16).standard_normal((sz.n_aux, sz.n_aux))
+    tc.MultiplyRightWithAuxMatrix(Ruser)
+    assert tc.metric_path_info() == {"cholesky_calls": 1, "eigensolver_calls": 1}
+    ref = copy.deepcopy(prob["tc_o"])
+    R, _ = orc.Pseudo_InvSqrt_GWBSE(prob["aux_coulomb"], None)
+    ref.MultiplyRightWithAuxMatrix(R)
+    ref.MultiplyRightWithAuxMatrix(Ruser)
+    assert rel(tc.get_raw(), ref.M) < 1e-9
     # G0W0 + BSE through both factors
     out = {}
     for mode in ("1", "0"):

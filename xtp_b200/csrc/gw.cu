@@ -150,7 +150,7 @@ void GW::prepare_ppm() {
   ppm_fac_dev.ensure((size_t)na);
   ctx->h2d(ppm_freq_dev.p, ppm_freq.data(), (size_t)na);
   ctx->h2d(ppm_fac_dev.p, fac.data(), (size_t)na);
-  tc->rotate(phi, na);
+  tc->rotate(phi, na, true);            // phi diagonalises the epsilon formed with the pending factor: covariant
   trace.mark("tensor rotation");
   // the tensor now lives in the eigenbasis of eps(0) at these energies (see TCMatrix::Eps0Basis)
   tc->eps0.valid = true;

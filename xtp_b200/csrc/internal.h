@@ -246,7 +246,10 @@ struct TCMatrix {
   ~TCMatrix();
   TCMatrix(TCMatrix&&) = delete;
   // M[m] <- M[m] * R for all m (R on the device, naux x naux, ld = ldr)
-  void rotate(const double* R_dev, long long ldr);
+  // covariant = true: R was derived from the tensor THROUGH the pending factor (the eigenvectors of an epsilon formed
+  // with it), so M (Rp R) is the same for every Rp with Rp Rp^T = V^-1 and a pending Cholesky factor may be folded in;
+  // any other R (a caller's matrix) meets the reference's symmetric factor: a pending Cholesky factor is flushed first
+  void rotate(const double* R_dev, long long ldr, bool covariant = false);
   // Deferred aux rotation.  The Coulomb-metric factor V^-1/2 (xtpb_tc_apply_coulomb_metric) is not applied to the
   // 29 GB tensor at once: the next full rotation (the PPM eigenvectors) is folded into it (M <- M (Rp R), one pass
   // instead of two), epsilon is formed from the un-rotated tensor and sandwiched (Rp^T E Rp, two N_aux^3 products),

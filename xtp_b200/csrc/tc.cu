@@ -578,7 +578,8 @@ long long TCMatrix::apply_coulomb_metric(const double* V_host, long long ldv, co
   return removed;
 }
 
-void TCMatrix::rotate(const double* R_dev, long long ldr) {
+void TCMatrix::rotate(const double* R_dev, long long ldr, bool covariant) {
+  if (pending && metric_src.cholesky && !covariant) flush();
   ++generation;
   eps0.valid = false;         // the caller re-validates when R is an eps(0) eigenbasis (GW::prepare_ppm)
   DBuf folded;
