@@ -228,6 +228,11 @@ class GwbseJob:
         tc = self.tc
         tc.coulomb_metric_begin(self.V)     # TCMatrix_gwbse::Fill = Fill3cMO + metric: the metric's eigensolver runs underneath
         tc.fill_begin(self.C)
+        if not resident and self.world == 1 and not self.gw_kw:
+            # G0W0 with the plasmon-pole model from host buffers: the fill is PCIe-bound, so the two epsilon matrices of
+            # Sigma_PPM::PrepareScreening are accumulated underneath the transfers (the RPA input energies are known
+            # before the fill, as in GWBSE::Evaluate); the resident leg keeps the one launch per frequency after it
+            tc.ppm_prefetch_begin(self.energies[sz.rpamin:sz.rpamax + 1], sz.homo)
         n_loc = self.p_hi - self.p_lo
         if self.world > 1:
             # collective Fill3cMO: every rank contributes the slices of its aux range (device-resident or pinned host)

@@ -136,6 +136,18 @@ int xtpb_tc_apply_coulomb_metric(xtpb_tc* tc, const double* V_host, xtpb_index l
  * underneath the fill; otherwise nothing is started (see xtpb_tc_metric_path_info). */
 int xtpb_tc_coulomb_metric_begin(xtpb_tc* tc, const double* V_host, xtpb_index ldv, const double* S_host,
                                  xtpb_index lds);
+/* Optional hint, given AFTER xtpb_tc_fill_begin and BEFORE the xtpb_tc_fill_block* calls of a single-rank fill: the
+ * caller is going to run Sigma_PPM::PrepareScreening (xtpb_gw_prepare_screening / xtpb_gw_calculate_gw_perturbation with
+ * the plasmon-pole model) with these RPA input energies (rpamin .. rpamax, as handed to the GW object after the scissor
+ * shift), this HOMO index and this eta.  The two epsilon matrices of the plasmon-pole model (w = 0 on the real axis,
+ * w = 0.5 Ha on the imaginary axis) are then accumulated panel by panel while the aux blocks arrive (ascending,
+ * contiguous from 0), i.e. underneath the host-to-device transfers of a PCIe-bound fill; PrepareScreening picks the
+ * result up when energies, eta and tensor contents match exactly and recomputes otherwise.  Ignored with several
+ * ranks.  (The reference's GWBSE::Evaluate knows these energies before it calls TCMatrix_gwbse::Fill.) */
+int xtpb_tc_ppm_prefetch_begin(xtpb_tc* tc, const double* rpa_energies_host, xtpb_index homo, double eta);
+/* complete = 1 once both matrices are accumulated for all aux functions; aux_functions_done: rows finished so far;
+ * matrices_used: how many prefetched matrices PrepareScreening has picked up on this tensor.  Pointers may be NULL. */
+int xtpb_tc_ppm_prefetch_info(xtpb_tc* tc, int* complete, xtpb_index* aux_functions_done, xtpb_index* matrices_used);
 /* How xtpb_tc_apply_coulomb_metric obtained its factor R (R R^T = V^-1) so far on this tensor.  eigensolver: the
  * reference's construction, S^-1/2 (S^-1/2 V S^-1/2)^-1/2 with eigenvalues below etol dropped.  cholesky: when two
  * Cholesky factorisations prove that S - etol and V - etol S are positive definite (no function would be removed),

@@ -173,6 +173,52 @@ def test_coulomb_metric_cholesky_path(ctx, prob, monkeypatch):
     assert tc.metric_path_info() == {"cholesky_calls": 0, "eigensolver_calls": 1}
 
 
+def test_ppm_epsilon_prefetch_under_fill(ctx):
+    """xtpb_tc_ppm_prefetch_begin: the plasmon-pole model's two epsilon matrices are accumulated panel by panel while the
+    aux blocks arrive (several 256-row panels here) and PrepareScreening picks them up; G0W0 energies equal those of the
+    plain sequence.  Other energies, a rotation in between, or an out-of-order fill: the screening is recomputed."""
+    from xtp_b200 import api
+    sz = synth.Sizes(n_basis=96, n_aux=600, homo=11)
+    p = synth.make_problem(sz, seed=77)
+    e_rpa = p["energies"][sz.rpamin:sz.rpamax + 1]
+
+    def step(hint, order=None, energies=None, rotate=False):
+        tc = api.TCMatrix_gwbse(ctx).Initialize(sz.n_aux, sz.rpamin, sz.mmax, sz.rpamin, sz.rpamax)
+        tc.fill_begin(p["C"])
+        if hint:
+            tc.ppm_prefetch_begin(e_rpa if energies is None else energies, sz.homo)
+        blocks = list(range(0, sz.n_aux, 100))
+        for p0 in (blocks if order is None else order):
+            tc.fill_block(p0, p["ao3c"][p0:p0 + 100])
+        tc.apply_coulomb_metric(p["aux_coulomb"])
+        if rotate:
+            tc.MultiplyRightWithAuxMatrix(np.eye(sz.n_aux))
+        info = tc.ppm_prefetch_info()
+        gw = api.GW(ctx, tc, p["vxc"], p["energies"])
+        gw.configure(api.gw_options(homo=sz.homo, qpmin=sz.qpmin, qpmax=sz.qpmax, rpamin=sz.rpamin, rpamax=sz.rpamax,
+                                    qp_grid_steps=201))
+        gw.CalculateGWPerturbation()
+        return gw.getGWAResults(), info, tc.ppm_prefetch_info()
+
+    plain, info0, _ = step(False)
+    assert not info0["complete"]
+    qp, info, after = step(True)
+    assert info["complete"] and info["aux_functions_done"] == sz.n_aux and after["matrices_used"] == 2
+    np.testing.assert_allclose(qp, plain, rtol=0, atol=1e-9)
+    # energies that are not the ones the GW object uses: nothing is picked up, same result
+    qp2, info2, after2 = step(True, energies=e_rpa + 1e-3)
+    assert info2["complete"] and after2["matrices_used"] == 0
+    np.testing.assert_allclose(qp2, plain, rtol=0, atol=1e-9)
+    # the tensor changes after the fill: stale
+    qp3, _, after3 = step(True, rotate=True)
+    assert after3["matrices_used"] == 0
+    np.testing.assert_allclose(qp3, plain, rtol=0, atol=1e-8)
+    # out-of-order blocks disarm the prefetch
+    qp4, info4, after4 = step(True, order=[100, 0, 200, 300, 400, 500])
+    assert not info4["complete"] and after4["matrices_used"] == 0
+    np.testing.assert_allclose(qp4, plain, rtol=0, atol=1e-9)
+
+
 def test_multiply_right_with_aux_matrix(ctx, prob):
     sz = prob["sizes"]
     R = np.random.default_rng(2).standard_normal((sz.n_aux, sz.n_aux))

@@ -103,6 +103,8 @@ PROTOTYPES = {
     "xtpb_tc_apply_coulomb_metric": (C.c_int, [vp, dptr, idx, dptr, idx, C.c_double, iptr]),
     "xtpb_tc_coulomb_metric_begin": (C.c_int, [vp, dptr, idx, dptr, idx]),
     "xtpb_tc_metric_path_info": (C.c_int, [vp, iptr, iptr]),
+    "xtpb_tc_ppm_prefetch_begin": (C.c_int, [vp, dptr, idx, C.c_double]),
+    "xtpb_tc_ppm_prefetch_info": (C.c_int, [vp, C.POINTER(C.c_int), iptr, iptr]),
     "xtpb_rpa_epsilon": (C.c_int, [vp, dptr, idx, idx, idx, C.c_double, dptr, C.c_int, C.c_int, dptr]),
     "xtpb_gw_options_default": (None, [C.POINTER(GwOptions)]),
     "xtpb_gaussian_quadrature": (C.c_int, [C.c_int, idx, dptr, dptr, iptr]),

@@ -257,6 +257,17 @@ class TCMatrix_gwbse:
         self.Fill3cMO(ao3c, C_mo)
         self.removedfunctions = self.apply_coulomb_metric(aux_coulomb, aux_overlap, etol)
 
+    def ppm_prefetch_begin(self, rpa_energies, homo, eta=1e-3):
+        """Hint (after fill_begin, before the fill blocks): accumulate the plasmon-pole model's two epsilon matrices
+        for these RPA input energies while the aux blocks arrive (xtpb_tc_ppm_prefetch_begin)."""
+        e = np.ascontiguousarray(rpa_energies, dtype=np.float64)
+        check(_lib.lib().xtpb_tc_ppm_prefetch_begin(self._h, _d(e), int(homo), float(eta)))
+
+    def ppm_prefetch_info(self):
+        done, rows, used = C.c_int(0), idx(0), idx(0)
+        check(_lib.lib().xtpb_tc_ppm_prefetch_info(self._h, C.byref(done), C.byref(rows), C.byref(used)))
+        return {"complete": bool(done.value), "aux_functions_done": int(rows.value), "matrices_used": int(used.value)}
+
     def metric_path_info(self):
         """How apply_coulomb_metric obtained its factor so far (xtpb_tc_metric_path_info)."""
         ch, ei = idx(0), idx(0)

@@ -136,6 +136,7 @@ int xtpb_tc_set_raw_dev(xtpb_tc* tc, const double* M_dev) {
   t.metric_src = TCMatrix::MetricSources{};
   t.eps0.valid = false;
   ++t.generation;
+  ++t.content_gen;
   XTPB_CUDA(cudaMemcpy2DAsync(t.M.p, t.ldn * 8, M_dev, t.ntotal * 8, t.ntotal * 8, t.mtotal * t.naux,
                               cudaMemcpyDeviceToDevice, t.ctx->stream));
   t.ctx->sync();
@@ -212,6 +213,21 @@ int xtpb_tc_coulomb_metric_begin(xtpb_tc* tc, const double* V_host, xtpb_index l
   XTPB_API_BEGIN
   XTPB_REQUIRE(tc && V_host, "null pointer");
   tc->impl.metric_hint(V_host, ldv, S_host, lds);
+  XTPB_API_END
+}
+int xtpb_tc_ppm_prefetch_begin(xtpb_tc* tc, const double* rpa_energies_host, xtpb_index homo, double eta) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(tc && rpa_energies_host, "null pointer");
+  tc->impl.ppm_prefetch_begin(rpa_energies_host, homo - tc->impl.nmin + 1, eta);
+  XTPB_API_END
+}
+int xtpb_tc_ppm_prefetch_info(xtpb_tc* tc, int* complete, xtpb_index* aux_functions_done,
+                              xtpb_index* matrices_used) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(tc, "null pointer");
+  if (complete) *complete = tc->impl.ppm_pre.complete ? 1 : 0;
+  if (aux_functions_done) *aux_functions_done = tc->impl.ppm_pre.done_upto;
+  if (matrices_used) *matrices_used = tc->impl.ppm_pre.taken;
   XTPB_API_END
 }
 int xtpb_tc_metric_path_info(xtpb_tc* tc, xtpb_index* cholesky_calls, xtpb_index* eigensolver_calls) {

@@ -99,7 +99,7 @@ void GW::prepare_ppm() {
   DBuf eps((size_t)(2 * na * na)), T1((size_t)(na * na)), lam((size_t)na);
   const double w_r = 0.0, w_i = 0.5;    // screening_r, screening_i [Ha]
   PhaseTrace trace(ctx, "ppm");
-  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_r, 1, false, 0.0, eps.p);
+  rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_r, 1, false, 0.0, eps.p, -1, &rpa_energies);
   trace.mark("eps(0)");
   double* phi = eps.p;                  // eigh overwrites eps(0) with its eigenvectors
   std::vector<double> lambda((size_t)na);
@@ -109,12 +109,12 @@ void GW::prepare_ppm() {
   if (overlap) {
     tc->metric_prefetch_join();         // (a prefetch nobody consumed would still own the helper stream)
     ctx->eigh_async_begin((int)na, phi, na, lam.p, lambda.data());
-    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
+    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na, -1, &rpa_energies);
     trace.mark("eps(0.5i) under eigh");
     ctx->eigh_async_join();
     trace.mark("eigh join (exposed)");
   } else {
-    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na);
+    rpa_epsilon_dev(*tc, energies_dev.p, n_occ, opt.eta, &w_i, 1, true, 0.0, eps.p + na * na, -1, &rpa_energies);
     ctx->eigh((int)na, phi, na, lam.p);
     ctx->d2h(lambda.data(), lam.p, (size_t)na);
   }
@@ -628,6 +628,7 @@ void GW::calculate_gw_perturbation() {
       XTPB_CUDA(cudaMemcpyAsync(tc->M.p, backup.p, tc->M.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       tc->eps0.valid = false;
       ++tc->generation;
+      ++tc->content_gen;
     }
     if (!(screening_done && i_gw == 0)) prepare_screening();
     if (evgw && opt.gw_mixing_order > 0) mixing.update_input(freqs);

@@ -214,6 +214,7 @@ struct TCMatrix {
   long long naux, mmin, mmax, nmin, nmax, mtotal, ntotal;
   long long ldn, slab;          // device layout [m][P][ldn], ldn = ntotal rounded up to even
   unsigned long long generation = 0;   // bumped by everything that writes the tensor (caches keyed on its contents)
+  unsigned long long content_gen = 0;  // ... except a change of the pending factor only (the stored elements stay)
   // Multi-GPU: the second index is distributed cyclically, rank r holds the columns n = r, r + world, ... of
   // nmin..nmax.  `ntotal` is the LOCAL column count (== ntotal_glob when world == 1); every stage that sums over
   // the second index produces a partial result that is all-reduced.
@@ -300,6 +301,25 @@ struct TCMatrix {
     DBuf V, S;
     double etol = 0.0;
   } metric_src;
+  // Optional: accumulate the two epsilon matrices of Sigma_PPM::PrepareScreening (w = 0 on the real axis, w = 0.5 on the
+  // imaginary axis) WHILE Fill3cMO runs: as soon as the tensor rows of another 256 aux functions are complete, the panel
+  // E[P0..P1) x [0..P1) is contracted (same flops as the one SYRK-shaped launch per frequency afterwards).  When the
+  // fill is fed from host memory it is PCIe-bound and the GPU idles a third of the time: the 0.6 s of epsilon work at
+  // C60 size then hide underneath the transfers.  Single rank, aux blocks filled in ascending order.  The raw
+  // accumulations are handed to rpa_epsilon_dev when energies, eta, frequency and tensor contents match exactly.
+  struct PpmPrefetch {
+    bool armed = false, complete = false;
+    std::vector<double> energies;
+    long long n_occ = 0, filled_upto = 0, done_upto = 0;
+    double eta = 0.0;
+    DBuf E, d;                         // E: [2][naux][naux];  d: chi0 weights [2][n_occ][K]
+    unsigned long long content_gen = 0;
+    long long taken = 0;               // matrices handed to rpa_epsilon_dev so far (tests, reports)
+  } ppm_pre;
+  void ppm_prefetch_begin(const double* rpa_energies_host, long long n_occ, double eta);
+  void ppm_prefetch_advance(long long P0, long long nP);
+  bool ppm_prefetch_take(const std::vector<double>& energies, long long n_occ, double eta, double omega, bool imag,
+                         double* out_dev);
   struct MetricHint { bool given = false; const double* V = nullptr; const double* S = nullptr; } hint;
   long long metric_cholesky_count = 0, metric_eig_count = 0;   // which path apply_coulomb_metric took (tests, reports)
   // dst[i][Q][j] = sum_P M[m0+i][P][n0+j] R[P,Q]   (window rotation into a caller-owned buffer)
@@ -311,8 +331,10 @@ struct TCMatrix {
 // owner_shift < 0: every rank receives every matrix (all-reduce).  owner_shift >= 0 (frequency sharding, world > 1):
 // matrix w is summed onto rank (w + owner_shift) % world only -- the other ranks' copies hold partial sums and must not
 // be used; the caller inverts / consumes matrix w on its owner (Sigma_CDA's quadrature nodes and residue poles).
+// energies_host (optional): the same energies on the host, for the exact comparison with a PPM prefetch (see TCMatrix).
 void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
-                     int n_omega, bool imag, double gamma_extra, double* out_dev, int owner_shift = -1);
+                     int n_omega, bool imag, double gamma_extra, double* out_dev, int owner_shift = -1,
+                     const std::vector<double>* energies_host = nullptr);
 
 // E <- R^T E R (E symmetric, full storage in; lower triangle out on one rank, full matrix out when the product is
 // split over the ranks); T: n x n scratch.  tc.cu.

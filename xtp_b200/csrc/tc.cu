@@ -35,6 +35,7 @@ void TCMatrix::set_raw(const double* host) {
   metric_src = MetricSources{};
   eps0.valid = false;
   ++generation;
+  ++content_gen;
   if (world == 1) {
     ctx->h2d_2d(M.p, ldn, host, ntotal, ntotal, mtotal * naux);
     ctx->sync();
@@ -75,8 +76,10 @@ void TCMatrix::fill_begin(long long nb, const double* C_host, long long ldc_host
   XTPB_REQUIRE(nb > 0 && ldc_host >= nb, "bad MO coefficient matrix");
   pending = false;            // a new fill starts from the un-rotated tensor
   metric_src = MetricSources{};
+  ppm_pre.armed = ppm_pre.complete = false;
   eps0.valid = false;
   ++generation;
+  ++content_gen;
   n_basis = nb;
   ldc = round_up(nb, 2);
   Cm.alloc((size_t)(ldc * mtotal));
@@ -108,6 +111,7 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
   XTPB_REQUIRE(world == 1, "with more than one rank use the collective fill (xtpb_tc_fill_sharded_packed)");
   XTPB_REQUIRE(P0 >= 0 && nP >= 0 && P0 + nP <= naux && ld_ao >= n_basis, "bad aux block");
   ++generation;
+  ++content_gen;
   ProfScope prof(PROF_FILL);
   const long long ldw = round_up(n_basis, 2);
   const long long wslice = ldw * mtotal;
@@ -140,7 +144,79 @@ void TCMatrix::fill_block_dev(long long P0, long long nP, const double* ao, long
     }
     contract(g, ctx->ws, ctx->stream);
     contract(h, ctx->ws, ctx->stream);
+    ppm_prefetch_advance(P0 + p, cnt);
   }
+}
+
+void TCMatrix::ppm_prefetch_begin(const double* e_host, long long n_occ_, double eta_) {
+  XTPB_REQUIRE(n_basis > 0, "fill_begin must be called before the PPM prefetch hint");
+  ppm_pre.armed = ppm_pre.complete = false;
+  static const bool on = [] { const char* e = getenv("XTPB_PPM_PREFETCH"); return !(e && e[0] == '0'); }();
+  if (!on || world != 1 || nmin != mmin || n_occ_ <= 0 || n_occ_ >= ntotal || n_occ_ > mtotal) return;   // hint only
+  ppm_pre.energies.assign(e_host, e_host + ntotal);
+  ppm_pre.n_occ = n_occ_;
+  ppm_pre.eta = eta_;
+  ppm_pre.filled_upto = ppm_pre.done_upto = 0;
+  const int a0 = (int)(n_occ_ & ~1LL), K = (int)(ntotal - a0);
+  ppm_pre.E.ensure((size_t)(2 * naux * naux));
+  ppm_pre.d.ensure((size_t)(2 * n_occ_ * K + 2));
+  DBuf e_dev((size_t)ntotal);
+  ctx->h2d(e_dev.p, e_host, (size_t)ntotal);
+  double* om_dev = ppm_pre.d.p + 2 * n_occ_ * K;
+  const double om[2] = {0.0, 0.5};                  // screening_r, screening_i of the plasmon-pole model [Ha]
+  ctx->h2d(om_dev, om, 2);
+  k_chi0_weights(ppm_pre.d.p, e_dev.p, e_dev.p, (int)n_occ_, (int)n_occ_, a0, K, om_dev, 1, false, eta_, ctx->stream);
+  k_chi0_weights(ppm_pre.d.p + n_occ_ * K, e_dev.p, e_dev.p, (int)n_occ_, (int)n_occ_, a0, K, om_dev + 1, 1, true, eta_,
+                 ctx->stream);
+  ctx->sync();                                      // e_dev is freed on return
+  ppm_pre.armed = true;
+}
+
+void TCMatrix::ppm_prefetch_advance(long long P0, long long nP) {
+  if (!ppm_pre.armed) return;
+  if (P0 != ppm_pre.filled_upto) {                  // out of order: the panels would have holes
+    ppm_pre.armed = false;
+    return;
+  }
+  ppm_pre.filled_upto += nP;
+  const long long kPanel = 256;
+  const long long P1 = ppm_pre.filled_upto == naux
+                           ? naux
+                           : ppm_pre.done_upto + (ppm_pre.filled_upto - ppm_pre.done_upto) / kPanel * kPanel;
+  if (P1 > ppm_pre.done_upto) {
+    const long long Pa = ppm_pre.done_upto;
+    const int a0 = (int)(ppm_pre.n_occ & ~1LL), K = (int)(ntotal - a0);
+    ProfScope prof(PROF_EPSILON);
+    GemmParams g{};
+    g.A = GemmOperand{M.p + a0 + Pa * ldn, ldn, 1, slab, 0};          // rows P in [Pa, P1), outer = occupied level
+    g.B = GemmOperand{M.p + a0, ldn, 1, slab, 0};                      // rows Q in [0, P1)
+    g.C = ppm_pre.E.p + Pa; g.c_sm = 1; g.c_sn = naux; g.c_batch = naux * naux;
+    g.d = ppm_pre.d.p; g.d_outer = K; g.d_batch = ppm_pre.n_occ * K;
+    g.M = (int)(P1 - Pa); g.N = (int)P1; g.K = K; g.n_outer = (int)ppm_pre.n_occ; g.n_batch = 2;
+    g.alpha = 1.0; g.beta = 0.0;
+    contract(g, ctx->ws, ctx->stream);
+    ppm_pre.done_upto = P1;
+  }
+  if (ppm_pre.done_upto == naux) {
+    ppm_pre.armed = false;
+    ppm_pre.complete = true;
+    ppm_pre.content_gen = content_gen;
+  }
+}
+
+bool TCMatrix::ppm_prefetch_take(const std::vector<double>& e, long long n_occ_, double eta_, double omega, bool imag,
+                                 double* out_dev) {
+  if (!ppm_pre.complete || ppm_pre.content_gen != content_gen || n_occ_ != ppm_pre.n_occ || eta_ != ppm_pre.eta ||
+      e.size() != ppm_pre.energies.size() || !std::equal(e.begin(), e.end(), ppm_pre.energies.begin()))
+    return false;
+  int idx = -1;
+  if (!imag && omega == 0.0) idx = 0;
+  if (imag && omega == 0.5) idx = 1;
+  if (idx < 0) return false;
+  XTPB_CUDA(cudaMemcpyAsync(out_dev, ppm_pre.E.p + (long long)idx * naux * naux, (size_t)(naux * naux) * 8,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  ++ppm_pre.taken;
+  return true;
 }
 
 // Host-side Fill3cMO for a range of aux functions: the caller's AO slices (full symmetric n_basis x n_basis with
@@ -222,6 +298,7 @@ void TCMatrix::fill_sharded_packed(const double* packed, bool on_device) {
   long long lo, hi;
   aux_range(rank, lo, hi);
   ++generation;
+  ++content_gen;
   if (world == 1) {
     if (on_device) fill_block_packed_dev(lo, hi - lo, packed);
     else fill_block_host(lo, hi - lo, packed, 0, true);
@@ -581,6 +658,7 @@ long long TCMatrix::apply_coulomb_metric(const double* V_host, long long ldv, co
 void TCMatrix::rotate(const double* R_dev, long long ldr, bool covariant) {
   if (pending && metric_src.cholesky && !covariant) flush();
   ++generation;
+  ++content_gen;
   eps0.valid = false;         // the caller re-validates when R is an eps(0) eigenbasis (GW::prepare_ppm)
   DBuf folded;
   if (pending) {      // M <- M (Rp R): fold the deferred factor into this rotation
@@ -656,7 +734,8 @@ void congruence_sym(Context* ctx, double* E, const double* R, double* T, long lo
 // eps(w) = 1 + sum_{m occ} A_m^T diag(d_m(w)) A_m with A_m = M[m](unocc, :)   (upstream RPA::calculate_epsilon)
 // One lower-triangular SYRK-style launch per call; the frequency index is the batch dimension.
 void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, double eta, const double* omegas_host,
-                     int n_omega, bool imag, double, double* out_dev, int owner_shift) {
+                     int n_omega, bool imag, double, double* out_dev, int owner_shift,
+                     const std::vector<double>* energies_host) {
   Context* ctx = tc.ctx;
   ProfScope prof(PROF_EPSILON);
   XTPB_REQUIRE(n_occ > 0 && n_occ < tc.ntotal_glob && n_occ <= tc.mtotal, "RPA needs occupied and unoccupied levels");
@@ -670,7 +749,11 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
   double* om_dev = d.p + (size_t)n_omega * n_occ * std::max(K, 1);
   ctx->h2d(om_dev, omegas_host, n_omega);
   const size_t out_count = (size_t)n_omega * tc.naux * tc.naux;
-  if (K > 0) {
+  // accumulated underneath Fill3cMO already (TCMatrix::PpmPrefetch)?  Then only the finishing steps remain.
+  const bool prefetched = energies_host && n_omega == 1 && owner_shift < 0 && ctx->world == 1 &&
+                          tc.ppm_prefetch_take(*energies_host, n_occ, eta, omegas_host[0], imag, out_dev);
+  if (prefetched) {
+  } else if (K > 0) {
     k_chi0_weights(d.p, energies_dev, e_loc, (int)n_occ, (int)n_occ_loc, a0, K, om_dev, n_omega, imag, eta,
                    ctx->stream);
     GemmParams g{};
