@@ -228,10 +228,12 @@ class GwbseJob:
         tc = self.tc
         tc.coulomb_metric_begin(self.V)     # TCMatrix_gwbse::Fill = Fill3cMO + metric: the metric's eigensolver runs underneath
         tc.fill_begin(self.C)
-        if not resident and self.world == 1 and not self.gw_kw:
-            # G0W0 with the plasmon-pole model from host buffers: the fill is PCIe-bound, so the two epsilon matrices of
-            # Sigma_PPM::PrepareScreening are accumulated underneath the transfers (the RPA input energies are known
-            # before the fill, as in GWBSE::Evaluate); the resident leg keeps the one launch per frequency after it
+        if os.environ.get("XTPB_BENCH_PPM_PREFETCH") == "1" and not resident and self.world == 1 and not self.gw_kw:
+            # Experiment, off by default: accumulate the two epsilon matrices of Sigma_PPM::PrepareScreening underneath
+            # the PCIe-bound fill of the e2e leg (xtpb_tc_ppm_prefetch_begin).  Measured at C60 size: e2e 4.35-4.43 s
+            # with the hint against 4.32 s without (profiles/r02_ppm_prefetch_experiment.json): the 256-row panels
+            # contract ~25 % less efficiently than the one SYRK-shaped launch per frequency and turn the fill GPU-bound
+            # (1.87 s against 1.39 s), which eats the 0.56 s the screening saves.
             tc.ppm_prefetch_begin(self.energies[sz.rpamin:sz.rpamax + 1], sz.homo)
         n_loc = self.p_hi - self.p_lo
         if self.world > 1:

@@ -231,7 +231,11 @@ void TCMatrix::fill_block_host(long long P0, long long nP, const double* ao_host
   const long long full_slice = ldt * n_basis;
   const long long host_slice = packed ? n_basis * (n_basis + 1) / 2 : ld_ao * n_basis;
   const long long dev_slice = packed ? host_slice : full_slice;
-  const long long sub_max = std::max<long long>(1, std::min<long long>(nP, (1LL << 26) / full_slice));   // <= 512 MiB full
+  // chunk = what one staging buffer holds (<= 512 MiB of full slices).  With the PPM prefetch armed the contractions come
+  // in bursts (a 256-row epsilon panel every few chunks, ~30 ms at C60 size) and the copy stream can only run one
+  // chunk ahead of them, so the chunks are made long enough (<= 4 GiB) for a burst to fit underneath one copy
+  const long long stage_doubles = ppm_pre.armed ? (1LL << 29) : (1LL << 26);
+  const long long sub_max = std::max<long long>(1, std::min<long long>(nP, stage_doubles / full_slice));
   for (int b = 0; b < 2; ++b) stage2[b].ensure((size_t)(sub_max * dev_slice));
   if (packed) unpacked.ensure((size_t)(sub_max * full_slice));
   if (!copy_stream) {
