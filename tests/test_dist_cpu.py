@@ -239,6 +239,24 @@ def _worker(rank, world, port, results):
         tail_free.configure(orc.SigmaOptions(sz.homo, sz.qpmin, sz.qpmax, sz.rpamin, sz.rpamax, order=8, alpha=0.0))
         tail_free.kappa0, tail_free.dielinv, tail_free.gq = cda.kappa0, cda.dielinv, cda.gq
         np.testing.assert_allclose(res, tail_free.CalcResidueContribution(freq, level), rtol=0, atol=1e-10)
+        # ---- replicated N_aux^3 products split by column blocks (tc.cu: congruence_sym and the folded rotation):
+        # every rank holds E (symmetric) and a general R; rank r forms columns [n r / world, n (r+1) / world) of E R and
+        # of R^T (E R); one broadcast per block completes the matrix on every rank
+        rng2 = np.random.default_rng(77)
+        na = sz.n_aux
+        Es = rng2.standard_normal((na, na))
+        Es = Es + Es.T
+        Rg = np.triu(rng2.standard_normal((na, na))) + 3.0 * np.eye(na)        # e.g. the Cholesky factor of the metric
+        a, b = dist.aux_range(na, rank, world)
+        Tblk = Es @ Rg[:, a:b]
+        out = np.zeros((na, na))
+        out[:, a:b] = Rg.T @ Tblk
+        for r_ in range(world):
+            a_, b_ = dist.aux_range(na, r_, world)
+            blk = torch.from_numpy(np.ascontiguousarray(out[:, a_:b_]))
+            tdist.broadcast(blk, src=r_)
+            out[:, a_:b_] = blk.numpy()
+        np.testing.assert_allclose(out, Rg.T @ Es @ Rg, rtol=1e-12, atol=1e-10)
         results[rank] = "ok"
     except Exception as exc:  # noqa: BLE001
         import traceback
