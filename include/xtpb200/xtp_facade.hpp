@@ -141,13 +141,26 @@ class TCMatrix_gwbse {
   void Fill3cMO_block_packed(Index P0, Index nP, const double* ao3c_packed) {
     check(xtpb_tc_fill_block_packed(h_, P0, nP, ao3c_packed));
   }
-  // Optional, BEFORE the Fill3cMO calls: start the first eigendecomposition of the metric step on the library's helper
-  // thread so that it runs underneath the MO transform; ApplyCoulombMetric with the SAME matrices (which must stay
-  // alive and unmoved until then) joins it.
+  // Optional, BEFORE the Fill3cMO calls: announce the matrices of the metric step (on the eigensolver path its first
+  // decomposition then runs on the library's helper thread underneath the MO transform); ApplyCoulombMetric with the
+  // SAME matrices (which must stay alive and unmoved until then) consumes the hint.
   void CoulombMetricBegin(const Matrix& aux_coulomb, const Matrix* aux_overlap = nullptr) {
     check(xtpb_tc_coulomb_metric_begin(h_, aux_coulomb.data(), aux_coulomb.rows(),
                                        aux_overlap ? aux_overlap->data() : nullptr,
                                        aux_overlap ? aux_overlap->rows() : 0));
+  }
+  // Optional, after FillBegin on a single rank: Sigma_PPM::PrepareScreening will run with these RPA input energies
+  // (rpamin..rpamax); the plasmon-pole model's two epsilon matrices are then accumulated while the aux blocks arrive
+  // (xtpb_tc_ppm_prefetch_begin; pays only when the fill waits for a slow host link).
+  template <class Vector>
+  void PpmPrefetchBegin(const Vector& rpa_input_energies, Index homo, double eta = 1e-3) {
+    check(xtpb_tc_ppm_prefetch_begin(h_, rpa_input_energies.data(), homo, eta));
+  }
+  // which path the metric step took so far: {Cholesky factor, reference eigensolver construction}
+  std::pair<Index, Index> MetricPathInfo() const {
+    Index chol = 0, eig = 0;
+    check(xtpb_tc_metric_path_info(h_, &chol, &eig));
+    return {chol, eig};
   }
   // second half of Fill: Pseudo_InvSqrt_GWBSE(auxoverlap, 5e-7) + MultiplyRightWithAuxMatrix
   Index ApplyCoulombMetric(const Matrix& aux_coulomb, const Matrix* aux_overlap = nullptr, double etol = 5e-7) {

@@ -517,15 +517,23 @@ void TCMatrix::flush() {
   rotate(pendR.p, naux);
 }
 
+// the Cholesky path needs the deferred rotation (the factor must stay pending until the PPM eigenvectors absorb it)
+static bool metric_cholesky_enabled() {
+  static const bool on = [] {
+    const char* c = getenv("XTPB_METRIC_CHOLESKY");
+    const char* l = getenv("XTPB_LAZY_METRIC");
+    return !(c && c[0] == '0') && !(l && l[0] == '0');
+  }();
+  return on;
+}
+
 void TCMatrix::metric_hint(const double* V_host, long long ldv, const double* S_host, long long lds) {
-  static const bool chol = [] { const char* e = getenv("XTPB_METRIC_CHOLESKY"); return !(e && e[0] == '0'); }();
-  static const bool lazy = [] { const char* e = getenv("XTPB_LAZY_METRIC"); return !(e && e[0] == '0'); }();
   hint.given = true;
   hint.V = V_host;
   hint.S = S_host;
   // eigen path only: start its first eigendecomposition underneath the fill.  With the Cholesky path the decision
   // needs etol (known at apply time) and ~0.04 s of factorisations, so nothing is started here.
-  if (!(chol && lazy)) {
+  if (!metric_cholesky_enabled()) {
     if (S_host) metric_prefetch_begin(S_host, lds, true);
     else metric_prefetch_begin(V_host, ldv, false);
   }
@@ -597,8 +605,6 @@ long long TCMatrix::metric_factor_eig(double* A, double* S, double etol, bool pr
 
 long long TCMatrix::apply_coulomb_metric(const double* V_host, long long ldv, const double* S_host, long long lds,
                                          double etol) {
-  static const bool chol = [] { const char* e = getenv("XTPB_METRIC_CHOLESKY"); return !(e && e[0] == '0'); }();
-  static const bool lazy = [] { const char* e = getenv("XTPB_LAZY_METRIC"); return !(e && e[0] == '0'); }();
   const long long na = naux;
   if (hint.given) {
     const bool same = hint.V == V_host && hint.S == S_host;
@@ -618,7 +624,7 @@ long long TCMatrix::apply_coulomb_metric(const double* V_host, long long ldv, co
     S.alloc((size_t)(na * na));
     if (!prefetched) ctx->h2d_2d(S.p, na, S_host, lds, na, na);
   }
-  if (chol && lazy && !prefetched && etol > 0.0) {
+  if (metric_cholesky_enabled() && !prefetched && etol > 0.0) {
     // would the reference remove a function?  S - etol > 0 and V - etol S > 0 (V - etol without an overlap), decided
     // by Cholesky factorisations of copies
     DBuf T((size_t)(na * na));
@@ -756,8 +762,7 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
   // accumulated underneath Fill3cMO already (TCMatrix::PpmPrefetch)?  Then only the finishing steps remain.
   const bool prefetched = energies_host && n_omega == 1 && owner_shift < 0 && ctx->world == 1 &&
                           tc.ppm_prefetch_take(*energies_host, n_occ, eta, omegas_host[0], imag, out_dev);
-  if (prefetched) {
-  } else if (K > 0) {
+  if (!prefetched && K > 0) {
     k_chi0_weights(d.p, energies_dev, e_loc, (int)n_occ, (int)n_occ_loc, a0, K, om_dev, n_omega, imag, eta,
                    ctx->stream);
     GemmParams g{};
@@ -768,7 +773,7 @@ void rpa_epsilon_dev(TCMatrix& tc, const double* energies_dev, long long n_occ, 
     g.M = (int)tc.naux; g.N = (int)tc.naux; g.K = K; g.n_outer = (int)n_occ; g.n_batch = n_omega;
     g.alpha = 1.0; g.beta = 0.0; g.lower = 1;
     contract(g, ctx->ws, ctx->stream);
-  } else {
+  } else if (!prefetched) {
     XTPB_CUDA(cudaMemsetAsync(out_dev, 0, out_count * 8, ctx->stream));
   }
   const bool sharded = owner_shift >= 0 && ctx->world > 1;
