@@ -395,6 +395,11 @@ int xtpb_contract_host(xtpb_ctx* ctx, const xtpb_contract_desc* desc, const doub
 /* times `reps` launches of the same contraction on device buffers filled with pseudo-random data; returns
  * the mean milliseconds per launch (CUDA events on the library stream). */
 int xtpb_contract_bench(xtpb_ctx* ctx, const xtpb_contract_desc* desc, int reps, double* ms_per_launch);
+/* The launcher's plan for a shape on a device with n_sms SMs -- host arithmetic only, needs no device: tile_cfg
+ * (0: 128x128, 1: 128x64, 2: 128x32 CTA tiles) and the split-K factor (1 = none), honouring desc->force_cfg /
+ * force_splits.  Exposed so that the heuristics (small-grid split, tail-balancing split of long contractions) can be
+ * tested on a CPU box. */
+int xtpb_contract_plan(const xtpb_contract_desc* desc, int n_sms, int* tile_cfg, int* split_k);
 
 #ifdef __cplusplus
 }

@@ -155,6 +155,7 @@ PROTOTYPES = {
     "xtpb_host_eigh": (C.c_int, [idx, dptr, idx, dptr]),
     "xtpb_contract_host": (C.c_int, [vp, C.POINTER(ContractDesc), dptr, dptr, dptr, dptr]),
     "xtpb_contract_bench": (C.c_int, [vp, C.POINTER(ContractDesc), C.c_int, dptr]),
+    "xtpb_contract_plan": (C.c_int, [C.POINTER(ContractDesc), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
 _lib = None

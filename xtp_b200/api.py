@@ -842,6 +842,13 @@ def contract_host(ctx: Context, desc: "_lib.ContractDesc", A, B, d, Cmat):
     return Cmat
 
 
+def contract_plan(desc: "_lib.ContractDesc", n_sms=148):
+    """(tile_cfg, split_k) the launcher would choose for this shape on n_sms SMs (xtpb_contract_plan; no device needed)."""
+    cfg, sp = C.c_int(0), C.c_int(0)
+    check(_lib.lib().xtpb_contract_plan(C.byref(desc), int(n_sms), C.byref(cfg), C.byref(sp)))
+    return int(cfg.value), int(sp.value)
+
+
 def contract_bench(ctx: Context, desc: "_lib.ContractDesc", reps=10):
     ms = C.c_double()
     check(_lib.lib().xtpb_contract_bench(ctx._h, C.byref(desc), int(reps), C.byref(ms)))

@@ -738,6 +738,18 @@ static GemmParams params_from_desc(const xtpb_contract_desc* d, const double* A,
   g.alpha = d->alpha; g.beta = d->beta; g.lower = d->lower;
   return g;
 }
+int xtpb_contract_plan(const xtpb_contract_desc* desc, int n_sms, int* tile_cfg, int* split_k) {
+  XTPB_API_BEGIN
+  XTPB_REQUIRE(desc && n_sms > 0, "bad arguments");
+  int cfg = desc->force_cfg >= 8 ? desc->force_cfg - 8 : (desc->force_cfg >= 4 ? (desc->force_cfg == 7 ? -1 : desc->force_cfg - 4)
+                                                                                : desc->force_cfg);
+  int splits = desc->force_splits;
+  contract_plan((int)desc->M, (int)desc->N, (int)desc->K, (int)desc->n_outer, (int)desc->n_batch, desc->lower, n_sms, cfg,
+                splits);
+  if (tile_cfg) *tile_cfg = cfg;
+  if (split_k) *split_k = splits;
+  XTPB_API_END
+}
 int xtpb_contract_host(xtpb_ctx* ctx, const xtpb_contract_desc* desc, const double* A_host, const double* B_host,
                        const double* d_host, double* C_host) {
   XTPB_API_BEGIN

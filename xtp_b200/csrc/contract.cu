@@ -300,6 +300,58 @@ bool aligned16(const GemmOperand& o, bool kc, int n_outer, int n_batch) {
 
 }  // namespace
 
+// Launch plan of a contraction (host arithmetic only, no device): tile configuration `cfg` (0: 128x128, 1: 128x64,
+// 2: 128x32; < 0 on entry = choose) and split-K factor `splits` (<= 0 on entry = choose) for `sms` SMs.
+void contract_plan(int M, int N, int K, int n_outer, int n_batch, int lower, int sms, int& cfg, int& splits) {
+  if (cfg < 0) {
+    if (N <= 32) cfg = 2;
+    else if (N <= 64) cfg = 1;
+    else {
+      const long long pad128 = round_up(N, 128), pad64 = round_up(N, 64);
+      cfg = (pad64 < pad128) ? 1 : 0;
+    }
+    if (lower) cfg = 0;
+  }
+  const int bn = cfg == 0 ? 128 : (cfg == 1 ? 64 : 32);
+  const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn) * n_batch;
+  const long long nkt = (long long)((K + BK - 1) / BK) * n_outer;
+  if (splits > 0) return;
+  splits = 1;
+  // fewer than two waves of tiles: split the contraction index so that ~3 waves of CTAs are in flight (tail
+  // balance for the tensor-bound shapes, bytes in flight for the HBM-bound tall-skinny ones)
+  if (tiles < 2LL * sms && nkt >= 16) {
+    splits = (int)std::min<long long>({(3LL * sms + tiles - 1) / tiles, nkt / 8, 64LL});
+    if (splits < 1) splits = 1;
+  } else if (nkt >= 512) {
+    // Long contractions with a handful of waves (the eps(w) SYRK at C60 size: 946 lower-triangle tiles = 6.4 waves of
+    // 40 ms tiles, of which the seventh runs 0.4 full): splitting the contraction index s ways turns the tail into
+    // ceil(s * tiles / slots) / s waves.  Taken when the saved tile time clearly exceeds the extra pass over the
+    // partial results (and the workspace stays below 2 GiB); deterministic like every split-K launch.
+    long long real_tiles = tiles;
+    if (lower) {          // tiles on or below the diagonal (BM = BN = 128 for lower-triangular outputs)
+      const long long tm = (M + 127) / 128, tn = (N + 127) / 128;
+      real_tiles = 0;
+      for (long long j = 0; j < tn; ++j) real_tiles += std::max<long long>(0, tm - j);
+      real_tiles *= n_batch;
+    }
+    const long long slots = (long long)sms * (cfg == 0 ? 1 : 2);
+    auto waves = [&](int s_) { return double((real_tiles * s_ + slots - 1) / slots) / s_; };
+    const double tile_us = 2.1 * double(nkt) * (bn / 128.0);             // one CTA, whole contraction index
+    const double mn_bytes = 8.0 * double(M) * double(N) * n_batch * (lower ? 0.5 : 1.0);
+    int best = 1;
+    double best_gain = 0.0;
+    for (int s_ = 2; s_ <= 8; ++s_) {
+      if (nkt / s_ < 256 || mn_bytes * (lower ? 2.0 : 1.0) * s_ > 2147483648.0) break;
+      const double saved_us = (waves(1) - waves(s_)) * tile_us;
+      const double reduce_us = (s_ + 1) * mn_bytes / 4.0e6 + 10.0;       // ~4 TB/s over partials + output
+      const double gain = saved_us - 3.0 * reduce_us;
+      if (gain > best_gain + 1e-9) { best_gain = gain; best = s_; }
+    }
+    static const bool tail_split = [] { const char* e = getenv("XTPB_TAIL_SPLIT"); return !(e && e[0] == '0'); }();
+    if (tail_split) splits = best;
+  }
+}
+
 int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, int force_splits) {
   XTPB_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0 && p.n_outer >= 1 && p.n_batch >= 1, "bad contraction sizes");
   XTPB_REQUIRE((p.A.s_row == 1) != (p.A.s_k == 1) || (p.A.s_row == 1 && p.A.s_k == 1 && (p.M == 1 || p.K == 1)) ||
@@ -320,57 +372,8 @@ int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg, in
   p.a_vec = aligned16(p.A, a_kc, p.n_outer, p.n_batch) ? 1 : 0;
   p.b_vec = aligned16(p.B, b_kc, p.n_outer, p.n_batch) ? 1 : 0;
 
-  int cfg = force_cfg;
-  if (cfg < 0) {
-    if (p.N <= 32) cfg = 2;
-    else if (p.N <= 64) cfg = 1;
-    else {
-      const long long pad128 = round_up(p.N, 128), pad64 = round_up(p.N, 64);
-      cfg = (pad64 < pad128) ? 1 : 0;
-    }
-    if (p.lower) cfg = 0;
-  }
-  const int bn = cfg == 0 ? 128 : (cfg == 1 ? 64 : 32);
-  const long long tiles = (long long)((p.M + 127) / 128) * ((p.N + bn - 1) / bn) * p.n_batch;
-  const long long nkt = (long long)((p.K + BK - 1) / BK) * p.n_outer;
-  int splits = force_splits;
-  if (splits <= 0) {
-    splits = 1;
-    const int sms = num_sms();
-    // fewer than two waves of tiles: split the contraction index so that ~3 waves of CTAs are in flight (tail
-    // balance for the tensor-bound shapes, bytes in flight for the HBM-bound tall-skinny ones)
-    if (tiles < 2LL * sms && nkt >= 16) {
-      splits = (int)std::min<long long>({(3LL * sms + tiles - 1) / tiles, nkt / 8, 64LL});
-      if (splits < 1) splits = 1;
-    } else if (nkt >= 512) {
-      // Long contractions with a handful of waves (the eps(w) SYRK at C60 size: 946 lower-triangle tiles = 6.4 waves of
-      // 40 ms tiles, of which the seventh runs 0.4 full): splitting the contraction index s ways turns the tail into
-      // ceil(s * tiles / slots) / s waves.  Taken when the saved tile time clearly exceeds the extra pass over the
-      // partial results (and the workspace stays below 2 GiB); deterministic like every split-K launch.
-      long long real_tiles = tiles;
-      if (p.lower) {        // tiles on or below the diagonal (BM = BN = 128 for lower-triangular outputs)
-        const long long tm = (p.M + 127) / 128, tn = (p.N + 127) / 128;
-        real_tiles = 0;
-        for (long long j = 0; j < tn; ++j) real_tiles += std::max<long long>(0, tm - j);
-        real_tiles *= p.n_batch;
-      }
-      const long long slots = (long long)sms * (cfg == 0 ? 1 : 2);
-      auto waves = [&](int s_) { return double((real_tiles * s_ + slots - 1) / slots) / s_; };
-      const double tile_us = 2.1 * double(nkt) * (bn / 128.0);             // one CTA, whole contraction index
-      const double mn_bytes = 8.0 * double(p.M) * double(p.N) * p.n_batch * (p.lower ? 0.5 : 1.0);
-      int best = 1;
-      double best_gain = 0.0;
-      for (int s_ = 2; s_ <= 8; ++s_) {
-        if (nkt / s_ < 256 || mn_bytes * (p.lower ? 2.0 : 1.0) * s_ > 2147483648.0) break;
-        const double saved_us = (waves(1) - waves(s_)) * tile_us;
-        const double reduce_us = (s_ + 1) * mn_bytes / 4.0e6 + 10.0;       // ~4 TB/s over partials + output
-        const double gain = saved_us - 3.0 * reduce_us;
-        if (gain > best_gain + 1e-9) { best_gain = gain; best = s_; }
-      }
-      static const bool tail_split = [] { const char* e = getenv("XTPB_TAIL_SPLIT"); return !(e && e[0] == '0'); }();
-      if (tail_split) splits = best;
-    }
-  }
+  int cfg = force_cfg, splits = force_splits;
+  contract_plan(p.M, p.N, p.K, p.n_outer, p.n_batch, p.lower, num_sms(), cfg, splits);
   XTPB_REQUIRE((long long)p.n_batch * splits <= 65535, "batch*splits exceeds gridDim.z");
   p.splits = splits;
   p.ws = nullptr;

@@ -17,6 +17,9 @@ struct Workspace {
 // cp.async; 8..10 tile 0..2 on the TMA instance whatever the size.
 // `force_splits`: 0 auto.  Returns the number of kernels launched.
 int contract(GemmParams p, Workspace& ws, cudaStream_t stream, int force_cfg = -1, int force_splits = 0);
+// The launcher's choices for a shape on a device with `sms` SMs (host arithmetic only): cfg / splits as in contract();
+// values >= 0 / > 0 on entry are kept (forced), others are chosen.
+void contract_plan(int M, int N, int K, int n_outer, int n_batch, int lower, int sms, int& cfg, int& splits);
 
 // C[j,i] = C[i,j] for i>j (column-major n x n, leading dimension ld), optionally adds `diag_add` to the diagonal.
 void symmetrize_from_lower(double* C, int n, long long ld, double diag_add, cudaStream_t stream);
